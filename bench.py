@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- CTC loss+gradient throughput, the metric of BASELINE.json.
+
+  python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (benchmarks/ctc.cpp:150-165: parallelMap(fwd) +
+parallelMap(bwd)) over one synthetic minibatch of B=256 utterances, T=1000, C=64, U=100 per
+GPU (BASELINE.json configs[1]; weak scaling, so N GPUs = configs[4]'s 256/GPU).
+
+  value   utterances/s with the emissions already resident in HBM (device pointers in,
+          device gradients out, B losses read back)
+  e2e     the same call with HOST buffers (pinned): H2D of the emissions and D2H of the
+          gradients + losses inside the timed region
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event time
+  cpu_baseline  the reference itself (oracle/_ref, parallelMap on all host threads) on a
+          bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_DEF, C_DEF, U_DEF, B_DEF = 1000, 64, 100, 256
+
+
+def make_inputs(first, count, T, C, U):
+    e = np.empty((count, T, C), np.float32)
+    tg = []
+    for i in range(count):
+        rng = np.random.default_rng(1234 + first + i)
+        e[i] = rng.uniform(-5.0, 5.0, (T, C)).astype(np.float32)
+        tg.append(rng.integers(1, C, U).astype(np.int32))
+    return e, tg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference(sample, T, C, U, repeats=1):
+    """The real reference (oracle/_ref) on `sample` utterances, all host threads."""
+    from oracle import pyoracle as po
+    if not po.have_ref():
+        po.build(ref=False)
+        # the C restatement, single thread (kind "port")
+        e, tg = make_inputs(0, min(sample, 8), T, C, U)
+        t0 = time.perf_counter()
+        for b in range(e.shape[0]):
+            po.ctc_loss(e[b], tg[b], 0, True)
+        dt = time.perf_counter() - t0
+        return {"value": e.shape[0] / dt, "unit": "utt/s", "cores": 1, "kind": "port",
+                "sample": "%d utterances T=%d C=%d U=%d, oracle/gtn_oracle.c" % (e.shape[0], T, C, U)}
+    cores = po.libref().ref_hardware_threads()
+    e, tg = make_inputs(0, sample, T, C, U)
+    po.ref_ctc_batch(e[:min(sample, 2 * max(cores, 1))], tg[:min(sample, 2 * max(cores, 1))])  # warm the pool
+    best = None
+    for _ in range(repeats):
+        _, _, sec = po.ref_ctc_batch(e, tg)
+        best = sec if best is None else min(best, sec)
+    return {"value": sample / best, "unit": "utt/s", "cores": min(cores, sample), "kind": "reference",
+            "sample": "%d utterances T=%d C=%d U=%d via parallelMap on %d threads (benchmarks/ctc.cpp:150-165)"
+                      % (sample, T, C, U, min(cores, sample)), "seconds": best}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    T, C, U = args.T, args.C, args.U
+    sample = args.cpu_sample
+    from oracle import pyoracle as po
+    e, tg = make_inputs(0, sample, T, C, U)
+    kind = "reference" if po.have_ref() else "port"
+    if kind == "reference":
+        cores = min(po.libref().ref_hardware_threads(), sample)
+        step = lambda: po.ref_ctc_batch(e, tg)[2]
+    else:
+        cores = 1
+
+        def step():
+            t0 = time.perf_counter()
+            for b in range(sample):
+                po.ctc_loss(e[b], tg[b], 0, True)
+            return time.perf_counter() - t0
+    for _ in range(args.warmup):
+        step()
+    secs = [step() for _ in range(args.steps)]
+    ms = 1e3 * float(np.mean(secs))
+    val = sample / (ms / 1e3)
+    print(json.dumps({
+        "impl": "reference", "metric": "ctc_fwd_bwd_utterances_per_s", "value": val, "unit": "utt/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "CTC loss+grad T=%d C=%d U=%d (BASELINE.json configs[1]), %d-utterance sample per step"
+                               % (T, C, U, sample)},
+        "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": kind,
+                         "sample": "%d utterances per step" % sample},
+        "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_DEF, help="utterances per GPU")
+    ap.add_argument("--T", type=int, default=T_DEF)
+    ap.add_argument("--C", type=int, default=C_DEF)
+    ap.add_argument("--U", type=int, default=U_DEF)
+    ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from gtn_b200 import capi
+    L = capi.lib()
+    import ctypes as Ct
+    ctx = capi.Ctx(local)
+    B, T, C, U = args.batch, args.T, args.C, args.U
+    e, tg = make_inputs(rank * B, B, T, C, U)
+    lens = np.full(B, U, np.int32)
+    cat = np.ascontiguousarray(np.concatenate(tg), np.int32)
+    nbytes = e.nbytes
+    e_dev = ctx.to_device(e)
+    g_dev = ctx.alloc(nbytes)
+    losses = np.zeros(B, np.float32)
+
+    # pinned host buffers for the end-to-end leg
+    hp_e, hp_g = Ct.c_void_p(), Ct.c_void_p()
+    ctx._check(L.gtnb_host_alloc(ctx.h, nbytes, Ct.byref(hp_e)))
+    ctx._check(L.gtnb_host_alloc(ctx.h, nbytes, Ct.byref(hp_g)))
+    Ct.memmove(hp_e.value, e.ctypes.data, nbytes)
+
+    i32p, f32p = capi._i32p, capi._f32p
+
+    def step_dev():
+        ctx._check(L.gtnb_ctc_loss(ctx.h, B, T, C, e_dev.ptr, 1, None, cat.ctypes.data_as(i32p),
+                                   lens.ctypes.data_as(i32p), 0, losses.ctypes.data_as(f32p),
+                                   g_dev.ptr, 1))
+
+    def step_e2e():
+        ctx._check(L.gtnb_ctc_loss(ctx.h, B, T, C, hp_e.value, 0, None, cat.ctypes.data_as(i32p),
+                                   lens.ctypes.data_as(i32p), 0, losses.ctypes.data_as(f32p),
+                                   hp_g.value, 0))
+
+    # lattice sizes for the algorithmic byte counts (untimed)
+    from tests import util
+    from oracle import pyoracle as po  # graph builder only (host arrays), never timed
+    views = [util.view_of(po.Graph.ctc(t, 0, True)) for t in tg]
+    lat = ctx.compose_linear(views, [T] * B, C, e_dev, T * C)
+    nn, na = lat.sizes()
+    lat.free()
+    sumN, sumA = int(nn.sum()), int(na.sum())
+    TC = T * C
+    alg_bytes = {  # per launch, whole batch -- SURVEY.md section 8(d), DESIGN.md "Algorithmic bytes"
+        "sd_forward": 8 * sumA + 12 * sumN,
+        "sd_backward": 12 * sumA + 16 * sumN,
+        "compose_grad": 12 * sumA + 4 * TC * B,
+        "compose_emit": 16 * sumA + 4 * sumN + 4 * TC * B,
+        "linear_rows": 8 * TC * B,
+    }
+    b_csr = 32 * sumA + 28 * sumN + 12 * TC * B
+
+    for _ in range(args.warmup):
+        step_dev()
+    ctx.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.profile(True)
+    ctx.profile_read()
+    launches0 = ctx.launches
+    barrier()
+    times = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.flush_l2()  # inputs (65.5 MB) are smaller than the 126 MB L2
+        ctx.timer_start()
+        step_dev()
+        times.append(ctx.timer_stop())
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+
+    # end-to-end leg (host buffers)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_times = []
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        step_e2e()
+        e2e_times.append(ctx.timer_stop())
+    barrier()
+    clocks = sampler.stop()
+
+    ms = float(np.mean(times))
+    e2e_ms = float(np.mean(e2e_times))
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        # dominant kernel by CUDA-event time
+        dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
+        name, (cnt, tot_ms) = dom
+        roofline = None
+        if name in alg_bytes and cnt:
+            per_launch_ms = tot_ms / cnt
+            ach = alg_bytes[name] / (per_launch_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                        "kernel_ms": per_launch_ms, "algorithmic_bytes": alg_bytes[name]}
+        kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
+                       "GBps": (alg_bytes[k] / (v[1] / v[0] * 1e-3) / 1e9) if k in alg_bytes and v[0] else None}
+                   for k, v in prof.items()}
+        out = {
+            "metric": "ctc_fwd_bwd_utterances_per_s", "value": world * B / (ms * 1e-3), "unit": "utt/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "CTC loss+grad B=%d/GPU T=%d C=%d U=%d (BASELINE.json configs[1]; x N GPUs = configs[4])"
+                                   % (B, T, C, U),
+                       "l2": "flushed between timed iterations (256 MB memset)", "parallelism": "dp%d" % world,
+                       "lattice_nodes": sumN, "lattice_arcs": sumA},
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "utt/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(nbytes + cat.nbytes + lens.nbytes),
+                    "d2h_bytes_per_step": int(nbytes + losses.nbytes)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_whole_step_csr": {"achieved": b_csr / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                                        "frac": b_csr / (ms * 1e-3) / 1e9 / peak, "bytes": b_csr},
+            "kernels": kernels,
+            "wall_s": wall,
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_reference(args.cpu_sample, T, C, U)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

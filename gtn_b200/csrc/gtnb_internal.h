@@ -1,0 +1,242 @@
+/*
+ * Internal declarations shared by the C-ABI translation units.
+ * Nothing here is visible through include/gtn_b200.h.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "gtn_b200.h"
+
+namespace gtnb {
+
+constexpr uint32_t kRowMask = 0x3FFFFFFFu; // low 30 bits of a row_ptr entry
+constexpr uint32_t kStartBit = 0x40000000u; // node is a start node
+constexpr uint32_t kAcceptBit = 0x80000000u; // node is an accept node
+constexpr int kAlign = 4; // elements; keeps every per-graph slab 16-byte aligned
+
+/*
+ * Per-graph descriptor, one per batch entry, resident in HBM.  All bases are
+ * ELEMENT offsets into the batch-wide arrays of gtnb_lattice.
+ *
+ * Layout of graph b (device numbering):
+ *   nodes  [0, N)   sorted by level; level l = [lvl_node_ptr[l], lvl_node_ptr[l+1])
+ *                   nodes [lvl_node_ptr[L], N) are never scheduled by the
+ *                   reference's Kahn sweep but are accept nodes with no
+ *                   in-arcs: their score is the vector's initial 0.0f
+ *                   (shortest.cpp:89).
+ *   arcs   [0, A)   CSR by destination: in-arcs of node n are
+ *                   [row_ptr[n] & kRowMask, row_ptr[n+1] & kRowMask) in the
+ *                   reference's g.in(n) order; the top two bits of row_ptr[n]
+ *                   carry the start / accept flags of node n.
+ */
+struct GraphMeta {
+  long long node_base; // row_ptr, scores, node_grad, back_ptr, node_orig
+  long long arc_base; // src, w, gi_*, arc_grad, arc_orig, relax_rank
+  long long lvl_base; // lvl_node_ptr, lvl_arc_ptr  (L+1 entries)
+  long long acc_base; // accept_nodes
+  long long blvl_base; // backward level ptr (LB+1 entries), packed graphs only
+  long long bnode_base; // backward node list
+  long long sg_node_base; // small-graph (compose operand) slabs
+  long long sg_arc_base;
+  long long emis_off; // utterance's first emission, in floats
+  long long grad_graph_off; // this graph's slab in gtnb_compose_grad's grad_graph_dev
+  int L; // number of forward levels
+  int N; // number of device nodes
+  int A; // number of device arcs
+  int n_accept;
+  int LB; // number of backward levels (packed graphs), -1 = reverse forward levels
+  int status; // GTNB_OK or GTNB_ERR_INVALID_ARGUMENT
+  int T; // frames (composed lattices)
+  int sg_N; // small-graph node / arc counts (composed lattices)
+  int sg_A;
+  int cap_N; // slab capacities
+  int cap_A;
+  int cap_L;
+};
+
+} // namespace gtnb
+
+struct gtnb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  int sm_count = 148;
+  // pinned staging for small host->device uploads
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+  // optional per-kernel CUDA-event timing (gtnb_profile_*)
+  struct ProfEntry {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  bool profiling = false;
+  std::vector<ProfEntry> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  std::string prof_text;
+};
+
+struct gtnb_lattice {
+  int B = 0;
+  bool composed = false;
+  bool linear_first = false;
+  bool shared_graph = false;
+  bool level_local = false; // every arc goes level l-1 -> l
+  bool forward_done = false;
+  bool sizes_known = false;
+  int forward_mode = -1;
+  int C = 0;
+  int max_lvl_nodes = 0, max_lvl_arcs = 0; // upper bounds over the batch
+  int max_T = 0;
+  long long tot_N = 0, tot_A = 0, tot_L = 0, tot_acc = 0, tot_bl = 0, tot_bn = 0;
+  long long tot_sgN = 0, tot_sgA = 0;
+
+  std::vector<gtnb::GraphMeta> meta_h;
+  gtnb::GraphMeta* meta = nullptr;
+
+  // lattice proper
+  int32_t* lvl_node_ptr = nullptr;
+  int32_t* lvl_arc_ptr = nullptr;
+  uint32_t* row_ptr = nullptr;
+  int32_t* src = nullptr;
+  float* w = nullptr;
+  int32_t* acc_nodes = nullptr;
+  // provenance of composed arcs (gradInfo)
+  int32_t* gi_graph = nullptr;
+  int32_t* gi_linear = nullptr;
+  // packed graphs: mapping back to Graph numbering + backward schedule
+  int32_t* node_orig = nullptr;
+  int32_t* arc_orig = nullptr;
+  int32_t* relax_rank = nullptr;
+  int32_t* blvl_ptr = nullptr;
+  int32_t* bnodes = nullptr;
+  // saved state
+  float* scores = nullptr;
+  float* out_scores = nullptr; // [B]
+  int32_t* best_accept = nullptr; // [B] tropical: best accept node
+  float* node_grad = nullptr;
+  float* arc_grad = nullptr;
+  int32_t* back_ptr = nullptr;
+  // compose operands kept on the device
+  const float* emissions = nullptr;
+  int64_t emissions_stride = 0;
+  uint8_t* sg_flags = nullptr; // per small-graph node
+  int32_t* sg_in_ptr = nullptr; // [sgN + 1] per graph
+  int32_t* sg_in_src = nullptr; // per in-entry (sgA)
+  int32_t* sg_in_label = nullptr; // matched label, -1 = can never match
+  int32_t* sg_in_arc = nullptr; // Graph arc id
+  float* sg_in_w = nullptr;
+  int32_t* sg_ilabel = nullptr; // by arc id
+  int32_t* sg_olabel = nullptr;
+  uint32_t* alive = nullptr; // [B][max_T+1][W] bitmasks
+  int alive_words = 0;
+
+  // host copies needed to answer queries on packed graphs
+  std::vector<std::vector<int32_t>> h_node_orig, h_arc_orig, h_ilabel, h_olabel;
+  std::vector<int32_t> h_arcs_orig_count; // Graph's own arc count (>= device A)
+};
+
+namespace gtnb {
+
+int fail(gtnb_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(gtnb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+
+#define GTNB_CUDA(ctx, call)                                              \
+  do {                                                                    \
+    cudaError_t e__ = (call);                                             \
+    if (e__ != cudaSuccess)                                               \
+      return ::gtnb::cuda_fail((ctx), e__, #call, __FILE__, __LINE__);    \
+  } while (0)
+
+#define GTNB_CHECK_LAUNCH(ctx)                                            \
+  do {                                                                    \
+    (ctx)->launches++;                                                    \
+    cudaError_t e__ = cudaGetLastError();                                 \
+    if (e__ != cudaSuccess)                                               \
+      return ::gtnb::cuda_fail((ctx), e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+inline cudaEvent_t prof_event(gtnb_ctx* ctx) {
+  cudaEvent_t e;
+  if (!ctx->ev_pool.empty()) {
+    e = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+inline void prof_begin(gtnb_ctx* ctx, const char* name) {
+  if (!ctx->profiling) return;
+  gtnb_ctx::ProfEntry pe{name, prof_event(ctx), prof_event(ctx)};
+  cudaEventRecord(pe.a, ctx->stream);
+  ctx->prof.push_back(pe);
+}
+inline void prof_end(gtnb_ctx* ctx) {
+  if (!ctx->profiling || ctx->prof.empty()) return;
+  cudaEventRecord(ctx->prof.back().b, ctx->stream);
+}
+
+/* Launch a kernel on the context's stream, count it, time it when profiling. */
+#define GTNB_LAUNCH(ctx, name, ...)  \
+  do {                               \
+    ::gtnb::prof_begin((ctx), name); \
+    __VA_ARGS__;                     \
+    ::gtnb::prof_end((ctx));         \
+    GTNB_CHECK_LAUNCH(ctx);          \
+  } while (0)
+
+template <typename T>
+int dev_alloc(gtnb_ctx* ctx, T** p, long long n) {
+  *p = nullptr;
+  if (n <= 0) n = 1;
+  // +16 elements of slack: staged copies round their windows up to 16 bytes
+  GTNB_CUDA(ctx, cudaMallocAsync((void**)p, sizeof(T) * (size_t)(n + 16), ctx->stream));
+  return GTNB_OK;
+}
+
+template <typename T>
+void dev_free(gtnb_ctx* ctx, T*& p) {
+  if (p) cudaFreeAsync((void*)p, ctx->stream);
+  p = nullptr;
+}
+
+// Upload through pinned staging is overkill for the small metadata here;
+// pageable cudaMemcpyAsync is synchronous wrt the host and safe.
+template <typename T>
+int upload(gtnb_ctx* ctx, T* dst, const T* src, long long n) {
+  if (n <= 0) return GTNB_OK;
+  GTNB_CUDA(ctx, cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  return GTNB_OK;
+}
+
+inline long long align_up(long long v, long long a) {
+  return (v + a - 1) / a * a;
+}
+
+// kernels (k_shortest.cu)
+int launch_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int mode);
+int launch_backward(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev);
+int launch_traceback(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, int32_t* path_dev, int32_t* len_dev);
+int launch_gather_prov(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, const int32_t* path_dev, const int32_t* len_dev, int32_t* prov_graph, int32_t* prov_linear);
+// kernels (k_compose.cu)
+int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat);
+int launch_compose_grad(gtnb_ctx* ctx, gtnb_lattice* lat, float* grad_graph, float* grad_emis, int64_t grad_stride);
+// kernels (k_linear.cu)
+int launch_linear_forward(
+    gtnb_ctx* ctx, int B, const int32_t* T_dev, int maxT, int C, const float* emis, int64_t stride,
+    int tropical, float* scores, float* grad, int64_t grad_stride, const float* deltas, float delta_all);
+
+enum { MODE_LOG = 0, MODE_TROPICAL = 1, MODE_PATH = 2 };
+
+} // namespace gtnb

@@ -1,0 +1,245 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bit-exact for indices / paths, 1e-4 relative (+1e-5 abs, see tests/util.py) for
+scores and gradients -- BASELINE.json:north_star.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_graph(oracle, flags, src, dst, il, ol, w):
+    return oracle.Graph.from_arrays(flags, src, dst, il, ol, w)
+
+
+# ---------------------------------------------------------------------------
+# generic graphs through gtnb_pack
+# ---------------------------------------------------------------------------
+
+def test_known_answers_forward(ctx, oracle):
+    """test/functions_test.cpp:231-389 'Test Forward' known answers."""
+    inf = np.inf
+    cases = []
+    # empty graph -> -inf (:233-236)
+    cases.append((np.zeros(0, np.uint8), [], [], [], -inf))
+    # two -inf arcs (:297-304) ; inf arc (:306-314) ; single node (:316-320)
+    cases.append((np.array([1, 2], np.uint8), [0, 0], [1, 1], [-inf, -inf], -inf))
+    cases.append((np.array([1, 2], np.uint8), [0, 0], [1, 1], [inf, 0.0], inf))
+    cases.append((np.array([3], np.uint8), [], [], [], 0.0))
+    # simple case (:322-334) = 6.8152
+    cases.append((np.array([1, 0, 2], np.uint8), [0, 0, 0, 1, 1, 1], [1, 1, 1, 2, 2, 2],
+                  [1, 2, 3, 1, 2, 3], 6.8152))
+    views = []
+    for flags, src, dst, w, _ in cases:
+        lab = np.zeros(len(src), np.int32)
+        views.append(util.capi.make_view(flags, np.asarray(src, np.int32), np.asarray(dst, np.int32),
+                                         lab, lab, np.asarray(w, np.float32)))
+    lat = ctx.pack(views)
+    got = lat.forward()
+    for g, c in zip(got, cases):
+        if np.isinf(c[4]):
+            assert g == c[4]
+        else:
+            assert abs(g - c[4]) < 1e-3
+    lat.free()
+
+
+def test_invalid_graphs_raise(ctx):
+    """self-loop / cycle / orphan predecessor -> invalid_argument (functions_test.cpp:238-291)."""
+    bad = [
+        (np.array([3], np.uint8), [0], [0]),
+        (np.array([1, 0, 2], np.uint8), [0, 1, 1], [1, 2, 1]),
+        (np.array([1, 0, 2], np.uint8), [0, 1, 2], [1, 2, 2]),
+        (np.array([1, 0, 2], np.uint8), [0, 1, 2], [1, 2, 0]),
+        (np.array([1, 0, 2], np.uint8), [0, 1], [2, 2]),
+    ]
+    for flags, src, dst in bad:
+        lab = np.zeros(len(src), np.int32)
+        v = util.capi.make_view(flags, np.asarray(src, np.int32), np.asarray(dst, np.int32), lab, lab,
+                                np.zeros(len(src), np.float32))
+        lat = ctx.pack([v])
+        with pytest.raises(ValueError):
+            lat.forward()
+        with pytest.raises(ValueError):
+            lat.viterbi_path(8)
+        lat.free()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_dags_vs_oracle(ctx, oracle, seed):
+    rng = np.random.default_rng(seed)
+    graphs, views = [], []
+    for _ in range(24):
+        n = int(rng.integers(2, 40))
+        a = int(rng.integers(n, 4 * n))
+        flags, src, dst, il, ol, w = util.random_dag(rng, n, a)
+        # extra start / accept nodes now and then
+        if rng.random() < 0.5:
+            flags[int(rng.integers(0, n))] |= 1
+        if rng.random() < 0.5:
+            flags[int(rng.integers(0, n))] |= 2
+        g = _oracle_graph(oracle, flags, src, dst, il, ol, w)
+        graphs.append(g)
+        views.append(util.view_of(g))
+    lat = ctx.pack(views)
+    for tropical in (False, True):
+        got = lat.forward(tropical=tropical)
+        lat.backward(tropical=tropical)
+        for b, g in enumerate(graphs):
+            s, gr = oracle.forward_score_and_grad(g, tropical)
+            assert util.close(got[b], s), (b, got[b], s)
+            mine = lat.arc_grads(b, g.num_arcs)
+            if tropical:
+                assert np.array_equal(mine, gr), (b, mine, gr)
+            else:
+                assert util.close(mine, gr), (b, np.abs(mine - gr).max())
+    lat.free()
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_viterbi_path_ties_vs_oracle(ctx, oracle, seed):
+    """Integer weights force ties; the path must be the reference's (first-relaxed wins)."""
+    rng = np.random.default_rng(seed)
+    graphs, views = [], []
+    for _ in range(32):
+        n = int(rng.integers(2, 30))
+        a = int(rng.integers(n, 5 * n))
+        flags, src, dst, il, ol, w = util.random_dag(rng, n, a, int_weights=True)
+        g = _oracle_graph(oracle, flags, src, dst, il, ol, w)
+        graphs.append(g)
+        views.append(util.view_of(g))
+    lat = ctx.pack(views)
+    out = lat.viterbi_path(64)
+    for b, g in enumerate(graphs):
+        want = oracle.shortest_path(g)
+        assert want is not None
+        assert out["lens"][b] == len(want)
+        assert np.array_equal(out["arcs"][b, :len(want)], want), (b, out["arcs"][b, :len(want)], want)
+    lat.free()
+
+
+# ---------------------------------------------------------------------------
+# frame-synchronous compose + CTC
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("blank_last", [False, True])
+def test_compose_ctc_structure_and_scores(ctx, oracle, blank_last):
+    rng = np.random.default_rng(7)
+    B, T, C, U = 6, 40, 9, 5
+    e = rng.uniform(-5, 5, (B, T, C)).astype(np.float32)
+    blank = C - 1 if blank_last else 0
+    targets = [rng.integers(0 if blank_last else 1, C - 1 if blank_last else C, U) for _ in range(B)]
+    targets[1] = np.array([2, 2, 2, 3, 3])  # repeats: no skip arcs
+    e_dev = ctx.to_device(e)
+    ctcs = [oracle.Graph.ctc(t, blank, True) for t in targets]
+    views = [util.view_of(g) for g in ctcs]
+    lat = ctx.compose_linear(views, [T] * B, C, e_dev, T * C)
+    nn, na = lat.sizes()
+    got = lat.forward()
+    got_t = lat.forward(tropical=True)
+    for b in range(B):
+        ref = oracle.intersect(ctcs[b], oracle.Graph.linear(T, C, e[b]))
+        assert (nn[b], na[b]) == (ref.num_nodes, ref.num_arcs)
+        s, _, _, _ = oracle.shortest_distance(ref, False)
+        st, _, _, _ = oracle.shortest_distance(ref, True)
+        assert util.close(got[b], s)
+        assert got_t[b] == st  # tropical: adds only, same association -> bit exact
+        d = lat.download(b)
+        # same multiset of (ilabel, olabel, weight) arcs as the reference's lattice
+        ra = ref.arrays()
+        mine = sorted(zip(d["ilabel"].tolist(), d["olabel"].tolist(), d["w"].tolist()))
+        theirs = sorted(zip(ra["ilabel"].tolist(), ra["olabel"].tolist(), ra["w"].tolist()))
+        assert mine == theirs
+    lat.free()
+    e_dev.free()
+
+
+def test_ctc_loss_and_grad_small(ctx, oracle):
+    B, T, C, U = 5, 60, 12, 7
+    e, targets = util.bench_inputs(B, T, C, U)
+    losses, grads = ctx.ctc_loss(e, targets, blank=0)
+    for b in range(B):
+        lo, go = oracle.ctc_loss(e[b], targets[b], 0, True)
+        assert util.close(losses[b], lo), (losses[b], lo)
+        assert util.grad_close(grads[b], go, 5.0 * T), np.abs(grads[b] - go).max()
+
+
+def test_ctc_reference_known_answers(ctx):
+    """test/criterion_test.cpp:84-179: TensorFlow CTC cases (loss + emission gradients)."""
+    T, N = 5, 6
+    probs3 = np.array([
+        0.633766, 0.221185, 0.0917319, 0.0129757, 0.0142857, 0.0260553,
+        0.111121, 0.588392, 0.278779, 0.0055756, 0.00569609, 0.010436,
+        0.0357786, 0.633813, 0.321418, 0.00249248, 0.00272882, 0.0037688,
+        0.0663296, 0.643849, 0.280111, 0.00283995, 0.0035545, 0.00331533,
+        0.458235, 0.396634, 0.123377, 0.00648837, 0.00903441, 0.00623107], np.float32)
+    grad3 = np.array([
+        -0.366234, 0.221185, 0.0917319, 0.0129757, 0.0142857, 0.0260553,
+        0.111121, -0.411608, 0.278779, 0.0055756, 0.00569609, 0.010436,
+        0.0357786, 0.633813, -0.678582, 0.00249248, 0.00272882, 0.0037688,
+        0.0663296, -0.356151, 0.280111, 0.00283995, 0.0035545, 0.00331533,
+        -0.541765, 0.396634, 0.123377, 0.00648837, 0.00903441, 0.00623107], np.float32)
+    probs4 = np.array([
+        0.30176, 0.28562, 0.0831517, 0.0862751, 0.0816851, 0.161508,
+        0.24082, 0.397533, 0.0557226, 0.0546814, 0.0557528, 0.19549,
+        0.230246, 0.450868, 0.0389607, 0.038309, 0.0391602, 0.202456,
+        0.280884, 0.429522, 0.0326593, 0.0339046, 0.0326856, 0.190345,
+        0.423286, 0.315517, 0.0338439, 0.0393744, 0.0339315, 0.154046], np.float32)
+    grad4 = np.array([
+        -0.69824, 0.28562, 0.0831517, 0.0862751, 0.0816851, 0.161508,
+        0.24082, -0.602467, 0.0557226, 0.0546814, 0.0557528, 0.19549,
+        0.230246, 0.450868, 0.0389607, 0.038309, 0.0391602, -0.797544,
+        0.280884, -0.570478, 0.0326593, 0.0339046, 0.0326856, 0.190345,
+        -0.576714, 0.315517, 0.0338439, 0.0393744, 0.0339315, 0.154046], np.float32)
+    e = np.log(np.stack([probs3, probs4]).reshape(2, T, N))
+    losses, grads = ctx.ctc_loss(e, [[0, 1, 2, 1, 0], [0, 1, 1, 0]], blank=N - 1)
+    assert abs(losses[0] - 3.34211) < 1e-4
+    assert abs(losses[1] - 5.42262) < 1e-4
+    assert np.abs(grads[0].ravel() - grad3).max() < 1e-5
+    assert np.abs(grads[1].ravel() - grad4).max() < 1e-5
+
+
+def test_ctc_config1_plumbing(ctx, oracle):
+    """BASELINE.json configs[0]: B=1 T=100 C=28 U=10."""
+    e, targets = util.bench_inputs(1, 100, 28, 10)
+    losses, grads = ctx.ctc_loss(e, targets)
+    lo, go = oracle.ctc_loss(e[0], targets[0], 0, True)
+    assert util.close(losses[0], lo)
+    assert util.grad_close(grads[0], go, 5.0 * 100)
+
+
+def test_ctc_ragged_and_edge(ctx, oracle):
+    """ragged input lengths, empty target, target too long for T (infeasible -> +inf loss)."""
+    B, T, C = 4, 30, 6
+    rng = np.random.default_rng(11)
+    e = rng.uniform(-5, 5, (B, T, C)).astype(np.float32)
+    targets = [rng.integers(1, C, 4), np.zeros(0, np.int32), rng.integers(1, C, 3),
+               np.array([1, 1, 1, 1, 1, 1, 1, 1])]
+    lens = np.array([30, 12, 1, 10], np.int32)
+    losses, grads = ctx.ctc_loss(e, targets, input_lens=lens)
+    for b in range(B):
+        lo, go = oracle.ctc_loss(e[b, :lens[b]], targets[b], 0, True)
+        assert util.close(losses[b], lo), (b, losses[b], lo)
+        if np.isfinite(lo):
+            assert util.grad_close(grads[b, :lens[b]], go, 5.0 * T), b
+        assert not grads[b, lens[b]:].any()
+
+
+def test_ctc_full_size_properties(ctx):
+    """BASELINE config 2 shape (a slice of it): size-independent properties at T=1000, C=64.
+
+    sum_c grad[t, c] == 0 for every frame (softmax part sums to 1, occupation
+    part sums to 1), and the loss is invariant to adding a per-frame constant.
+    """
+    B, T, C, U = 8, 1000, 64, 100
+    e, targets = util.bench_inputs(B, T, C, U)
+    losses, grads = ctx.ctc_loss(e, targets)
+    assert np.all(np.isfinite(losses)) and np.all(losses > 0)
+    # (the reference's own fp32 row sums drift to 2.9e-3 here: tests/golden/README.md)
+    assert np.abs(grads.sum(axis=2)).max() < 1e-2
+    shift = np.random.default_rng(5).uniform(-1, 1, (B, T, 1)).astype(np.float32)
+    losses2, _ = ctx.ctc_loss(e + shift, targets, want_grad=False)
+    assert np.allclose(losses, losses2, rtol=1e-4)
