@@ -46,6 +46,7 @@ SYMBOLS = [
     ("gtnb_ctx_synchronize", C.c_int, [_vp]),
     ("gtnb_ctx_stream", _vp, [_vp]),
     ("gtnb_ctx_launch_count", C.c_int64, [_vp]),
+    ("gtnb_ctx_set_flag", C.c_int, [_vp, C.c_char_p, C.c_int]),
     ("gtnb_device_alloc", C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     ("gtnb_device_free", C.c_int, [_vp, _vp]),
     ("gtnb_host_alloc", C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -231,6 +232,9 @@ class Ctx:
         ms = C.c_float()
         self._check(lib().gtnb_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def set_flag(self, name, value):
+        self._check(lib().gtnb_ctx_set_flag(self.h, name.encode(), int(value)))
 
     def profile(self, on=True):
         self._check(lib().gtnb_profile_enable(self.h, int(on)))

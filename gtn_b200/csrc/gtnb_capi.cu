@@ -163,6 +163,14 @@ int gtnb_timer_stop(gtnb_ctx* ctx, float* ms) {
   GTNB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
   return GTNB_OK;
 }
+int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value) {
+  if (ctx && name && std::string(name) == "staged") {
+    ctx->use_staged = value != 0;
+    return GTNB_OK;
+  }
+  return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctx_set_flag: unknown flag");
+}
+
 int gtnb_profile_enable(gtnb_ctx* ctx, int on) {
   ctx->profiling = on != 0;
   return GTNB_OK;
@@ -423,11 +431,9 @@ void free_lattice_device(gtnb_ctx* ctx, gtnb_lattice* lat) {
   dev_free(ctx, lat->lvl_node_ptr);
   dev_free(ctx, lat->lvl_arc_ptr);
   dev_free(ctx, lat->row_ptr);
-  dev_free(ctx, lat->src);
-  dev_free(ctx, lat->w);
+  dev_free(ctx, lat->arcs);
   dev_free(ctx, lat->acc_nodes);
-  dev_free(ctx, lat->gi_graph);
-  dev_free(ctx, lat->gi_linear);
+  dev_free(ctx, lat->gi);
   dev_free(ctx, lat->node_orig);
   dev_free(ctx, lat->arc_orig);
   dev_free(ctx, lat->relax_rank);
@@ -549,8 +555,7 @@ int gtnb_pack(gtnb_ctx* ctx, int B, const gtnb_graph_view* graphs, gtnb_lattice*
     TRY(dev_alloc(ctx, &lat->lvl_node_ptr, tl));
     TRY(dev_alloc(ctx, &lat->lvl_arc_ptr, tl));
     TRY(dev_alloc(ctx, &lat->row_ptr, tn));
-    TRY(dev_alloc(ctx, &lat->src, ta));
-    TRY(dev_alloc(ctx, &lat->w, ta));
+    TRY(dev_alloc(ctx, &lat->arcs, ta));
     TRY(dev_alloc(ctx, &lat->acc_nodes, tc));
     TRY(dev_alloc(ctx, &lat->arc_orig, ta));
     TRY(dev_alloc(ctx, &lat->relax_rank, ta));
@@ -569,10 +574,20 @@ int gtnb_pack(gtnb_ctx* ctx, int B, const gtnb_graph_view* graphs, gtnb_lattice*
     TRY(upload_slabs(ctx, lat->lvl_arc_ptr, lb, pi));
     for (int b = 0; b < B; b++) pu[b] = &P[b].row_ptr;
     TRY(upload_slabs(ctx, lat->row_ptr, nb, pu));
-    for (int b = 0; b < B; b++) pi[b] = &P[b].src;
-    TRY(upload_slabs(ctx, lat->src, ab, pi));
-    for (int b = 0; b < B; b++) pf[b] = &P[b].w;
-    TRY(upload_slabs(ctx, lat->w, ab, pf));
+    {
+      std::vector<std::vector<int2>> inter(B);
+      std::vector<const std::vector<int2>*> pa(B);
+      for (int b = 0; b < B; b++) {
+        inter[b].resize(P[b].src.size());
+        for (size_t a = 0; a < P[b].src.size(); a++) {
+          int wb;
+          std::memcpy(&wb, &P[b].w[a], 4);
+          inter[b][a] = make_int2(P[b].src[a], wb);
+        }
+        pa[b] = &inter[b];
+      }
+      TRY(upload_slabs(ctx, lat->arcs, ab, pa));
+    }
     for (int b = 0; b < B; b++) pi[b] = &P[b].acc;
     TRY(upload_slabs(ctx, lat->acc_nodes, cb, pi));
     for (int b = 0; b < B; b++) pi[b] = &P[b].arc_orig;
@@ -650,19 +665,15 @@ int gtnb_lattice_download(
   std::vector<uint32_t> rp(m.N + 1);
   std::vector<int32_t> src(std::max(m.A, 1)), gg(std::max(m.A, 1), -1), gl(std::max(m.A, 1), -1);
   std::vector<float> w(std::max(m.A, 1));
+  std::vector<int2> arcs_h(std::max(m.A, 1)), gi_h(std::max(m.A, 1));
   GTNB_CUDA(ctx, cudaMemcpyAsync(rp.data(), lat->row_ptr + m.node_base, sizeof(uint32_t) * (m.N + 1),
                                  cudaMemcpyDeviceToHost, ctx->stream));
   if (m.A > 0) {
-    GTNB_CUDA(ctx, cudaMemcpyAsync(src.data(), lat->src + m.arc_base, sizeof(int32_t) * m.A,
+    GTNB_CUDA(ctx, cudaMemcpyAsync(arcs_h.data(), lat->arcs + m.arc_base, sizeof(int2) * m.A,
                                    cudaMemcpyDeviceToHost, ctx->stream));
-    GTNB_CUDA(ctx, cudaMemcpyAsync(w.data(), lat->w + m.arc_base, sizeof(float) * m.A,
-                                   cudaMemcpyDeviceToHost, ctx->stream));
-    if (lat->gi_graph) {
-      GTNB_CUDA(ctx, cudaMemcpyAsync(gg.data(), lat->gi_graph + m.arc_base, sizeof(int32_t) * m.A,
+    if (lat->gi)
+      GTNB_CUDA(ctx, cudaMemcpyAsync(gi_h.data(), lat->gi + m.arc_base, sizeof(int2) * m.A,
                                      cudaMemcpyDeviceToHost, ctx->stream));
-      GTNB_CUDA(ctx, cudaMemcpyAsync(gl.data(), lat->gi_linear + m.arc_base, sizeof(int32_t) * m.A,
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-    }
   }
   std::vector<int32_t> il, ol;
   if (lat->composed && (arc_ilabel || arc_olabel)) {
@@ -674,6 +685,14 @@ int gtnb_lattice_download(
                                    cudaMemcpyDeviceToHost, ctx->stream));
   }
   GTNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int a = 0; a < m.A; a++) {
+    src[a] = arcs_h[a].x;
+    std::memcpy(&w[a], &arcs_h[a].y, 4);
+    if (lat->gi) {
+      gg[a] = gi_h[a].x;
+      gl[a] = gi_h[a].y;
+    }
+  }
   if (lat->composed) {
     // device numbering IS the Graph numbering of a composed lattice
     for (int n = 0; n < m.N; n++) {
@@ -753,7 +772,6 @@ int gtnb_backward(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* d
     if ((rc = upload(ctx, deltas_dev, deltas_host, lat->B))) return rc;
   }
   if (!lat->arc_grad && (rc = dev_alloc(ctx, &lat->arc_grad, lat->tot_A))) return rc;
-  if (!lat->node_grad && (rc = dev_alloc(ctx, &lat->node_grad, lat->tot_N))) return rc;
   rc = launch_backward(ctx, lat, tropical, deltas_dev);
   dev_free(ctx, deltas_dev);
   return rc;
@@ -1021,10 +1039,8 @@ int gtnb_compose_linear(
     TRY(dev_alloc(ctx, &lat->lvl_node_ptr, tl));
     TRY(dev_alloc(ctx, &lat->lvl_arc_ptr, tl));
     TRY(dev_alloc(ctx, &lat->row_ptr, tn));
-    TRY(dev_alloc(ctx, &lat->src, ta));
-    TRY(dev_alloc(ctx, &lat->w, ta));
-    TRY(dev_alloc(ctx, &lat->gi_graph, ta));
-    TRY(dev_alloc(ctx, &lat->gi_linear, ta));
+    TRY(dev_alloc(ctx, &lat->arcs, ta));
+    TRY(dev_alloc(ctx, &lat->gi, ta));
     TRY(dev_alloc(ctx, &lat->acc_nodes, tc));
     TRY(dev_alloc(ctx, &lat->scores, tn));
     TRY(dev_alloc(ctx, &lat->out_scores, B));

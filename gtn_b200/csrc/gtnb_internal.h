@@ -80,6 +80,7 @@ struct gtnb_ctx {
     const char* name;
     cudaEvent_t a, b;
   };
+  bool use_staged = true; // gtnb_ctx_set_flag("staged", 0) forces the generic kernels
   bool profiling = false;
   std::vector<ProfEntry> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -108,12 +109,10 @@ struct gtnb_lattice {
   int32_t* lvl_node_ptr = nullptr;
   int32_t* lvl_arc_ptr = nullptr;
   uint32_t* row_ptr = nullptr;
-  int32_t* src = nullptr;
-  float* w = nullptr;
+  int2* arcs = nullptr; // per arc {x = source node, y = bits of the fp32 weight}
   int32_t* acc_nodes = nullptr;
   // provenance of composed arcs (gradInfo)
-  int32_t* gi_graph = nullptr;
-  int32_t* gi_linear = nullptr;
+  int2* gi = nullptr; // per arc {x = arc of the graph operand, y = arc of the linear operand}
   // packed graphs: mapping back to Graph numbering + backward schedule
   int32_t* node_orig = nullptr;
   int32_t* arc_orig = nullptr;
@@ -229,6 +228,10 @@ int launch_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int mode);
 int launch_backward(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev);
 int launch_traceback(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, int32_t* path_dev, int32_t* len_dev);
 int launch_gather_prov(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, const int32_t* path_dev, const int32_t* len_dev, int32_t* prov_graph, int32_t* prov_linear);
+// kernels (k_staged.cu): TMA-staged persistent kernels for level-local lattices
+bool staged_supported(const gtnb_lattice* lat);
+int launch_forward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int mode);
+int launch_backward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev);
 // kernels (k_compose.cu)
 int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat);
 int launch_compose_grad(gtnb_ctx* ctx, gtnb_lattice* lat, float* grad_graph, float* grad_emis, int64_t grad_stride);

@@ -272,10 +272,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_emit_kernel(
     const int32_t* __restrict__ lvl_node_ptr,
     const int32_t* __restrict__ lvl_arc_ptr,
     uint32_t* __restrict__ row_ptr,
-    int32_t* __restrict__ src,
-    float* __restrict__ w,
-    int32_t* __restrict__ gi_graph,
-    int32_t* __restrict__ gi_linear) {
+    int2* __restrict__ arcs,
+    int2* __restrict__ gi) {
   __shared__ int pre[kWarpsPerBlock][kMaxWords]; // popcount prefix of alive[t-1]
   const int b = blockIdx.y;
   const GraphMeta m = meta[b];
@@ -294,10 +292,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_emit_kernel(
   const int32_t* np = lvl_node_ptr + m.lvl_base;
   const int32_t* apn = lvl_arc_ptr + m.lvl_base;
   uint32_t* rp = row_ptr + m.node_base;
-  int32_t* so = src + m.arc_base;
-  float* wo = w + m.arc_base;
-  int32_t* gg = gi_graph + m.arc_base;
-  int32_t* gl = gi_linear + m.arc_base;
+  int2* ao = arcs + m.arc_base;
+  int2* go = gi + m.arc_base;
   const float* em = emissions + m.emis_off + (long long)(t - 1) * C;
 
   const int nb = np[t];
@@ -348,10 +344,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_emit_kernel(
           const int s = is[e];
           const int lab = il[e];
           if (lab >= 0 && ((ap[s >> 5] >> (s & 31)) & 1u)) {
-            so[pos] = pb + pre[warp][s >> 5] + __popc(ap[s >> 5] & ((1u << (s & 31)) - 1u));
-            wo[pos] = iw[e] + em[lab]; // first.weight(i) + second.weight(j), compose.cpp:435
-            gg[pos] = ia[e];
-            gl[pos] = (t - 1) * C + lab;
+            // weight = first.weight(i) + second.weight(j), compose.cpp:435
+            ao[pos] = make_int2(pb + pre[warp][s >> 5] + __popc(ap[s >> 5] & ((1u << (s & 31)) - 1u)),
+                                __float_as_int(iw[e] + em[lab]));
+            go[pos] = make_int2(ia[e], (t - 1) * C + lab);
             pos++;
           }
         }
@@ -368,22 +364,21 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_emit_kernel(
 __global__ void __launch_bounds__(256) compose_grad_kernel(
     const GraphMeta* __restrict__ meta,
     const float* __restrict__ arc_grad,
-    const int32_t* __restrict__ gi_graph,
-    const int32_t* __restrict__ gi_linear,
+    const int2* __restrict__ gi,
     float* __restrict__ grad_graph,
     float* __restrict__ grad_emis,
     long long grad_stride) {
   const int b = blockIdx.y;
   const GraphMeta m = meta[b];
   const float* ag = arc_grad + m.arc_base;
-  const int32_t* gg = gi_graph + m.arc_base;
-  const int32_t* gl = gi_linear + m.arc_base;
+  const int2* gp = gi + m.arc_base;
   float* g1 = grad_graph ? grad_graph + m.grad_graph_off : nullptr;
   float* g2 = grad_emis ? grad_emis + (long long)b * grad_stride : nullptr;
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < m.A; a += gridDim.x * blockDim.x) {
     const float g = ag[a];
-    if (g1) atomicAdd(&g1[gg[a]], g);
-    if (g2) atomicAdd(&g2[gl[a]], g);
+    const int2 p = gp[a];
+    if (g1) atomicAdd(&g1[p.x], g);
+    if (g2) atomicAdd(&g2[p.y], g);
   }
 }
 
@@ -407,7 +402,7 @@ int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat) {
   GTNB_LAUNCH(ctx, "compose_emit", compose_emit_kernel<<<grid, 32 * kWarpsPerBlock, 0, ctx->stream>>>(
       lat->meta, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_arc,
       lat->sg_in_w, lat->alive, W, maxT, lat->C, lat->emissions, lat->lvl_node_ptr,
-      lat->lvl_arc_ptr, lat->row_ptr, lat->src, lat->w, lat->gi_graph, lat->gi_linear));
+      lat->lvl_arc_ptr, lat->row_ptr, lat->arcs, lat->gi));
   return GTNB_OK;
 }
 
@@ -419,7 +414,7 @@ int launch_compose_grad(
   int gx = std::min((capA + 1023) / 1024, 4096);
   dim3 grid(gx, lat->B);
   GTNB_LAUNCH(ctx, "compose_grad", compose_grad_kernel<<<grid, 256, 0, ctx->stream>>>(
-      lat->meta, lat->arc_grad, lat->gi_graph, lat->gi_linear, grad_graph, grad_emis,
+      lat->meta, lat->arc_grad, lat->gi, grad_graph, grad_emis,
       (long long)grad_stride));
   return GTNB_OK;
 }

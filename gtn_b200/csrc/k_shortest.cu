@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "gtnb_internal.h"
 
 namespace gtnb {
@@ -51,8 +53,7 @@ __global__ void __launch_bounds__(kThreads) sd_forward_generic(
     const GraphMeta* __restrict__ meta,
     const int32_t* __restrict__ lvl_node_ptr,
     const uint32_t* __restrict__ row_ptr,
-    const int32_t* __restrict__ src,
-    const float* __restrict__ w,
+    const int2* __restrict__ arcs,
     const int32_t* __restrict__ relax_rank, // MODE_PATH only, nullable
     const int32_t* __restrict__ acc_nodes,
     float* __restrict__ scores,
@@ -70,8 +71,7 @@ __global__ void __launch_bounds__(kThreads) sd_forward_generic(
   }
   const int32_t* lp = lvl_node_ptr + m.lvl_base;
   const uint32_t* rp = row_ptr + m.node_base;
-  const int32_t* s = src + m.arc_base;
-  const float* ww = w + m.arc_base;
+  const int2* ar = arcs + m.arc_base;
   const int32_t* rr = relax_rank ? relax_rank + m.arc_base : nullptr;
   float* sc = scores + m.node_base;
   int32_t* bp = (MODE == MODE_PATH) ? back_ptr + m.node_base : nullptr;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) sd_forward_generic(
         float best = is_start ? 0.0f : neg_inf();
         int barc = -1, brank = -1;
         for (int a = r0; a < r1; a++) {
-          const float v = __ldcg(&sc[s[a]]) + ww[a];
+          const float v = __ldcg(&sc[ar[a].x]) + __int_as_float(ar[a].y);
           const int rk = rr ? rr[a] : a;
           if (v > best || (v == best && barc >= 0 && rk < brank)) {
             best = v;
@@ -111,14 +111,14 @@ __global__ void __launch_bounds__(kThreads) sd_forward_generic(
       } else {
         float mx = neg_inf();
         for (int a = r0; a < r1; a++) {
-          const float v = __ldcg(&sc[s[a]]) + ww[a];
+          const float v = __ldcg(&sc[ar[a].x]) + __int_as_float(ar[a].y);
           if (v > mx) mx = v;
         }
         if (is_start && 0.0f > mx) mx = 0.0f;
         const int count = (r1 - r0) + (is_start ? 1 : 0);
         float sum = -1.0f;
         if (MODE == MODE_LOG && count > 0 && mx != CUDART_INF_F && mx != -CUDART_INF_F) {
-          for (int a = r0; a < r1; a++) sum += expf((__ldcg(&sc[s[a]]) + ww[a]) - mx);
+          for (int a = r0; a < r1; a++) sum += expf((__ldcg(&sc[ar[a].x]) + __int_as_float(ar[a].y)) - mx);
           if (is_start) sum += expf(0.0f - mx);
         }
         sc[n] = finish_score(count, mx, sum, MODE != MODE_LOG);
@@ -165,8 +165,7 @@ __global__ void __launch_bounds__(kThreads) sd_backward_generic(
     const int32_t* __restrict__ blvl_ptr, // nullable
     const int32_t* __restrict__ bnodes,
     const uint32_t* __restrict__ row_ptr,
-    const int32_t* __restrict__ src,
-    const float* __restrict__ w,
+    const int2* __restrict__ arcs,
     const int32_t* __restrict__ acc_nodes,
     const float* __restrict__ scores,
     const float* __restrict__ out_scores,
@@ -178,8 +177,7 @@ __global__ void __launch_bounds__(kThreads) sd_backward_generic(
   const int tid = threadIdx.x;
   if (m.status != GTNB_OK) return;
   const uint32_t* rp = row_ptr + m.node_base;
-  const int32_t* s = src + m.arc_base;
-  const float* ww = w + m.arc_base;
+  const int2* ar = arcs + m.arc_base;
   const float* sc = scores + m.node_base;
   float* ng = node_grad + m.node_base;
   float* ag = arc_grad + m.arc_base;
@@ -235,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) sd_backward_generic(
         float mx = neg_inf();
         int arg = -1;
         for (int a = r0; a < r1; a++) {
-          const float v = sc[s[a]] + ww[a];
+          const float v = sc[ar[a].x] + __int_as_float(ar[a].y);
           if (v > mx) {
             mx = v;
             arg = a;
@@ -243,20 +241,20 @@ __global__ void __launch_bounds__(kThreads) sd_backward_generic(
         }
         if ((r0raw & kStartBit) && 0.0f > mx) arg = -1;
         if (arg >= 0) {
-          atomicAdd(&ng[s[arg]], g);
+          atomicAdd(&ng[ar[arg].x], g);
           ag[arg] = g * delta;
         }
       } else {
         float mx = neg_inf();
         for (int a = r0; a < r1; a++) {
-          const float v = sc[s[a]] + ww[a];
+          const float v = sc[ar[a].x] + __int_as_float(ar[a].y);
           if (v > mx) mx = v;
         }
         if ((r0raw & kStartBit) && 0.0f > mx) mx = 0.0f;
         const float denom = expf(sc[n] - mx);
         for (int a = r0; a < r1; a++) {
-          const float cur = g * expf(sc[s[a]] + ww[a] - mx) / denom;
-          atomicAdd(&ng[s[a]], cur);
+          const float cur = g * expf(sc[ar[a].x] + __int_as_float(ar[a].y) - mx) / denom;
+          atomicAdd(&ng[ar[a].x], cur);
           ag[a] = cur * delta;
         }
       }
@@ -271,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) sd_backward_generic(
 
 __global__ void traceback_kernel(
     const GraphMeta* __restrict__ meta,
-    const int32_t* __restrict__ src,
+    const int2* __restrict__ arcs,
     const int32_t* __restrict__ back_ptr,
     const int32_t* __restrict__ best_accept,
     int B,
@@ -285,7 +283,7 @@ __global__ void traceback_kernel(
     path_len[b] = -1;
     return;
   }
-  const int32_t* s = src + m.arc_base;
+  const int2* ar = arcs + m.arc_base;
   const int32_t* bp = back_ptr + m.node_base;
   int32_t* p = path + (long long)b * max_len;
   int n = best_accept[b];
@@ -298,7 +296,7 @@ __global__ void traceback_kernel(
     const int a = bp[n];
     if (len < max_len) p[len] = a;
     len++;
-    n = s[a];
+    n = ar[a].x;
   }
   const int k = len < max_len ? len : max_len;
   for (int i = 0; i < k / 2; i++) {
@@ -311,8 +309,7 @@ __global__ void traceback_kernel(
 
 __global__ void gather_prov_kernel(
     const GraphMeta* __restrict__ meta,
-    const int32_t* __restrict__ gi_graph,
-    const int32_t* __restrict__ gi_linear,
+    const int2* __restrict__ gi,
     int max_len,
     const int32_t* __restrict__ path,
     const int32_t* __restrict__ path_len,
@@ -324,17 +321,22 @@ __global__ void gather_prov_kernel(
   if (i >= len) return;
   const long long k = (long long)b * max_len + i;
   const long long a = meta[b].arc_base + path[k];
-  pg[k] = gi_graph[a];
-  pl[k] = gi_linear[a];
+  pg[k] = gi[a].x;
+  pl[k] = gi[a].y;
 }
 
 } // namespace
 
+static bool use_staged(const gtnb_ctx* ctx, const gtnb_lattice* lat) {
+  return ctx->use_staged && staged_supported(lat);
+}
+
 int launch_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int mode) {
   if (lat->B == 0) return GTNB_OK;
+  if (use_staged(ctx, lat)) return launch_forward_staged(ctx, lat, mode);
   dim3 grid(lat->B), block(kThreads);
 #define ARGS                                                                           \
-  lat->meta, lat->lvl_node_ptr, lat->row_ptr, lat->src, lat->w,                        \
+  lat->meta, lat->lvl_node_ptr, lat->row_ptr, lat->arcs,                        \
       (mode == MODE_PATH ? lat->relax_rank : nullptr), lat->acc_nodes, lat->scores,    \
       lat->back_ptr, lat->out_scores, lat->best_accept
   if (mode == MODE_LOG)
@@ -349,10 +351,15 @@ int launch_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int mode) {
 
 int launch_backward(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev) {
   if (lat->B == 0) return GTNB_OK;
+  if (use_staged(ctx, lat)) return launch_backward_staged(ctx, lat, tropical, deltas_dev);
+  if (!lat->node_grad) {
+    int rc = dev_alloc(ctx, &lat->node_grad, lat->tot_N);
+    if (rc) return rc;
+  }
   dim3 grid(lat->B), block(kThreads);
 #define ARGS                                                                              \
-  lat->meta, lat->lvl_node_ptr, lat->blvl_ptr, lat->bnodes, lat->row_ptr, lat->src,       \
-      lat->w, lat->acc_nodes, lat->scores, lat->out_scores, lat->best_accept, deltas_dev, \
+  lat->meta, lat->lvl_node_ptr, lat->blvl_ptr, lat->bnodes, lat->row_ptr, lat->arcs,      \
+      lat->acc_nodes, lat->scores, lat->out_scores, lat->best_accept, deltas_dev, \
       lat->node_grad, lat->arc_grad
   if (tropical)
     GTNB_LAUNCH(ctx, "sd_backward", sd_backward_generic<true><<<grid, block, 0, ctx->stream>>>(ARGS));
@@ -365,7 +372,7 @@ int launch_backward(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float*
 int launch_traceback(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, int32_t* path_dev, int32_t* len_dev) {
   if (lat->B == 0) return GTNB_OK;
   GTNB_LAUNCH(ctx, "traceback", traceback_kernel<<<(lat->B + 63) / 64, 64, 0, ctx->stream>>>(
-      lat->meta, lat->src, lat->back_ptr, lat->best_accept, lat->B, max_len, path_dev, len_dev));
+      lat->meta, lat->arcs, lat->back_ptr, lat->best_accept, lat->B, max_len, path_dev, len_dev));
   return GTNB_OK;
 }
 
@@ -375,7 +382,7 @@ int launch_gather_prov(
   if (lat->B == 0 || max_len == 0) return GTNB_OK;
   dim3 grid((max_len + 127) / 128, lat->B);
   GTNB_LAUNCH(ctx, "gather_prov", gather_prov_kernel<<<grid, 128, 0, ctx->stream>>>(
-      lat->meta, lat->gi_graph, lat->gi_linear, max_len, path_dev, len_dev, pg, pl));
+      lat->meta, lat->gi, max_len, path_dev, len_dev, pg, pl));
   return GTNB_OK;
 }
 

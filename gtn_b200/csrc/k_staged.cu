@@ -1,0 +1,705 @@
+/*
+ * k_staged.cu -- the hot kernels: shortest-distance forward / backward over
+ * frame-synchronous ("level-local") lattices, one persistent warp-specialised
+ * CTA per utterance.
+ *
+ *   producer warp   walks the levels ahead of the math: for level l it issues
+ *                   cp.async.bulk (TMA 1-D bulk copies, SASS UBLKCP) of the
+ *                   level's row_ptr window and arc-record window ({src, weight}
+ *                   pairs; backward also the saved node scores) from HBM into a
+ *                   ring of shared-memory stages, completion tracked by mbarrier
+ *                   transaction counts.
+ *   consumer warps  wait on the stage's "full" mbarrier, evaluate every node of
+ *                   the level from shared memory (frontier scores live in a
+ *                   shared double buffer), write node scores / arc gradients back
+ *                   coalesced, and hand the stage back through an "empty"
+ *                   mbarrier.  G lanes cooperate on one destination node and
+ *                   reduce max / sum(exp) with warp shuffles (G = 1 for CTC-like
+ *                   lattices with <= 4 in-arcs per node: fully unrolled).
+ *
+ * Reference semantics: shortestDistance (shortest.cpp:86-188), its gradient
+ * (shortest.cpp:33-82) and shortestPath's relaxation (shortest.cpp:190-238);
+ * k_shortest.cu holds the generic (any-DAG, libm-precise) versions these are
+ * tested against.  The log-semiring math here uses ex2.approx / lg2.approx
+ * (relative error ~1e-6, far inside the 1e-4 bar); the tropical semiring and
+ * the path recursion are exact (adds and compares only).
+ *
+ * Windows: level l's nodes are [lo, hi), its in-arcs [alo, ahi).  Bulk copies
+ * need 16-byte aligned addresses and sizes, so a stage holds the supersets
+ * [lo & ~3, align4(hi + 1)) of row_ptr / scores and [alo & ~1, align2(ahi)) of
+ * the 8-byte arc records; per-graph slabs start on 4-element boundaries and
+ * every array has 16 elements of slack, so the extra elements are always mapped.
+ */
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "gtnb_internal.h"
+
+namespace gtnb {
+
+namespace {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers = 32 * kConsumerWarps;
+constexpr int kStagedThreads = kConsumers + 32;
+constexpr int kMaxLevelsInSmem = 6144;
+constexpr int kMaxStages = 8;
+
+__device__ __forceinline__ float neg_inf() {
+  return -CUDART_INF_F;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+/* TMA 1-D bulk copy global -> shared, completion on an mbarrier */
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+}
+
+/* exp / log1p on the SFU: ex2.approx(x * log2 e), lg2.approx */
+__device__ __forceinline__ float fexp(float x) {
+  return __expf(x);
+}
+__device__ __forceinline__ float flog1p(float x) {
+  // x = sum(exp(s - max)) - 1 >= 0; series near 0 keeps the relative accuracy log1p is used for
+  return (x < 1e-3f) ? x * (1.0f - 0.5f * x) : __logf(1.0f + x);
+}
+
+/* Shared-memory carve-up, computed on the host and passed by value. */
+struct Layout {
+  int win_nodes; // elements per row_ptr / score window
+  int win_arcs; // arc records per window
+  int off_lvln, off_lvla, off_bufs, off_stage; // byte offsets
+  int stage_bytes;
+  int st_arcs, st_psc; // byte offsets inside a stage (row_ptr at 0)
+  int total;
+  int log2_stages;
+};
+
+Layout make_layout(int max_lvl_nodes, int max_lvl_arcs, int L, int log2_stages, int n_bufs, bool with_scores) {
+  Layout o;
+  o.log2_stages = log2_stages;
+  o.win_nodes = ((max_lvl_nodes + 1 + 3 + 3) / 4) * 4 + 4;
+  o.win_arcs = ((max_lvl_arcs + 1 + 1) / 2) * 2 + 2;
+  int lvl_cap = ((L + 1 + 3) / 4) * 4;
+  int off = 2 * 8 * kMaxStages; // full[], empty[]
+  o.off_lvln = off;
+  off += 4 * lvl_cap;
+  o.off_lvla = off;
+  off += 4 * lvl_cap;
+  o.off_bufs = off;
+  off += 4 * n_bufs * o.win_nodes;
+  off = (off + 127) / 128 * 128;
+  o.off_stage = off;
+  o.st_arcs = (4 * o.win_nodes + 15) / 16 * 16;
+  o.st_psc = o.st_arcs + 8 * o.win_arcs;
+  o.stage_bytes = o.st_psc + (with_scores ? 4 * o.win_nodes : 0);
+  o.stage_bytes = (o.stage_bytes + 127) / 128 * 128;
+  o.total = off + o.stage_bytes * (1 << log2_stages);
+  return o;
+}
+
+/* ------------------------------------------------------------------ */
+/* forward                                                             */
+/* ------------------------------------------------------------------ */
+
+template <int MODE, int G>
+__global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
+    const GraphMeta* __restrict__ meta,
+    const int32_t* __restrict__ lvl_node_ptr,
+    const int32_t* __restrict__ lvl_arc_ptr,
+    const uint32_t* __restrict__ row_ptr,
+    const int2* __restrict__ arcs,
+    const int32_t* __restrict__ acc_nodes,
+    float* __restrict__ scores,
+    int32_t* __restrict__ back_ptr,
+    float* __restrict__ out_scores,
+    int32_t* __restrict__ best_accept,
+    const Layout lay) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GraphMeta m = meta[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int S = 1 << lay.log2_stages;
+  const uint32_t sbase = smem_u32(smem);
+  int* s_lvln = reinterpret_cast<int*>(smem + lay.off_lvln);
+  int* s_lvla = reinterpret_cast<int*>(smem + lay.off_lvla);
+  float* s_sc = reinterpret_cast<float*>(smem + lay.off_bufs);
+
+  const int L = m.L;
+  for (int i = tid; i <= L; i += kStagedThreads) {
+    s_lvln[i] = lvl_node_ptr[m.lvl_base + i];
+    s_lvla[i] = lvl_arc_ptr[m.lvl_base + i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(sbase + 8 * s, 1);
+      mbar_init(sbase + 8 * (kMaxStages + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= kConsumers) {
+    // ===== producer =====
+    if (tid == kConsumers) {
+      const uint32_t* rp = row_ptr + m.node_base;
+      const int2* ga = arcs + m.arc_base;
+      int s = 0;
+      uint32_t par = 0; // wraps & 1: the slot's previous use is empty-phase (wraps - 1)
+      for (int l = 0; l < L; l++) {
+        if (l >= S) mbar_wait(sbase + 8 * (kMaxStages + s), par ^ 1);
+        const uint32_t st = sbase + lay.off_stage + s * lay.stage_bytes;
+        const uint32_t fb = sbase + 8 * s;
+        const int lo = s_lvln[l], hi = s_lvln[l + 1];
+        const int alo = s_lvla[l], ahi = s_lvla[l + 1];
+        const int n0 = lo & ~3, n1 = (hi + 1 + 3) & ~3;
+        const int a0 = alo & ~1, a1 = (ahi + 1) & ~1;
+        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, ab = (uint32_t)(a1 - a0) * 8u;
+        mbar_expect_tx(fb, nb + ab);
+        bulk_g2s(st, rp + n0, nb, fb);
+        if (ab) bulk_g2s(st + lay.st_arcs, ga + a0, ab, fb);
+        if (++s == S) {
+          s = 0;
+          par ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  float* sc = scores + m.node_base;
+  int32_t* bp = (MODE == MODE_PATH) ? back_ptr + m.node_base : nullptr;
+  const int sub = tid % G;
+  const int slot = tid / G;
+  int s = 0;
+  uint32_t par = 0;
+  int lo = s_lvln[0];
+  int prev_lo = 0;
+  for (int l = 0; l < L; l++) {
+    const int hi = s_lvln[l + 1];
+    const int a0 = s_lvla[l] & ~1;
+    const unsigned char* st = smem + lay.off_stage + s * lay.stage_bytes;
+    const uint32_t* st_rp = reinterpret_cast<const uint32_t*>(st) + (lo & 3);
+    const int2* st_arc = reinterpret_cast<const int2*>(st + lay.st_arcs) - a0;
+    const float* prev = s_sc + ((l & 1) ^ 1) * lay.win_nodes - prev_lo;
+    float* cur = s_sc + (l & 1) * lay.win_nodes;
+    const int cnt = hi - lo;
+    mbar_wait(sbase + 8 * s, par);
+    for (int i0 = 0; i0 < cnt; i0 += kConsumers / G) {
+      const int i = i0 + slot;
+      const bool live = i < cnt;
+      uint32_t r0raw = 0;
+      int r0 = 0, r1 = 0;
+      if (live) {
+        r0raw = st_rp[i];
+        r0 = (int)(r0raw & kRowMask);
+        r1 = (int)(st_rp[i + 1] & kRowMask);
+      }
+      const bool is_start = (r0raw & kStartBit) != 0;
+      const int deg = r1 - r0;
+      if (MODE == MODE_PATH) {
+        // strictly-greater relaxations in arc order; a start node begins at 0 (shortest.cpp:202-218)
+        float best = neg_inf();
+        int barc = 0x7fffffff;
+        for (int a = r0 + sub; a < r1; a += G) {
+          const int2 rec = st_arc[a];
+          const float v = prev[rec.x] + __int_as_float(rec.y);
+          if (v > best) {
+            best = v;
+            barc = a;
+          }
+        }
+        if (G > 1) {
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, barc, o);
+            if (ob > best || (ob == best && oa < barc)) {
+              best = ob;
+              barc = oa;
+            }
+          }
+        }
+        if (is_start && !(best > 0.0f)) {
+          best = 0.0f;
+          barc = 0x7fffffff;
+        }
+        if (live && sub == 0) {
+          cur[i] = best;
+          sc[lo + i] = best;
+          bp[lo + i] = (barc == 0x7fffffff) ? -1 : barc;
+        }
+      } else if (G == 1 && deg <= 4) {
+        // CTC-like rows: at most 4 in-arcs, fully unrolled, absent arcs contribute
+        // exp(-inf) = 0 in the reference's summation order (shortest.cpp:109-113)
+        float v0 = neg_inf(), v1 = neg_inf(), v2 = neg_inf(), v3 = neg_inf();
+        if (deg > 0) {
+          const int2 rec = st_arc[r0];
+          v0 = prev[rec.x] + __int_as_float(rec.y);
+        }
+        if (deg > 1) {
+          const int2 rec = st_arc[r0 + 1];
+          v1 = prev[rec.x] + __int_as_float(rec.y);
+        }
+        if (deg > 2) {
+          const int2 rec = st_arc[r0 + 2];
+          v2 = prev[rec.x] + __int_as_float(rec.y);
+        }
+        if (deg > 3) {
+          const int2 rec = st_arc[r0 + 3];
+          v3 = prev[rec.x] + __int_as_float(rec.y);
+        }
+        const float vs = is_start ? 0.0f : neg_inf();
+        const float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), vs);
+        float score = mx; // covers the empty row (-inf), +-inf maxima and the tropical semiring
+        if (MODE == MODE_LOG && mx != CUDART_INF_F && mx != -CUDART_INF_F) {
+          float sum = -1.0f;
+          sum += fexp(v0 - mx);
+          sum += fexp(v1 - mx);
+          sum += fexp(v2 - mx);
+          sum += fexp(v3 - mx);
+          sum += fexp(vs - mx);
+          score = mx + flog1p(sum);
+        }
+        if (live) {
+          cur[i] = score;
+          sc[lo + i] = score;
+        }
+      } else {
+        float mx = neg_inf();
+        for (int a = r0 + sub; a < r1; a += G) {
+          const int2 rec = st_arc[a];
+          mx = fmaxf(mx, prev[rec.x] + __int_as_float(rec.y));
+        }
+        if (G > 1) {
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (is_start) mx = fmaxf(mx, 0.0f);
+        float score = mx;
+        if (MODE == MODE_LOG && mx != CUDART_INF_F && mx != -CUDART_INF_F) {
+          float sum = (sub == 0) ? -1.0f : 0.0f;
+          for (int a = r0 + sub; a < r1; a += G) {
+            const int2 rec = st_arc[a];
+            sum += fexp((prev[rec.x] + __int_as_float(rec.y)) - mx);
+          }
+          if (G > 1) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          }
+          if (is_start) sum += fexp(0.0f - mx);
+          score = mx + flog1p(sum);
+        }
+        if (live && sub == 0) {
+          cur[i] = score;
+          sc[lo + i] = score;
+        }
+      }
+    }
+    consumer_bar();
+    if (tid == 0) mbar_arrive(sbase + 8 * (kMaxStages + s));
+    if (++s == S) {
+      s = 0;
+      par ^= 1;
+    }
+    prev_lo = lo;
+    lo = hi;
+  }
+
+  // accept nodes (all in the last level): shortest.cpp:147-159 / :226-237
+  if (tid == 0) {
+    const int32_t* acc = acc_nodes + m.acc_base;
+    float mx = neg_inf();
+    int best = -1;
+    for (int k = 0; k < m.n_accept; k++) {
+      const float v = __ldcg(&sc[acc[k]]);
+      if (v > mx) {
+        mx = v;
+        best = acc[k];
+      }
+    }
+    float out;
+    if (MODE == MODE_LOG) {
+      if (m.n_accept == 0) {
+        out = neg_inf();
+      } else if (mx == CUDART_INF_F || mx == -CUDART_INF_F) {
+        out = mx;
+      } else {
+        float sum = -1.0f;
+        for (int k = 0; k < m.n_accept; k++) sum += expf(__ldcg(&sc[acc[k]]) - mx);
+        out = mx + log1pf(sum);
+      }
+    } else {
+      out = (m.n_accept == 0) ? neg_inf() : mx;
+    }
+    out_scores[blockIdx.x] = out;
+    best_accept[blockIdx.x] = best;
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* backward                                                            */
+/* ------------------------------------------------------------------ */
+
+/* one arc of the log-semiring gradient (shortest.cpp:71-75) */
+__device__ __forceinline__ float arc_grad_log(float g, float v, float sn, float mx, bool exact) {
+  // g * exp(v - max) / exp(score - max) == g * exp(v - score) whenever the score is finite;
+  // the exact form reproduces the reference's NaNs for +-inf scores (autograd_test.cpp:340-386)
+  return exact ? g * expf(v - mx) / expf(sn - mx) : g * fexp(v - sn);
+}
+
+template <bool TROPICAL, int G>
+__global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
+    const GraphMeta* __restrict__ meta,
+    const int32_t* __restrict__ lvl_node_ptr,
+    const int32_t* __restrict__ lvl_arc_ptr,
+    const uint32_t* __restrict__ row_ptr,
+    const int2* __restrict__ arcs,
+    const int32_t* __restrict__ acc_nodes,
+    const float* __restrict__ scores,
+    const float* __restrict__ out_scores,
+    const int32_t* __restrict__ best_accept,
+    const float* __restrict__ deltas,
+    float* __restrict__ arc_grad,
+    const Layout lay) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GraphMeta m = meta[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int S = 1 << lay.log2_stages;
+  const uint32_t sbase = smem_u32(smem);
+  int* s_lvln = reinterpret_cast<int*>(smem + lay.off_lvln);
+  int* s_lvla = reinterpret_cast<int*>(smem + lay.off_lvla);
+  // buffers: 3 node-gradient buffers + 1 score window for the top level
+  float* s_ng = reinterpret_cast<float*>(smem + lay.off_bufs);
+  float* s_top = s_ng + 3 * lay.win_nodes;
+
+  const int L = m.L;
+  for (int i = tid; i <= L; i += kStagedThreads) {
+    s_lvln[i] = lvl_node_ptr[m.lvl_base + i];
+    s_lvla[i] = lvl_arc_ptr[m.lvl_base + i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(sbase + 8 * s, 1);
+      mbar_init(sbase + 8 * (kMaxStages + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const float* gsc = scores + m.node_base;
+  const int iters = L - 1; // levels L-1 .. 1 own in-arcs
+
+  if (tid >= kConsumers) {
+    // ===== producer: iteration k handles level l = L-1-k; its stage carries the
+    // row_ptr / arc windows of level l and the saved scores of level l-1 =====
+    if (tid == kConsumers) {
+      const uint32_t* rp = row_ptr + m.node_base;
+      const int2* ga = arcs + m.arc_base;
+      int s = 0;
+      uint32_t par = 0;
+      for (int k = 0; k < iters; k++) {
+        const int l = L - 1 - k;
+        if (k >= S) mbar_wait(sbase + 8 * (kMaxStages + s), par ^ 1);
+        const uint32_t st = sbase + lay.off_stage + s * lay.stage_bytes;
+        const uint32_t fb = sbase + 8 * s;
+        const int plo = s_lvln[l - 1], lo = s_lvln[l], hi = s_lvln[l + 1];
+        const int alo = s_lvla[l], ahi = s_lvla[l + 1];
+        const int n0 = lo & ~3, n1 = (hi + 1 + 3) & ~3;
+        const int a0 = alo & ~1, a1 = (ahi + 1) & ~1;
+        const int p0 = plo & ~3, p1 = (lo + 3) & ~3;
+        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, ab = (uint32_t)(a1 - a0) * 8u;
+        const uint32_t pb = (uint32_t)(p1 - p0) * 4u;
+        mbar_expect_tx(fb, nb + ab + pb);
+        bulk_g2s(st, rp + n0, nb, fb);
+        if (ab) bulk_g2s(st + lay.st_arcs, ga + a0, ab, fb);
+        if (pb) bulk_g2s(st + lay.st_psc, gsc + p0, pb, fb);
+        if (++s == S) {
+          s = 0;
+          par ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  float* ag = arc_grad + m.arc_base;
+  const float delta = deltas ? deltas[blockIdx.x] : 1.0f;
+  const int sub = tid % G;
+  const int slot = tid / G;
+
+  // top level: its own scores, and the accept seeds (shortest.cpp:49-60)
+  {
+    const int lo = L > 0 ? s_lvln[L - 1] : 0, hi = L > 0 ? s_lvln[L] : 0;
+    for (int i = tid; i < hi - lo; i += kConsumers) s_top[i] = gsc[lo + i];
+    for (int i = tid; i < 3 * lay.win_nodes; i += kConsumers) s_ng[i] = 0.0f;
+    consumer_bar();
+    if (tid == 0 && L > 0) {
+      const int32_t* acc = acc_nodes + m.acc_base;
+      if (TROPICAL) {
+        const int best = best_accept[blockIdx.x];
+        if (best >= 0) s_ng[best - lo] += 1.0f;
+      } else {
+        float mx = neg_inf();
+        for (int k = 0; k < m.n_accept; k++) mx = fmaxf(mx, s_top[acc[k] - lo]);
+        const float denom = expf(out_scores[blockIdx.x] - mx);
+        for (int k = 0; k < m.n_accept; k++) s_ng[acc[k] - lo] += expf(s_top[acc[k] - lo] - mx) / denom;
+      }
+    }
+    consumer_bar();
+  }
+
+  int s = 0;
+  uint32_t par = 0;
+  int b_cur = 0; // node-gradient buffer roles rotate: cur -> zero -> prev -> cur
+  const float* own = s_top; // scores of the level being processed
+  for (int k = 0; k < iters; k++) {
+    const int l = L - 1 - k;
+    const int plo = s_lvln[l - 1], lo = s_lvln[l], hi = s_lvln[l + 1];
+    const int a0 = s_lvla[l] & ~1;
+    const unsigned char* st = smem + lay.off_stage + s * lay.stage_bytes;
+    const uint32_t* st_rp = reinterpret_cast<const uint32_t*>(st) + (lo & 3);
+    const int2* st_arc = reinterpret_cast<const int2*>(st + lay.st_arcs) - a0;
+    const float* st_psc = reinterpret_cast<const float*>(st + lay.st_psc) + (plo & 3) - plo;
+    const int b_prev = b_cur == 2 ? 0 : b_cur + 1;
+    const int b_zero = b_prev == 2 ? 0 : b_prev + 1;
+    const float* ng_cur = s_ng + b_cur * lay.win_nodes;
+    float* ng_prev = s_ng + b_prev * lay.win_nodes - plo;
+    float* ng_zero = s_ng + b_zero * lay.win_nodes;
+    const int cnt = hi - lo;
+    mbar_wait(sbase + 8 * s, par);
+    for (int i0 = 0; i0 < cnt; i0 += kConsumers / G) {
+      const int i = i0 + slot;
+      const bool live = i < cnt;
+      uint32_t r0raw = 0;
+      int r0 = 0, r1 = 0;
+      float g = 0.0f, sn = 0.0f;
+      if (live) {
+        r0raw = st_rp[i];
+        r0 = (int)(r0raw & kRowMask);
+        r1 = (int)(st_rp[i + 1] & kRowMask);
+        g = ng_cur[i];
+        sn = own[i];
+      }
+      if (TROPICAL) {
+        // the arc the forward pass cached as its first maximum (shortest.cpp:124-127,131-134)
+        float mx = neg_inf();
+        int arg = 0x7fffffff;
+        for (int a = r0 + sub; a < r1; a += G) {
+          const int2 rec = st_arc[a];
+          const float v = st_psc[rec.x] + __int_as_float(rec.y);
+          if (v > mx) {
+            mx = v;
+            arg = a;
+          }
+        }
+        if (G > 1) {
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > mx || (om == mx && oa < arg)) {
+              mx = om;
+              arg = oa;
+            }
+          }
+        }
+        const bool start_wins = (r0raw & kStartBit) && 0.0f > mx;
+        for (int a = r0 + sub; a < r1; a += G) {
+          const bool hit = (a == arg) && !start_wins;
+          ag[a] = (hit ? g : 0.0f) * delta;
+          if (hit) atomicAdd(&ng_prev[st_arc[a].x], g);
+        }
+      } else {
+        const bool exact = !(fabsf(sn) < CUDART_INF_F); // +-inf / NaN score: reference formula verbatim
+        float mx = 0.0f;
+        if (exact) {
+          mx = neg_inf();
+          for (int a = r0; a < r1; a++) {
+            const int2 rec = st_arc[a];
+            mx = fmaxf(mx, st_psc[rec.x] + __int_as_float(rec.y));
+          }
+          if (r0raw & kStartBit) mx = fmaxf(mx, 0.0f);
+        }
+        if (G == 1 && r1 - r0 <= 4) {
+          const int deg = r1 - r0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (j < deg) {
+              const int2 rec = st_arc[r0 + j];
+              const float cur = arc_grad_log(g, st_psc[rec.x] + __int_as_float(rec.y), sn, mx, exact);
+              atomicAdd(&ng_prev[rec.x], cur);
+              ag[r0 + j] = cur * delta;
+            }
+          }
+        } else {
+          for (int a = r0 + sub; a < r1; a += G) {
+            const int2 rec = st_arc[a];
+            const float cur = arc_grad_log(g, st_psc[rec.x] + __int_as_float(rec.y), sn, mx, exact);
+            atomicAdd(&ng_prev[rec.x], cur);
+            ag[a] = cur * delta;
+          }
+        }
+      }
+    }
+    for (int i = tid; i < lay.win_nodes; i += kConsumers) ng_zero[i] = 0.0f;
+    consumer_bar();
+    // the previous iteration's stage held this level's own scores: free it now,
+    // and keep this iteration's score window (level l-1) as the next "own"
+    if (tid == 0 && k > 0) mbar_arrive(sbase + 8 * (kMaxStages + (s == 0 ? S - 1 : s - 1)));
+    own = reinterpret_cast<const float*>(st + lay.st_psc) + (plo & 3);
+    b_cur = b_prev;
+    if (++s == S) {
+      s = 0;
+      par ^= 1;
+    }
+  }
+}
+
+struct StagedPlan {
+  bool ok;
+  int G, max_L;
+  Layout fwd, bwd;
+};
+
+StagedPlan plan(const gtnb_lattice* lat) {
+  StagedPlan p;
+  p.ok = false;
+  if (!lat->composed || !lat->level_local) return p;
+  int max_L = 0;
+  long long sumA = 0, sumN = 0;
+  for (int b = 0; b < lat->B; b++) {
+    max_L = std::max(max_L, lat->meta_h[b].L);
+    sumA += lat->meta_h[b].sg_A;
+    sumN += lat->meta_h[b].sg_N;
+  }
+  if (max_L + 1 > kMaxLevelsInSmem) return p;
+  p.max_L = max_L;
+  const double deg = sumN ? (double)sumA / (double)sumN : 0.0;
+  p.G = deg <= 4.0 ? 1 : (deg <= 16.0 ? 4 : (deg <= 48.0 ? 16 : 32));
+  const int budget = 200 * 1024;
+  for (int ls = 3; ls >= 1; ls--) {
+    Layout f = make_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, max_L, ls, 2, false);
+    Layout bw = make_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, max_L, ls, 4, true);
+    // keep two CTAs per SM resident when the graph is small enough
+    const int cap = (bw.total <= 100 * 1024 || ls == 1) ? budget : 100 * 1024;
+    if (bw.total <= cap && f.total <= cap) {
+      p.ok = true;
+      p.fwd = f;
+      p.bwd = bw;
+      return p;
+    }
+  }
+  return p;
+}
+
+template <typename K>
+int set_smem(gtnb_ctx* ctx, K kernel, int bytes) {
+  GTNB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return GTNB_OK;
+}
+
+} // namespace
+
+bool staged_supported(const gtnb_lattice* lat) {
+  return plan(lat).ok;
+}
+
+#define FWD_ARGS                                                                      \
+  lat->meta, lat->lvl_node_ptr, lat->lvl_arc_ptr, lat->row_ptr, lat->arcs,            \
+      lat->acc_nodes, lat->scores, lat->back_ptr, lat->out_scores, lat->best_accept, p.fwd
+
+#define LAUNCH_FWD(MODE_, G_)                                                                  \
+  do {                                                                                         \
+    int rc__ = set_smem(ctx, sd_forward_staged<MODE_, G_>, p.fwd.total);                       \
+    if (rc__) return rc__;                                                                     \
+    GTNB_LAUNCH(ctx, "sd_forward",                                                             \
+                sd_forward_staged<MODE_, G_><<<lat->B, kStagedThreads, p.fwd.total, ctx->stream>>>(FWD_ARGS)); \
+  } while (0)
+
+#define DISPATCH_G_FWD(MODE_)                \
+  do {                                       \
+    switch (p.G) {                           \
+      case 1: LAUNCH_FWD(MODE_, 1); break;   \
+      case 4: LAUNCH_FWD(MODE_, 4); break;   \
+      case 16: LAUNCH_FWD(MODE_, 16); break; \
+      default: LAUNCH_FWD(MODE_, 32); break; \
+    }                                        \
+  } while (0)
+
+int launch_forward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int mode) {
+  const StagedPlan p = plan(lat);
+  if (!p.ok) return GTNB_ERR_UNSUPPORTED;
+  if (mode == MODE_LOG)
+    DISPATCH_G_FWD(MODE_LOG);
+  else if (mode == MODE_TROPICAL)
+    DISPATCH_G_FWD(MODE_TROPICAL);
+  else
+    DISPATCH_G_FWD(MODE_PATH);
+  return GTNB_OK;
+}
+
+#define BWD_ARGS                                                                      \
+  lat->meta, lat->lvl_node_ptr, lat->lvl_arc_ptr, lat->row_ptr, lat->arcs,            \
+      lat->acc_nodes, lat->scores, lat->out_scores, lat->best_accept, deltas_dev,     \
+      lat->arc_grad, p.bwd
+
+#define LAUNCH_BWD(TROP_, G_)                                                                  \
+  do {                                                                                         \
+    int rc__ = set_smem(ctx, sd_backward_staged<TROP_, G_>, p.bwd.total);                      \
+    if (rc__) return rc__;                                                                     \
+    GTNB_LAUNCH(ctx, "sd_backward",                                                            \
+                sd_backward_staged<TROP_, G_><<<lat->B, kStagedThreads, p.bwd.total, ctx->stream>>>(BWD_ARGS)); \
+  } while (0)
+
+#define DISPATCH_G_BWD(TROP_)                \
+  do {                                       \
+    switch (p.G) {                           \
+      case 1: LAUNCH_BWD(TROP_, 1); break;   \
+      case 4: LAUNCH_BWD(TROP_, 4); break;   \
+      case 16: LAUNCH_BWD(TROP_, 16); break; \
+      default: LAUNCH_BWD(TROP_, 32); break; \
+    }                                        \
+  } while (0)
+
+int launch_backward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev) {
+  const StagedPlan p = plan(lat);
+  if (!p.ok) return GTNB_ERR_UNSUPPORTED;
+  if (tropical)
+    DISPATCH_G_BWD(true);
+  else
+    DISPATCH_G_BWD(false);
+  return GTNB_OK;
+}
+
+} // namespace gtnb

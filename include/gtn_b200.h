@@ -97,6 +97,13 @@ int gtnb_version(void);
 /* number of kernels this context has launched so far (bench bookkeeping) */
 int64_t gtnb_ctx_launch_count(const gtnb_ctx* ctx);
 
+/*
+ * Tuning / testing switches.  "staged" (default 1): use the TMA-staged persistent
+ * kernels for composed lattices; 0 forces the generic any-DAG kernels (libm-precise),
+ * which is how the tests cross-check the two families.
+ */
+int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value);
+
 /* device / pinned memory helpers so callers need no CUDA runtime of their own */
 int gtnb_device_alloc(gtnb_ctx* ctx, size_t bytes, void** out);
 int gtnb_device_free(gtnb_ctx* ctx, void* p);

@@ -243,3 +243,40 @@ def test_ctc_full_size_properties(ctx):
     shift = np.random.default_rng(5).uniform(-1, 1, (B, T, 1)).astype(np.float32)
     losses2, _ = ctx.ctc_loss(e + shift, targets, want_grad=False)
     assert np.allclose(losses, losses2, rtol=1e-4)
+
+
+def test_staged_and_generic_kernels_agree(ctx, oracle):
+    """The TMA-staged kernels (SFU exp/log) against the generic libm-precise kernels on the
+    same composed lattices: log scores/gradients within tolerance, tropical bit-exact."""
+    B, T, C, U = 6, 200, 20, 12
+    e, targets = util.bench_inputs(B, T, C, U)
+    e_dev = ctx.to_device(e)
+    views = [util.view_of(oracle.Graph.ctc(t, 0, True)) for t in targets]
+    res = {}
+    for staged in (1, 0):
+        ctx.set_flag("staged", staged)
+        lat = ctx.compose_linear(views, [T] * B, C, e_dev, T * C)
+        _, na = lat.sizes()
+        s_log = lat.forward()
+        lat.backward(deltas=np.full(B, -1.0, np.float32))
+        g_log = [lat.arc_grads(b, int(na[b])) for b in range(B)]
+        s_trop = lat.forward(tropical=True)
+        lat.backward(tropical=True)
+        g_trop = [lat.arc_grads(b, int(na[b])) for b in range(B)]
+        path = lat.viterbi_path(T)
+        res[staged] = (s_log, g_log, s_trop, g_trop, path)
+        lat.free()
+    ctx.set_flag("staged", 1)
+    assert util.close(res[1][0], res[0][0])
+    assert np.array_equal(res[1][2], res[0][2])
+    for b in range(B):
+        assert util.grad_close(res[1][1][b], res[0][1][b], 5.0 * T)
+        assert np.array_equal(res[1][3][b], res[0][3][b])
+    assert np.array_equal(res[1][4]["arcs"], res[0][4]["arcs"])
+    assert np.array_equal(res[1][4]["ilabels"], res[0][4]["ilabels"])
+    # forced alignment against the oracle (viterbiPath(intersect(ctc, emissions)))
+    for b in range(B):
+        p, s = oracle.viterbi_ctc(e[b], targets[b], 0, True)
+        assert np.array_equal(res[1][4]["ilabels"][b], p), b
+        assert res[1][2][b] == s
+    e_dev.free()
