@@ -31,6 +31,51 @@ int fail(gtnb_ctx* ctx, int code, const std::string& msg) {
   return code;
 }
 
+int stage_begin(gtnb_ctx* ctx) {
+  if (!ctx->stage_ev) GTNB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
+  if (ctx->stage_pending) GTNB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev));
+  ctx->stage_pending = false;
+  ctx->stage_used = 0;
+  return GTNB_OK;
+}
+
+int stage_upload(gtnb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (bytes == 0) return GTNB_OK;
+  const size_t need = ctx->stage_used + ((bytes + 255) & ~(size_t)255);
+  if (need > ctx->stage_bytes) {
+    // copies already issued from the old buffer must finish before it is released
+    GTNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    size_t nb = std::max(need * 2, (size_t)1 << 20);
+    unsigned char* fresh = nullptr;
+    GTNB_CUDA(ctx, cudaMallocHost((void**)&fresh, nb));
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    ctx->stage = fresh;
+    ctx->stage_bytes = nb;
+    ctx->stage_used = 0;
+  }
+  unsigned char* p = ctx->stage + ctx->stage_used;
+  std::memcpy(p, src_host, bytes);
+  ctx->stage_used += (bytes + 255) & ~(size_t)255;
+  GTNB_CUDA(ctx, cudaMemcpyAsync(dst_dev, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return GTNB_OK;
+}
+
+int stage_end(gtnb_ctx* ctx) {
+  GTNB_CUDA(ctx, cudaEventRecord(ctx->stage_ev, ctx->stream));
+  ctx->stage_pending = true;
+  return GTNB_OK;
+}
+
+int readback_reserve(gtnb_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->readback_bytes) return GTNB_OK;
+  if (ctx->readback) cudaFreeHost(ctx->readback);
+  ctx->readback = nullptr;
+  ctx->readback_bytes = 0;
+  GTNB_CUDA(ctx, cudaMallocHost((void**)&ctx->readback, bytes * 2));
+  ctx->readback_bytes = bytes * 2;
+  return GTNB_OK;
+}
+
 int cuda_fail(gtnb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
   char buf[512];
   snprintf(buf, sizeof(buf), "[gtn_b200] CUDA error %d (%s) in %s at %s:%d",
@@ -95,6 +140,8 @@ void gtnb_ctx_destroy(gtnb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->stage) cudaFreeHost(ctx->stage);
+  if (ctx->readback) cudaFreeHost(ctx->readback);
+  if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (auto& pe : ctx->prof) {
@@ -473,6 +520,144 @@ int upload_slabs(
 }
 
 } // namespace
+
+
+namespace gtnb {
+
+/*
+ * Size and allocate a composed lattice batch (level == frame).  Capacities are
+ * upper bounds ((T+1) * N nodes, T * A arcs per utterance) so no device->host
+ * round trip is needed before the kernels run; the exact counts are written
+ * into the device-side GraphMeta by compose_scan_kernel.
+ */
+int composed_alloc(
+    gtnb_ctx* ctx, int B, const SgDims* dims, int n_graphs, int linear_first, const int32_t* T,
+    int C, const float* emissions_dev, int64_t emissions_stride, std::vector<long long>& sgn,
+    std::vector<long long>& sga, gtnb_lattice** out) {
+  *out = nullptr;
+  int maxN = 0, maxA = 0;
+  for (int g = 0; g < n_graphs; g++) {
+    maxN = std::max(maxN, dims[g].N);
+    maxA = std::max(maxA, dims[g].A);
+  }
+  gtnb_lattice* lat = new gtnb_lattice();
+  lat->B = B;
+  lat->composed = true;
+  lat->linear_first = linear_first != 0;
+  lat->shared_graph = n_graphs == 1;
+  lat->level_local = true;
+  lat->sizes_known = false;
+  lat->C = C;
+  lat->emissions = emissions_dev;
+  lat->emissions_stride = emissions_stride;
+  lat->max_lvl_nodes = maxN;
+  lat->max_lvl_arcs = maxA;
+  lat->alive_words = (maxN + 31) / 32;
+  lat->meta_h.resize(B);
+
+  sgn.assign(n_graphs, 0);
+  sga.assign(n_graphs, 0);
+  long long tsn = 0, tsa = 0;
+  for (int g = 0; g < n_graphs; g++) {
+    sgn[g] = tsn;
+    sga[g] = tsa;
+    tsn += align_up(dims[g].N + 1, kAlign);
+    tsa += align_up(std::max(dims[g].A, 1), kAlign);
+  }
+  lat->tot_sgN = tsn;
+  lat->tot_sgA = tsa;
+
+  long long tn = 0, ta = 0, tl = 0, tc = 0, gg_off = 0;
+  int maxT = 0;
+  for (int b = 0; b < B; b++) {
+    if (T[b] < 0) {
+      delete lat;
+      return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_compose_linear: negative T");
+    }
+    const int g = n_graphs == 1 ? 0 : b;
+    const SgDims& s = dims[g];
+    GraphMeta& m = lat->meta_h[b];
+    std::memset(&m, 0, sizeof(m));
+    long long capN = align_up((long long)(T[b] + 1) * s.N + 1, kAlign);
+    long long capA = align_up(std::max<long long>((long long)T[b] * s.A, 1), kAlign);
+    if (capA >= (1ll << 30) || capN >= (1ll << 30)) {
+      delete lat;
+      return fail(ctx, GTNB_ERR_UNSUPPORTED,
+                  "gtnb_compose_linear: lattice too large to materialise (use the factored path)");
+    }
+    m.node_base = tn;
+    m.arc_base = ta;
+    m.lvl_base = tl;
+    m.acc_base = tc;
+    m.sg_node_base = sgn[g];
+    m.sg_arc_base = sga[g];
+    m.emis_off = (long long)b * emissions_stride;
+    m.grad_graph_off = gg_off;
+    if (n_graphs != 1) gg_off += s.A;
+    m.L = T[b] + 1;
+    m.n_accept = s.n_acc; // provisional: the graph's accept count, compose_scan_kernel rewrites it
+    m.LB = -1;
+    m.status = GTNB_OK;
+    m.T = T[b];
+    m.sg_N = s.N;
+    m.sg_A = s.A;
+    m.cap_N = (int)capN;
+    m.cap_A = (int)capA;
+    m.cap_L = (int)align_up(T[b] + 2, kAlign);
+    tn += capN;
+    ta += capA;
+    tl += m.cap_L;
+    tc += align_up(std::max<long long>(s.n_acc, 1), kAlign);
+    maxT = std::max(maxT, T[b]);
+  }
+  lat->tot_N = tn;
+  lat->tot_A = ta;
+  lat->tot_L = tl;
+  lat->tot_acc = tc;
+  lat->max_T = maxT;
+
+  size_t need = (size_t)(tn * 8 + ta * 20 + tl * 8) + (size_t)B * (maxT + 1) * lat->alive_words * 4;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  if (need > total_b) {
+    delete lat;
+    return fail(ctx, GTNB_ERR_UNSUPPORTED,
+                "gtnb_compose_linear: materialised lattice would not fit in HBM (use the factored path)");
+  }
+  int rc = GTNB_OK;
+#define TRYA(x)               \
+  do {                        \
+    if ((rc = (x))) goto bad; \
+  } while (0)
+  TRYA(dev_alloc(ctx, &lat->meta, B));
+  TRYA(dev_alloc(ctx, &lat->lvl_node_ptr, tl));
+  TRYA(dev_alloc(ctx, &lat->lvl_arc_ptr, tl));
+  TRYA(dev_alloc(ctx, &lat->row_ptr, tn));
+  TRYA(dev_alloc(ctx, &lat->arcs, ta));
+  TRYA(dev_alloc(ctx, &lat->gi, ta));
+  TRYA(dev_alloc(ctx, &lat->acc_nodes, tc));
+  TRYA(dev_alloc(ctx, &lat->scores, tn));
+  TRYA(dev_alloc(ctx, &lat->out_scores, B));
+  TRYA(dev_alloc(ctx, &lat->best_accept, B));
+  TRYA(dev_alloc(ctx, &lat->sg_flags, tsn));
+  TRYA(dev_alloc(ctx, &lat->sg_in_ptr, tsn));
+  TRYA(dev_alloc(ctx, &lat->sg_in_src, tsa));
+  TRYA(dev_alloc(ctx, &lat->sg_in_label, tsa));
+  TRYA(dev_alloc(ctx, &lat->sg_in_arc, tsa));
+  TRYA(dev_alloc(ctx, &lat->sg_in_w, tsa));
+  TRYA(dev_alloc(ctx, &lat->sg_ilabel, tsa));
+  TRYA(dev_alloc(ctx, &lat->sg_olabel, tsa));
+  TRYA(dev_alloc(ctx, &lat->alive, (long long)B * (maxT + 1) * lat->alive_words));
+#undef TRYA
+  *out = lat;
+  return GTNB_OK;
+bad:
+  free_lattice_device(ctx, lat);
+  delete lat;
+  return rc;
+}
+
+} // namespace gtnb
 
 extern "C" {
 
@@ -943,117 +1128,19 @@ int gtnb_compose_linear(
     maxA = std::max(maxA, s.A);
   }
 
-  gtnb_lattice* lat = new gtnb_lattice();
-  lat->B = B;
-  lat->composed = true;
-  lat->linear_first = linear_first != 0;
-  lat->shared_graph = (n_graphs == 1 && B != 1) || n_graphs == 1;
-  lat->level_local = true;
-  lat->sizes_known = false;
-  lat->C = C;
-  lat->emissions = emissions_dev;
-  lat->emissions_stride = emissions_stride;
-  lat->max_lvl_nodes = maxN;
-  lat->max_lvl_arcs = maxA;
-  lat->alive_words = (maxN + 31) / 32;
-  lat->meta_h.resize(B);
-
-  std::vector<long long> sgn(n_graphs), sga(n_graphs), sgacc(n_graphs);
-  long long tsn = 0, tsa = 0;
-  for (int g = 0; g < n_graphs; g++) {
-    sgn[g] = tsn;
-    sga[g] = tsa;
-    tsn += align_up(sg[g].N + 1, kAlign);
-    tsa += align_up(std::max(sg[g].A, 1), kAlign);
-  }
-  lat->tot_sgN = tsn;
-  lat->tot_sgA = tsa;
-
-  long long tn = 0, ta = 0, tl = 0, tc = 0, gg_off = 0;
-  int maxT = 0;
-  for (int b = 0; b < B; b++) {
-    if (T[b] < 0) {
-      delete lat;
-      return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_compose_linear: negative T");
-    }
-    const SG& s = sg[n_graphs == 1 ? 0 : b];
-    int g = n_graphs == 1 ? 0 : b;
-    GraphMeta& m = lat->meta_h[b];
-    std::memset(&m, 0, sizeof(m));
-    long long capN = align_up((long long)(T[b] + 1) * s.N + 1, kAlign);
-    long long capA = align_up(std::max<long long>((long long)T[b] * s.A, 1), kAlign);
-    if (capA >= (1ll << 30) || capN >= (1ll << 30)) {
-      delete lat;
-      return fail(ctx, GTNB_ERR_UNSUPPORTED,
-                  "gtnb_compose_linear: lattice too large to materialise (use the factored path)");
-    }
-    m.node_base = tn;
-    m.arc_base = ta;
-    m.lvl_base = tl;
-    m.acc_base = tc;
-    m.sg_node_base = sgn[g];
-    m.sg_arc_base = sga[g];
-    m.emis_off = (long long)b * emissions_stride;
-    m.grad_graph_off = gg_off;
-    if (n_graphs != 1) gg_off += s.A;
-    m.L = T[b] + 1;
-    m.N = 0;
-    m.A = 0;
-    m.n_accept = 0;
-    m.LB = -1;
-    m.status = GTNB_OK;
-    m.T = T[b];
-    m.sg_N = s.N;
-    m.sg_A = s.A;
-    m.cap_N = (int)capN;
-    m.cap_A = (int)capA;
-    m.cap_L = (int)align_up(T[b] + 2, kAlign);
-    tn += capN;
-    ta += capA;
-    tl += m.cap_L;
-    tc += align_up(std::max<long long>(s.acc.size(), 1), kAlign);
-    maxT = std::max(maxT, T[b]);
-  }
-  lat->tot_N = tn;
-  lat->tot_A = ta;
-  lat->tot_L = tl;
-  lat->tot_acc = tc;
-  lat->max_T = maxT;
-
-  size_t need = (size_t)(tn * 8 + ta * 20 + tl * 8) + (size_t)B * (maxT + 1) * lat->alive_words * 4;
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  if (need > total_b) {
-    delete lat;
-    return fail(ctx, GTNB_ERR_UNSUPPORTED,
-                "gtnb_compose_linear: materialised lattice would not fit in HBM (use the factored path)");
-  }
-
-  int rc = GTNB_OK;
+  std::vector<SgDims> dims(n_graphs);
+  for (int g = 0; g < n_graphs; g++) dims[g] = SgDims{sg[g].N, sg[g].A, (int)sg[g].acc.size()};
+  std::vector<long long> sgn, sga;
+  gtnb_lattice* lat = nullptr;
+  int rc = composed_alloc(ctx, B, dims.data(), n_graphs, linear_first, T, C, emissions_dev,
+                          emissions_stride, sgn, sga, &lat);
+  if (rc) return rc;
+  const long long tc = lat->tot_acc;
 #define TRY(x)              \
   do {                      \
     if ((rc = (x))) goto bad; \
   } while (0)
   {
-    TRY(dev_alloc(ctx, &lat->meta, B));
-    TRY(dev_alloc(ctx, &lat->lvl_node_ptr, tl));
-    TRY(dev_alloc(ctx, &lat->lvl_arc_ptr, tl));
-    TRY(dev_alloc(ctx, &lat->row_ptr, tn));
-    TRY(dev_alloc(ctx, &lat->arcs, ta));
-    TRY(dev_alloc(ctx, &lat->gi, ta));
-    TRY(dev_alloc(ctx, &lat->acc_nodes, tc));
-    TRY(dev_alloc(ctx, &lat->scores, tn));
-    TRY(dev_alloc(ctx, &lat->out_scores, B));
-    TRY(dev_alloc(ctx, &lat->best_accept, B));
-    TRY(dev_alloc(ctx, &lat->sg_flags, tsn));
-    TRY(dev_alloc(ctx, &lat->sg_in_ptr, tsn));
-    TRY(dev_alloc(ctx, &lat->sg_in_src, tsa));
-    TRY(dev_alloc(ctx, &lat->sg_in_label, tsa));
-    TRY(dev_alloc(ctx, &lat->sg_in_arc, tsa));
-    TRY(dev_alloc(ctx, &lat->sg_in_w, tsa));
-    TRY(dev_alloc(ctx, &lat->sg_ilabel, tsa));
-    TRY(dev_alloc(ctx, &lat->sg_olabel, tsa));
-    TRY(dev_alloc(ctx, &lat->alive, (long long)B * (maxT + 1) * lat->alive_words));
     TRY(upload(ctx, lat->meta, lat->meta_h.data(), B));
     std::vector<const std::vector<int32_t>*> pi(n_graphs);
     std::vector<const std::vector<uint8_t>*> pb(n_graphs);
@@ -1080,7 +1167,6 @@ int gtnb_compose_linear(
     for (int b = 0; b < B; b++) {
       const SG& s = sg[n_graphs == 1 ? 0 : b];
       std::copy(s.acc.begin(), s.acc.end(), acc_stage.begin() + lat->meta_h[b].acc_base);
-      lat->meta_h[b].n_accept = (int)s.acc.size(); // provisional: small-graph accept count
     }
     TRY(upload(ctx, lat->meta, lat->meta_h.data(), B));
     TRY(upload(ctx, lat->acc_nodes, acc_stage.data(), tc));

@@ -1,7 +1,8 @@
 /*
  * gtnb_criteria.cu -- whole-minibatch criteria: what the reference does with
  * parallelMap(fwd) + parallelMap(bwd) (benchmarks/ctc.cpp:150-165) as ONE call
- * that only enqueues device work.
+ * that only enqueues device work: no per-utterance host objects, one pinned
+ * staging upload, one small read-back.
  */
 #include <algorithm>
 #include <cstring>
@@ -10,77 +11,6 @@
 #include "gtnb_internal.h"
 
 using namespace gtnb;
-
-namespace {
-
-/* CTC target graph, benchmarks/ctc.cpp:40-58 (including its arcSort()). */
-struct CtcGraphHost {
-  std::vector<uint8_t> flags;
-  std::vector<int32_t> src, dst, label, in_ptr, in_arcs, out_ptr, out_arcs, accept;
-
-  void build(const int32_t* target, int U, int blank) {
-    const int L = 2 * U + 1;
-    flags.assign(L, 0);
-    src.clear();
-    dst.clear();
-    label.clear();
-    std::vector<std::vector<int32_t>> in(L), out(L);
-    auto add = [&](int s, int d, int lab) {
-      int a = (int)src.size();
-      src.push_back(s);
-      dst.push_back(d);
-      label.push_back(lab);
-      out[s].push_back(a);
-      in[d].push_back(a);
-    };
-    accept.clear();
-    for (int l = 0; l < L; l++) {
-      const int idx = (l - 1) / 2;
-      flags[l] = (l == 0 ? 1 : 0) | ((l == L - 1 || l == L - 2) ? 2 : 0);
-      if (flags[l] & 2) accept.push_back(l);
-      const int lab = (l % 2) ? target[idx] : blank;
-      add(l, l, lab);
-      if (l > 0) add(l - 1, l, lab);
-      if ((l % 2) && l > 1 && lab != target[idx - 1]) add(l - 2, l, lab);
-    }
-    // Graph::arcSort (graph.cpp:162-177): per-node sort of the in/out lists by label
-    auto by_label = [&](int a, int b) { return label[a] < label[b]; };
-    in_ptr.assign(L + 1, 0);
-    out_ptr.assign(L + 1, 0);
-    in_arcs.clear();
-    out_arcs.clear();
-    for (int n = 0; n < L; n++) {
-      std::stable_sort(in[n].begin(), in[n].end(), by_label);
-      std::stable_sort(out[n].begin(), out[n].end(), by_label);
-      in_arcs.insert(in_arcs.end(), in[n].begin(), in[n].end());
-      out_arcs.insert(out_arcs.end(), out[n].begin(), out[n].end());
-      in_ptr[n + 1] = (int)in_arcs.size();
-      out_ptr[n + 1] = (int)out_arcs.size();
-    }
-  }
-
-  gtnb_graph_view view() const {
-    gtnb_graph_view v;
-    std::memset(&v, 0, sizeof(v));
-    v.num_nodes = (int)flags.size();
-    v.num_arcs = (int)src.size();
-    v.node_flags = flags.data();
-    v.arc_src = src.data();
-    v.arc_dst = dst.data();
-    v.arc_ilabel = label.data();
-    v.arc_olabel = label.data();
-    v.weights = nullptr;
-    v.in_ptr = in_ptr.data();
-    v.in_arcs = in_arcs.data();
-    v.out_ptr = out_ptr.data();
-    v.out_arcs = out_arcs.data();
-    v.accept = accept.data();
-    v.num_accept = (int)accept.size();
-    return v;
-  }
-};
-
-} // namespace
 
 extern "C" int gtnb_ctc_loss(
     gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
@@ -94,37 +24,46 @@ extern "C" int gtnb_ctc_loss(
   int rc = GTNB_OK;
   float* e_dev = nullptr;
   float* g_dev = nullptr;
-  float *z_dev = nullptr;
+  float* z_dev = nullptr;
+  float* deltas_dev = nullptr;
+  int32_t* small_dev = nullptr; // [targets | offsets | lens | T]
   gtnb_lattice* lat = nullptr;
-  std::vector<float> z(B), s(B);
+  std::vector<long long> sgn, sga;
 
-  // host: B tiny target graphs
-  std::vector<CtcGraphHost> ctc(B);
-  std::vector<gtnb_graph_view> views(B);
-  std::vector<int32_t> Tb(B);
-  {
-    long long off = 0;
-    for (int b = 0; b < B; b++) {
-      ctc[b].build(targets + off, target_lens[b], blank);
-      off += target_lens[b];
-      views[b] = ctc[b].view();
-      Tb[b] = input_lens ? input_lens[b] : T;
-      if (Tb[b] < 0 || Tb[b] > T)
-        return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctc_loss: input_lens out of range");
-    }
+  // host: only sizes.  Graph b has 2U+1 nodes; arcs = self loops + step arcs + skip arcs
+  // (benchmarks/ctc.cpp:40-58), skip arcs exist where consecutive labels differ.
+  std::vector<SgDims> dims(B);
+  std::vector<int32_t> Tb(B), off(B);
+  long long tot_t = 0;
+  for (int b = 0; b < B; b++) {
+    const int U = target_lens[b];
+    if (U < 0) return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctc_loss: negative target length");
+    if (U > 0 && !targets) return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctc_loss: targets is NULL");
+    off[b] = (int32_t)tot_t;
+    const int32_t* tg = targets + tot_t;
+    int skips = 0;
+    for (int u = 1; u < U; u++) skips += tg[u] != tg[u - 1];
+    const int L = 2 * U + 1;
+    dims[b] = SgDims{L, L + (L - 1) + skips, L >= 2 ? 2 : 1};
+    tot_t += U;
+    Tb[b] = input_lens ? input_lens[b] : T;
+    if (Tb[b] < 0 || Tb[b] > T)
+      return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctc_loss: input_lens out of range");
   }
+  int maxT = 0;
+  for (int b = 0; b < B; b++) maxT = std::max(maxT, Tb[b]);
 
 #define TRY(x)                 \
   do {                         \
     if ((rc = (x))) goto done; \
   } while (0)
-#define TRYCUDA(call)                                                      \
-  do {                                                                     \
-    cudaError_t e__ = (call);                                              \
-    if (e__ != cudaSuccess) {                                              \
-      rc = cuda_fail(ctx, e__, #call, __FILE__, __LINE__);                 \
-      goto done;                                                           \
-    }                                                                      \
+#define TRYCUDA(call)                                      \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) {                              \
+      rc = cuda_fail(ctx, e__, #call, __FILE__, __LINE__); \
+      goto done;                                           \
+    }                                                      \
   } while (0)
 
   if (emissions_on_device) {
@@ -141,29 +80,56 @@ extern "C" int gtnb_ctc_loss(
     TRYCUDA(cudaMemsetAsync(g_dev, 0, sizeof(float) * per * B, ctx->stream));
   }
   TRY(dev_alloc(ctx, &z_dev, B));
+  TRY(dev_alloc(ctx, &deltas_dev, B));
+  TRY(dev_alloc(ctx, &small_dev, tot_t + 3ll * B));
+  TRY(composed_alloc(ctx, B, dims.data(), B, 0, Tb.data(), C, e_dev, per, sgn, sga, &lat));
+
+  // one pinned staging pass for everything the kernels need from the host
+  TRY(stage_begin(ctx));
+  TRY(stage_upload(ctx, lat->meta, lat->meta_h.data(), sizeof(GraphMeta) * B));
+  if (tot_t) TRY(stage_upload(ctx, small_dev, targets, sizeof(int32_t) * tot_t));
+  TRY(stage_upload(ctx, small_dev + tot_t, off.data(), sizeof(int32_t) * B));
+  TRY(stage_upload(ctx, small_dev + tot_t + B, target_lens, sizeof(int32_t) * B));
+  TRY(stage_upload(ctx, small_dev + tot_t + 2ll * B, Tb.data(), sizeof(int32_t) * B));
+  {
+    std::vector<float> minus1(B, -1.0f); // subtract's gradFunc, functions.cpp:53-58
+    TRY(stage_upload(ctx, deltas_dev, minus1.data(), sizeof(float) * B));
+  }
+  TRY(stage_end(ctx));
 
   // forwardScore(emissions) and its +1 gradient
-  TRY(gtnb_linear_forward(ctx, B, Tb.data(), C, e_dev, per, 0, z_dev, g_dev, per, nullptr, 1.0f));
-  // intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
-  TRY(gtnb_compose_linear(ctx, B, views.data(), B, 0, Tb.data(), C, e_dev, per, &lat));
-  TRY(gtnb_forward(ctx, lat, 0, nullptr, nullptr));
+  TRY(launch_linear_forward(ctx, B, small_dev + tot_t + 2ll * B, maxT, C, e_dev, per, 0, z_dev, g_dev,
+                            per, nullptr, 1.0f));
+  // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
+  TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
+  TRY(launch_compose(ctx, lat));
+  TRY(launch_forward(ctx, lat, MODE_LOG));
+  lat->forward_done = true;
+  lat->forward_mode = MODE_LOG;
   if (grads) {
-    std::vector<float> deltas(B, -1.0f); // subtract's gradFunc, functions.cpp:53-58
-    TRY(gtnb_backward(ctx, lat, 0, deltas.data()));
-    TRY(gtnb_compose_grad(ctx, lat, nullptr, g_dev, per));
+    if (!lat->arc_grad) TRY(dev_alloc(ctx, &lat->arc_grad, lat->tot_A));
+    TRY(launch_backward(ctx, lat, 0, deltas_dev));
+    TRY(launch_compose_grad(ctx, lat, nullptr, g_dev, per));
     if (!grads_on_device)
       TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  TRYCUDA(cudaMemcpyAsync(z.data(), z_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
-  TRYCUDA(cudaMemcpyAsync(s.data(), lat->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
-  TRYCUDA(cudaStreamSynchronize(ctx->stream));
-  for (int b = 0; b < B; b++) losses_host[b] = z[b] - s[b]; // subtract, functions.cpp:52
+  TRY(readback_reserve(ctx, 2 * sizeof(float) * B));
+  {
+    float* z = reinterpret_cast<float*>(ctx->readback);
+    float* s = z + B;
+    TRYCUDA(cudaMemcpyAsync(z, z_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    TRYCUDA(cudaMemcpyAsync(s, lat->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    TRYCUDA(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < B; b++) losses_host[b] = z[b] - s[b]; // subtract, functions.cpp:52
+  }
 
 done:
   if (lat) gtnb_lattice_destroy(ctx, lat);
   if (!emissions_on_device) dev_free(ctx, e_dev);
   if (grads && !grads_on_device) dev_free(ctx, g_dev);
   dev_free(ctx, z_dev);
+  dev_free(ctx, deltas_dev);
+  dev_free(ctx, small_dev);
   return rc;
 #undef TRY
 #undef TRYCUDA

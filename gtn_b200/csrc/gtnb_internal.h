@@ -72,9 +72,15 @@ struct gtnb_ctx {
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   int sm_count = 148;
-  // pinned staging for small host->device uploads
-  void* stage = nullptr;
-  size_t stage_bytes = 0;
+  // pinned staging: every small host->device upload of one API call is packed here and
+  // copied asynchronously (pageable copies would stall the stream each time)
+  unsigned char* stage = nullptr;
+  size_t stage_bytes = 0, stage_used = 0;
+  cudaEvent_t stage_ev = nullptr;
+  bool stage_pending = false;
+  // pinned read-back buffer for small device->host results
+  unsigned char* readback = nullptr;
+  size_t readback_bytes = 0;
   // optional per-kernel CUDA-event timing (gtnb_profile_*)
   struct ProfEntry {
     const char* name;
@@ -146,6 +152,21 @@ struct gtnb_lattice {
 };
 
 namespace gtnb {
+
+struct SgDims {
+  int N, A, n_acc;
+};
+int composed_alloc(
+    gtnb_ctx* ctx, int B, const SgDims* dims, int n_graphs, int linear_first, const int32_t* T,
+    int C, const float* emissions_dev, int64_t emissions_stride, std::vector<long long>& sgn,
+    std::vector<long long>& sga, gtnb_lattice** out);
+int stage_begin(gtnb_ctx* ctx);
+int stage_upload(gtnb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int stage_end(gtnb_ctx* ctx);
+int readback_reserve(gtnb_ctx* ctx, size_t bytes);
+int launch_ctc_build(
+    gtnb_ctx* ctx, gtnb_lattice* lat, const int32_t* targets_dev, const int32_t* tgt_off_dev,
+    const int32_t* tgt_len_dev, int blank);
 
 int fail(gtnb_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(gtnb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
