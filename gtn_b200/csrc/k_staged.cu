@@ -39,9 +39,12 @@ namespace gtnb {
 
 namespace {
 
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumers = 32 * kConsumerWarps;
-constexpr int kStagedThreads = kConsumers + 32;
+// consumer warps per CTA.  The level time is set by the instruction stream of ONE warp
+// (measured: ~7 issue-to-issue cycles per instruction), so one node per thread and as
+// few instructions per level as possible beats fewer, fatter warps.
+constexpr int consumer_warps(int /*G*/) {
+  return 8;
+}
 constexpr int kMaxLevelsInSmem = 6144;
 constexpr int kMaxStages = 8;
 
@@ -80,17 +83,46 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+template <int NC>
 __device__ __forceinline__ void consumer_bar() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
 }
 
-/* exp / log1p on the SFU: ex2.approx(x * log2 e), lg2.approx */
+/* shared-memory accesses through 32-bit shared-window addresses: keeps the per-level
+ * address arithmetic in 32-bit integer ops instead of 64-bit generic pointers */
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int2 lds_v2(uint32_t addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+/* exp / log1p on the SFU: one MUFU each (ex2.approx.ftz / lg2.approx.ftz) */
 __device__ __forceinline__ float fexp(float x) {
-  return __expf(x);
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
 }
 __device__ __forceinline__ float flog1p(float x) {
   // x = sum(exp(s - max)) - 1 >= 0; series near 0 keeps the relative accuracy log1p is used for
-  return (x < 1e-3f) ? x * (1.0f - 0.5f * x) : __logf(1.0f + x);
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(1.0f + x));
+  return (x < 1e-3f) ? x * (1.0f - 0.5f * x) : y * 0.6931471805599453f;
 }
 
 /* Shared-memory carve-up, computed on the host and passed by value. */
@@ -127,12 +159,72 @@ Layout make_layout(int max_lvl_nodes, int max_lvl_arcs, int L, int log2_stages, 
   return o;
 }
 
+
+/* ---- per-node evaluation, one thread per node (G == 1) ---------------- */
+
+/* any in-degree, start nodes included: the reference's loop verbatim (shortest.cpp:121-136) */
+template <int MODE>
+__device__ __noinline__ float fwd_node_any(uint32_t r0raw, int r0, int r1, const int2* st_arc, const float* prev) {
+  const bool is_start = (r0raw & kStartBit) != 0;
+  float mx = neg_inf();
+#pragma unroll 1
+  for (int a = r0; a < r1; a++) {
+    const int2 rec = st_arc[a];
+    mx = fmaxf(mx, prev[rec.x] + __int_as_float(rec.y));
+  }
+  if (is_start) mx = fmaxf(mx, 0.0f);
+  if (MODE != MODE_LOG || mx == CUDART_INF_F || mx == -CUDART_INF_F) return mx;
+  float sum = -1.0f;
+#pragma unroll 1
+  for (int a = r0; a < r1; a++) {
+    const int2 rec = st_arc[a];
+    sum += fexp((prev[rec.x] + __int_as_float(rec.y)) - mx);
+  }
+  if (is_start) sum += fexp(0.0f - mx);
+  return mx + flog1p(sum);
+}
+
+/* the common row: <= 3 in-arcs, not a start node (every CTC / forced-alignment lattice row
+ * past frame 0): fully unrolled, absent arcs contribute exp(-inf) = 0 in arc order.
+ * R = shared address of row_ptr[node 0 of the level], A = shared address arc record 0 would
+ * have, P = shared address score of node 0 would have (both may lie before the window). */
+template <int MODE>
+__device__ __forceinline__ float fwd_node(
+    int i, uint32_t R, uint32_t A, uint32_t P, const int2* st_arc, const float* prev) {
+  const uint32_t r0raw = lds_u32(R + 4u * i);
+  const uint32_t r1raw = lds_u32(R + 4u * i + 4u);
+  const int r0 = (int)(r0raw & kRowMask);
+  const int deg = (int)(r1raw & kRowMask) - r0;
+  if (deg > 3 || (r0raw & kStartBit)) return fwd_node_any<MODE>(r0raw, r0, r0 + deg, st_arc, prev);
+  const uint32_t a = A + 8u * r0;
+  float v0 = neg_inf(), v1 = neg_inf(), v2 = neg_inf();
+  if (deg > 0) {
+    const int2 rec = lds_v2(a);
+    v0 = lds_f32(P + 4u * rec.x) + __int_as_float(rec.y);
+  }
+  if (deg > 1) {
+    const int2 rec = lds_v2(a + 8u);
+    v1 = lds_f32(P + 4u * rec.x) + __int_as_float(rec.y);
+  }
+  if (deg > 2) {
+    const int2 rec = lds_v2(a + 16u);
+    v2 = lds_f32(P + 4u * rec.x) + __int_as_float(rec.y);
+  }
+  const float mx = fmaxf(fmaxf(v0, v1), v2);
+  if (MODE != MODE_LOG || mx == CUDART_INF_F || mx == -CUDART_INF_F) return mx;
+  float sum = -1.0f;
+  sum += fexp(v0 - mx);
+  sum += fexp(v1 - mx);
+  sum += fexp(v2 - mx);
+  return mx + flog1p(sum);
+}
+
 /* ------------------------------------------------------------------ */
 /* forward                                                             */
 /* ------------------------------------------------------------------ */
 
 template <int MODE, int G>
-__global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
+__global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_forward_staged(
     const GraphMeta* __restrict__ meta,
     const int32_t* __restrict__ lvl_node_ptr,
     const int32_t* __restrict__ lvl_arc_ptr,
@@ -145,6 +237,8 @@ __global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
     int32_t* __restrict__ best_accept,
     const Layout lay) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kConsumers = 32 * consumer_warps(G);
+  constexpr int kStagedThreads = kConsumers + 32;
   const GraphMeta m = meta[blockIdx.x];
   const int tid = threadIdx.x;
   const int S = 1 << lay.log2_stages;
@@ -174,6 +268,7 @@ __global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
       const int2* ga = arcs + m.arc_base;
       int s = 0;
       uint32_t par = 0; // wraps & 1: the slot's previous use is empty-phase (wraps - 1)
+#pragma unroll 1
       for (int l = 0; l < L; l++) {
         if (l >= S) mbar_wait(sbase + 8 * (kMaxStages + s), par ^ 1);
         const uint32_t st = sbase + lay.off_stage + s * lay.stage_bytes;
@@ -214,6 +309,20 @@ __global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
     float* cur = s_sc + (l & 1) * lay.win_nodes;
     const int cnt = hi - lo;
     mbar_wait(sbase + 8 * s, par);
+    if (G == 1 && MODE != MODE_PATH) {
+      // one thread per node
+      const uint32_t stb = sbase + lay.off_stage + s * lay.stage_bytes;
+      const uint32_t R = stb + 4u * (lo & 3);
+      const uint32_t A = stb + lay.st_arcs - 8u * a0;
+      const uint32_t bufs = sbase + lay.off_bufs;
+      const uint32_t P = bufs + 4u * (((l & 1) ^ 1) * lay.win_nodes - prev_lo);
+      const uint32_t Cw = bufs + 4u * ((l & 1) * lay.win_nodes);
+      for (int i = tid; i < cnt; i += kConsumers) {
+        const float sv = fwd_node<MODE>(i, R, A, P, st_arc, prev);
+        sts_f32(Cw + 4u * i, sv);
+        sc[lo + i] = sv;
+      }
+    } else
     for (int i0 = 0; i0 < cnt; i0 += kConsumers / G) {
       const int i = i0 + slot;
       const bool live = i < cnt;
@@ -258,44 +367,9 @@ __global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
           sc[lo + i] = best;
           bp[lo + i] = (barc == 0x7fffffff) ? -1 : barc;
         }
-      } else if (G == 1 && deg <= 4) {
-        // CTC-like rows: at most 4 in-arcs, fully unrolled, absent arcs contribute
-        // exp(-inf) = 0 in the reference's summation order (shortest.cpp:109-113)
-        float v0 = neg_inf(), v1 = neg_inf(), v2 = neg_inf(), v3 = neg_inf();
-        if (deg > 0) {
-          const int2 rec = st_arc[r0];
-          v0 = prev[rec.x] + __int_as_float(rec.y);
-        }
-        if (deg > 1) {
-          const int2 rec = st_arc[r0 + 1];
-          v1 = prev[rec.x] + __int_as_float(rec.y);
-        }
-        if (deg > 2) {
-          const int2 rec = st_arc[r0 + 2];
-          v2 = prev[rec.x] + __int_as_float(rec.y);
-        }
-        if (deg > 3) {
-          const int2 rec = st_arc[r0 + 3];
-          v3 = prev[rec.x] + __int_as_float(rec.y);
-        }
-        const float vs = is_start ? 0.0f : neg_inf();
-        const float mx = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), vs);
-        float score = mx; // covers the empty row (-inf), +-inf maxima and the tropical semiring
-        if (MODE == MODE_LOG && mx != CUDART_INF_F && mx != -CUDART_INF_F) {
-          float sum = -1.0f;
-          sum += fexp(v0 - mx);
-          sum += fexp(v1 - mx);
-          sum += fexp(v2 - mx);
-          sum += fexp(v3 - mx);
-          sum += fexp(vs - mx);
-          score = mx + flog1p(sum);
-        }
-        if (live) {
-          cur[i] = score;
-          sc[lo + i] = score;
-        }
       } else {
         float mx = neg_inf();
+#pragma unroll 1
         for (int a = r0 + sub; a < r1; a += G) {
           const int2 rec = st_arc[a];
           mx = fmaxf(mx, prev[rec.x] + __int_as_float(rec.y));
@@ -308,6 +382,7 @@ __global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
         float score = mx;
         if (MODE == MODE_LOG && mx != CUDART_INF_F && mx != -CUDART_INF_F) {
           float sum = (sub == 0) ? -1.0f : 0.0f;
+#pragma unroll 1
           for (int a = r0 + sub; a < r1; a += G) {
             const int2 rec = st_arc[a];
             sum += fexp((prev[rec.x] + __int_as_float(rec.y)) - mx);
@@ -325,7 +400,7 @@ __global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
         }
       }
     }
-    consumer_bar();
+    consumer_bar<kConsumers>();
     if (tid == 0) mbar_arrive(sbase + 8 * (kMaxStages + s));
     if (++s == S) {
       s = 0;
@@ -370,6 +445,57 @@ __global__ void __launch_bounds__(kStagedThreads) sd_forward_staged(
 /* backward                                                            */
 /* ------------------------------------------------------------------ */
 
+
+/* any row, reference formula verbatim (shortest.cpp:62-80), libm-precise */
+__device__ __noinline__ void bwd_node_any(
+    uint32_t r0raw, int r0, int r1, float g, float sn, float delta, const int2* st_arc,
+    const float* st_psc, float* ng_prev, float* ag) {
+  float mx = neg_inf();
+#pragma unroll 1
+  for (int a = r0; a < r1; a++) {
+    const int2 rec = st_arc[a];
+    mx = fmaxf(mx, st_psc[rec.x] + __int_as_float(rec.y));
+  }
+  if (r0raw & kStartBit) mx = fmaxf(mx, 0.0f);
+  const float denom = expf(sn - mx);
+#pragma unroll 1
+  for (int a = r0; a < r1; a++) {
+    const int2 rec = st_arc[a];
+    const float cur = g * expf(st_psc[rec.x] + __int_as_float(rec.y) - mx) / denom;
+    atomicAdd(&ng_prev[rec.x], cur);
+    ag[a] = cur * delta;
+  }
+}
+
+/* the common row: <= 3 in-arcs, finite score.  g * exp(v - max) / exp(score - max)
+ * == g * exp(v - score) then, one SFU op per arc.  R / A / P as in fwd_node (P = saved
+ * scores of the level below), NGc / OWN = this level's node gradients / scores, NGp = the
+ * node-gradient accumulator of the level below (address node 0 of that level would have). */
+__device__ __forceinline__ void bwd_node(
+    int i, uint32_t R, uint32_t A, uint32_t P, uint32_t NGc, uint32_t OWN, uint32_t NGp,
+    float delta, float* ag, const int2* st_arc, const float* st_psc, float* ng_prev) {
+  const uint32_t r0raw = lds_u32(R + 4u * i);
+  const uint32_t r1raw = lds_u32(R + 4u * i + 4u);
+  const int r0 = (int)(r0raw & kRowMask);
+  const int deg = (int)(r1raw & kRowMask) - r0;
+  const float g = lds_f32(NGc + 4u * i);
+  const float sn = lds_f32(OWN + 4u * i);
+  if (deg > 3 || (r0raw & kStartBit) || !(fabsf(sn) < CUDART_INF_F)) {
+    bwd_node_any(r0raw, r0, r0 + deg, g, sn, delta, st_arc, st_psc, ng_prev, ag);
+    return;
+  }
+  const uint32_t a = A + 8u * r0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    if (j < deg) {
+      const int2 rec = lds_v2(a + 8u * j);
+      const float cur = g * fexp(lds_f32(P + 4u * rec.x) + __int_as_float(rec.y) - sn);
+      red_shared_add(NGp + 4u * rec.x, cur);
+      ag[r0 + j] = cur * delta;
+    }
+  }
+}
+
 /* one arc of the log-semiring gradient (shortest.cpp:71-75) */
 __device__ __forceinline__ float arc_grad_log(float g, float v, float sn, float mx, bool exact) {
   // g * exp(v - max) / exp(score - max) == g * exp(v - score) whenever the score is finite;
@@ -378,7 +504,7 @@ __device__ __forceinline__ float arc_grad_log(float g, float v, float sn, float 
 }
 
 template <bool TROPICAL, int G>
-__global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
+__global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_backward_staged(
     const GraphMeta* __restrict__ meta,
     const int32_t* __restrict__ lvl_node_ptr,
     const int32_t* __restrict__ lvl_arc_ptr,
@@ -392,6 +518,8 @@ __global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
     float* __restrict__ arc_grad,
     const Layout lay) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kConsumers = 32 * consumer_warps(G);
+  constexpr int kStagedThreads = kConsumers + 32;
   const GraphMeta m = meta[blockIdx.x];
   const int tid = threadIdx.x;
   const int S = 1 << lay.log2_stages;
@@ -427,6 +555,7 @@ __global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
       const int2* ga = arcs + m.arc_base;
       int s = 0;
       uint32_t par = 0;
+#pragma unroll 1
       for (int k = 0; k < iters; k++) {
         const int l = L - 1 - k;
         if (k >= S) mbar_wait(sbase + 8 * (kMaxStages + s), par ^ 1);
@@ -463,7 +592,7 @@ __global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
     const int lo = L > 0 ? s_lvln[L - 1] : 0, hi = L > 0 ? s_lvln[L] : 0;
     for (int i = tid; i < hi - lo; i += kConsumers) s_top[i] = gsc[lo + i];
     for (int i = tid; i < 3 * lay.win_nodes; i += kConsumers) s_ng[i] = 0.0f;
-    consumer_bar();
+    consumer_bar<kConsumers>();
     if (tid == 0 && L > 0) {
       const int32_t* acc = acc_nodes + m.acc_base;
       if (TROPICAL) {
@@ -476,7 +605,7 @@ __global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
         for (int k = 0; k < m.n_accept; k++) s_ng[acc[k] - lo] += expf(s_top[acc[k] - lo] - mx) / denom;
       }
     }
-    consumer_bar();
+    consumer_bar<kConsumers>();
   }
 
   int s = 0;
@@ -498,6 +627,18 @@ __global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
     float* ng_zero = s_ng + b_zero * lay.win_nodes;
     const int cnt = hi - lo;
     mbar_wait(sbase + 8 * s, par);
+    if (G == 1 && !TROPICAL) {
+      const uint32_t stb = sbase + lay.off_stage + s * lay.stage_bytes;
+      const uint32_t R = stb + 4u * (lo & 3);
+      const uint32_t A = stb + lay.st_arcs - 8u * a0;
+      const uint32_t P = stb + lay.st_psc + 4u * ((plo & 3) - plo);
+      const uint32_t bufs = sbase + lay.off_bufs;
+      const uint32_t NGc = bufs + 4u * (b_cur * lay.win_nodes);
+      const uint32_t NGp = bufs + 4u * (b_prev * lay.win_nodes - plo);
+      const uint32_t OWN = smem_u32(own);
+      for (int i = tid; i < cnt; i += kConsumers)
+        bwd_node(i, R, A, P, NGc, OWN, NGp, delta, ag, st_arc, st_psc, ng_prev);
+    } else
     for (int i0 = 0; i0 < cnt; i0 += kConsumers / G) {
       const int i = i0 + slot;
       const bool live = i < cnt;
@@ -545,24 +686,16 @@ __global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
         float mx = 0.0f;
         if (exact) {
           mx = neg_inf();
+#pragma unroll 1
           for (int a = r0; a < r1; a++) {
             const int2 rec = st_arc[a];
             mx = fmaxf(mx, st_psc[rec.x] + __int_as_float(rec.y));
           }
           if (r0raw & kStartBit) mx = fmaxf(mx, 0.0f);
         }
-        if (G == 1 && r1 - r0 <= 4) {
-          const int deg = r1 - r0;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (j < deg) {
-              const int2 rec = st_arc[r0 + j];
-              const float cur = arc_grad_log(g, st_psc[rec.x] + __int_as_float(rec.y), sn, mx, exact);
-              atomicAdd(&ng_prev[rec.x], cur);
-              ag[r0 + j] = cur * delta;
-            }
-          }
+        if (false) {
         } else {
+#pragma unroll 1
           for (int a = r0 + sub; a < r1; a += G) {
             const int2 rec = st_arc[a];
             const float cur = arc_grad_log(g, st_psc[rec.x] + __int_as_float(rec.y), sn, mx, exact);
@@ -573,7 +706,7 @@ __global__ void __launch_bounds__(kStagedThreads) sd_backward_staged(
       }
     }
     for (int i = tid; i < lay.win_nodes; i += kConsumers) ng_zero[i] = 0.0f;
-    consumer_bar();
+    consumer_bar<kConsumers>();
     // the previous iteration's stage held this level's own scores: free it now,
     // and keep this iteration's score window (level l-1) as the next "own"
     if (tid == 0 && k > 0) mbar_arrive(sbase + 8 * (kMaxStages + (s == 0 ? S - 1 : s - 1)));
@@ -644,7 +777,7 @@ bool staged_supported(const gtnb_lattice* lat) {
     int rc__ = set_smem(ctx, sd_forward_staged<MODE_, G_>, p.fwd.total);                       \
     if (rc__) return rc__;                                                                     \
     GTNB_LAUNCH(ctx, "sd_forward",                                                             \
-                sd_forward_staged<MODE_, G_><<<lat->B, kStagedThreads, p.fwd.total, ctx->stream>>>(FWD_ARGS)); \
+                sd_forward_staged<MODE_, G_><<<lat->B, 32 * consumer_warps(G_) + 32, p.fwd.total, ctx->stream>>>(FWD_ARGS)); \
   } while (0)
 
 #define DISPATCH_G_FWD(MODE_)                \
@@ -679,7 +812,7 @@ int launch_forward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int mode) {
     int rc__ = set_smem(ctx, sd_backward_staged<TROP_, G_>, p.bwd.total);                      \
     if (rc__) return rc__;                                                                     \
     GTNB_LAUNCH(ctx, "sd_backward",                                                            \
-                sd_backward_staged<TROP_, G_><<<lat->B, kStagedThreads, p.bwd.total, ctx->stream>>>(BWD_ARGS)); \
+                sd_backward_staged<TROP_, G_><<<lat->B, 32 * consumer_warps(G_) + 32, p.bwd.total, ctx->stream>>>(BWD_ARGS)); \
   } while (0)
 
 #define DISPATCH_G_BWD(TROP_)                \
