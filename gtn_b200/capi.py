@@ -72,8 +72,9 @@ SYMBOLS = [
     ("gtnb_backward", C.c_int, [_vp, _vp, C.c_int, _f32p]),
     ("gtnb_lattice_arc_grads", C.c_int, [_vp, _vp, C.c_int, _f32p]),
     ("gtnb_lattice_arc_grads_dev", _vp, [_vp]),
+    ("gtnb_lattice_set_arc_grads", C.c_int, [_vp, _vp, C.c_int, _f32p]),
     ("gtnb_compose_grad", C.c_int, [_vp, _vp, _vp, _vp, C.c_int64]),
-    ("gtnb_viterbi_path", C.c_int, [_vp, _vp, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p]),
+    ("gtnb_viterbi_path", C.c_int, [_vp, _vp, C.c_int, _i32p, _i32p, _i32p, _f32p, _i32p, _i32p]),
     ("gtnb_linear_forward", C.c_int,
      [_vp, C.c_int, _i32p, C.c_int, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_float]),
     ("gtnb_ctc_loss", C.c_int,
@@ -366,13 +367,14 @@ class Lattice:
         ol = np.full_like(arcs, -1)
         lens = np.zeros(max(B, 1), np.int32)
         status = np.zeros(max(B, 1), np.int32)
+        pw = np.zeros(arcs.shape, np.float32)
         rc = lib().gtnb_viterbi_path(
             self.ctx.h, self.h, max_len, _p(arcs, _i32p), _p(il, _i32p), _p(ol, _i32p),
-            _p(lens, _i32p), _p(status, _i32p))
+            _p(pw, _f32p), _p(lens, _i32p), _p(status, _i32p))
         if want_status:
             if rc not in (OK, ERR_INVALID_ARGUMENT):
                 self.ctx._check(rc)
         else:
             self.ctx._check(rc)
-        out = dict(arcs=arcs[:B], ilabels=il[:B], olabels=ol[:B], lens=lens[:B])
+        out = dict(arcs=arcs[:B], ilabels=il[:B], olabels=ol[:B], lens=lens[:B], weights=pw[:B])
         return (out, status[:B]) if want_status else out

@@ -1,0 +1,67 @@
+/*
+ * gtn/device.h -- glue between the gtn:: C++ surface and the C ABI
+ * (include/gtn_b200.h).  Not part of the reference's surface.
+ */
+#pragma once
+
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gtn/graph.h"
+#include "gtn_b200.h"
+
+namespace gtn {
+namespace detail {
+
+/* One C-ABI context (device + stream).  Every thread gets its own, lazily: the
+ * reference's parallelMap worker threads therefore run "one utterance per stream". */
+struct Context {
+  gtnb_ctx* ctx{nullptr};
+  std::mutex lock; // a lattice may be used from a thread other than its creator
+  ~Context();
+};
+
+std::shared_ptr<Context> threadContext();
+
+/** Map a C-ABI status to the exception type the reference throws. */
+void check(const std::shared_ptr<Context>& c, int status);
+
+struct DeviceBuffer {
+  std::shared_ptr<Context> owner;
+  float* ptr{nullptr};
+  size_t count{0};
+  DeviceBuffer(std::shared_ptr<Context> c, size_t n);
+  ~DeviceBuffer();
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+};
+
+struct LatticeHandle {
+  std::shared_ptr<Context> owner;
+  gtnb_lattice* lat{nullptr};
+  int B{0};
+  bool composed{false};
+  std::shared_ptr<DeviceBuffer> emissions; // kept alive for the lattice's lifetime
+  std::vector<int> frames; // T per entry (composed lattices)
+  int labels{0}; // C
+  bool linearFirst{false};
+  int scoreMode{-1}; // semiring of the node scores currently saved in the lattice (-1: none)
+  ~LatticeHandle();
+};
+
+/* Host arrays backing a gtnb_graph_view of a Graph (valid while alive). */
+struct ViewStorage {
+  std::vector<uint8_t> flags;
+  std::vector<int32_t> src, dst, il, ol, inPtr, inArcs, outPtr, outArcs, start, accept;
+  std::vector<float> w;
+  gtnb_graph_view view;
+};
+void makeView(const Graph& g, ViewStorage& s);
+
+/** True if `p` points to device memory. */
+bool isDevicePointer(const void* p);
+
+} // namespace detail
+} // namespace gtn

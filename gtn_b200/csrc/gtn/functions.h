@@ -1,0 +1,53 @@
+/*
+ * gtn/functions.h -- the hot-path functions of the reference's gtn/functions.h:19-152,
+ * same names, argument meaning and error behaviour.  compose / intersect with a
+ * gtn::linearGraph operand, forwardScore, viterbiScore, viterbiPath and their
+ * gradients run as sm_100a kernels through the C ABI; general (epsilon / non-linear)
+ * composition is host graph construction, as in the reference.
+ *
+ * Rational operations (concat, closure, union_, remove) are outside the scope of
+ * this build.
+ */
+#pragma once
+
+#include <vector>
+
+#include "gtn/graph.h"
+
+namespace gtn {
+
+/** Negate a scalar graph (functions.cpp:18-30). */
+Graph negate(const Graph& g);
+/** Add two scalar graphs (functions.cpp:32-46). */
+Graph add(const Graph& g1, const Graph& g2);
+/** Subtract two scalar graphs (functions.cpp:48-64). */
+Graph subtract(const Graph& g1, const Graph& g2);
+
+enum class Projection {
+  NONE = 0,
+  INPUT = 1,
+  OUTPUT = 2,
+};
+/** Recorded copy of a graph, optionally projected (functions.cpp:66-91). */
+Graph clone(const Graph& g, Projection projection = Projection::NONE);
+Graph projectInput(const Graph& g);
+Graph projectOutput(const Graph& g);
+
+/** Compose two transducers (functions.cpp:225-237). */
+Graph compose(const Graph& g1, const Graph& g2);
+/** Intersect two acceptors (functions.cpp:239-251). */
+Graph intersect(const Graph& g1, const Graph& g2);
+
+/** Shortest distance in the log semiring (functions.cpp:320-322). */
+Graph forwardScore(const Graph& g);
+/** Shortest distance in the tropical semiring (functions.cpp:324-326). */
+Graph viterbiScore(const Graph& g);
+/** Best path as a chain graph (functions.cpp:328-330). */
+Graph viterbiPath(const Graph& g);
+
+namespace detail {
+/** Host graph construction for the general case (epsilons, arbitrary operands). */
+Graph composeHost(const Graph& first, const Graph& second, bool intersectMode);
+} // namespace detail
+
+} // namespace gtn

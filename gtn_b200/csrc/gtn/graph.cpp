@@ -1,0 +1,480 @@
+/*
+ * gtn/graph.cpp -- gtn::Graph (reference: /root/reference/gtn/graph.cpp) plus the
+ * lazy host view of device-resident lattices.  Written against the reference's
+ * documented behaviour; error messages match the ones its tests pin.
+ */
+#include "gtn/graph.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <utility>
+
+#include "gtn/device.h"
+
+namespace gtn {
+
+/* ---- detail: contexts, buffers, views -------------------------------- */
+
+namespace detail {
+
+Context::~Context() {
+  if (ctx) gtnb_ctx_destroy(ctx);
+}
+
+std::shared_ptr<Context> threadContext() {
+  thread_local std::shared_ptr<Context> tls;
+  if (!tls) {
+    auto c = std::make_shared<Context>();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int rc = gtnb_ctx_create(dev, nullptr, &c->ctx);
+    if (rc != GTNB_OK) {
+      throw std::runtime_error(std::string(gtnb_last_error(nullptr)));
+    }
+    tls = c;
+  }
+  return tls;
+}
+
+void check(const std::shared_ptr<Context>& c, int status) {
+  if (status == GTNB_OK) return;
+  std::string msg = gtnb_last_error(c ? c->ctx : nullptr);
+  switch (status) {
+    case GTNB_ERR_INVALID_ARGUMENT:
+      throw std::invalid_argument(msg);
+    case GTNB_ERR_LOGIC:
+      throw std::logic_error(msg);
+    default:
+      throw std::runtime_error(msg);
+  }
+}
+
+DeviceBuffer::DeviceBuffer(std::shared_ptr<Context> c, size_t n) : owner(std::move(c)), count(n) {
+  void* p = nullptr;
+  std::lock_guard<std::mutex> l(owner->lock);
+  check(owner, gtnb_device_alloc(owner->ctx, sizeof(float) * std::max<size_t>(n, 4), &p));
+  ptr = static_cast<float*>(p);
+}
+
+DeviceBuffer::~DeviceBuffer() {
+  if (ptr && owner && owner->ctx) {
+    std::lock_guard<std::mutex> l(owner->lock);
+    gtnb_device_free(owner->ctx, ptr);
+  }
+}
+
+LatticeHandle::~LatticeHandle() {
+  if (lat && owner && owner->ctx) {
+    std::lock_guard<std::mutex> l(owner->lock);
+    gtnb_lattice_destroy(owner->ctx, lat);
+  }
+}
+
+bool isDevicePointer(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+void makeView(const Graph& g, ViewStorage& s) {
+  const int N = (int)g.numNodes(), A = (int)g.numArcs();
+  s.flags.resize(N);
+  s.src.resize(A);
+  s.dst.resize(A);
+  s.il.resize(A);
+  s.ol.resize(A);
+  s.w.resize(A);
+  s.inPtr.assign(N + 1, 0);
+  s.outPtr.assign(N + 1, 0);
+  s.inArcs.clear();
+  s.outArcs.clear();
+  for (int n = 0; n < N; n++) {
+    s.flags[n] = (g.isStart(n) ? 1 : 0) | (g.isAccept(n) ? 2 : 0);
+    for (auto a : g.in(n)) s.inArcs.push_back(a);
+    for (auto a : g.out(n)) s.outArcs.push_back(a);
+    s.inPtr[n + 1] = (int)s.inArcs.size();
+    s.outPtr[n + 1] = (int)s.outArcs.size();
+  }
+  const float* w = A ? g.weights() : nullptr;
+  for (int a = 0; a < A; a++) {
+    s.src[a] = g.srcNode(a);
+    s.dst[a] = g.dstNode(a);
+    s.il[a] = g.ilabel(a);
+    s.ol[a] = g.olabel(a);
+    s.w[a] = w[a];
+  }
+  s.start.assign(g.start().begin(), g.start().end());
+  s.accept.assign(g.accept().begin(), g.accept().end());
+  std::memset(&s.view, 0, sizeof(s.view));
+  s.view.num_nodes = N;
+  s.view.num_arcs = A;
+  s.view.node_flags = s.flags.data();
+  s.view.arc_src = s.src.data();
+  s.view.arc_dst = s.dst.data();
+  s.view.arc_ilabel = s.il.data();
+  s.view.arc_olabel = s.ol.data();
+  s.view.weights = s.w.data();
+  s.view.in_ptr = s.inPtr.data();
+  s.view.in_arcs = s.inArcs.data();
+  s.view.out_ptr = s.outPtr.data();
+  s.view.out_arcs = s.outArcs.data();
+  s.view.start = s.start.data();
+  s.view.num_start = (int)s.start.size();
+  s.view.accept = s.accept.data();
+  s.view.num_accept = (int)s.accept.size();
+}
+
+} // namespace detail
+
+/* ---- construction ------------------------------------------------------ */
+
+Graph::Graph(GradFunc gradFunc, std::vector<Graph> inputs) {
+  sharedGrad_->calcGrad = false;
+  // a graph computes a gradient if any of its inputs does (graph.cpp:16-27)
+  for (auto& g : inputs) {
+    sharedGrad_->calcGrad |= g.calcGrad();
+  }
+  if (calcGrad()) {
+    sharedGrad_->gradFunc = std::move(gradFunc);
+    sharedGrad_->inputs = std::move(inputs);
+  }
+}
+
+Graph::Graph(bool calcGrad /* = true */) {
+  sharedGrad_->calcGrad = calcGrad;
+}
+
+Graph Graph::fromLattice(
+    std::shared_ptr<detail::LatticeHandle> lattice,
+    int index,
+    GradFunc gradFunc,
+    std::vector<Graph> inputs) {
+  Graph g(std::move(gradFunc), std::move(inputs));
+  g.sharedGraph_->lattice = std::move(lattice);
+  g.sharedGraph_->latticeIndex = index;
+  g.sharedGraph_->hostReady = false;
+  return g;
+}
+
+/* ---- lazy host view ---------------------------------------------------- */
+
+const Graph::SharedGraph& Graph::host() const {
+  if (!sharedGraph_->hostReady) materialize();
+  return *sharedGraph_;
+}
+
+Graph::SharedGraph& Graph::host() {
+  if (!sharedGraph_->hostReady) materialize();
+  return *sharedGraph_;
+}
+
+void Graph::materialize() const {
+  auto& sg = *sharedGraph_;
+  std::lock_guard<std::mutex> l(sg.materialize_lock);
+  if (sg.hostReady) return;
+  auto lat = sg.lattice;
+  std::vector<int32_t> nn(lat->B), na(lat->B);
+  {
+    std::lock_guard<std::mutex> cl(lat->owner->lock);
+    detail::check(lat->owner, gtnb_lattice_sizes(lat->owner->ctx, lat->lat, nn.data(), na.data()));
+  }
+  const int N = nn[sg.latticeIndex], A = na[sg.latticeIndex];
+  std::vector<uint8_t> flags(std::max(N, 1));
+  std::vector<int32_t> src(std::max(A, 1)), dst(std::max(A, 1)), il(std::max(A, 1)), ol(std::max(A, 1));
+  std::vector<float> w(std::max(A, 1));
+  {
+    std::lock_guard<std::mutex> cl(lat->owner->lock);
+    detail::check(
+        lat->owner,
+        gtnb_lattice_download(
+            lat->owner->ctx, lat->lat, sg.latticeIndex, flags.data(), src.data(), dst.data(),
+            il.data(), ol.data(), w.data(), nullptr, nullptr));
+  }
+  sg.nodes.clear();
+  sg.arcs.clear();
+  sg.start.clear();
+  sg.accept.clear();
+  sg.nodes.reserve(N);
+  sg.arcs.reserve(A);
+  for (int n = 0; n < N; n++) {
+    sg.nodes.emplace_back(flags[n] & 1, (flags[n] & 2) != 0);
+    if (flags[n] & 1) sg.start.push_back(n);
+    if (flags[n] & 2) sg.accept.push_back(n);
+  }
+  if (sharedWeights_) sharedWeights_->host.assign(w.begin(), w.begin() + A);
+  for (int a = 0; a < A; a++) {
+    sg.arcs.emplace_back(src[a], dst[a], il[a], ol[a]);
+    sg.nodes[src[a]].out.push_back(a);
+    sg.nodes[dst[a]].in.push_back(a);
+  }
+  sg.hostReady = true;
+}
+
+size_t Graph::numArcs() const {
+  auto& sg = *sharedGraph_;
+  if (!sg.hostReady) {
+    auto lat = sg.lattice;
+    std::vector<int32_t> nn(lat->B), na(lat->B);
+    std::lock_guard<std::mutex> cl(lat->owner->lock);
+    detail::check(lat->owner, gtnb_lattice_sizes(lat->owner->ctx, lat->lat, nn.data(), na.data()));
+    return (size_t)na[sg.latticeIndex];
+  }
+  return sg.arcs.size();
+}
+
+size_t Graph::numNodes() const {
+  auto& sg = *sharedGraph_;
+  if (!sg.hostReady) {
+    auto lat = sg.lattice;
+    std::vector<int32_t> nn(lat->B), na(lat->B);
+    std::lock_guard<std::mutex> cl(lat->owner->lock);
+    detail::check(lat->owner, gtnb_lattice_sizes(lat->owner->ctx, lat->lat, nn.data(), na.data()));
+    return (size_t)nn[sg.latticeIndex];
+  }
+  return sg.nodes.size();
+}
+
+/* ---- topology edits ---------------------------------------------------- */
+
+int Graph::addNode(bool start /* = false */, bool accept /* = false */) {
+  auto& sg = host();
+  int idx = static_cast<int>(sg.nodes.size());
+  sg.nodes.emplace_back(start, accept);
+  if (start) sg.start.push_back(idx);
+  if (accept) sg.accept.push_back(idx);
+  sg.ilabelSorted = false;
+  sg.olabelSorted = false;
+  sg.linearFrames = sg.linearLabels = -1;
+  return idx;
+}
+
+size_t Graph::addArc(size_t srcNode, size_t dstNode, int label) {
+  return addArc(srcNode, dstNode, label, label);
+}
+
+size_t Graph::addArc(size_t srcNode, size_t dstNode, int ilabel, int olabel, float weight /* = 0 */) {
+  assert(ilabel >= epsilon && olabel >= epsilon);
+  auto& sg = host();
+  int idx = static_cast<int>(sg.arcs.size());
+  sg.arcs.emplace_back(static_cast<int>(srcNode), static_cast<int>(dstNode), ilabel, olabel);
+  hostWeights().push_back(weight);
+  sg.nodes[srcNode].out.push_back(idx);
+  sg.nodes[dstNode].in.push_back(idx);
+  sg.ilabelSorted = false;
+  sg.olabelSorted = false;
+  sg.linearFrames = sg.linearLabels = -1;
+  return idx;
+}
+
+float Graph::item() const {
+  if (numArcs() != 1) {
+    throw std::invalid_argument("[Graph::item] Cannot convert Graph with more than 1 arc to a scalar.");
+  }
+  return weight(0);
+}
+
+Graph Graph::deepCopy(const Graph& src) {
+  Graph out(src.calcGrad());
+  const auto& sg = src.host();
+  out.sharedGraph_->arcs = sg.arcs;
+  out.sharedGraph_->nodes = sg.nodes;
+  out.sharedGraph_->start = sg.start;
+  out.sharedGraph_->accept = sg.accept;
+  out.sharedGraph_->linearFrames = sg.linearFrames;
+  out.sharedGraph_->linearLabels = sg.linearLabels;
+  out.sharedWeights_->host = src.hostWeights();
+  return out;
+}
+
+void Graph::arcSort(bool olabel /* = false */) {
+  auto& sg = host();
+  if ((olabel && sg.olabelSorted) || (!olabel && sg.ilabelSorted)) {
+    return;
+  }
+  sg.olabelSorted = olabel;
+  sg.ilabelSorted = !olabel;
+  auto less = [olabel, &arcs = sg.arcs](int a, int b) {
+    return olabel ? arcs[a].olabel < arcs[b].olabel : arcs[a].ilabel < arcs[b].ilabel;
+  };
+  for (auto& n : sg.nodes) {
+    std::sort(n.in.begin(), n.in.end(), less);
+    std::sort(n.out.begin(), n.out.end(), less);
+  }
+}
+
+/* ---- weights ----------------------------------------------------------- */
+
+std::vector<float>& Graph::hostWeights() const {
+  assert(sharedWeights_ != nullptr);
+  auto& sw = *sharedWeights_;
+  if (sw.lazyFetch) {
+    std::lock_guard<std::mutex> l(sw.lock);
+    if (sw.lazyFetch) {
+      sw.lazyFetch(sw.host);
+      sw.lazyFetch = nullptr;
+    }
+  }
+  if (sw.hostStale) {
+    std::lock_guard<std::mutex> l(sw.lock);
+    if (sw.hostStale) {
+      sw.host.resize(sw.device->count);
+      auto& c = sw.device->owner;
+      std::lock_guard<std::mutex> cl(c->lock);
+      detail::check(c, gtnb_memcpy_d2h(c->ctx, sw.host.data(), sw.device->ptr, sizeof(float) * sw.device->count));
+      detail::check(c, gtnb_ctx_synchronize(c->ctx));
+      sw.hostStale = false;
+    }
+  }
+  return sw.host;
+}
+
+float* Graph::weights() {
+  host();
+  auto& hw = hostWeights();
+  // the caller may write through the pointer: the device copy can no longer be trusted
+  sharedWeights_->device.reset();
+  return hw.data();
+}
+
+const float* Graph::weights() const {
+  host();
+  return hostWeights().data();
+}
+
+float Graph::weight(size_t i) const {
+  host();
+  return hostWeights()[i];
+}
+
+void Graph::setWeight(size_t i, float weight) {
+  host();
+  hostWeights()[i] = weight;
+  sharedWeights_->device.reset();
+}
+
+std::shared_ptr<detail::DeviceBuffer> Graph::deviceWeights() const {
+  return sharedWeights_ ? sharedWeights_->device : nullptr;
+}
+
+void Graph::setWeights(const float* weights) {
+  const size_t n = numArcs();
+  auto& sw = *sharedWeights_;
+  if (n > 0 && detail::isDevicePointer(weights)) {
+    auto c = detail::threadContext();
+    auto buf = std::make_shared<detail::DeviceBuffer>(c, n);
+    {
+      std::lock_guard<std::mutex> cl(c->lock);
+      cudaStream_t st = (cudaStream_t)gtnb_ctx_stream(c->ctx);
+      if (cudaMemcpyAsync(buf->ptr, weights, sizeof(float) * n, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        throw std::runtime_error("[Graph::setWeights] device copy failed");
+    }
+    std::lock_guard<std::mutex> l(sw.lock);
+    sw.device = buf;
+    sw.hostStale = true;
+    return;
+  }
+  std::lock_guard<std::mutex> l(sw.lock);
+  sw.host.resize(n);
+  std::copy(weights, weights + n, sw.host.data());
+  sw.device.reset();
+  sw.hostStale = false;
+}
+
+void Graph::labelsToArray(int* out, bool ilabel) {
+  for (size_t i = 0; i < numArcs(); ++i) {
+    out[i] = ilabel ? this->ilabel(i) : olabel(i);
+  }
+}
+
+std::vector<int> Graph::labelsToVector(bool ilabel) {
+  std::vector<int> out(numArcs());
+  labelsToArray(out.data(), ilabel);
+  return out;
+}
+
+/* ---- gradients --------------------------------------------------------- */
+
+Graph& Graph::grad() {
+  return const_cast<Graph&>(static_cast<const Graph&>(*this).grad());
+}
+
+const Graph& Graph::grad() const {
+  if (!calcGrad()) {
+    throw std::logic_error("[Graph::grad] Gradient calculation disabled.");
+  }
+  if (!sharedGrad_->grad) {
+    throw std::logic_error("[Graph::grad] Gradient not calculated yet.");
+  }
+  return *sharedGrad_->grad;
+}
+
+void Graph::addGrad(std::vector<float>&& other) {
+  if (calcGrad()) {
+    if (other.size() != numArcs()) {
+      throw std::logic_error("[Graph::addGrad] Invalid grad size.");
+    }
+    std::lock_guard<std::mutex> lock(sharedGraph_->grad_lock);
+    if (isGradAvailable()) {
+      auto& gw = sharedGrad_->grad->hostWeights();
+      for (size_t i = 0; i < other.size(); i++) gw[i] += other[i];
+    } else {
+      // the gradient graph shares the topology (graph.cpp:102-104)
+      sharedGrad_->grad = std::make_unique<Graph>(false);
+      sharedGrad_->grad->sharedGraph_ = sharedGraph_;
+      sharedGrad_->grad->sharedWeights_->host = std::move(other);
+    }
+  }
+}
+
+void Graph::addLazyGrad(size_t n, std::function<void(std::vector<float>&)> fetch) {
+  if (!calcGrad()) return;
+  {
+    std::lock_guard<std::mutex> lock(sharedGraph_->grad_lock);
+    if (!isGradAvailable()) {
+      sharedGrad_->grad = std::make_unique<Graph>(false);
+      sharedGrad_->grad->sharedGraph_ = sharedGraph_;
+      sharedGrad_->grad->sharedWeights_->lazyFetch = std::move(fetch);
+      return;
+    }
+  }
+  std::vector<float> now(n);
+  fetch(now);
+  addGrad(std::move(now));
+}
+
+void Graph::addGrad(const std::vector<float>& other) {
+  addGrad(std::vector<float>(other));
+}
+
+void Graph::addGrad(const Graph& other) {
+  addGrad(other.hostWeights());
+}
+
+void Graph::setCalcGrad(bool calcGrad) {
+  sharedGrad_->calcGrad = calcGrad;
+  if (!calcGrad) {
+    sharedGrad_->gradFunc = nullptr;
+    sharedGrad_->inputs.clear();
+    sharedGrad_->grad.reset();
+  }
+}
+
+void Graph::setInputs(std::vector<Graph> inputs) {
+  sharedGrad_->inputs = std::move(inputs);
+}
+
+void Graph::zeroGrad() {
+  sharedGrad_->grad.reset();
+}
+
+std::uintptr_t Graph::id() {
+  return reinterpret_cast<std::uintptr_t>(sharedGrad_.get());
+}
+
+} // namespace gtn

@@ -989,10 +989,25 @@ int gtnb_lattice_arc_grads(gtnb_ctx* ctx, gtnb_lattice* lat, int b, float* out_h
   return GTNB_OK;
 }
 
+int gtnb_lattice_set_arc_grads(gtnb_ctx* ctx, gtnb_lattice* lat, int b, const float* grads_host) {
+  if (!ctx || !lat || b < 0 || b >= lat->B || !grads_host)
+    return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_lattice_set_arc_grads: bad arguments");
+  if (!lat->composed)
+    return fail(ctx, GTNB_ERR_LOGIC, "gtnb_lattice_set_arc_grads: only for composed lattices");
+  GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = fetch_sizes(ctx, lat);
+  if (rc) return rc;
+  if (!lat->arc_grad && (rc = dev_alloc(ctx, &lat->arc_grad, lat->tot_A))) return rc;
+  const GraphMeta& m = lat->meta_h[b];
+  GTNB_CUDA(ctx, cudaMemcpyAsync(lat->arc_grad + m.arc_base, grads_host, sizeof(float) * m.A,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+  return GTNB_OK;
+}
+
 int gtnb_viterbi_path(
     gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, int32_t* path_arcs_host,
-    int32_t* path_ilabels_host, int32_t* path_olabels_host, int32_t* path_len_host,
-    int32_t* status_host) {
+    int32_t* path_ilabels_host, int32_t* path_olabels_host, float* path_weights_host,
+    int32_t* path_len_host, int32_t* status_host) {
   if (!ctx || !lat || max_len < 0 || !path_len_host)
     return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_viterbi_path: bad arguments");
   GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1023,19 +1038,26 @@ int gtnb_viterbi_path(
   // composed lattices: labels come from the provenance arrays (gathered on device by traceback
   // into the upper half of path_dev would be nicer; the paths are tiny so do it here)
   std::vector<int32_t> prov_g, prov_l;
-  if (lat->composed && want_labels) {
-    // fetch provenance for just the path arcs
+  if ((lat->composed && want_labels) || path_weights_host) {
+    // fetch provenance / weights for just the path arcs
     prov_g.resize(path.size());
     prov_l.resize(path.size());
     int32_t *pg = nullptr, *pl = nullptr;
+    float* pw = nullptr;
     if ((rc = dev_alloc(ctx, &pg, tot))) return rc;
     if ((rc = dev_alloc(ctx, &pl, tot))) return rc;
-    if ((rc = launch_gather_prov(ctx, lat, max_len, path_dev, len_dev, pg, pl))) return rc;
-    GTNB_CUDA(ctx, cudaMemcpyAsync(prov_g.data(), pg, sizeof(int32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream));
-    GTNB_CUDA(ctx, cudaMemcpyAsync(prov_l.data(), pl, sizeof(int32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream));
+    if (path_weights_host && (rc = dev_alloc(ctx, &pw, tot))) return rc;
+    if ((rc = launch_gather_prov(ctx, lat, max_len, path_dev, len_dev, pg, pl, pw))) return rc;
+    if (lat->gi) {
+      GTNB_CUDA(ctx, cudaMemcpyAsync(prov_g.data(), pg, sizeof(int32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream));
+      GTNB_CUDA(ctx, cudaMemcpyAsync(prov_l.data(), pl, sizeof(int32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (pw)
+      GTNB_CUDA(ctx, cudaMemcpyAsync(path_weights_host, pw, sizeof(float) * tot, cudaMemcpyDeviceToHost, ctx->stream));
     GTNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     dev_free(ctx, pg);
     dev_free(ctx, pl);
+    dev_free(ctx, pw);
   }
   for (int b = 0; b < B; b++) {
     int len = path_len_host[b];

@@ -248,7 +248,7 @@ inline long long align_up(long long v, long long a) {
 int launch_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int mode);
 int launch_backward(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev);
 int launch_traceback(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, int32_t* path_dev, int32_t* len_dev);
-int launch_gather_prov(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, const int32_t* path_dev, const int32_t* len_dev, int32_t* prov_graph, int32_t* prov_linear);
+int launch_gather_prov(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, const int32_t* path_dev, const int32_t* len_dev, int32_t* prov_graph, int32_t* prov_linear, float* path_w);
 // kernels (k_staged.cu): TMA-staged persistent kernels for level-local lattices
 bool staged_supported(const gtnb_lattice* lat);
 int launch_forward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int mode);

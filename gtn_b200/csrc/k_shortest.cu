@@ -309,20 +309,25 @@ __global__ void traceback_kernel(
 
 __global__ void gather_prov_kernel(
     const GraphMeta* __restrict__ meta,
-    const int2* __restrict__ gi,
+    const int2* __restrict__ gi, // nullable
+    const int2* __restrict__ arcs,
     int max_len,
     const int32_t* __restrict__ path,
     const int32_t* __restrict__ path_len,
     int32_t* __restrict__ pg,
-    int32_t* __restrict__ pl) {
+    int32_t* __restrict__ pl,
+    float* __restrict__ pw) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int len = path_len[b] < max_len ? path_len[b] : max_len;
   if (i >= len) return;
   const long long k = (long long)b * max_len + i;
   const long long a = meta[b].arc_base + path[k];
-  pg[k] = gi[a].x;
-  pl[k] = gi[a].y;
+  if (gi) {
+    pg[k] = gi[a].x;
+    pl[k] = gi[a].y;
+  }
+  if (pw) pw[k] = __int_as_float(arcs[a].y);
 }
 
 } // namespace
@@ -378,11 +383,11 @@ int launch_traceback(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, int32_t* pat
 
 int launch_gather_prov(
     gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, const int32_t* path_dev,
-    const int32_t* len_dev, int32_t* pg, int32_t* pl) {
+    const int32_t* len_dev, int32_t* pg, int32_t* pl, float* pw) {
   if (lat->B == 0 || max_len == 0) return GTNB_OK;
   dim3 grid((max_len + 127) / 128, lat->B);
   GTNB_LAUNCH(ctx, "gather_prov", gather_prov_kernel<<<grid, 128, 0, ctx->stream>>>(
-      lat->meta, lat->gi, max_len, path_dev, len_dev, pg, pl));
+      lat->meta, lat->gi, lat->arcs, max_len, path_dev, len_dev, pg, pl, pw));
   return GTNB_OK;
 }
 

@@ -205,6 +205,12 @@ int gtnb_backward(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* d
 
 /* copy graph b's arc gradients (Graph arc numbering) to the host */
 int gtnb_lattice_arc_grads(gtnb_ctx* ctx, gtnb_lattice* lat, int b, float* out_host);
+/*
+ * Overwrite graph b's arc gradients from the host (composed lattices; Graph arc
+ * numbering == device numbering there).  Lets compose's gradFunc run on the device
+ * when the deltas were produced or accumulated on the host (autograd.h:37).
+ */
+int gtnb_lattice_set_arc_grads(gtnb_ctx* ctx, gtnb_lattice* lat, int b, const float* grads_host);
 /* device pointer to all arc gradients (device arc order) -- advanced use */
 const float* gtnb_lattice_arc_grads_dev(const gtnb_lattice* lat);
 
@@ -237,6 +243,7 @@ int gtnb_viterbi_path(
     int32_t* path_arcs_host,
     int32_t* path_ilabels_host,
     int32_t* path_olabels_host,
+    float* path_weights_host, /* nullable: weights of the path's arcs */
     int32_t* path_len_host,
     int32_t* status_host);
 
