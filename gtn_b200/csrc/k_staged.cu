@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_forward_staged
   int32_t* bp = (MODE == MODE_PATH) ? back_ptr + m.node_base : nullptr;
   const int sub = tid % G;
   const int slot = tid / G;
+  // lanes cooperating on one node; shuffles stay inside the group so that groups may diverge
+  const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
   int s = 0;
   uint32_t par = 0;
   int lo = s_lvln[0];
@@ -350,8 +352,8 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_forward_staged
         if (G > 1) {
 #pragma unroll
           for (int o = G / 2; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oa = __shfl_xor_sync(0xffffffffu, barc, o);
+            const float ob = __shfl_xor_sync(gmask, best, o);
+            const int oa = __shfl_xor_sync(gmask, barc, o);
             if (ob > best || (ob == best && oa < barc)) {
               best = ob;
               barc = oa;
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_forward_staged
         }
         if (G > 1) {
 #pragma unroll
-          for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, o));
         }
         if (is_start) mx = fmaxf(mx, 0.0f);
         float score = mx;
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_forward_staged
           }
           if (G > 1) {
 #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
           }
           if (is_start) sum += fexp(0.0f - mx);
           score = mx + flog1p(sum);
@@ -586,6 +588,8 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_backward_stage
   const float delta = deltas ? deltas[blockIdx.x] : 1.0f;
   const int sub = tid % G;
   const int slot = tid / G;
+  // lanes cooperating on one node; shuffles stay inside the group so that groups may diverge
+  const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
 
   // top level: its own scores, and the accept seeds (shortest.cpp:49-60)
   {
@@ -667,8 +671,8 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_backward_stage
         if (G > 1) {
 #pragma unroll
           for (int o = G / 2; o > 0; o >>= 1) {
-            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            const float om = __shfl_xor_sync(gmask, mx, o);
+            const int oa = __shfl_xor_sync(gmask, arg, o);
             if (om > mx || (om == mx && oa < arg)) {
               mx = om;
               arg = oa;

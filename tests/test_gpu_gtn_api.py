@@ -303,7 +303,8 @@ def test_parallel_overloads_match_oracle(gtn, oracle):
     gtn.parallel_for(work, list(range(B)))
     for b in range(B):
         assert util.close(out[b][0], losses[b].item(), rtol=1e-6)
-        assert np.array_equal(out[b][1], ems[b].grad().weights_to_numpy())
+        # float atomics make the accumulation order (not the values) run-dependent
+        assert np.allclose(out[b][1], ems[b].grad().weights_to_numpy(), rtol=1e-4, atol=1e-6)
 
 
 def test_lattice_is_lazy_and_inspectable(gtn, oracle):
