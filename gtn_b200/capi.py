@@ -77,6 +77,8 @@ SYMBOLS = [
     ("gtnb_viterbi_path", C.c_int, [_vp, _vp, C.c_int, _i32p, _i32p, _i32p, _f32p, _i32p, _i32p]),
     ("gtnb_linear_forward", C.c_int,
      [_vp, C.c_int, _i32p, C.c_int, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_float]),
+    ("gtnb_viterbi_dense", C.c_int,
+     [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _i32p, _f32p, _i32p, _f32p]),
     ("gtnb_ctc_loss", C.c_int,
      [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _i32p, _i32p, _i32p, C.c_int, _f32p, _vp,
       C.c_int]),
@@ -280,6 +282,20 @@ class Ctx:
         out = scores.download((B,))
         scores.free()
         return out
+
+    def viterbi_dense(self, emissions, trans_w, input_lens=None):
+        """Host-buffer entry: emissions [B,T,C], trans_w [C + C*C] -> (paths [B,T], scores [B])."""
+        e = np.ascontiguousarray(emissions, dtype=np.float32)
+        B, T, Cn = e.shape
+        tw = np.ascontiguousarray(trans_w, dtype=np.float32)
+        assert tw.size == Cn + Cn * Cn
+        il = None if input_lens is None else np.ascontiguousarray(input_lens, np.int32)
+        paths = np.full((B, max(T, 1)), -1, np.int32)
+        scores = np.zeros(max(B, 1), np.float32)
+        self._check(lib().gtnb_viterbi_dense(
+            self.h, B, T, Cn, e.ctypes.data, 0, _p(il, _i32p), _p(tw, _f32p), _p(paths, _i32p),
+            _p(scores, _f32p)))
+        return paths[:, :T], scores[:B]
 
     def ctc_loss(self, emissions, targets, blank=0, want_grad=True, input_lens=None):
         """Host-buffer entry point: emissions [B,T,C] float32 numpy -> (losses, grads)."""

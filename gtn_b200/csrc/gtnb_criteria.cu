@@ -134,3 +134,69 @@ done:
 #undef TRY
 #undef TRYCUDA
 }
+
+/*
+ * viterbiPath(compose(linearGraph(T, C; e_b), transitions)) for a whole minibatch, with the
+ * dense transitions graph of test/criterion_test.cpp:244-254 / :316-326, through the
+ * factored kernel (k_dense.cu): the T*C*C lattice is never materialised.
+ */
+extern "C" int gtnb_viterbi_dense(
+    gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
+    const int32_t* input_lens, const float* trans_w_host, int32_t* paths_host, float* scores_host) {
+  if (!ctx || B < 0 || T < 0 || C <= 0 || !emissions || !trans_w_host)
+    return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_viterbi_dense: bad arguments");
+  if (B == 0) return GTNB_OK;
+  GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long per = (long long)T * C;
+  int rc = GTNB_OK;
+  float *e_dev = nullptr, *tr_dev = nullptr, *sc_dev = nullptr;
+  int32_t *T_dev = nullptr, *paths_dev = nullptr;
+  uint8_t* bp = nullptr;
+#define TRY(x)                 \
+  do {                         \
+    if ((rc = (x))) goto done; \
+  } while (0)
+#define TRYCUDA(call)                                      \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) {                              \
+      rc = cuda_fail(ctx, e__, #call, __FILE__, __LINE__); \
+      goto done;                                           \
+    }                                                      \
+  } while (0)
+  if (input_lens)
+    for (int b = 0; b < B; b++)
+      if (input_lens[b] < 0 || input_lens[b] > T)
+        return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_viterbi_dense: input_lens out of range");
+  if (emissions_on_device) {
+    e_dev = const_cast<float*>(emissions);
+  } else {
+    TRY(dev_alloc(ctx, &e_dev, per * B));
+    TRYCUDA(cudaMemcpyAsync(e_dev, emissions, sizeof(float) * per * B, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  TRY(dev_alloc(ctx, &tr_dev, (long long)C + (long long)C * C));
+  TRY(dev_alloc(ctx, &sc_dev, B));
+  TRY(dev_alloc(ctx, &paths_dev, (long long)B * std::max(T, 1)));
+  TRY(dev_alloc(ctx, &bp, (long long)B * std::max(T, 1) * C));
+  if (input_lens) TRY(dev_alloc(ctx, &T_dev, B));
+  TRY(stage_begin(ctx));
+  TRY(stage_upload(ctx, tr_dev, trans_w_host, sizeof(float) * ((size_t)C + (size_t)C * C)));
+  if (input_lens) TRY(stage_upload(ctx, T_dev, input_lens, sizeof(int32_t) * B));
+  TRY(stage_end(ctx));
+  TRY(launch_viterbi_dense(ctx, B, T, C, T_dev, e_dev, per, tr_dev, bp, paths_dev, sc_dev));
+  if (paths_host && T > 0)
+    TRYCUDA(cudaMemcpyAsync(paths_host, paths_dev, sizeof(int32_t) * (size_t)B * T, cudaMemcpyDeviceToHost, ctx->stream));
+  if (scores_host)
+    TRYCUDA(cudaMemcpyAsync(scores_host, sc_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  TRYCUDA(cudaStreamSynchronize(ctx->stream));
+done:
+  if (!emissions_on_device) dev_free(ctx, e_dev);
+  dev_free(ctx, tr_dev);
+  dev_free(ctx, sc_dev);
+  dev_free(ctx, paths_dev);
+  dev_free(ctx, bp);
+  dev_free(ctx, T_dev);
+  return rc;
+#undef TRY
+#undef TRYCUDA
+}

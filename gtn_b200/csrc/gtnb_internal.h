@@ -253,6 +253,10 @@ int launch_gather_prov(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, const int3
 bool staged_supported(const gtnb_lattice* lat);
 int launch_forward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int mode);
 int launch_backward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev);
+// kernels (k_dense.cu): factored dense-trellis Viterbi
+int launch_viterbi_dense(
+    gtnb_ctx* ctx, int B, int T_max, int C, const int32_t* T_dev, const float* emis, int64_t stride,
+    const float* trans_dev, uint8_t* bp, int32_t* paths, float* scores);
 // kernels (k_compose.cu)
 int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat);
 int launch_compose_grad(gtnb_ctx* ctx, gtnb_lattice* lat, float* grad_graph, float* grad_emis, int64_t grad_stride);

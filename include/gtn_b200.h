@@ -293,6 +293,28 @@ int gtnb_ctc_loss(
     float* grads,
     int grads_on_device);
 
+/*
+ * viterbiPath + viterbiScore of compose(linearGraph(T, C; e_b), transitions) for a whole
+ * minibatch (test/criterion_test.cpp:308-345, BASELINE.json configs[3]) WITHOUT
+ * materialising the T*C*C lattice (32.75 M arcs per utterance at T=2000, C=128).
+ * transitions is the dense graph of criterion_test.cpp:316-326: node 0 start, nodes 1..C
+ * accept, arcs 0 -> i+1 (label i, weight trans_w[i]) and j+1 -> i+1 (label i, weight
+ * trans_w[C + i*C + j]).  paths_host [B][T]: the best path's labels (-1 where there is no
+ * accepting path / beyond input_lens[b]); scores_host [B]: viterbiScore.  Paths are
+ * bit-identical to the reference's, ties included.  Needs C <= 256, C % 4 == 0.
+ */
+int gtnb_viterbi_dense(
+    gtnb_ctx* ctx,
+    int B,
+    int T,
+    int C,
+    const float* emissions,
+    int emissions_on_device,
+    const int32_t* input_lens,
+    const float* trans_w_host,
+    int32_t* paths_host,
+    float* scores_host);
+
 #ifdef __cplusplus
 }
 #endif

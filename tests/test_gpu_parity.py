@@ -280,3 +280,78 @@ def test_staged_and_generic_kernels_agree(ctx, oracle):
         assert np.array_equal(res[1][4]["ilabels"][b], p), b
         assert res[1][2][b] == s
     e_dev.free()
+
+
+# ---------------------------------------------------------------------------
+# dense-trellis Viterbi (BASELINE.json configs[3]) through the factored kernel
+# ---------------------------------------------------------------------------
+
+def test_viterbi_dense_golden_ties(ctx):
+    """Integer scores: ties on every frame; paths must equal the reference's (golden fixture)."""
+    gold = np.load(util.__file__.replace("util.py", "golden/reference_golden.npz"))
+    e, tw = gold["vit_e"], gold["vit_tw"]
+    # C = 6 in the fixture is not a multiple of 4: pad states with -inf-like scores that never win
+    B, T, C = e.shape
+    Cp = 8
+    ep = np.full((B, T, Cp), -1e30, np.float32)
+    ep[:, :, :C] = e
+    twp = np.full(Cp + Cp * Cp, -1e30, np.float32)
+    twp[:C] = tw[:C]
+    tr = tw[C:].reshape(C, C)
+    trp = np.full((Cp, Cp), -1e30, np.float32)
+    trp[:C, :C] = tr
+    twp[Cp:] = trp.ravel()
+    paths, scores = ctx.viterbi_dense(ep, twp)
+    assert np.array_equal(paths, gold["vit_paths"])
+    assert np.array_equal(scores, gold["vit_scores"])
+
+
+def test_viterbi_dense_vs_oracle_and_materialised(ctx, oracle):
+    """Random float scores, C multiple of 4: the factored kernel, the materialised lattice path
+    (gtnb_compose_linear + gtnb_viterbi_path) and the oracle agree bit for bit."""
+    rng = np.random.default_rng(21)
+    B, T, C = 5, 40, 8
+    e = rng.uniform(-5, 5, (B, T, C)).astype(np.float32)
+    e[0] = np.round(e[0])  # one utterance with ties
+    tw = rng.uniform(-5, 5, C + C * C).astype(np.float32)
+    tw_int = np.round(tw)
+    for trans in (tw, tw_int):
+        paths, scores = ctx.viterbi_dense(e, trans)
+        e_dev = ctx.to_device(e)
+        view = util.view_of(oracle.Graph.transitions(C, trans))
+        lat = ctx.compose_linear([view], [T] * B, C, e_dev, T * C, linear_first=True, B=B)
+        out = lat.viterbi_path(T)
+        sc = lat.forward(tropical=True)
+        for b in range(B):
+            p, s = oracle.viterbi_dense(e[b], trans)
+            assert np.array_equal(paths[b], p), b
+            assert scores[b] == s
+            assert np.array_equal(out["ilabels"][b], p), b
+            assert sc[b] == s
+        lat.free()
+        e_dev.free()
+
+
+def test_viterbi_dense_full_size_properties(ctx):
+    """configs[3] shape (T=2000, C=128; a 16-utterance slice of the B=512 batch): the path's own
+    score, re-accumulated on the host in the kernel's association, equals the returned
+    viterbiScore bit for bit, and no single-frame substitution improves it."""
+    B, T, C = 16, 2000, 128
+    rng = np.random.default_rng(99)
+    e = rng.uniform(-5, 5, (B, T, C)).astype(np.float32)
+    tw = rng.uniform(-5, 5, C + C * C).astype(np.float32)
+    paths, scores = ctx.viterbi_dense(e, tw)
+    tr = tw[C:].reshape(C, C)  # tr[i, j] = w(j -> i)
+    for b in range(B):
+        p = paths[b]
+        assert p.min() >= 0 and p.max() < C
+        s = np.float32(0.0) + (e[b, 0, p[0]] + tw[p[0]])
+        for t in range(1, T):
+            s = np.float32(s + np.float32(e[b, t, p[t]] + tr[p[t], p[t - 1]]))
+        assert s == scores[b], (b, s, scores[b])
+    # local optimality on one utterance: changing any single interior frame cannot score higher
+    b, p = 0, paths[0].astype(np.int64)
+    for t in range(1, T - 1, 97):
+        alt = e[b, t] + tr[:, p[t - 1]] + tr[p[t + 1], :]
+        cur = e[b, t, p[t]] + tr[p[t], p[t - 1]] + tr[p[t + 1], p[t]]
+        assert alt.max() <= cur + 1e-3
