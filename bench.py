@@ -43,54 +43,100 @@ def make_inputs(first, count, T, C, U):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  Uses NVML
+    in-process (the same counters nvidia-smi prints; forking `nvidia-smi -lms` next to a
+    3 ms step measurably perturbs it), falling back to `nvidia-smi -lms 200`."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.05):
         self.index = index
-        self.rows = []
+        self.period = period
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = False
+        self.thread = None
         self.proc = None
+        self.how = None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if mx:
+                    self.mx.append(mx)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _smi_read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.sm.append(float(r[1]))
+                self.mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.how = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
+                self.proc.wait(timeout=5)
             except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.how}
 
 
 def load_peaks():
@@ -166,7 +212,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_DEF, help="utterances per GPU")
@@ -317,6 +363,7 @@ def main():
                     "d2h_bytes_per_step": int(nbytes + losses.nbytes)},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "ms_per_step_median": float(np.median(times)), "ms_per_step_min": float(np.min(times)),
             "roofline": roofline,
             "roofline_whole_step_csr": {"achieved": b_csr / (ms * 1e-3) / 1e9, "unit": "GB/s",
                                         "frac": b_csr / (ms * 1e-3) / 1e9 / peak, "bytes": b_csr},

@@ -77,6 +77,8 @@ SYMBOLS = [
     ("gtnb_viterbi_path", C.c_int, [_vp, _vp, C.c_int, _i32p, _i32p, _i32p, _f32p, _i32p, _i32p]),
     ("gtnb_linear_forward", C.c_int,
      [_vp, C.c_int, _i32p, C.c_int, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_float]),
+    ("gtnb_asg_loss", C.c_int,
+     [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _f32p, _i32p, _i32p, _f32p, _vp, C.c_int, _f32p]),
     ("gtnb_viterbi_dense", C.c_int,
      [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _i32p, _f32p, _i32p, _f32p]),
     ("gtnb_ctc_loss", C.c_int,
@@ -282,6 +284,22 @@ class Ctx:
         out = scores.download((B,))
         scores.free()
         return out
+
+    def asg_loss(self, emissions, trans_w, targets, want_grad=True):
+        """Host-buffer entry: -> (losses [B], grads [B,T,C] or None, trans_grad [C + C*C] or None)."""
+        e = np.ascontiguousarray(emissions, dtype=np.float32)
+        B, T, Cn = e.shape
+        tw = np.ascontiguousarray(trans_w, dtype=np.float32)
+        lens = np.asarray([len(t) for t in targets], np.int32)
+        cat = np.ascontiguousarray(
+            np.concatenate([np.asarray(t, np.int32) for t in targets]) if B else np.zeros(0, np.int32), np.int32)
+        losses = np.zeros(B, np.float32)
+        grads = np.zeros_like(e) if want_grad else None
+        tg = np.zeros(Cn + Cn * Cn, np.float32) if want_grad else None
+        self._check(lib().gtnb_asg_loss(
+            self.h, B, T, Cn, e.ctypes.data, 0, _p(tw, _f32p), _p(cat, _i32p), _p(lens, _i32p),
+            _p(losses, _f32p), None if grads is None else grads.ctypes.data, 0, _p(tg, _f32p)))
+        return losses, grads, tg
 
     def viterbi_dense(self, emissions, trans_w, input_lens=None):
         """Host-buffer entry: emissions [B,T,C], trans_w [C + C*C] -> (paths [B,T], scores [B])."""

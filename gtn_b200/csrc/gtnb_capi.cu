@@ -601,6 +601,7 @@ int composed_alloc(
     m.T = T[b];
     m.sg_N = s.N;
     m.sg_A = s.A;
+    m.sg_all_valid = s.all_valid;
     m.cap_N = (int)capN;
     m.cap_A = (int)capA;
     m.cap_L = (int)align_up(T[b] + 2, kAlign);
@@ -1151,7 +1152,11 @@ int gtnb_compose_linear(
   }
 
   std::vector<SgDims> dims(n_graphs);
-  for (int g = 0; g < n_graphs; g++) dims[g] = SgDims{sg[g].N, sg[g].A, (int)sg[g].acc.size()};
+  for (int g = 0; g < n_graphs; g++) {
+    int all_valid = 1;
+    for (int lab : sg[g].in_label) all_valid &= lab >= 0;
+    dims[g] = SgDims{sg[g].N, sg[g].A, (int)sg[g].acc.size(), all_valid};
+  }
   std::vector<long long> sgn, sga;
   gtnb_lattice* lat = nullptr;
   int rc = composed_alloc(ctx, B, dims.data(), n_graphs, linear_first, T, C, emissions_dev,

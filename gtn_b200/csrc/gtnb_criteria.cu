@@ -42,9 +42,11 @@ extern "C" int gtnb_ctc_loss(
     off[b] = (int32_t)tot_t;
     const int32_t* tg = targets + tot_t;
     int skips = 0;
+    int all_valid = blank >= 0 && blank < C;
     for (int u = 1; u < U; u++) skips += tg[u] != tg[u - 1];
+    for (int u = 0; u < U; u++) all_valid &= tg[u] >= 0 && tg[u] < C;
     const int L = 2 * U + 1;
-    dims[b] = SgDims{L, L + (L - 1) + skips, L >= 2 ? 2 : 1};
+    dims[b] = SgDims{L, L + (L - 1) + skips, L >= 2 ? 2 : 1, all_valid};
     tot_t += U;
     Tb[b] = input_lens ? input_lens[b] : T;
     if (Tb[b] < 0 || Tb[b] > T)
@@ -196,6 +198,180 @@ done:
   dev_free(ctx, paths_dev);
   dev_free(ctx, bp);
   dev_free(ctx, T_dev);
+  return rc;
+#undef TRY
+#undef TRYCUDA
+}
+
+/*
+ * ASG criterion for a whole minibatch (test/criterion_test.cpp:244-305, examples/asg.cpp:59-81):
+ *   loss_b = forwardScore(compose(e_b, transitions))
+ *          - forwardScore(compose(compose(fal_b, transitions), e_b))
+ * with the dense transitions graph shared by the batch; gradients w.r.t. the emissions and
+ * (accumulated over the batch, graph.cpp:96-100) the transitions.  The denominator lattice
+ * is materialised on the device (C + (T-1) C^2 arcs per utterance); compose(fal_b,
+ * transitions) is a 2U-arc chain built on the host from the target (pure construction).
+ */
+extern "C" int gtnb_asg_loss(
+    gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
+    const float* trans_w_host, const int32_t* targets, const int32_t* target_lens,
+    float* losses_host, float* grads, int grads_on_device, float* trans_grad_host) {
+  if (!ctx || B < 0 || T < 0 || C <= 0 || !emissions || !trans_w_host || !target_lens || !losses_host)
+    return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_asg_loss: bad arguments");
+  if (B == 0) return GTNB_OK;
+  GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long per = (long long)T * C;
+  const int nTrans = C + C * C;
+  const bool want = grads || trans_grad_host;
+  int rc = GTNB_OK;
+  float *e_dev = nullptr, *g_dev = nullptr, *tg_dev = nullptr, *ft_grad = nullptr, *minus1 = nullptr;
+  int32_t* ft_map_dev = nullptr;
+  gtnb_lattice *den = nullptr, *num = nullptr;
+
+  // transitions graph view (criterion_test.cpp:244-254)
+  std::vector<uint8_t> tflags(C + 1, 2);
+  tflags[0] = 1;
+  std::vector<int32_t> tsrc(nTrans), tdst(nTrans), tlab(nTrans);
+  for (int i = 0; i < C; i++) {
+    tsrc[i] = 0;
+    tdst[i] = i + 1;
+    tlab[i] = i;
+  }
+  for (int i = 0; i < C; i++)
+    for (int j = 0; j < C; j++) {
+      const int a = C + i * C + j;
+      tsrc[a] = j + 1;
+      tdst[a] = i + 1;
+      tlab[a] = i;
+    }
+  gtnb_graph_view tview;
+  std::memset(&tview, 0, sizeof(tview));
+  tview.num_nodes = C + 1;
+  tview.num_arcs = nTrans;
+  tview.node_flags = tflags.data();
+  tview.arc_src = tsrc.data();
+  tview.arc_dst = tdst.data();
+  tview.arc_ilabel = tview.arc_olabel = tlab.data();
+  tview.weights = trans_w_host;
+
+  // compose(fal_b, transitions): node l = "l labels consumed"; arcs: 0->1, then per node a
+  // self loop and the step to the next label, in the reference's creation order
+  struct Ft {
+    std::vector<uint8_t> flags;
+    std::vector<int32_t> src, dst, lab, map;
+    std::vector<float> w;
+  };
+  std::vector<Ft> ft(B);
+  std::vector<gtnb_graph_view> fviews(B);
+  std::vector<int32_t> ft_map;
+  std::vector<int32_t> Tb(B, T);
+  long long toff = 0;
+  for (int b = 0; b < B; b++) {
+    const int U = target_lens[b];
+    if (U < 0) return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_asg_loss: negative target length");
+    const int32_t* y = targets + toff;
+    toff += U;
+    for (int u = 0; u < U; u++)
+      if (y[u] < 0 || y[u] >= C) return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_asg_loss: label out of range");
+    Ft& f = ft[b];
+    f.flags.assign(U + 1, 0);
+    f.flags[0] |= 1;
+    if (U > 0) f.flags[U] |= 2;
+    auto add = [&](int s, int d, int lab, int tarc) {
+      f.src.push_back(s);
+      f.dst.push_back(d);
+      f.lab.push_back(lab);
+      f.w.push_back(trans_w_host[tarc]);
+      f.map.push_back(tarc);
+    };
+    if (U > 0) add(0, 1, y[0], y[0]);
+    for (int l = 1; l <= U; l++) {
+      add(l, l, y[l - 1], C + y[l - 1] * C + y[l - 1]);
+      if (l < U) add(l, l + 1, y[l], C + y[l] * C + y[l - 1]);
+    }
+    gtnb_graph_view& v = fviews[b];
+    std::memset(&v, 0, sizeof(v));
+    v.num_nodes = U + 1;
+    v.num_arcs = (int)f.src.size();
+    v.node_flags = f.flags.data();
+    v.arc_src = f.src.data();
+    v.arc_dst = f.dst.data();
+    v.arc_ilabel = v.arc_olabel = f.lab.data();
+    v.weights = f.w.data();
+    ft_map.insert(ft_map.end(), f.map.begin(), f.map.end());
+  }
+  const long long nFt = (long long)ft_map.size();
+
+#define TRY(x)                 \
+  do {                         \
+    if ((rc = (x))) goto done; \
+  } while (0)
+#define TRYCUDA(call)                                      \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) {                              \
+      rc = cuda_fail(ctx, e__, #call, __FILE__, __LINE__); \
+      goto done;                                           \
+    }                                                      \
+  } while (0)
+  if (emissions_on_device) {
+    e_dev = const_cast<float*>(emissions);
+  } else {
+    TRY(dev_alloc(ctx, &e_dev, per * B));
+    TRYCUDA(cudaMemcpyAsync(e_dev, emissions, sizeof(float) * per * B, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (want) {
+    if (grads && grads_on_device)
+      g_dev = grads;
+    else
+      TRY(dev_alloc(ctx, &g_dev, per * B));
+    TRYCUDA(cudaMemsetAsync(g_dev, 0, sizeof(float) * per * B, ctx->stream));
+    TRY(dev_alloc(ctx, &tg_dev, nTrans));
+    TRYCUDA(cudaMemsetAsync(tg_dev, 0, sizeof(float) * nTrans, ctx->stream));
+    TRY(dev_alloc(ctx, &ft_grad, std::max<long long>(nFt, 1)));
+    TRYCUDA(cudaMemsetAsync(ft_grad, 0, sizeof(float) * std::max<long long>(nFt, 1), ctx->stream));
+    TRY(dev_alloc(ctx, &ft_map_dev, std::max<long long>(nFt, 1)));
+    TRY(dev_alloc(ctx, &minus1, B));
+  }
+  TRY(gtnb_compose_linear(ctx, B, &tview, 1, 1, Tb.data(), C, e_dev, per, &den));
+  TRY(gtnb_compose_linear(ctx, B, fviews.data(), B, 0, Tb.data(), C, e_dev, per, &num));
+  TRY(gtnb_forward(ctx, den, 0, nullptr, nullptr));
+  TRY(gtnb_forward(ctx, num, 0, nullptr, nullptr));
+  if (want) {
+    std::vector<float> m1(B, -1.0f);
+    TRY(gtnb_backward(ctx, den, 0, nullptr)); // +1 (subtract's gradFunc, functions.cpp:53-58)
+    TRY(gtnb_backward(ctx, num, 0, m1.data())); // -1
+    TRY(gtnb_compose_grad(ctx, den, tg_dev, g_dev, per));
+    TRY(gtnb_compose_grad(ctx, num, ft_grad, g_dev, per));
+    if (nFt) {
+      TRY(stage_begin(ctx));
+      TRY(stage_upload(ctx, ft_map_dev, ft_map.data(), sizeof(int32_t) * nFt));
+      TRY(stage_end(ctx));
+      TRY(launch_scatter_add(ctx, tg_dev, ft_map_dev, ft_grad, nFt));
+    }
+    if (grads && !grads_on_device)
+      TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (trans_grad_host)
+      TRYCUDA(cudaMemcpyAsync(trans_grad_host, tg_dev, sizeof(float) * nTrans, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  TRY(readback_reserve(ctx, 2 * sizeof(float) * B));
+  {
+    float* d = reinterpret_cast<float*>(ctx->readback);
+    float* n = d + B;
+    TRYCUDA(cudaMemcpyAsync(d, den->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    TRYCUDA(cudaMemcpyAsync(n, num->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    TRYCUDA(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < B; b++) losses_host[b] = d[b] - n[b];
+  }
+done:
+  if (den) gtnb_lattice_destroy(ctx, den);
+  if (num) gtnb_lattice_destroy(ctx, num);
+  if (!emissions_on_device) dev_free(ctx, e_dev);
+  if (!(grads && grads_on_device)) dev_free(ctx, g_dev);
+  dev_free(ctx, tg_dev);
+  dev_free(ctx, ft_grad);
+  dev_free(ctx, ft_map_dev);
+  dev_free(ctx, minus1);
   return rc;
 #undef TRY
 #undef TRYCUDA

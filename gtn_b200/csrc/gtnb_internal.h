@@ -55,6 +55,7 @@ struct GraphMeta {
   int T; // frames (composed lattices)
   int sg_N; // small-graph node / arc counts (composed lattices)
   int sg_A;
+  int sg_all_valid; // every arc label of the graph operand can match an emission label
   int cap_N; // slab capacities
   int cap_A;
   int cap_L;
@@ -155,6 +156,7 @@ namespace gtnb {
 
 struct SgDims {
   int N, A, n_acc;
+  int all_valid = 0;
 };
 int composed_alloc(
     gtnb_ctx* ctx, int B, const SgDims* dims, int n_graphs, int linear_first, const int32_t* T,
@@ -167,6 +169,9 @@ int readback_reserve(gtnb_ctx* ctx, size_t bytes);
 int launch_ctc_build(
     gtnb_ctx* ctx, gtnb_lattice* lat, const int32_t* targets_dev, const int32_t* tgt_off_dev,
     const int32_t* tgt_len_dev, int blank);
+
+int launch_scatter_add(gtnb_ctx* ctx, float* dst, const int32_t* idx, const float* src, long long n);
+int launch_sub(gtnb_ctx* ctx, const float* a, const float* b, float* out, int n);
 
 int fail(gtnb_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(gtnb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);

@@ -161,6 +161,26 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_count_kernel(
   const uint32_t* at = alive + ((size_t)b * (maxT + 1) + t) * W;
   const uint32_t* ap = at - W;
   int nodes = 0, arcs = 0;
+  // steady state: every graph node alive in this frame and the one before, every label
+  // matchable -> the level is the whole graph: nothing to count
+  if (t > 0 && m.sg_all_valid) {
+    int ct = 0, cp = 0;
+    for (int c = lane; c < Wg; c += 32) {
+      ct += __popc(at[c]);
+      cp += __popc(ap[c]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      ct += __shfl_xor_sync(0xffffffffu, ct, o);
+      cp += __shfl_xor_sync(0xffffffffu, cp, o);
+    }
+    if (ct == m.sg_N && cp == m.sg_N) {
+      if (lane == 0) {
+        lvl_node_ptr[m.lvl_base + t] = m.sg_N;
+        lvl_arc_ptr[m.lvl_base + t] = m.sg_A;
+      }
+      return;
+    }
+  }
   for (int c = 0; c < Wg; c++) {
     const uint32_t word = at[c];
     nodes += __popc(word);
@@ -299,6 +319,22 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_emit_kernel(
   const int nb = np[t];
   const int ab = apn[t];
   const int pb = t > 0 ? np[t - 1] : 0;
+  // steady state (see compose_count_kernel): the level is the whole graph in its canonical
+  // in-arc order; lattice arc k of the level is graph in-entry k, node d has rank d
+  if (t > 0 && m.sg_all_valid && np[t + 1] - nb == m.sg_N && nb - pb == m.sg_N) {
+    for (int d = lane; d < m.sg_N; d += 32) {
+      uint32_t flags = 0;
+      if (t == m.T && (fl[d] & 2)) flags |= kAcceptBit;
+      rp[nb + d] = (uint32_t)(ab + ip[d]) | flags;
+    }
+    for (int e = lane; e < m.sg_A; e += 32) {
+      const int lab = il[e];
+      ao[ab + e] = make_int2(pb + is[e], __float_as_int(iw[e] + em[lab]));
+      go[ab + e] = make_int2(ia[e], (t - 1) * C + lab);
+    }
+    if (t == m.T && lane == 0) rp[np[m.T + 1]] = (uint32_t)apn[m.T + 1];
+    return;
+  }
   if (t > 0) {
     int run = 0;
     for (int c0 = 0; c0 < Wg; c0 += 32) {
@@ -363,22 +399,42 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_emit_kernel(
 
 __global__ void __launch_bounds__(256) compose_grad_kernel(
     const GraphMeta* __restrict__ meta,
+    const uint32_t* __restrict__ row_ptr,
     const float* __restrict__ arc_grad,
     const int2* __restrict__ gi,
     float* __restrict__ grad_graph,
     float* __restrict__ grad_emis,
     long long grad_stride) {
+  // one thread per lattice node: its in-arcs are contiguous and (in every CTC / ASG lattice)
+  // share the emission they came from, so their gradients are summed in registers and leave
+  // as ONE atomic per node instead of one per arc
   const int b = blockIdx.y;
   const GraphMeta m = meta[b];
+  const uint32_t* rp = row_ptr + m.node_base;
   const float* ag = arc_grad + m.arc_base;
   const int2* gp = gi + m.arc_base;
   float* g1 = grad_graph ? grad_graph + m.grad_graph_off : nullptr;
   float* g2 = grad_emis ? grad_emis + (long long)b * grad_stride : nullptr;
-  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < m.A; a += gridDim.x * blockDim.x) {
-    const float g = ag[a];
-    const int2 p = gp[a];
-    if (g1) atomicAdd(&g1[p.x], g);
-    if (g2) atomicAdd(&g2[p.y], g);
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < m.N; n += gridDim.x * blockDim.x) {
+    const int r0 = (int)(rp[n] & kRowMask), r1 = (int)(rp[n + 1] & kRowMask);
+    if (r1 == r0) continue;
+    int key = -1;
+    float acc = 0.0f;
+    for (int a = r0; a < r1; a++) {
+      const float g = ag[a];
+      const int2 p = gp[a];
+      if (g1) atomicAdd(&g1[p.x], g);
+      if (g2) {
+        if (p.y == key) {
+          acc += g;
+        } else {
+          if (key >= 0) atomicAdd(&g2[key], acc);
+          key = p.y;
+          acc = g;
+        }
+      }
+    }
+    if (g2 && key >= 0) atomicAdd(&g2[key], acc);
   }
 }
 
@@ -409,12 +465,12 @@ int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat) {
 int launch_compose_grad(
     gtnb_ctx* ctx, gtnb_lattice* lat, float* grad_graph, float* grad_emis, int64_t grad_stride) {
   if (lat->B == 0) return GTNB_OK;
-  int capA = 1;
-  for (int b = 0; b < lat->B; b++) capA = std::max(capA, lat->meta_h[b].cap_A);
-  int gx = std::min((capA + 1023) / 1024, 4096);
+  int capN = 1;
+  for (int b = 0; b < lat->B; b++) capN = std::max(capN, lat->meta_h[b].cap_N);
+  int gx = std::min((capN + 255) / 256, 4096);
   dim3 grid(gx, lat->B);
   GTNB_LAUNCH(ctx, "compose_grad", compose_grad_kernel<<<grid, 256, 0, ctx->stream>>>(
-      lat->meta, lat->arc_grad, lat->gi, grad_graph, grad_emis,
+      lat->meta, lat->row_ptr, lat->arc_grad, lat->gi, grad_graph, grad_emis,
       (long long)grad_stride));
   return GTNB_OK;
 }

@@ -11,6 +11,8 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "gtnb_internal.h"
 
 namespace gtnb {
@@ -128,4 +130,34 @@ int launch_ctc_build(
   return GTNB_OK;
 }
 
+} // namespace gtnb
+
+namespace gtnb {
+namespace {
+__global__ void scatter_add_kernel(float* __restrict__ dst, const int32_t* __restrict__ idx,
+                                   const float* __restrict__ src, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&dst[idx[i]], src[i]);
+}
+__global__ void sub_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] - b[i];
+}
+} // namespace
+
+/* dst[idx[i]] += src[i]: the gradFunc of the host-composed (forced alignment x transitions)
+ * graph (compose.cpp:496-518) applied on the device */
+int launch_scatter_add(gtnb_ctx* ctx, float* dst, const int32_t* idx, const float* src, long long n) {
+  if (n <= 0) return GTNB_OK;
+  int blocks = (int)std::min<long long>((n + 255) / 256, 1024);
+  GTNB_LAUNCH(ctx, "scatter_add", scatter_add_kernel<<<blocks, 256, 0, ctx->stream>>>(dst, idx, src, n));
+  return GTNB_OK;
+}
+
+int launch_sub(gtnb_ctx* ctx, const float* a, const float* b, float* out, int n) {
+  if (n <= 0) return GTNB_OK;
+  GTNB_LAUNCH(ctx, "sub", sub_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a, b, out, n));
+  return GTNB_OK;
+}
 } // namespace gtnb

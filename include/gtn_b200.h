@@ -294,6 +294,31 @@ int gtnb_ctc_loss(
     int grads_on_device);
 
 /*
+ * ASG criterion for a whole minibatch (test/criterion_test.cpp:244-305, examples/asg.cpp:59-81,
+ * BASELINE.json configs[2]):
+ *   loss_b = forwardScore(compose(e_b, transitions))
+ *          - forwardScore(compose(compose(fal_b, transitions), e_b))
+ * transitions: the dense graph described at gtnb_viterbi_dense, weights trans_w_host
+ * [C + C*C], shared by the batch.  grads (nullable): d loss_b / d e_b, [B][T][C];
+ * trans_grad_host (nullable): sum over the batch of d loss_b / d transitions, [C + C*C]
+ * (the reference accumulates it under grad_lock, graph.cpp:96-100).
+ */
+int gtnb_asg_loss(
+    gtnb_ctx* ctx,
+    int B,
+    int T,
+    int C,
+    const float* emissions,
+    int emissions_on_device,
+    const float* trans_w_host,
+    const int32_t* targets,
+    const int32_t* target_lens,
+    float* losses_host,
+    float* grads,
+    int grads_on_device,
+    float* trans_grad_host);
+
+/*
  * viterbiPath + viterbiScore of compose(linearGraph(T, C; e_b), transitions) for a whole
  * minibatch (test/criterion_test.cpp:308-345, BASELINE.json configs[3]) WITHOUT
  * materialising the T*C*C lattice (32.75 M arcs per utterance at T=2000, C=128).

@@ -355,3 +355,50 @@ def test_viterbi_dense_full_size_properties(ctx):
         alt = e[b, t] + tr[:, p[t - 1]] + tr[p[t + 1], :]
         cur = e[b, t, p[t]] + tr[p[t], p[t - 1]] + tr[p[t + 1], p[t]]
         assert alt.max() <= cur + 1e-3
+
+
+# ---------------------------------------------------------------------------
+# ASG (BASELINE.json configs[2]) through the batched criterion
+# ---------------------------------------------------------------------------
+
+def test_asg_golden(ctx):
+    """Three utterances sharing one transitions graph (fixture made by the real reference)."""
+    gold = np.load(util.__file__.replace("util.py", "golden/reference_golden.npz"))
+    e, tw, tg = gold["asg_e"], gold["asg_tw"], gold["asg_targets"]
+    losses, grads, tgrad = ctx.asg_loss(e, tw, [t for t in tg])
+    assert util.close(losses, gold["asg_loss"])
+    assert util.grad_close(grads, gold["asg_grad"], 5.0 * e.shape[1])
+    assert util.grad_close(tgrad, gold["asg_tgrad"], 5.0 * e.shape[1])
+
+
+def test_asg_vs_oracle_medium(ctx, oracle):
+    rng = np.random.default_rng(31)
+    B, T, C, U = 6, 60, 16, 7
+    e = rng.uniform(-5, 5, (B, T, C)).astype(np.float32)
+    tw = rng.uniform(-5, 5, C + C * C).astype(np.float32)
+    targets = [rng.integers(0, C, U).astype(np.int32) for _ in range(B)]
+    targets[2] = np.array([3, 3, 3, 4], np.int32)  # repeats
+    losses, grads, tgrad = ctx.asg_loss(e, tw, targets)
+    tsum = np.zeros_like(tgrad)
+    for b in range(B):
+        lo, go, tg = oracle.asg_loss(e[b], tw, targets[b])
+        tsum += tg
+        assert util.close(losses[b], lo), (b, losses[b], lo)
+        assert util.grad_close(grads[b], go, 5.0 * T), b
+    assert util.grad_close(tgrad, tsum, 5.0 * T * B)
+
+
+def test_asg_config3_shape_properties(ctx):
+    """configs[2] shape (T=500, C=64, U=50; a 16-utterance slice of B=128): posteriors sum to
+    one per frame on both lattices, so every frame's emission gradient sums to 0, and the
+    transition gradient sums to 0 too (T-1 dense transitions + 1 start arc on each side)."""
+    B, T, C, U = 16, 500, 64, 50
+    rng = np.random.default_rng(41)
+    e = rng.uniform(-5, 5, (B, T, C)).astype(np.float32)
+    tw = rng.uniform(-5, 5, C + C * C).astype(np.float32)
+    targets = [rng.integers(0, C, U).astype(np.int32) for _ in range(B)]
+    losses, grads, tgrad = ctx.asg_loss(e, tw, targets)
+    assert np.all(np.isfinite(losses)) and np.all(losses > 0)
+    assert np.abs(grads.sum(axis=2)).max() < 1e-2
+    assert abs(tgrad.sum()) < 1e-3 * T * B  # fp32 drift over T frames (see tests/golden/README.md)
+    assert abs(tgrad[:C].sum()) < 1e-2 * B
