@@ -79,7 +79,8 @@ extern "C" int gtnb_ctc_loss(
       g_dev = grads;
     else
       TRY(dev_alloc(ctx, &g_dev, per * B));
-    TRYCUDA(cudaMemsetAsync(g_dev, 0, sizeof(float) * per * B, ctx->stream));
+    // with full-length utterances the normaliser's gradient overwrites every element
+    if (input_lens) TRYCUDA(cudaMemsetAsync(g_dev, 0, sizeof(float) * per * B, ctx->stream));
   }
   TRY(dev_alloc(ctx, &z_dev, B));
   TRY(dev_alloc(ctx, &deltas_dev, B));
@@ -101,7 +102,7 @@ extern "C" int gtnb_ctc_loss(
 
   // forwardScore(emissions) and its +1 gradient
   TRY(launch_linear_forward(ctx, B, small_dev + tot_t + 2ll * B, maxT, C, e_dev, per, 0, z_dev, g_dev,
-                            per, nullptr, 1.0f));
+                            per, nullptr, 1.0f, input_lens ? 0 : 1));
   // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
   TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
   TRY(launch_compose(ctx, lat));

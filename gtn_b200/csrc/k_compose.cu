@@ -327,10 +327,30 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_emit_kernel(
       if (t == m.T && (fl[d] & 2)) flags |= kAcceptBit;
       rp[nb + d] = (uint32_t)(ab + ip[d]) | flags;
     }
-    for (int e = lane; e < m.sg_A; e += 32) {
-      const int lab = il[e];
-      ao[ab + e] = make_int2(pb + is[e], __float_as_int(iw[e] + em[lab]));
-      go[ab + e] = make_int2(ia[e], (t - 1) * C + lab);
+    // four independent entries per lane in flight: all loads first, then the stores
+    for (int e0 = lane; e0 < m.sg_A; e0 += 128) {
+      int lab[4], srcn[4], arcid[4];
+      float wv[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int e = e0 + 32 * k;
+        const bool ok = e < m.sg_A;
+        lab[k] = ok ? il[e] : 0;
+        srcn[k] = ok ? is[e] : 0;
+        arcid[k] = ok ? ia[e] : 0;
+        wv[k] = ok ? iw[e] : 0.0f;
+      }
+      float ev[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) ev[k] = em[lab[k]];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int e = e0 + 32 * k;
+        if (e < m.sg_A) {
+          ao[ab + e] = make_int2(pb + srcn[k], __float_as_int(wv[k] + ev[k]));
+          go[ab + e] = make_int2(arcid[k], (t - 1) * C + lab[k]);
+        }
+      }
     }
     if (t == m.T && lane == 0) rp[np[m.T + 1]] = (uint32_t)apn[m.T + 1];
     return;

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(32 * kRowWarps) linear_rows_kernel(
     float* __restrict__ grad,
     long long grad_stride,
     const float* __restrict__ deltas,
-    float delta_all) {
+    float delta_all,
+    int overwrite) {
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * kRowWarps + warp;
@@ -66,12 +67,17 @@ __global__ void __launch_bounds__(32 * kRowWarps) linear_rows_kernel(
     const float delta = deltas ? deltas[b] : delta_all;
     float* g = grad + (long long)b * grad_stride + (long long)t * C;
     if (TROPICAL) {
-      for (int c = lane; c < C; c += 32)
-        if (c == arg) g[c] += delta;
+      for (int c = lane; c < C; c += 32) {
+        const float v = (c == arg) ? delta : 0.0f;
+        g[c] = overwrite ? v : g[c] + v;
+      }
     } else {
       // g = exp(e - mx) / exp(lse - mx)   (shortest.cpp:71-72 on a chain)
       const float denom = expf(score - mx);
-      for (int c = lane; c < C; c += 32) g[c] += expf(e[c] - mx) / denom * delta;
+      for (int c = lane; c < C; c += 32) {
+        const float v = expf(e[c] - mx) / denom * delta;
+        g[c] = overwrite ? v : g[c] + v;
+      }
     }
   }
 }
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(256) linear_reduce_kernel(
 int launch_linear_forward(
     gtnb_ctx* ctx, int B, const int32_t* T_dev, int maxT, int C, const float* emis, int64_t stride,
     int tropical, float* scores, float* grad, int64_t grad_stride, const float* deltas,
-    float delta_all) {
+    float delta_all, int overwrite) {
   if (B == 0) return GTNB_OK;
   float* row_score = nullptr;
   int rc = dev_alloc(ctx, &row_score, (long long)B * std::max(maxT, 1));
@@ -107,10 +113,10 @@ int launch_linear_forward(
     dim3 grid((maxT + kRowWarps - 1) / kRowWarps, B);
     if (tropical)
       GTNB_LAUNCH(ctx, "linear_rows", linear_rows_kernel<true><<<grid, 32 * kRowWarps, 0, ctx->stream>>>(
-          T_dev, maxT, C, emis, stride, row_score, grad, grad_stride, deltas, delta_all));
+          T_dev, maxT, C, emis, stride, row_score, grad, grad_stride, deltas, delta_all, overwrite));
     else
       GTNB_LAUNCH(ctx, "linear_rows", linear_rows_kernel<false><<<grid, 32 * kRowWarps, 0, ctx->stream>>>(
-          T_dev, maxT, C, emis, stride, row_score, grad, grad_stride, deltas, delta_all));
+          T_dev, maxT, C, emis, stride, row_score, grad, grad_stride, deltas, delta_all, overwrite));
   }
   GTNB_LAUNCH(ctx, "linear_reduce", linear_reduce_kernel<<<B, 256, 0, ctx->stream>>>(T_dev, maxT, row_score, scores));
   dev_free(ctx, row_score);

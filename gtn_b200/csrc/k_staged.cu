@@ -63,6 +63,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+/* producer-side wait: the slot frees up a whole level later, so sleep between polls instead
+ * of burning the consumers' issue slots */
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -270,7 +288,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_forward_staged
       uint32_t par = 0; // wraps & 1: the slot's previous use is empty-phase (wraps - 1)
 #pragma unroll 1
       for (int l = 0; l < L; l++) {
-        if (l >= S) mbar_wait(sbase + 8 * (kMaxStages + s), par ^ 1);
+        if (l >= S) mbar_wait_relaxed(sbase + 8 * (kMaxStages + s), par ^ 1);
         const uint32_t st = sbase + lay.off_stage + s * lay.stage_bytes;
         const uint32_t fb = sbase + 8 * s;
         const int lo = s_lvln[l], hi = s_lvln[l + 1];
@@ -560,7 +578,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_backward_stage
 #pragma unroll 1
       for (int k = 0; k < iters; k++) {
         const int l = L - 1 - k;
-        if (k >= S) mbar_wait(sbase + 8 * (kMaxStages + s), par ^ 1);
+        if (k >= S) mbar_wait_relaxed(sbase + 8 * (kMaxStages + s), par ^ 1);
         const uint32_t st = sbase + lay.off_stage + s * lay.stage_bytes;
         const uint32_t fb = sbase + 8 * s;
         const int plo = s_lvln[l - 1], lo = s_lvln[l], hi = s_lvln[l + 1];
