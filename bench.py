@@ -285,7 +285,7 @@ def main():
     alg_bytes = {  # per launch, whole batch -- SURVEY.md section 8(d), DESIGN.md "Algorithmic bytes"
         "sd_forward": 8 * sumA + 12 * sumN,
         "sd_backward": 12 * sumA + 16 * sumN,
-        "compose_grad": 12 * sumA + 4 * TC * B,
+        "compose_grad": 12 * sumA + 4 * sumN + 4 * TC * B,
         "compose_emit": 16 * sumA + 4 * sumN + 4 * TC * B,
         "linear_rows": 8 * TC * B,
     }
@@ -336,6 +336,12 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
+        # DRAM bytes per launch measured by `ncu --set full` (dram__bytes_read.sum +
+        # dram__bytes_write.sum), committed with the ncu summary they come from
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp) and (B, T, C, U) == (B_DEF, T_DEF, C_DEF, U_DEF):
+            traffic = json.load(open(tp)).get("bytes_per_launch", {})
         # dominant kernel by CUDA-event time
         dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
         name, (cnt, tot_ms) = dom
@@ -344,7 +350,7 @@ def main():
             per_launch_ms = tot_ms / cnt
             ach = alg_bytes[name] / (per_launch_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": ach / peak, "traffic": traffic.get(name), "peak_source": peak_src,
                         "kernel_ms": per_launch_ms, "algorithmic_bytes": alg_bytes[name]}
         kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
                        "GBps": (alg_bytes[k] / (v[1] / v[0] * 1e-3) / 1e9) if k in alg_bytes and v[0] else None}

@@ -602,6 +602,7 @@ int composed_alloc(
     m.sg_N = s.N;
     m.sg_A = s.A;
     m.sg_all_valid = s.all_valid;
+    m.sg_uniform = s.uniform;
     m.cap_N = (int)capN;
     m.cap_A = (int)capA;
     m.cap_L = (int)align_up(T[b] + 2, kAlign);

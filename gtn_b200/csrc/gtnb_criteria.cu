@@ -46,7 +46,7 @@ extern "C" int gtnb_ctc_loss(
     for (int u = 1; u < U; u++) skips += tg[u] != tg[u - 1];
     for (int u = 0; u < U; u++) all_valid &= tg[u] >= 0 && tg[u] < C;
     const int L = 2 * U + 1;
-    dims[b] = SgDims{L, L + (L - 1) + skips, L >= 2 ? 2 : 1, all_valid};
+    dims[b] = SgDims{L, L + (L - 1) + skips, L >= 2 ? 2 : 1, all_valid, /*uniform=*/1};
     tot_t += U;
     Tb[b] = input_lens ? input_lens[b] : T;
     if (Tb[b] < 0 || Tb[b] > T)
@@ -110,9 +110,15 @@ extern "C" int gtnb_ctc_loss(
   lat->forward_done = true;
   lat->forward_mode = MODE_LOG;
   if (grads) {
-    if (!lat->arc_grad) TRY(dev_alloc(ctx, &lat->arc_grad, lat->tot_A));
-    TRY(launch_backward(ctx, lat, 0, deltas_dev));
-    TRY(launch_compose_grad(ctx, lat, nullptr, g_dev, per));
+    // shortestDistanceGrad and compose's gradFunc fused when the lattice qualifies
+    rc = launch_backward_fused(ctx, lat, deltas_dev, g_dev, per);
+    if (rc == GTNB_ERR_UNSUPPORTED) {
+      if (!lat->arc_grad) TRY(dev_alloc(ctx, &lat->arc_grad, lat->tot_A));
+      TRY(launch_backward(ctx, lat, 0, deltas_dev));
+      TRY(launch_compose_grad(ctx, lat, nullptr, g_dev, per));
+    } else if (rc) {
+      goto done;
+    }
     if (!grads_on_device)
       TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
   }

@@ -56,6 +56,7 @@ struct GraphMeta {
   int sg_N; // small-graph node / arc counts (composed lattices)
   int sg_A;
   int sg_all_valid; // every arc label of the graph operand can match an emission label
+  int sg_uniform; // all in-arcs of a graph node carry the same matched label
   int cap_N; // slab capacities
   int cap_A;
   int cap_L;
@@ -157,6 +158,7 @@ namespace gtnb {
 struct SgDims {
   int N, A, n_acc;
   int all_valid = 0;
+  int uniform = 0;
 };
 int composed_alloc(
     gtnb_ctx* ctx, int B, const SgDims* dims, int n_graphs, int linear_first, const int32_t* T,
@@ -258,6 +260,8 @@ int launch_gather_prov(gtnb_ctx* ctx, gtnb_lattice* lat, int max_len, const int3
 bool staged_supported(const gtnb_lattice* lat);
 int launch_forward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int mode);
 int launch_backward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev);
+int launch_backward_fused(
+    gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride);
 // kernels (k_dense.cu): factored dense-trellis Viterbi
 int launch_viterbi_dense(
     gtnb_ctx* ctx, int B, int T_max, int C, const int32_t* T_dev, const float* emis, int64_t stride,

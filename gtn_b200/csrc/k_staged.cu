@@ -152,6 +152,8 @@ struct Layout {
   int st_arcs, st_psc; // byte offsets inside a stage (row_ptr at 0)
   int total;
   int log2_stages;
+  int off_tab; // graph-operand tables of the fused criterion backward (0 = none)
+  int tab_nodes, tab_arcs;
 };
 
 Layout make_layout(int max_lvl_nodes, int max_lvl_arcs, int L, int log2_stages, int n_bufs, bool with_scores) {
@@ -174,6 +176,8 @@ Layout make_layout(int max_lvl_nodes, int max_lvl_arcs, int L, int log2_stages, 
   o.stage_bytes = o.st_psc + (with_scores ? 4 * o.win_nodes : 0);
   o.stage_bytes = (o.stage_bytes + 127) / 128 * 128;
   o.total = off + o.stage_bytes * (1 << log2_stages);
+  o.off_tab = 0;
+  o.tab_nodes = o.tab_arcs = 0;
   return o;
 }
 
@@ -741,6 +745,361 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_backward_stage
   }
 }
 
+
+/* ------------------------------------------------------------------ */
+/* criterion backward: shortestDistanceGrad + compose gradFunc fused   */
+/* ------------------------------------------------------------------ */
+
+
+/* rows the unrolled steady path does not cover (non-finite score, > 3 in-arcs): reference
+ * formula verbatim (shortest.cpp:62-80); arc gradients go to the shared arc buffer */
+__device__ __noinline__ float fused_row_any(float g, float sn, int e0, int e1, uint32_t Ae, uint32_t P, uint32_t CUR) {
+  const bool exact = !(fabsf(sn) < CUDART_INF_F);
+  float mx = 0.0f, acc = 0.0f;
+  if (exact) {
+    mx = neg_inf();
+#pragma unroll 1
+    for (int e = e0; e < e1; e++) {
+      const int2 rec = lds_v2(Ae + 8u * e);
+      mx = fmaxf(mx, lds_f32(P + 4u * rec.x) + __int_as_float(rec.y));
+    }
+  }
+#pragma unroll 1
+  for (int e = e0; e < e1; e++) {
+    const int2 rec = lds_v2(Ae + 8u * e);
+    const float cur = arc_grad_log(g, lds_f32(P + 4u * rec.x) + __int_as_float(rec.y), sn, mx, exact);
+    sts_f32(CUR + 4u * e, cur);
+    acc += cur;
+  }
+  return acc;
+}
+
+/* one level of the fused backward outside the fast path: (a) steady but the graph has more
+ * nodes than consumer threads -- same two phases, several nodes per thread; (b) not steady
+ * (the cone at both ends of the lattice) -- zero the accumulator, scatter with shared atomics,
+ * emission gradients through the per-arc provenance */
+__device__ __noinline__ void fused_level_slow(
+    bool steady, int tid, int N1, int cnt, int alo, int win_nodes, uint32_t R, uint32_t A, uint32_t P,
+    uint32_t NGc, uint32_t NGp, uint32_t NGp0, uint32_t OWN, uint32_t CUR, float delta, float* gem,
+    float* gem_l, const int2* ggi, const int* t_inptr, const int* t_label, const int* t_outptr,
+    const int* t_outent) {
+  constexpr int kConsumers = 32 * consumer_warps(1);
+  if (steady) {
+    const uint32_t Ae = A + 8u * alo;
+    for (int i = tid; i < N1; i += kConsumers) {
+      const int e0 = t_inptr[i], e1 = t_inptr[i + 1];
+      const float acc = fused_row_any(lds_f32(NGc + 4u * i), lds_f32(OWN + 4u * i), e0, e1, Ae, P, CUR);
+      if (e1 > e0) atomicAdd(&gem_l[t_label[i]], acc * delta);
+    }
+    consumer_bar<kConsumers>();
+    for (int u = tid; u < N1; u += kConsumers) {
+      float sum = 0.0f;
+#pragma unroll 1
+      for (int q = t_outptr[u]; q < t_outptr[u + 1]; q++) sum += lds_f32(CUR + 4u * t_outent[q]);
+      sts_f32(NGp0 + 4u * u, sum);
+    }
+    consumer_bar<kConsumers>();
+    return;
+  }
+  for (int i = tid; i < win_nodes; i += kConsumers) sts_f32(NGp0 + 4u * i, 0.0f);
+  consumer_bar<kConsumers>();
+  for (int i = tid; i < cnt; i += kConsumers) {
+    const uint32_t r0raw = lds_u32(R + 4u * i);
+    const int r0 = (int)(r0raw & kRowMask);
+    const int r1 = (int)(lds_u32(R + 4u * i + 4u) & kRowMask);
+    const float g = lds_f32(NGc + 4u * i);
+    const float sn = lds_f32(OWN + 4u * i);
+    const bool exact = !(fabsf(sn) < CUDART_INF_F) || (r0raw & kStartBit);
+    float mx = 0.0f;
+    if (exact) {
+      mx = neg_inf();
+#pragma unroll 1
+      for (int a = r0; a < r1; a++) {
+        const int2 rec = lds_v2(A + 8u * a);
+        mx = fmaxf(mx, lds_f32(P + 4u * rec.x) + __int_as_float(rec.y));
+      }
+      if (r0raw & kStartBit) mx = fmaxf(mx, 0.0f);
+    }
+#pragma unroll 1
+    for (int a = r0; a < r1; a++) {
+      const int2 rec = lds_v2(A + 8u * a);
+      const float v = lds_f32(P + 4u * rec.x) + __int_as_float(rec.y);
+      const float cur = arc_grad_log(g, v, sn, mx, exact);
+      red_shared_add(NGp + 4u * rec.x, cur);
+      atomicAdd(&gem[ggi[a].y], cur * delta);
+    }
+  }
+  consumer_bar<kConsumers>();
+}
+
+/*
+ * gtnb_ctc_loss only needs d loss / d emissions, never the lattice's own arc gradients.
+ * This kernel is sd_backward_staged<false, 1> with compose's gradFunc (compose.cpp:496-518)
+ * folded in: the arc gradients of a node are summed in registers and leave the SM as ONE
+ * red.global per node, aimed at the emission the node's in-arcs came from; arc_grad is
+ * never written and compose_grad_kernel never runs.
+ *
+ * It also removes the float shared-memory atomics of the generic kernel (fp32 atomicAdd
+ * on shared memory is a CAS loop on sm_100a: SASS ATOMS.CAST.SPIN): in the steady state
+ * of a frame-synchronous lattice (every graph node alive in frames l and l-1, every
+ * label matchable) level l IS the graph operand, arc k of the level is in-entry k of the
+ * graph, so the per-source sums are gathered through the graph's out-arc lists kept in
+ * shared memory: phase 1 (thread per destination) writes the arc gradients to a shared
+ * arc buffer, phase 2 (thread per source) sums its out-arcs.  Frames outside the steady
+ * state (the cone at both ends of a CTC lattice) take the generic atomics path.
+ */
+__global__ void __launch_bounds__(32 * consumer_warps(1) + 32) sd_backward_fused(
+    const GraphMeta* __restrict__ meta,
+    const int32_t* __restrict__ lvl_node_ptr,
+    const int32_t* __restrict__ lvl_arc_ptr,
+    const uint32_t* __restrict__ row_ptr,
+    const int2* __restrict__ arcs,
+    const int2* __restrict__ gi,
+    const int32_t* __restrict__ acc_nodes,
+    const float* __restrict__ scores,
+    const float* __restrict__ out_scores,
+    const float* __restrict__ deltas,
+    const int32_t* __restrict__ sg_in_ptr,
+    const int32_t* __restrict__ sg_in_src,
+    const int32_t* __restrict__ sg_in_label,
+    float* __restrict__ grad_emis,
+    long long grad_stride,
+    int C,
+    const Layout lay) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kConsumers = 32 * consumer_warps(1);
+  constexpr int kStagedThreads = kConsumers + 32;
+  const GraphMeta m = meta[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int S = 1 << lay.log2_stages;
+  const uint32_t sbase = smem_u32(smem);
+  int* s_lvln = reinterpret_cast<int*>(smem + lay.off_lvln);
+  int* s_lvla = reinterpret_cast<int*>(smem + lay.off_lvla);
+  float* s_ng = reinterpret_cast<float*>(smem + lay.off_bufs); // [0], [1]: node gradients (ping-pong)
+  float* s_top = s_ng + 3 * lay.win_nodes;
+  // graph-operand tables
+  int* t_inptr = reinterpret_cast<int*>(smem + lay.off_tab); // [N1 + 1]
+  int* t_label = t_inptr + lay.tab_nodes + 1; // [N1]   matched label of the node's in-arcs
+  int* t_outptr = t_label + lay.tab_nodes; // [N1 + 1]
+  int* t_outent = t_outptr + lay.tab_nodes + 1; // [A1]   in-entries grouped by source node
+  float* s_cur = reinterpret_cast<float*>(t_outent + lay.tab_arcs); // [A1]   arc gradients of the level
+
+  const int L = m.L;
+  for (int i = tid; i <= L; i += kStagedThreads) {
+    s_lvln[i] = lvl_node_ptr[m.lvl_base + i];
+    s_lvla[i] = lvl_arc_ptr[m.lvl_base + i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(sbase + 8 * s, 1);
+      mbar_init(sbase + 8 * (kMaxStages + s), consumer_warps(1)); // every consumer warp releases
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const float* gsc = scores + m.node_base;
+  const int iters = L - 1;
+
+  if (tid >= kConsumers) {
+    if (tid == kConsumers) {
+      const uint32_t* rp = row_ptr + m.node_base;
+      const int2* ga = arcs + m.arc_base;
+      int s = 0;
+      uint32_t par = 0;
+#pragma unroll 1
+      for (int k = 0; k < iters; k++) {
+        const int l = L - 1 - k;
+        if (k >= S) mbar_wait_relaxed(sbase + 8 * (kMaxStages + s), par ^ 1);
+        const uint32_t st = sbase + lay.off_stage + s * lay.stage_bytes;
+        const uint32_t fb = sbase + 8 * s;
+        const int plo = s_lvln[l - 1], lo = s_lvln[l], hi = s_lvln[l + 1];
+        const int alo = s_lvla[l], ahi = s_lvla[l + 1];
+        const int n0 = lo & ~3, n1 = (hi + 1 + 3) & ~3;
+        const int a0 = alo & ~1, a1 = (ahi + 1) & ~1;
+        const int p0 = plo & ~3, p1 = (lo + 3) & ~3;
+        const uint32_t nb = (uint32_t)(n1 - n0) * 4u, ab = (uint32_t)(a1 - a0) * 8u;
+        const uint32_t pb = (uint32_t)(p1 - p0) * 4u;
+        mbar_expect_tx(fb, nb + ab + pb);
+        bulk_g2s(st, rp + n0, nb, fb);
+        if (ab) bulk_g2s(st + lay.st_arcs, ga + a0, ab, fb);
+        if (pb) bulk_g2s(st + lay.st_psc, gsc + p0, pb, fb);
+        if (++s == S) {
+          s = 0;
+          par ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const float delta = deltas ? deltas[blockIdx.x] : 1.0f;
+  float* gem = grad_emis + (long long)blockIdx.x * grad_stride;
+  const int2* ggi = gi + m.arc_base;
+  const int N1 = m.sg_N, A1 = m.sg_A;
+  const bool steady_ok = m.sg_all_valid != 0;
+
+  // graph tables: in-arc pointers, the (uniform) label of each node's in-arcs, out-arc lists
+  {
+    const int32_t* ip = sg_in_ptr + m.sg_node_base;
+    const int32_t* is = sg_in_src + m.sg_arc_base;
+    const int32_t* il = sg_in_label + m.sg_arc_base;
+    int* t_src = reinterpret_cast<int*>(s_cur); // borrowed until the tables are built
+    for (int i = tid; i <= N1; i += kConsumers) t_inptr[i] = ip[i];
+    for (int e = tid; e < A1; e += kConsumers) t_src[e] = is[e];
+    consumer_bar<kConsumers>();
+    for (int u = tid; u < N1; u += kConsumers) {
+      t_label[u] = (t_inptr[u] < t_inptr[u + 1]) ? il[t_inptr[u]] : 0;
+      int c = 0;
+      for (int e = 0; e < A1; e++) c += (t_src[e] == u);
+      t_outptr[u + 1] = c;
+    }
+    consumer_bar<kConsumers>();
+    if (tid == 0) {
+      t_outptr[0] = 0;
+      for (int u = 0; u < N1; u++) t_outptr[u + 1] += t_outptr[u];
+    }
+    consumer_bar<kConsumers>();
+    for (int u = tid; u < N1; u += kConsumers) {
+      int pos = t_outptr[u];
+      for (int e = 0; e < A1; e++)
+        if (t_src[e] == u) t_outent[pos++] = e;
+    }
+    consumer_bar<kConsumers>();
+  }
+
+  // top level: its own scores, and the accept seeds (shortest.cpp:49-60)
+  {
+    const int lo = L > 0 ? s_lvln[L - 1] : 0, hi = L > 0 ? s_lvln[L] : 0;
+    for (int i = tid; i < hi - lo; i += kConsumers) s_top[i] = gsc[lo + i];
+    for (int i = tid; i < 2 * lay.win_nodes; i += kConsumers) s_ng[i] = 0.0f;
+    consumer_bar<kConsumers>();
+    if (tid == 0 && L > 0) {
+      const int32_t* acc = acc_nodes + m.acc_base;
+      float mx = neg_inf();
+      for (int k = 0; k < m.n_accept; k++) mx = fmaxf(mx, s_top[acc[k] - lo]);
+      const float denom = expf(out_scores[blockIdx.x] - mx);
+      for (int k = 0; k < m.n_accept; k++) s_ng[acc[k] - lo] += expf(s_top[acc[k] - lo] - mx) / denom;
+    }
+    consumer_bar<kConsumers>();
+  }
+
+  // per-thread constants of "my" graph node (thread u <-> node u while N1 <= kConsumers)
+  const bool one_to_one = N1 <= kConsumers;
+  int my_e0 = 0, my_e1 = 0, my_lab = 0, my_o0 = 0, my_o1 = 0;
+  if (tid < N1) {
+    my_e0 = t_inptr[tid];
+    my_e1 = t_inptr[tid + 1];
+    my_lab = t_label[tid];
+    my_o0 = t_outptr[tid];
+    my_o1 = t_outptr[tid + 1];
+  }
+  const int my_oe0 = (my_o1 - my_o0 > 0) ? t_outent[my_o0] : 0;
+  const int my_oe1 = (my_o1 - my_o0 > 1) ? t_outent[my_o0 + 1] : 0;
+  const int my_oe2 = (my_o1 - my_o0 > 2) ? t_outent[my_o0 + 2] : 0;
+  float g_reg = 0.0f;
+  bool g_in_reg = false;
+
+  int s = 0;
+  uint32_t par = 0;
+  int b_cur = 0;
+  const float* own = s_top;
+  auto is_steady = [&](int l) {
+    return steady_ok && l >= 1 && (s_lvln[l + 1] - s_lvln[l]) == N1 && (s_lvln[l] - s_lvln[l - 1]) == N1;
+  };
+  for (int k = 0; k < iters; k++) {
+    const int l = L - 1 - k;
+    const int plo = s_lvln[l - 1], lo = s_lvln[l], hi = s_lvln[l + 1];
+    const int alo = s_lvla[l];
+    const int a0 = alo & ~1;
+    const unsigned char* st = smem + lay.off_stage + s * lay.stage_bytes;
+    const int2* st_arc = reinterpret_cast<const int2*>(st + lay.st_arcs) - a0;
+    const float* st_psc = reinterpret_cast<const float*>(st + lay.st_psc) + (plo & 3) - plo;
+    const int b_prev = b_cur ^ 1;
+    const int cnt = hi - lo;
+    const uint32_t stb = sbase + lay.off_stage + s * lay.stage_bytes;
+    const uint32_t R = stb + 4u * (lo & 3);
+    const uint32_t A = stb + lay.st_arcs - 8u * a0;
+    const uint32_t P = stb + lay.st_psc + 4u * ((plo & 3) - plo);
+    const uint32_t bufs = sbase + lay.off_bufs;
+    const uint32_t NGc = bufs + 4u * (b_cur * lay.win_nodes);
+    const uint32_t NGp = bufs + 4u * (b_prev * lay.win_nodes - plo);
+    const uint32_t NGp0 = bufs + 4u * (b_prev * lay.win_nodes);
+    const uint32_t OWN = smem_u32(own);
+    const bool steady = is_steady(l);
+    const bool next_steady = (k + 1 < iters) && is_steady(l - 1);
+    float* gem_l = gem + (long long)(l - 1) * C;
+    // arc-gradient buffer of this level (double-buffered so that the gather of level l can
+    // still be running in other warps while level l-1 is being written)
+    const uint32_t CUR = smem_u32(s_cur) + 4u * ((k & 1) * lay.tab_arcs);
+    mbar_wait(sbase + 8 * s, par);
+    if (steady && one_to_one) {
+      const uint32_t Ae = A + 8u * alo; // arc record of in-entry 0
+      if (tid < N1) {
+        // phase 1: destination node `tid`; arc e of the level == in-entry e of the graph
+        const float g = g_in_reg ? g_reg : lds_f32(NGc + 4u * tid);
+        const float sn = lds_f32(OWN + 4u * tid);
+        const int deg = my_e1 - my_e0;
+        float acc = 0.0f;
+        if (!(fabsf(sn) < CUDART_INF_F) || deg > 3) {
+          acc = fused_row_any(g, sn, my_e0, my_e1, Ae, P, CUR);
+        } else {
+          const uint32_t ae = Ae + 8u * my_e0, ce = CUR + 4u * my_e0;
+          if (deg > 0) {
+            const int2 rec = lds_v2(ae);
+            const float cur = g * fexp(lds_f32(P + 4u * rec.x) + __int_as_float(rec.y) - sn);
+            sts_f32(ce, cur);
+            acc += cur;
+          }
+          if (deg > 1) {
+            const int2 rec = lds_v2(ae + 8u);
+            const float cur = g * fexp(lds_f32(P + 4u * rec.x) + __int_as_float(rec.y) - sn);
+            sts_f32(ce + 4u, cur);
+            acc += cur;
+          }
+          if (deg > 2) {
+            const int2 rec = lds_v2(ae + 16u);
+            const float cur = g * fexp(lds_f32(P + 4u * rec.x) + __int_as_float(rec.y) - sn);
+            sts_f32(ce + 8u, cur);
+            acc += cur;
+          }
+        }
+        if (deg > 0) atomicAdd(&gem_l[my_lab], acc * delta);
+      }
+      consumer_bar<kConsumers>();
+      if (tid < N1) {
+        // phase 2: source node `tid` gathers its out-arcs (no atomics, fixed order)
+        float sum = 0.0f;
+        const int od = my_o1 - my_o0;
+        if (od > 0) sum += lds_f32(CUR + 4u * my_oe0);
+        if (od > 1) sum += lds_f32(CUR + 4u * my_oe1);
+        if (od > 2) sum += lds_f32(CUR + 4u * my_oe2);
+#pragma unroll 1
+        for (int q = my_o0 + 3; q < my_o1; q++) sum += lds_f32(CUR + 4u * t_outent[q]);
+        g_reg = sum;
+        g_in_reg = true;
+        if (!next_steady) sts_f32(NGp0 + 4u * tid, sum);
+      }
+      if (!next_steady) consumer_bar<kConsumers>();
+    } else {
+      g_in_reg = false;
+      fused_level_slow(
+          steady, tid, N1, cnt, alo, lay.win_nodes, R, A, P, NGc, NGp, NGp0, OWN, CUR, delta, gem, gem_l,
+          ggi, t_inptr, t_label, t_outptr, t_outent);
+    }
+    // the previous iteration's stage held this level's own scores: every warp is done with it
+    __syncwarp();
+    if ((tid & 31) == 0 && k > 0) mbar_arrive(sbase + 8 * (kMaxStages + (s == 0 ? S - 1 : s - 1)));
+    own = reinterpret_cast<const float*>(st + lay.st_psc) + (plo & 3);
+    b_cur = b_prev;
+    if (++s == S) {
+      s = 0;
+      par ^= 1;
+    }
+  }
+}
+
 struct StagedPlan {
   bool ok;
   int G, max_L;
@@ -846,6 +1205,31 @@ int launch_forward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int mode) {
       default: LAUNCH_BWD(TROP_, 32); break; \
     }                                        \
   } while (0)
+
+/* shortestDistanceGrad + compose gradFunc in one kernel (log semiring, emission gradients
+ * only).  GTNB_ERR_UNSUPPORTED when the lattice does not qualify: the caller then runs
+ * launch_backward + launch_compose_grad. */
+int launch_backward_fused(
+    gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride) {
+  StagedPlan p = plan(lat);
+  if (!ctx->use_staged || !p.ok || p.G != 1 || !lat->gi) return GTNB_ERR_UNSUPPORTED;
+  for (int b = 0; b < lat->B; b++)
+    if (!lat->meta_h[b].sg_uniform) return GTNB_ERR_UNSUPPORTED;
+  Layout lay = p.bwd;
+  lay.tab_nodes = lat->max_lvl_nodes;
+  lay.tab_arcs = lat->max_lvl_arcs;
+  lay.off_tab = (lay.total + 15) / 16 * 16;
+  lay.total = lay.off_tab + 4 * (3 * lay.tab_nodes + 2 + 3 * lay.tab_arcs) + 16;
+  if (lay.total > 200 * 1024) return GTNB_ERR_UNSUPPORTED;
+  int rc = set_smem(ctx, sd_backward_fused, lay.total);
+  if (rc) return rc;
+  GTNB_LAUNCH(ctx, "sd_backward_fused",
+              sd_backward_fused<<<lat->B, 32 * consumer_warps(1) + 32, lay.total, ctx->stream>>>(
+                  lat->meta, lat->lvl_node_ptr, lat->lvl_arc_ptr, lat->row_ptr, lat->arcs, lat->gi,
+                  lat->acc_nodes, lat->scores, lat->out_scores, deltas_dev, lat->sg_in_ptr,
+                  lat->sg_in_src, lat->sg_in_label, grad_emis, (long long)grad_stride, lat->C, lay));
+  return GTNB_OK;
+}
 
 int launch_backward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* deltas_dev) {
   const StagedPlan p = plan(lat);

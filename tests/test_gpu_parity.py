@@ -402,3 +402,50 @@ def test_asg_config3_shape_properties(ctx):
     assert np.abs(grads.sum(axis=2)).max() < 1e-2
     assert abs(tgrad.sum()) < 1e-3 * T * B  # fp32 drift over T frames (see tests/golden/README.md)
     assert abs(tgrad[:C].sum()) < 1e-2 * B
+
+
+def test_ctc_config2_utterance_vs_reference_and_float64(ctx):
+    """One utterance of BASELINE.json configs[1] (T=1000, C=64, U=100) against the golden fixture:
+    the reference's own fp32 result and a float64 evaluation of the same lattice.  The CUDA path
+    must be at least as close to the float64 truth as the reference is (x2 slack), and within the
+    conditioned tolerance of the reference (tests/util.py:grad_close)."""
+    gold = np.load(util.__file__.replace("util.py", "golden/reference_golden.npz"))
+    e, tg = util.bench_inputs(1, 1000, 64, 100)
+    losses, grads = ctx.ctc_loss(e, tg)
+    assert util.close(losses[0], gold["c2_loss"][0])
+    assert abs(losses[0] - float(gold["c2_loss_f64"])) <= 2e-4 * abs(float(gold["c2_loss_f64"]))
+    ref_err = np.abs(gold["c2_grad"][0] - gold["c2_grad_f64"]).max()
+    my_err = np.abs(grads[0] - gold["c2_grad_f64"]).max()
+    assert my_err <= 2.0 * ref_err + 1e-5, (my_err, ref_err)
+    assert util.grad_close(grads[0], gold["c2_grad"][0], 5000.0)
+
+
+def test_forced_alignment_full_size(ctx, oracle):
+    """viterbiPath(intersect(ctc, emissions)) at T=2000, C=128, U=200 (SURVEY.md section 8(d), C4's
+    second data point): bit-exact labels against the oracle for 2 utterances, and for 16 more the
+    size-independent property that the path collapses (CTC rule) to the target."""
+    B, T, C, U = 18, 2000, 128, 200
+    e, targets = util.bench_inputs(B, T, C, U, seed=777)
+    e_dev = ctx.to_device(e)
+    views = [util.view_of(oracle.Graph.ctc(t, 0, True)) for t in targets]
+    lat = ctx.compose_linear(views, [T] * B, C, e_dev, T * C)
+    out = lat.viterbi_path(T)
+    scores = lat.forward(tropical=True)
+    for b in range(2):
+        p, s = oracle.viterbi_ctc(e[b], targets[b], 0, True)
+        assert np.array_equal(out["ilabels"][b], p)
+        assert scores[b] == s
+    for b in range(B):
+        lab = out["ilabels"][b]
+        assert out["lens"][b] == T
+        keep = np.concatenate([[True], lab[1:] != lab[:-1]])
+        collapsed = lab[keep]
+        collapsed = collapsed[collapsed != 0]
+        assert np.array_equal(collapsed, targets[b]), b
+        # the path's score, re-accumulated on the host, is the returned viterbiScore
+        s = np.float32(0.0)
+        for t in range(T):
+            s = np.float32(s + np.float32(0.0 + e[b, t, lab[t]]))
+        assert s == scores[b]
+    lat.free()
+    e_dev.free()
