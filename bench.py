@@ -43,100 +43,66 @@ def make_inputs(first, count, T, C, U):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  Uses NVML
-    in-process (the same counters nvidia-smi prints; forking `nvidia-smi -lms` next to a
-    3 ms step measurably perturbs it), falling back to `nvidia-smi -lms 200`."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), through NVML
+    (the counters nvidia-smi prints).  An NVML query stalls kernel submission for milliseconds
+    (measured: a 50 ms polling thread turned 2.5 ms steps into a 4.5 ms mean), so samples are
+    taken synchronously BETWEEN two event-bracketed steps -- the GPU has been under load for
+    the whole region, and no step's CUDA-event bracket contains a query."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index, period=0.05):
+    def __init__(self, index):
         self.index = index
-        self.period = period
-        self.sm, self.mx, self.reasons = [], [], set()
-        self.stop_flag = False
-        self.thread = None
-        self.proc = None
-        self.how = None
-
-    def _nvml_loop(self):
-        import pynvml as nv
-        h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        names = {
-            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-        }
-        try:
-            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-        except Exception:
-            mx = None
-        while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                if mx:
-                    self.mx.append(mx)
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-            except Exception:
-                pass
-            time.sleep(self.period)
-
-    def _smi_read(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.proc.stdout:
-            r = [x.strip() for x in line.split(",")]
-            try:
-                self.sm.append(float(r[1]))
-                self.mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        self.reasons.add(nm)
-            except Exception:
-                pass
-
-    def start(self):
+        self.sm, self.reasons = [], set()
+        self.mx = None
+        self.h = None
+        self.nv = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            self.how = "nvml"
-            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
-            self.thread.start()
-            return
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        if nv is None:
+            return self._smi()
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, nm in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"),
+                            (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")):
+                if r & bit:
+                    self.reasons.add(nm)
         except Exception:
             pass
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.how = "nvidia-smi"
-            self.thread = threading.Thread(target=self._smi_read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
 
-    def stop(self):
-        self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
-        if self.thread:
-            self.thread.join(timeout=2)
+    def _smi(self):
+        try:
+            out = subprocess.run(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits"],
+                capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            self.sm.append(float(out[0]))
+            self.mx = float(out[1])
+            for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if out[2 + k].strip().lower().startswith("active"):
+                    self.reasons.add(nm)
+        except Exception:
+            pass
+
+    def result(self):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.how}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "nvml" if self.nv else "nvidia-smi",
+                "when": "between event-bracketed steps of the timed region"}
 
 
 def load_peaks():
@@ -285,6 +251,9 @@ def main():
     alg_bytes = {  # per launch, whole batch -- SURVEY.md section 8(d), DESIGN.md "Algorithmic bytes"
         "sd_forward": 8 * sumA + 12 * sumN,
         "sd_backward": 12 * sumA + 16 * sumN,
+        # shortestDistanceGrad + compose gradFunc fused (criterion path): arc records, row_ptr,
+        # saved scores in; emission gradients out (no arc gradients, no provenance in steady frames)
+        "sd_backward_fused": 8 * sumA + 8 * sumN + 4 * TC * B,
         "compose_grad": 12 * sumA + 4 * sumN + 4 * TC * B,
         "compose_emit": 16 * sumA + 4 * sumN + 4 * TC * B,
         "linear_rows": 8 * TC * B,
@@ -296,18 +265,20 @@ def main():
     ctx.synchronize()
 
     sampler = ClockSampler(local)
-    sampler.start()
+    every = max(1, args.steps // 8)
     ctx.profile(True)
     ctx.profile_read()
     launches0 = ctx.launches
     barrier()
     times = []
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         ctx.flush_l2()  # inputs (65.5 MB) are smaller than the 126 MB L2
         ctx.timer_start()
         step_dev()
         times.append(ctx.timer_stop())
+        if i % every == every // 2:
+            sampler.sample()
     barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.launches - launches0
@@ -319,13 +290,15 @@ def main():
         step_e2e()
     barrier()
     e2e_times = []
-    for _ in range(args.steps):
+    for i in range(args.steps):
         ctx.flush_l2()
         ctx.timer_start()
         step_e2e()
         e2e_times.append(ctx.timer_stop())
+        if i % every == every // 2:
+            sampler.sample()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.result()
 
     ms = float(np.mean(times))
     e2e_ms = float(np.mean(e2e_times))

@@ -142,6 +142,9 @@ void gtnb_ctx_destroy(gtnb_ctx* ctx) {
   if (ctx->stage) cudaFreeHost(ctx->stage);
   if (ctx->readback) cudaFreeHost(ctx->readback);
   if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (auto& pe : ctx->prof) {

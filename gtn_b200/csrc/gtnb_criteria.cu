@@ -5,6 +5,7 @@
  * staging upload, one small read-back.
  */
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,6 +29,7 @@ extern "C" int gtnb_ctc_loss(
   float* deltas_dev = nullptr;
   int32_t* small_dev = nullptr; // [targets | offsets | lens | T]
   gtnb_lattice* lat = nullptr;
+  cudaEvent_t h2d_event = nullptr;
   std::vector<long long> sgn, sga;
 
   // host: only sizes.  Graph b has 2U+1 nodes; arcs = self loops + step arcs + skip arcs
@@ -71,8 +73,19 @@ extern "C" int gtnb_ctc_loss(
   if (emissions_on_device) {
     e_dev = const_cast<float*>(emissions);
   } else {
+    // the copy runs on a second stream while this one builds the target graphs and the
+    // lattice structure (k_ctc.cu, compose alive / count / scan need no emissions)
     TRY(dev_alloc(ctx, &e_dev, per * B));
-    TRYCUDA(cudaMemcpyAsync(e_dev, emissions, sizeof(float) * per * B, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->copy_stream) {
+      TRYCUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      TRYCUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      TRYCUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    TRYCUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); // orders the copy after the allocation
+    TRYCUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    TRYCUDA(cudaMemcpyAsync(e_dev, emissions, sizeof(float) * per * B, cudaMemcpyHostToDevice, ctx->copy_stream));
+    TRYCUDA(cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+    h2d_event = ctx->ev_join;
   }
   if (grads) {
     if (grads_on_device)
@@ -100,12 +113,12 @@ extern "C" int gtnb_ctc_loss(
   }
   TRY(stage_end(ctx));
 
+  // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
+  TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
+  TRY(launch_compose(ctx, lat, h2d_event));
   // forwardScore(emissions) and its +1 gradient
   TRY(launch_linear_forward(ctx, B, small_dev + tot_t + 2ll * B, maxT, C, e_dev, per, 0, z_dev, g_dev,
                             per, nullptr, 1.0f, input_lens ? 0 : 1));
-  // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
-  TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
-  TRY(launch_compose(ctx, lat));
   TRY(launch_forward(ctx, lat, MODE_LOG));
   lat->forward_done = true;
   lat->forward_mode = MODE_LOG;

@@ -80,6 +80,10 @@ struct gtnb_ctx {
   size_t stage_bytes = 0, stage_used = 0;
   cudaEvent_t stage_ev = nullptr;
   bool stage_pending = false;
+  // second stream + events: overlap the host->device copy of the emissions with the
+  // composition passes that only need the target graphs
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // pinned read-back buffer for small device->host results
   unsigned char* readback = nullptr;
   size_t readback_bytes = 0;
@@ -267,7 +271,7 @@ int launch_viterbi_dense(
     gtnb_ctx* ctx, int B, int T_max, int C, const int32_t* T_dev, const float* emis, int64_t stride,
     const float* trans_dev, uint8_t* bp, int32_t* paths, float* scores);
 // kernels (k_compose.cu)
-int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat);
+int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat, cudaEvent_t emissions_ready = nullptr);
 int launch_compose_grad(gtnb_ctx* ctx, gtnb_lattice* lat, float* grad_graph, float* grad_emis, int64_t grad_stride);
 // kernels (k_linear.cu)
 int launch_linear_forward(

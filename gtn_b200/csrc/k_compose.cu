@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(256) compose_grad_kernel(
 
 } // namespace
 
-int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat) {
+int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat, cudaEvent_t emissions_ready) {
   if (lat->B == 0) return GTNB_OK;
   const int W = lat->alive_words;
   if (W > kMaxWords)
@@ -475,6 +475,9 @@ int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat) {
   GTNB_LAUNCH(ctx, "compose_scan", compose_scan_kernel<<<lat->B, 1024, 0, ctx->stream>>>(
       lat->meta, lat->sg_flags, lat->alive, W, maxT, lat->lvl_node_ptr, lat->lvl_arc_ptr,
       lat->acc_nodes));
+  // the structure passes above never touch the emissions: a host->device copy of them may
+  // still be in flight on another stream up to here
+  if (emissions_ready) GTNB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, emissions_ready, 0));
   GTNB_LAUNCH(ctx, "compose_emit", compose_emit_kernel<<<grid, 32 * kWarpsPerBlock, 0, ctx->stream>>>(
       lat->meta, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_arc,
       lat->sg_in_w, lat->alive, W, maxT, lat->C, lat->emissions, lat->lvl_node_ptr,

@@ -11,11 +11,9 @@ e_dev = ctx.to_device(e); g_dev = ctx.alloc(e.nbytes); losses = np.zeros(B,np.fl
 i32p,f32p = capi._i32p, capi._f32p
 def step():
     ctx._check(L.gtnb_ctc_loss(ctx.h,B,T,C,e_dev.ptr,1,None,cat.ctypes.data_as(i32p),lens.ctypes.data_as(i32p),0,losses.ctypes.data_as(f32p),g_dev.ptr,1))
-for prof in (False, True, False):
-    ctx.profile(prof)
+for flush in (False, True, True):
     ts=[]; ws=[]
-    for i in range(10):
-        ctx.flush_l2(); ctx.synchronize()
+    for i in range(60):
+        if flush: ctx.flush_l2()
         w0=time.perf_counter(); ctx.timer_start(); step(); ts.append(ctx.timer_stop()); ws.append((time.perf_counter()-w0)*1e3)
-    print('prof',prof,'event ms',[round(t,2) for t in ts]); print('      wall ms',[round(t,2) for t in ws])
-    if prof: ctx.profile_read()
+    ts=np.array(ts); print('flush',flush,'mean %.2f median %.2f min %.2f max %.2f'%(ts.mean(),np.median(ts),ts.min(),ts.max()), 'n>4ms', int((ts>4).sum()), [round(x,1) for x in ts[:25]])
