@@ -17,6 +17,8 @@
 #include <queue>
 #include <stdexcept>
 
+#include <cuda_runtime_api.h>
+
 #include "gtn/device.h"
 
 namespace gtn {
@@ -335,14 +337,29 @@ bool matchedSideHasEpsilon(const Graph& g, bool useIlabel) {
 std::shared_ptr<DeviceBuffer> emissionsOnDevice(const Graph& linear, const std::shared_ptr<Context>& c) {
   const size_t n = (size_t)linear.linearFrames() * (size_t)linear.linearLabels();
   auto dev = linear.deviceWeights();
-  if (dev && dev->count == n && dev->owner->ctx != nullptr) return dev;
+  // a cached copy is only valid for work on the stream that owns it
+  if (dev && dev->count == n && dev->owner == c) return dev;
   auto buf = std::make_shared<DeviceBuffer>(c, n);
+  if (dev && dev->count == n && n) {
+    // device weights owned by another thread's stream: drain it, then take a private copy so that
+    // the stream-ordered free of either buffer can never race the other stream's kernels
+    {
+      std::lock_guard<std::mutex> lo(dev->owner->lock);
+      check(dev->owner, gtnb_ctx_synchronize(dev->owner->ctx));
+    }
+    std::lock_guard<std::mutex> l(c->lock);
+    if (cudaMemcpyAsync(buf->ptr, dev->ptr, sizeof(float) * n, cudaMemcpyDeviceToDevice,
+                        (cudaStream_t)gtnb_ctx_stream(c->ctx)) != cudaSuccess)
+      throw std::runtime_error("[gtn] device copy of the emissions failed");
+    return buf;
+  }
   if (n) {
     const float* w = linear.weights();
     std::lock_guard<std::mutex> l(c->lock);
     check(c, gtnb_memcpy_h2d(c->ctx, buf->ptr, w, sizeof(float) * n));
     check(c, gtnb_ctx_synchronize(c->ctx));
   }
+  if (!dev) linear.cacheDeviceWeights(buf); // forwardScore(e) and intersect(ctc, e) share one upload
   return buf;
 }
 

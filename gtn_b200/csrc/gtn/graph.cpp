@@ -359,7 +359,15 @@ void Graph::setWeight(size_t i, float weight) {
 }
 
 std::shared_ptr<detail::DeviceBuffer> Graph::deviceWeights() const {
-  return sharedWeights_ ? sharedWeights_->device : nullptr;
+  if (!sharedWeights_) return nullptr;
+  std::lock_guard<std::mutex> l(sharedWeights_->lock);
+  return sharedWeights_->device;
+}
+
+void Graph::cacheDeviceWeights(std::shared_ptr<detail::DeviceBuffer> buf) const {
+  if (!sharedWeights_) return;
+  std::lock_guard<std::mutex> l(sharedWeights_->lock);
+  if (!sharedWeights_->device) sharedWeights_->device = std::move(buf);
 }
 
 void Graph::setWeights(const float* weights) {

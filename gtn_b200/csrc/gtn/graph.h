@@ -209,8 +209,10 @@ class Graph {
       int index,
       GradFunc gradFunc,
       std::vector<Graph> inputs);
-  /** Device copy of the weights if setWeights() was given a device pointer. */
+  /** Device copy of the weights (set by setWeights(device pointer) or cached by an earlier op). */
   std::shared_ptr<detail::DeviceBuffer> deviceWeights() const;
+  /** Remember a device copy of the current host weights; dropped as soon as they may change. */
+  void cacheDeviceWeights(std::shared_ptr<detail::DeviceBuffer> buf) const;
   /**
    * Install a gradient whose values still live on the device: `fetch` fills the host
    * vector the first time anybody reads it.  Falls back to an eager fetch + addGrad

@@ -174,13 +174,14 @@ int64_t gtnb_ctx_launch_count(const gtnb_ctx* ctx) {
 }
 
 int gtnb_device_alloc(gtnb_ctx* ctx, size_t bytes, void** out) {
+  // stream-ordered: cudaMalloc / cudaFree synchronise the whole device and would serialise the
+  // per-thread streams of the gtn:: C++ layer
   GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
-  GTNB_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 16));
+  GTNB_CUDA(ctx, cudaMallocAsync(out, bytes ? bytes : 16, ctx->stream));
   return GTNB_OK;
 }
 int gtnb_device_free(gtnb_ctx* ctx, void* p) {
-  GTNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  GTNB_CUDA(ctx, cudaFree(p));
+  GTNB_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
   return GTNB_OK;
 }
 int gtnb_host_alloc(gtnb_ctx* ctx, size_t bytes, void** out) {

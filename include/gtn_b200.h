@@ -104,7 +104,9 @@ int64_t gtnb_ctx_launch_count(const gtnb_ctx* ctx);
  */
 int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value);
 
-/* device / pinned memory helpers so callers need no CUDA runtime of their own */
+/* device / pinned memory helpers so callers need no CUDA runtime of their own.
+ * gtnb_device_alloc / _free are stream-ordered on the context's stream (cudaMallocAsync):
+ * the memory is valid for work enqueued on that stream; synchronise before using it elsewhere. */
 int gtnb_device_alloc(gtnb_ctx* ctx, size_t bytes, void** out);
 int gtnb_device_free(gtnb_ctx* ctx, void* p);
 int gtnb_host_alloc(gtnb_ctx* ctx, size_t bytes, void** out); /* pinned */

@@ -329,3 +329,42 @@ def test_lattice_is_lazy_and_inspectable(gtn, oracle):
     # and it still scores the same after materialisation
     s, _, _, _ = oracle.shortest_distance(ref)
     assert util.close(gtn.forward_score(lat).item(), s)
+
+
+def test_torch_ctc_loss_on_cuda_tensors(oracle):
+    """torch.autograd.Function on CUDA tensors, no host round trip."""
+    torch = pytest.importorskip("torch")
+    from gtn_b200 import torch_loss
+    B, T, C, U = 6, 80, 20, 9
+    e, targets = util.bench_inputs(B, T, C, U)
+    x = torch.tensor(e, device="cuda", requires_grad=True)
+    loss = torch_loss.ctc_loss(x, targets, blank=0, reduction="mean")
+    loss.backward()
+    want_l, want_g = [], []
+    for b in range(B):
+        lo, go = oracle.ctc_loss(e[b], targets[b], 0, True)
+        want_l.append(lo)
+        want_g.append(go / B)
+    assert util.close(loss.item(), float(np.mean(want_l)))
+    assert util.grad_close(x.grad.cpu().numpy(), np.stack(want_g), 5.0 * T)
+    # per-utterance losses and an arbitrary upstream gradient
+    x2 = torch.tensor(e, device="cuda", requires_grad=True)
+    per = torch_loss.ctc_loss(x2, targets, reduction="none")
+    wts = torch.arange(1, B + 1, device="cuda", dtype=torch.float32)
+    (per * wts).sum().backward()
+    assert util.close(per.detach().cpu().numpy(), np.asarray(want_l, np.float32))
+    assert util.grad_close(x2.grad.cpu().numpy(), np.stack(want_g) * B * np.arange(1, B + 1)[:, None, None],
+                           5.0 * T * B)
+
+
+def test_cpp_api_example_matches_batched_criterion():
+    """benchmarks/ctc.cpp:136-168 written against the drop-in C++ headers (parallelMap, one
+    utterance per stream) agrees with the batched C-ABI criterion; see csrc/examples/ctc_cpp_api.cpp."""
+    import json
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gtn_b200", "lib", "ctc_cpp_api")
+    out = subprocess.run([exe, "24", "150", "24", "15", "2"], capture_output=True, text=True, timeout=200)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["max_rel_loss_diff"] < 1e-4
