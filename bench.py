@@ -248,6 +248,7 @@ def main():
     lat.free()
     sumN, sumA = int(nn.sum()), int(na.sum())
     TC = T * C
+    pitch = (2 * U + 1 + 3) // 4 * 4
     alg_bytes = {  # per launch, whole batch -- SURVEY.md section 8(d), DESIGN.md "Algorithmic bytes"
         "sd_forward": 8 * sumA + 12 * sumN,
         "sd_backward": 12 * sumA + 16 * sumN,
@@ -257,7 +258,13 @@ def main():
         "compose_grad": 12 * sumA + 4 * sumN + 4 * TC * B,
         "compose_emit": 16 * sumA + 4 * sumN + 4 * TC * B,
         "linear_rows": 8 * TC * B,
+        # implicit-lattice criterion kernels (k_implicit.cu): SURVEY.md 8(d) "B_io" -- emissions in,
+        # dense per-frame node scores out (forward) / in (backward), emission gradients out
+        "implicit_forward": 4 * TC * B + 4 * (T + 1) * pitch * B,
+        "implicit_backward": 4 * TC * B + 4 * (T + 1) * pitch * B + 4 * TC * B,
     }
+    formulation = {"implicit_forward": "B_io (lattice never materialised)",
+                   "implicit_backward": "B_io (lattice never materialised)"}
     b_csr = 32 * sumA + 28 * sumN + 12 * TC * B
 
     for _ in range(args.warmup):
@@ -324,7 +331,10 @@ def main():
             ach = alg_bytes[name] / (per_launch_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "traffic": traffic.get(name), "peak_source": peak_src,
-                        "kernel_ms": per_launch_ms, "algorithmic_bytes": alg_bytes[name]}
+                        "kernel_ms": per_launch_ms, "algorithmic_bytes": alg_bytes[name],
+                        "formulation": formulation.get(name, "B_csr (materialised lattice)"),
+                        # the same step judged on the materialised-CSR byte count of SURVEY.md 8(d)
+                        "step_csr_equiv_GBps": b_csr / (ms * 1e-3) / 1e9}
         kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
                        "GBps": (alg_bytes[k] / (v[1] / v[0] * 1e-3) / 1e9) if k in alg_bytes and v[0] else None}
                    for k, v in prof.items()}

@@ -11,7 +11,10 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <queue>
+#include <set>
+#include <utility>
 
 #include "gtnb_internal.h"
 
@@ -81,6 +84,17 @@ int cuda_fail(gtnb_ctx* ctx, cudaError_t e, const char* what, const char* file, 
   snprintf(buf, sizeof(buf), "[gtn_b200] CUDA error %d (%s) in %s at %s:%d",
            (int)e, cudaGetErrorString(e), what, file, line);
   return fail(ctx, GTNB_ERR_RUNTIME, buf);
+}
+
+int ensure_max_smem(gtnb_ctx* ctx, const void* kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  std::lock_guard<std::mutex> l(mu);
+  const auto key = std::make_pair(ctx->device, kernel);
+  if (done.count(key)) return GTNB_OK;
+  GTNB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem));
+  done.insert(key);
+  return GTNB_OK;
 }
 
 } // namespace gtnb
@@ -217,6 +231,10 @@ int gtnb_timer_stop(gtnb_ctx* ctx, float* ms) {
 int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value) {
   if (ctx && name && std::string(name) == "staged") {
     ctx->use_staged = value != 0;
+    return GTNB_OK;
+  }
+  if (ctx && name && std::string(name) == "implicit") {
+    ctx->use_implicit = value != 0;
     return GTNB_OK;
   }
   return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctx_set_flag: unknown flag");
@@ -537,7 +555,7 @@ namespace gtnb {
 int composed_alloc(
     gtnb_ctx* ctx, int B, const SgDims* dims, int n_graphs, int linear_first, const int32_t* T,
     int C, const float* emissions_dev, int64_t emissions_stride, std::vector<long long>& sgn,
-    std::vector<long long>& sga, gtnb_lattice** out) {
+    std::vector<long long>& sga, gtnb_lattice** out, bool implicit_only) {
   *out = nullptr;
   int maxN = 0, maxA = 0;
   for (int g = 0; g < n_graphs; g++) {
@@ -584,7 +602,12 @@ int composed_alloc(
     std::memset(&m, 0, sizeof(m));
     long long capN = align_up((long long)(T[b] + 1) * s.N + 1, kAlign);
     long long capA = align_up(std::max<long long>((long long)T[b] * s.A, 1), kAlign);
-    if (capA >= (1ll << 30) || capN >= (1ll << 30)) {
+    if (implicit_only) {
+      // implicit lattice (k_implicit.cu): only dense per-frame node scores, rows padded to 16 bytes
+      capN = (long long)(T[b] + 1) * align_up(s.N, kAlign) + kAlign;
+      capA = kAlign;
+    }
+    if (!implicit_only && (capA >= (1ll << 30) || capN >= (1ll << 30))) {
       delete lat;
       return fail(ctx, GTNB_ERR_UNSUPPORTED,
                   "gtnb_compose_linear: lattice too large to materialise (use the factored path)");
@@ -607,7 +630,7 @@ int composed_alloc(
     m.sg_A = s.A;
     m.sg_all_valid = s.all_valid;
     m.sg_uniform = s.uniform;
-    m.cap_N = (int)capN;
+    m.cap_N = (int)std::min<long long>(capN, 0x7fffffff);
     m.cap_A = (int)capA;
     m.cap_L = (int)align_up(T[b] + 2, kAlign);
     tn += capN;
@@ -623,6 +646,7 @@ int composed_alloc(
   lat->max_T = maxT;
 
   size_t need = (size_t)(tn * 8 + ta * 20 + tl * 8) + (size_t)B * (maxT + 1) * lat->alive_words * 4;
+  if (implicit_only) need = (size_t)tn * 4;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   if (need > total_b) {
@@ -636,11 +660,13 @@ int composed_alloc(
     if ((rc = (x))) goto bad; \
   } while (0)
   TRYA(dev_alloc(ctx, &lat->meta, B));
-  TRYA(dev_alloc(ctx, &lat->lvl_node_ptr, tl));
-  TRYA(dev_alloc(ctx, &lat->lvl_arc_ptr, tl));
-  TRYA(dev_alloc(ctx, &lat->row_ptr, tn));
-  TRYA(dev_alloc(ctx, &lat->arcs, ta));
-  TRYA(dev_alloc(ctx, &lat->gi, ta));
+  if (!implicit_only) {
+    TRYA(dev_alloc(ctx, &lat->lvl_node_ptr, tl));
+    TRYA(dev_alloc(ctx, &lat->lvl_arc_ptr, tl));
+    TRYA(dev_alloc(ctx, &lat->row_ptr, tn));
+    TRYA(dev_alloc(ctx, &lat->arcs, ta));
+    TRYA(dev_alloc(ctx, &lat->gi, ta));
+  }
   TRYA(dev_alloc(ctx, &lat->acc_nodes, tc));
   TRYA(dev_alloc(ctx, &lat->scores, tn));
   TRYA(dev_alloc(ctx, &lat->out_scores, B));
@@ -653,7 +679,7 @@ int composed_alloc(
   TRYA(dev_alloc(ctx, &lat->sg_in_w, tsa));
   TRYA(dev_alloc(ctx, &lat->sg_ilabel, tsa));
   TRYA(dev_alloc(ctx, &lat->sg_olabel, tsa));
-  TRYA(dev_alloc(ctx, &lat->alive, (long long)B * (maxT + 1) * lat->alive_words));
+  if (!implicit_only) TRYA(dev_alloc(ctx, &lat->alive, (long long)B * (maxT + 1) * lat->alive_words));
 #undef TRYA
   *out = lat;
   return GTNB_OK;

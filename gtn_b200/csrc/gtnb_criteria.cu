@@ -13,10 +13,16 @@
 
 using namespace gtnb;
 
-extern "C" int gtnb_ctc_loss(
+/*
+ * One attempt.  allow_implicit: sweep the frames without building the lattice (k_implicit.cu)
+ * when the target graphs qualify; *needs_exact is set when that sweep met a non-finite weight,
+ * in which case the outputs are not to be used and the caller repeats the call materialised.
+ */
+static int ctc_loss_run(
     gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
     const int32_t* input_lens, const int32_t* targets, const int32_t* target_lens, int blank,
-    float* losses_host, float* grads, int grads_on_device) {
+    float* losses_host, float* grads, int grads_on_device, bool allow_implicit, bool* needs_exact) {
+  *needs_exact = false;
   if (!ctx || B < 0 || T < 0 || C <= 0 || !emissions || !target_lens || !losses_host)
     return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctc_loss: bad arguments");
   if (B == 0) return GTNB_OK;
@@ -28,6 +34,8 @@ extern "C" int gtnb_ctc_loss(
   float* z_dev = nullptr;
   float* deltas_dev = nullptr;
   int32_t* small_dev = nullptr; // [targets | offsets | lens | T]
+  int32_t* status_dev = nullptr;
+  bool implicit = false;
   gtnb_lattice* lat = nullptr;
   cudaEvent_t h2d_event = nullptr;
   std::vector<long long> sgn, sga;
@@ -98,7 +106,12 @@ extern "C" int gtnb_ctc_loss(
   TRY(dev_alloc(ctx, &z_dev, B));
   TRY(dev_alloc(ctx, &deltas_dev, B));
   TRY(dev_alloc(ctx, &small_dev, tot_t + 3ll * B));
-  TRY(composed_alloc(ctx, B, dims.data(), B, 0, Tb.data(), C, e_dev, per, sgn, sga, &lat));
+  implicit = allow_implicit && implicit_dims_supported(dims.data(), B);
+  TRY(composed_alloc(ctx, B, dims.data(), B, 0, Tb.data(), C, e_dev, per, sgn, sga, &lat, implicit));
+  if (implicit) {
+    TRY(dev_alloc(ctx, &status_dev, B));
+    TRYCUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * B, ctx->stream));
+  }
 
   // one pinned staging pass for everything the kernels need from the host
   TRY(stage_begin(ctx));
@@ -115,14 +128,27 @@ extern "C" int gtnb_ctc_loss(
 
   // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
   TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
-  TRY(launch_compose(ctx, lat, h2d_event));
+  if (implicit) {
+    if (h2d_event) TRYCUDA(cudaStreamWaitEvent(ctx->stream, h2d_event, 0));
+  } else {
+    TRY(launch_compose(ctx, lat, h2d_event));
+  }
   // forwardScore(emissions) and its +1 gradient
   TRY(launch_linear_forward(ctx, B, small_dev + tot_t + 2ll * B, maxT, C, e_dev, per, 0, z_dev, g_dev,
                             per, nullptr, 1.0f, input_lens ? 0 : 1));
-  TRY(launch_forward(ctx, lat, MODE_LOG));
-  lat->forward_done = true;
-  lat->forward_mode = MODE_LOG;
-  if (grads) {
+  if (implicit) {
+    TRY(launch_implicit_forward(ctx, lat, status_dev));
+    if (grads) {
+      TRY(launch_implicit_backward(ctx, lat, deltas_dev, g_dev, per));
+      if (!grads_on_device)
+        TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  } else {
+    TRY(launch_forward(ctx, lat, MODE_LOG));
+    lat->forward_done = true;
+    lat->forward_mode = MODE_LOG;
+  }
+  if (grads && !implicit) {
     // shortestDistanceGrad and compose's gradFunc fused when the lattice qualifies
     rc = launch_backward_fused(ctx, lat, deltas_dev, g_dev, per);
     if (rc == GTNB_ERR_UNSUPPORTED) {
@@ -135,17 +161,24 @@ extern "C" int gtnb_ctc_loss(
     if (!grads_on_device)
       TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  TRY(readback_reserve(ctx, 2 * sizeof(float) * B));
+  TRY(readback_reserve(ctx, 3 * sizeof(float) * B));
   {
     float* z = reinterpret_cast<float*>(ctx->readback);
     float* s = z + B;
+    int32_t* st = reinterpret_cast<int32_t*>(s + B);
     TRYCUDA(cudaMemcpyAsync(z, z_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
     TRYCUDA(cudaMemcpyAsync(s, lat->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (implicit)
+      TRYCUDA(cudaMemcpyAsync(st, status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->stream));
     TRYCUDA(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < B; b++) losses_host[b] = z[b] - s[b]; // subtract, functions.cpp:52
+    if (implicit)
+      for (int b = 0; b < B; b++)
+        if (st[b]) *needs_exact = true;
   }
 
 done:
+  dev_free(ctx, status_dev);
   if (lat) gtnb_lattice_destroy(ctx, lat);
   if (!emissions_on_device) dev_free(ctx, e_dev);
   if (grads && !grads_on_device) dev_free(ctx, g_dev);
@@ -155,6 +188,22 @@ done:
   return rc;
 #undef TRY
 #undef TRYCUDA
+}
+
+extern "C" int gtnb_ctc_loss(
+    gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
+    const int32_t* input_lens, const int32_t* targets, const int32_t* target_lens, int blank,
+    float* losses_host, float* grads, int grads_on_device) {
+  bool needs_exact = false;
+  int rc = ctc_loss_run(ctx, B, T, C, emissions, emissions_on_device, input_lens, targets, target_lens, blank,
+                        losses_host, grads, grads_on_device, ctx && ctx->use_implicit, &needs_exact);
+  if (rc == GTNB_OK && needs_exact)
+    // a non-finite emission: the materialised lattice reproduces the reference's inf / NaN
+    // propagation arc by arc (shortest.cpp:62-80), the implicit sweep cannot tell a missing
+    // node from one whose score is -inf
+    rc = ctc_loss_run(ctx, B, T, C, emissions, emissions_on_device, input_lens, targets, target_lens, blank,
+                      losses_host, grads, grads_on_device, false, &needs_exact);
+  return rc;
 }
 
 /*

@@ -93,6 +93,7 @@ struct gtnb_ctx {
     cudaEvent_t a, b;
   };
   bool use_staged = true; // gtnb_ctx_set_flag("staged", 0) forces the generic kernels
+  bool use_implicit = true; // gtnb_ctx_set_flag("implicit", 0): criteria materialise the lattice
   bool profiling = false;
   std::vector<ProfEntry> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -167,7 +168,7 @@ struct SgDims {
 int composed_alloc(
     gtnb_ctx* ctx, int B, const SgDims* dims, int n_graphs, int linear_first, const int32_t* T,
     int C, const float* emissions_dev, int64_t emissions_stride, std::vector<long long>& sgn,
-    std::vector<long long>& sga, gtnb_lattice** out);
+    std::vector<long long>& sga, gtnb_lattice** out, bool implicit_only = false);
 int stage_begin(gtnb_ctx* ctx);
 int stage_upload(gtnb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int stage_end(gtnb_ctx* ctx);
@@ -227,6 +228,12 @@ inline void prof_end(gtnb_ctx* ctx) {
     GTNB_CHECK_LAUNCH(ctx);          \
   } while (0)
 
+/* Opt a kernel in to the full dynamic shared-memory window, once per (device, kernel).  The
+ * attribute is process-wide: setting it per launch to that launch's size races between the
+ * per-thread contexts of the gtn:: layer (one thread lowers it under another's launch). */
+constexpr int kMaxDynamicSmem = 227 * 1024;
+int ensure_max_smem(gtnb_ctx* ctx, const void* kernel);
+
 template <typename T>
 int dev_alloc(gtnb_ctx* ctx, T** p, long long n) {
   *p = nullptr;
@@ -267,6 +274,11 @@ int launch_backward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const
 int launch_backward_fused(
     gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride);
 // kernels (k_dense.cu): factored dense-trellis Viterbi
+bool implicit_supported(const gtnb_lattice* lat);
+bool implicit_dims_supported(const SgDims* dims, int n_graphs);
+int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev);
+int launch_implicit_backward(
+    gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride);
 int launch_viterbi_dense(
     gtnb_ctx* ctx, int B, int T_max, int C, const int32_t* T_dev, const float* emis, int64_t stride,
     const float* trans_dev, uint8_t* bp, int32_t* paths, float* scores);

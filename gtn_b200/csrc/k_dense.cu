@@ -181,10 +181,12 @@ int launch_viterbi_dense(
   int G = 1;
   while (G < 32 && C * (G * 2) <= kDenseThreads) G *= 2;
   const size_t smem = sizeof(float) * ((size_t)C * (C + 32 / G) + 2 * (size_t)C);
+  if (smem > (size_t)kMaxDynamicSmem)
+    return fail(ctx, GTNB_ERR_UNSUPPORTED, "gtnb_viterbi_dense: transitions tile does not fit shared memory");
 #define LAUNCH_DENSE(G_)                                                                           \
   do {                                                                                             \
-    GTNB_CUDA(ctx, cudaFuncSetAttribute(viterbi_dense_kernel<G_>,                                  \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int rc__ = ensure_max_smem(ctx, (const void*)viterbi_dense_kernel<G_>);                        \
+    if (rc__) return rc__;                                                                         \
     GTNB_LAUNCH(ctx, "viterbi_dense",                                                              \
                 viterbi_dense_kernel<G_><<<B, kDenseThreads, smem, ctx->stream>>>(                 \
                     T_max, C, T_dev, emis, (long long)stride, trans_dev, bp, paths, scores));      \

@@ -1139,8 +1139,8 @@ StagedPlan plan(const gtnb_lattice* lat) {
 
 template <typename K>
 int set_smem(gtnb_ctx* ctx, K kernel, int bytes) {
-  GTNB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  return GTNB_OK;
+  if (bytes > kMaxDynamicSmem) return GTNB_ERR_UNSUPPORTED;
+  return ensure_max_smem(ctx, (const void*)kernel);
 }
 
 } // namespace

@@ -100,7 +100,9 @@ int64_t gtnb_ctx_launch_count(const gtnb_ctx* ctx);
 /*
  * Tuning / testing switches.  "staged" (default 1): use the TMA-staged persistent
  * kernels for composed lattices; 0 forces the generic any-DAG kernels (libm-precise),
- * which is how the tests cross-check the two families.
+ * which is how the tests cross-check the two families.  "implicit" (default 1): the
+ * criteria (gtnb_ctc_loss) sweep the frames of intersect(target graph, emissions) without
+ * materialising the lattice; 0 makes them build it and run the lattice kernels.
  */
 int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value);
 

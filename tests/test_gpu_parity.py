@@ -449,3 +449,59 @@ def test_forced_alignment_full_size(ctx, oracle):
         assert s == scores[b]
     lat.free()
     e_dev.free()
+
+
+# ---------------------------------------------------------------------------
+# implicit-lattice criterion kernels (k_implicit.cu) against the materialised path
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", [(4, 120, 16, 9), (3, 37, 8, 1), (2, 400, 32, 150), (2, 9, 5, 4)])
+def test_ctc_implicit_and_materialised_agree(ctx, oracle, shape):
+    """gtnb_ctc_loss sweeps the frames without building the lattice; with the flag off it builds
+    compose's lattice and runs the generic kernels.  Same losses / gradients, both equal to the
+    oracle.  (2, 400, 32, 150): 301 graph nodes > 256 threads (several nodes per thread);
+    (2, 9, 5, 4): T == 2U+1, almost every node pruned."""
+    B, T, C, U = shape
+    e, targets = util.bench_inputs(B, T, C, U, seed=4321)
+    lens = np.array([T - (3 * b) % max(T // 2, 1) for b in range(B)], np.int32)
+    res = {}
+    for imp in (1, 0):
+        ctx.set_flag("implicit", imp)
+        ctx.profile(True)
+        ctx.profile_read()
+        res[imp] = ctx.ctc_loss(e, targets, input_lens=lens)
+        names = set(ctx.profile_read())
+        ctx.profile(False)
+        assert ("implicit_forward" in names) == bool(imp), names
+        assert ("compose_emit" in names) == (not imp), names
+    ctx.set_flag("implicit", 1)
+    assert util.close(res[1][0], res[0][0])
+    for b in range(B):
+        lo, go = oracle.ctc_loss(e[b, :lens[b]], targets[b], 0, True)
+        assert util.close(res[1][0][b], lo), (b, res[1][0][b], lo)
+        if np.isfinite(lo):
+            assert util.grad_close(res[1][1][b, :lens[b]], go, 5.0 * T), b
+            assert util.grad_close(res[1][1][b], res[0][1][b], 5.0 * T), b
+        assert not res[1][1][b, lens[b]:].any()
+
+
+def test_ctc_implicit_falls_back_on_non_finite_emissions(ctx):
+    """-inf on a label the target uses: the reference propagates inf / NaN arc by arc
+    (shortest.cpp:62-80); the implicit sweep detects it and the call is repeated materialised,
+    so the result is the materialised path's, bit for bit in the NaN pattern."""
+    B, T, C, U = 3, 40, 6, 5
+    e, targets = util.bench_inputs(B, T, C, U, seed=99)
+    e[1, 7, int(targets[1][2])] = -np.inf
+    ctx.profile(True)
+    ctx.profile_read()
+    l1, g1 = ctx.ctc_loss(e, targets)
+    names = set(ctx.profile_read())
+    ctx.profile(False)
+    assert "implicit_forward" in names and "compose_emit" in names, names
+    ctx.set_flag("implicit", 0)
+    l0, g0 = ctx.ctc_loss(e, targets)
+    ctx.set_flag("implicit", 1)
+    assert np.array_equal(np.isnan(l1), np.isnan(l0)) and np.array_equal(np.isnan(g1), np.isnan(g0))
+    assert np.allclose(l1[~np.isnan(l1)], l0[~np.isnan(l0)], rtol=1e-5)
+    assert np.allclose(np.nan_to_num(g1, posinf=0, neginf=0), np.nan_to_num(g0, posinf=0, neginf=0),
+                       rtol=1e-4, atol=1e-5)
