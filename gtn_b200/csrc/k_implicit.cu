@@ -162,14 +162,48 @@ __device__ __forceinline__ bool load_tables(
   return bad;
 }
 
+/* Predicated read-only load straight into its destination register.  With a plain
+ * `if (p) x = __ldg(q)` in the unrolled frame loop ptxas gathers the eight prefetches of a
+ * block at its end, into temporaries, and copies them to the loop-carried registers at the
+ * back edge -- a full-latency stall every kPf frames (ncu: 21 % of all samples on that MOV). */
+__device__ __forceinline__ void ldg_if(bool p, float& dst, const float* src) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.s32 q, %2, 0;\n"
+      "@q ld.global.nc.f32 %0, [%1];\n"
+      "}\n"
+      : "+f"(dst)
+      : "l"(src), "r"((int)p));
+}
+/* Unpredicated variant for the steady part of the frame loop (address always valid): a strong
+ * (relaxed, CTA scope) load, which ptxas must keep on its side of the bar.sync it was written
+ * on, writing the loop-carried ring register directly. */
+__device__ __forceinline__ void ldg_keep(float& dst, const float* src) {
+  asm volatile("ld.relaxed.cta.global.f32 %0, [%1];" : "=f"(dst) : "l"(src) : "memory");
+}
+/* predicated red.global.add.f32 (no branch, no reconvergence point in the frame loop) */
+__device__ __forceinline__ void red_if(bool p, float* dst, float v) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.s32 q, %2, 0;\n"
+      "@q red.global.add.f32 [%0], %1;\n"
+      "}\n" ::"l"(dst),
+      "f"(v), "r"((int)p)
+      : "memory");
+}
+
 /* three in-arcs, branch-free: absent arcs carry -inf and add exp(-inf) = 0 in arc order
- * (shortest.cpp:102-114); an all--inf (or +inf) maximum is returned as is */
+ * (shortest.cpp:102-114); an all--inf (or +inf) maximum is returned as is.  The sum is >= 1
+ * (the maximum contributes exp(0)), where lg2.approx has an absolute error <= 2^-22: far
+ * below one ulp of any score this recursion produces after a few frames. */
 __device__ __forceinline__ float lse3(float v0, float v1, float v2) {
   const float mx = fmaxf(fmaxf(v0, v1), v2);
-  float sum = iexp(v0 - mx) - 1.0f;
-  sum += iexp(v1 - mx);
-  sum += iexp(v2 - mx);
-  const float r = mx + ilog1p(sum);
+  const float sum = (iexp(v0 - mx) + iexp(v1 - mx)) + iexp(v2 - mx);
+  float lg;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(sum));
+  const float r = fmaf(lg, 0.6931471805599453f, mx);
   return (fabsf(mx) == CUDART_INF_F) ? mx : r;
 }
 
@@ -270,8 +304,11 @@ __global__ void __launch_bounds__(kImpThreads) implicit_forward_kernel(
     int f0 = 0;
 #define GTNB_FWD_STEP(j, GUARDED)                                        \
   {                                                                      \
-    const float e = pf[j];                                               \
-    if (has && (!(GUARDED) || f0 + (j) + kPf < T)) pf[j] = __ldg(epf);   \
+    const float e = has ? pf[j] : 0.0f; /* idle threads load node 0's */ \
+    if (GUARDED)                                                         \
+      ldg_if(has && f0 + (j) + kPf < T, pf[j], epf);                     \
+    else                                                                 \
+      ldg_keep(pf[j], epf);                                              \
     epf += C;                                                            \
     const float* P = ((j)&1) ? S1 : S0;                                  \
     float* Q = ((j)&1) ? S0 : S1;                                        \
@@ -503,14 +540,18 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     Cw[a1] = c1;                                                                      \
     Cw[a2] = c2;                                                                      \
     const float acc = (c0 + c1) + c2;                                                 \
-    if (acc != 0.0f) atomicAdd(gl, acc * delta);                                      \
+    red_if(acc != 0.0f, gl, acc * delta);                                             \
     gl -= C;                                                                          \
     const float s_f = ps[j]; /* S_{t-2}[u] */                                         \
-    const float e_f = pe[j]; /* e[t-2][label] */                                      \
+    const float e_f = has ? pe[j] : 0.0f; /* e[t-2][label] */                         \
     Sw[tid] = s_f;                                                                    \
-    if (!(GUARDED) || T - 2 - (i0_ + (j)) - kPf >= 0) {                               \
-      if (act) ps[j] = __ldg(spf);                                                    \
-      if (has) pe[j] = __ldg(epf);                                                    \
+    if (GUARDED) {                                                                    \
+      const bool inb = T - 2 - (i0_ + (j)) - kPf >= 0;                                \
+      ldg_if(act && inb, ps[j], spf);                                                 \
+      ldg_if(has && inb, pe[j], epf);                                                 \
+    } else {                                                                          \
+      ldg_keep(ps[j], spf);                                                           \
+      ldg_keep(pe[j], epf);                                                           \
     }                                                                                 \
     spf -= pitch;                                                                     \
     epf -= C;                                                                         \
