@@ -309,6 +309,8 @@ def main():
 
     ms = float(np.mean(times))
     e2e_ms = float(np.mean(e2e_times))
+    if os.environ.get("GTNB_BENCH_DUMP"):
+        np.save(os.environ["GTNB_BENCH_DUMP"] + "_r%d.npy" % rank, np.array([times, e2e_times]))
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -86,6 +86,25 @@ int cuda_fail(gtnb_ctx* ctx, cudaError_t e, const char* what, const char* file, 
   return fail(ctx, GTNB_ERR_RUNTIME, buf);
 }
 
+int ensure_side_streams(gtnb_ctx* ctx, int n_streams, int n_events) {
+  if (!ctx->copy_stream) {
+    GTNB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    GTNB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    GTNB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  while ((int)ctx->side_streams.size() < n_streams) {
+    cudaStream_t s;
+    GTNB_CUDA(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    ctx->side_streams.push_back(s);
+  }
+  while ((int)ctx->side_events.size() < n_events) {
+    cudaEvent_t e;
+    GTNB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->side_events.push_back(e);
+  }
+  return GTNB_OK;
+}
+
 int ensure_max_smem(gtnb_ctx* ctx, const void* kernel) {
   static std::mutex mu;
   static std::set<std::pair<int, const void*>> done;
@@ -157,6 +176,8 @@ void gtnb_ctx_destroy(gtnb_ctx* ctx) {
   if (ctx->readback) cudaFreeHost(ctx->readback);
   if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto s : ctx->side_streams) cudaStreamDestroy(s);
+  for (auto e : ctx->side_events) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);

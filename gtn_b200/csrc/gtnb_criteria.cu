@@ -36,6 +36,9 @@ static int ctc_loss_run(
   int32_t* small_dev = nullptr; // [targets | offsets | lens | T]
   int32_t* status_dev = nullptr;
   bool implicit = false;
+  int K = 1; // sub-batches (implicit path with host buffers)
+  std::vector<int> chunk_lo;
+  cudaStream_t main_stream = ctx->stream;
   gtnb_lattice* lat = nullptr;
   cudaEvent_t h2d_event = nullptr;
   std::vector<long long> sgn, sga;
@@ -78,22 +81,24 @@ static int ctc_loss_run(
     }                                                      \
   } while (0)
 
+  implicit = allow_implicit && implicit_dims_supported(dims.data(), B);
+  // Host buffers: cut the batch into K sub-batches whose H2D copy, kernels and D2H copy run on
+  // their own streams, so that the two PCIe directions and the (latency-bound) sweeps overlap.
+  // Device buffers: K = 1, and the normaliser (k_linear.cu) runs beside the forward sweep.
+  if (implicit && (!emissions_on_device || (grads && !grads_on_device))) {
+    const long long bytes = (long long)sizeof(float) * per * B;
+    K = (int)std::min<long long>(std::max<long long>(bytes / (8ll << 20), 1), 8);
+    K = std::min(K, B);
+  }
+  TRY(ensure_side_streams(ctx, K, K + 2));
+  chunk_lo.resize(K + 1);
+  for (int k = 0; k <= K; k++) chunk_lo[k] = (int)((long long)B * k / K);
   if (emissions_on_device) {
     e_dev = const_cast<float*>(emissions);
   } else {
     // the copy runs on a second stream while this one builds the target graphs and the
     // lattice structure (k_ctc.cu, compose alive / count / scan need no emissions)
     TRY(dev_alloc(ctx, &e_dev, per * B));
-    if (!ctx->copy_stream) {
-      TRYCUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-      TRYCUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-      TRYCUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    }
-    TRYCUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); // orders the copy after the allocation
-    TRYCUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
-    TRYCUDA(cudaMemcpyAsync(e_dev, emissions, sizeof(float) * per * B, cudaMemcpyHostToDevice, ctx->copy_stream));
-    TRYCUDA(cudaEventRecord(ctx->ev_join, ctx->copy_stream));
-    h2d_event = ctx->ev_join;
   }
   if (grads) {
     if (grads_on_device)
@@ -106,7 +111,6 @@ static int ctc_loss_run(
   TRY(dev_alloc(ctx, &z_dev, B));
   TRY(dev_alloc(ctx, &deltas_dev, B));
   TRY(dev_alloc(ctx, &small_dev, tot_t + 3ll * B));
-  implicit = allow_implicit && implicit_dims_supported(dims.data(), B);
   TRY(composed_alloc(ctx, B, dims.data(), B, 0, Tb.data(), C, e_dev, per, sgn, sga, &lat, implicit));
   if (implicit) {
     TRY(dev_alloc(ctx, &status_dev, B));
@@ -125,25 +129,67 @@ static int ctc_loss_run(
     TRY(stage_upload(ctx, deltas_dev, minus1.data(), sizeof(float) * B));
   }
   TRY(stage_end(ctx));
+  if (!emissions_on_device) {
+    // enqueued AFTER the small staged upload: the copy engine serves one direction in
+    // submission order, and the graphs must not queue behind 65 MB of emissions
+    TRYCUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); // orders the copy after the allocation
+    TRYCUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    for (int k = 0; k < K; k++) {
+      const long long lo = (long long)chunk_lo[k] * per, n = (long long)(chunk_lo[k + 1] - chunk_lo[k]) * per;
+      TRYCUDA(cudaMemcpyAsync(e_dev + lo, emissions + lo, sizeof(float) * n, cudaMemcpyHostToDevice,
+                              ctx->copy_stream));
+      TRYCUDA(cudaEventRecord(ctx->side_events[k], ctx->copy_stream));
+    }
+    TRYCUDA(cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+    h2d_event = ctx->ev_join;
+  }
 
   // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
   TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
   if (implicit) {
-    if (h2d_event) TRYCUDA(cudaStreamWaitEvent(ctx->stream, h2d_event, 0));
-  } else {
-    TRY(launch_compose(ctx, lat, h2d_event));
-  }
-  // forwardScore(emissions) and its +1 gradient
-  TRY(launch_linear_forward(ctx, B, small_dev + tot_t + 2ll * B, maxT, C, e_dev, per, 0, z_dev, g_dev,
-                            per, nullptr, 1.0f, input_lens ? 0 : 1));
-  if (implicit) {
-    TRY(launch_implicit_forward(ctx, lat, status_dev));
-    if (grads) {
-      TRY(launch_implicit_backward(ctx, lat, deltas_dev, g_dev, per));
-      if (!grads_on_device)
-        TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
+    // everything below only needs what is already enqueued on the main stream (graphs, staging,
+    // the memset of the gradients) plus its own slice of the emissions
+    cudaEvent_t ev_setup = ctx->side_events[K], ev_lin = ctx->side_events[K + 1];
+    const int32_t* T_dev = small_dev + tot_t + 2ll * B;
+    TRYCUDA(cudaEventRecord(ev_setup, main_stream));
+    if (K == 1 && !h2d_event && !(grads && !grads_on_device)) {
+      // forwardScore(emissions) and its +1 gradient beside the forward sweep
+      TRYCUDA(cudaStreamWaitEvent(ctx->copy_stream, ev_setup, 0));
+      ctx->stream = ctx->copy_stream;
+      rc = launch_linear_forward(ctx, B, T_dev, maxT, C, e_dev, per, 0, z_dev, g_dev, per, nullptr, 1.0f,
+                                 input_lens ? 0 : 1);
+      ctx->stream = main_stream;
+      if (rc) goto done;
+      TRYCUDA(cudaEventRecord(ev_lin, ctx->copy_stream));
+      TRY(launch_implicit_forward(ctx, lat, status_dev));
+      TRYCUDA(cudaStreamWaitEvent(main_stream, ev_lin, 0));
+      if (grads) TRY(launch_implicit_backward(ctx, lat, deltas_dev, g_dev, per));
+    } else {
+      for (int k = 0; k < K && !rc; k++) {
+        const int b0 = chunk_lo[k], nb = chunk_lo[k + 1] - chunk_lo[k];
+        cudaStream_t cs = ctx->side_streams[k];
+        TRYCUDA(cudaStreamWaitEvent(cs, ev_setup, 0));
+        if (h2d_event) TRYCUDA(cudaStreamWaitEvent(cs, ctx->side_events[k], 0));
+        ctx->stream = cs;
+        rc = launch_linear_forward(ctx, nb, T_dev + b0, maxT, C, e_dev + (long long)b0 * per, per, 0,
+                                   z_dev + b0, g_dev ? g_dev + (long long)b0 * per : nullptr, per, nullptr,
+                                   1.0f, input_lens ? 0 : 1);
+        if (!rc) rc = launch_implicit_forward(ctx, lat, status_dev, b0, nb);
+        if (!rc && grads) rc = launch_implicit_backward(ctx, lat, deltas_dev, g_dev, per, b0, nb);
+        ctx->stream = main_stream;
+        if (rc) goto done;
+        if (grads && !grads_on_device)
+          TRYCUDA(cudaMemcpyAsync(grads + (long long)b0 * per, g_dev + (long long)b0 * per,
+                                  sizeof(float) * per * nb, cudaMemcpyDeviceToHost, cs));
+        TRYCUDA(cudaEventRecord(ctx->side_events[k], cs));
+        TRYCUDA(cudaStreamWaitEvent(main_stream, ctx->side_events[k], 0));
+      }
     }
   } else {
+    TRY(launch_compose(ctx, lat, h2d_event));
+    // forwardScore(emissions) and its +1 gradient
+    TRY(launch_linear_forward(ctx, B, small_dev + tot_t + 2ll * B, maxT, C, e_dev, per, 0, z_dev, g_dev,
+                              per, nullptr, 1.0f, input_lens ? 0 : 1));
     TRY(launch_forward(ctx, lat, MODE_LOG));
     lat->forward_done = true;
     lat->forward_mode = MODE_LOG;
@@ -178,6 +224,12 @@ static int ctc_loss_run(
   }
 
 done:
+  ctx->stream = main_stream;
+  if (rc && implicit) {
+    // an error mid-way: nothing may still be running on the side streams when the buffers go
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int k = 0; k < K && k < (int)ctx->side_streams.size(); k++) cudaStreamSynchronize(ctx->side_streams[k]);
+  }
   dev_free(ctx, status_dev);
   if (lat) gtnb_lattice_destroy(ctx, lat);
   if (!emissions_on_device) dev_free(ctx, e_dev);

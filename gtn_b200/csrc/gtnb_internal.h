@@ -84,6 +84,10 @@ struct gtnb_ctx {
   // composition passes that only need the target graphs
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // chunk streams / events: a host-buffer criterion call is cut into sub-batches whose
+  // H2D copy, kernels and D2H copy overlap each other (gtnb_criteria.cu)
+  std::vector<cudaStream_t> side_streams;
+  std::vector<cudaEvent_t> side_events;
   // pinned read-back buffer for small device->host results
   unsigned char* readback = nullptr;
   size_t readback_bytes = 0;
@@ -276,9 +280,11 @@ int launch_backward_fused(
 // kernels (k_dense.cu): factored dense-trellis Viterbi
 bool implicit_supported(const gtnb_lattice* lat);
 bool implicit_dims_supported(const SgDims* dims, int n_graphs);
-int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev);
+int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0 = 0, int nb = -1);
 int launch_implicit_backward(
-    gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride);
+    gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride,
+    int b0 = 0, int nb = -1);
+int ensure_side_streams(gtnb_ctx* ctx, int n_streams, int n_events);
 int launch_viterbi_dense(
     gtnb_ctx* ctx, int B, int T_max, int C, const int32_t* T_dev, const float* emis, int64_t stride,
     const float* trans_dev, uint8_t* bp, int32_t* paths, float* scores);

@@ -646,33 +646,37 @@ bool implicit_supported(const gtnb_lattice* lat) {
   return lay.total <= 200 * 1024;
 }
 
-int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev) {
-  if (lat->B == 0) return GTNB_OK;
+/* utterances [b0, b0 + nb) of the batch (nb < 0: all): one CTA each, on ctx->stream */
+int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0, int nb) {
+  if (nb < 0) nb = lat->B - b0;
+  if (nb <= 0) return GTNB_OK;
   const ImpLayout lay = make_imp_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, false);
   if (lay.total > 48 * 1024) {
     int rc = ensure_max_smem(ctx, (const void*)implicit_forward_kernel);
     if (rc) return rc;
   }
   GTNB_LAUNCH(ctx, "implicit_forward",
-              implicit_forward_kernel<<<lat->B, kImpThreads, lay.total, ctx->stream>>>(
-                  lat->meta, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_w,
-                  lat->emissions, lat->scores, lat->out_scores, status_dev, lat->C, lay));
+              implicit_forward_kernel<<<nb, kImpThreads, lay.total, ctx->stream>>>(
+                  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_w,
+                  lat->emissions, lat->scores, lat->out_scores + b0, status_dev + b0, lat->C, lay));
   return GTNB_OK;
 }
 
 int launch_implicit_backward(
-    gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride) {
-  if (lat->B == 0) return GTNB_OK;
+    gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride,
+    int b0, int nb) {
+  if (nb < 0) nb = lat->B - b0;
+  if (nb <= 0) return GTNB_OK;
   const ImpLayout lay = make_imp_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, true);
   if (lay.total > 48 * 1024) {
     int rc = ensure_max_smem(ctx, (const void*)implicit_backward_kernel);
     if (rc) return rc;
   }
   GTNB_LAUNCH(ctx, "implicit_backward",
-              implicit_backward_kernel<<<lat->B, kImpThreads, lay.total, ctx->stream>>>(
-                  lat->meta, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_w,
-                  lat->emissions, lat->scores, lat->out_scores, deltas_dev, grad_emis, (long long)grad_stride,
-                  lat->C, lay));
+              implicit_backward_kernel<<<nb, kImpThreads, lay.total, ctx->stream>>>(
+                  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_w,
+                  lat->emissions, lat->scores, lat->out_scores + b0, deltas_dev ? deltas_dev + b0 : nullptr,
+                  grad_emis + (long long)b0 * grad_stride, (long long)grad_stride, lat->C, lay));
   return GTNB_OK;
 }
 
