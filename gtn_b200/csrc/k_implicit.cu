@@ -176,6 +176,9 @@ __device__ __forceinline__ void ldg_if(bool p, float& dst, const float* src) {
       : "+f"(dst)
       : "l"(src), "r"((int)p));
 }
+/* (Measured alternatives, both slower at B=256: a 2-deep register ring behind prefetch.global.L1
+ * issued 8 frames ahead -- 0.33 vs 0.27 ms for the backward; prefetching the three source scores
+ * of every arc into registers instead of staging the row in shared memory -- 0.36 ms.) */
 /* Unpredicated variant for the steady part of the frame loop (address always valid): a strong
  * (relaxed, CTA scope) load, which ptxas must keep on its side of the bar.sync it was written
  * on, writing the loop-carried ring register directly. */
@@ -519,13 +522,10 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     float E0, E1, E2;
     {
       const float e = has ? __ldg(eml + (long long)(T - 1) * C) : 0.0f;
-      const bool ex = s_own > -CUDART_INF_F;
-      const float x0 = iexp(Sb[i0] + (w0 + e) - s_own);
-      const float x1 = iexp(Sb[i1] + (w1 + e) - s_own);
-      const float x2 = iexp(Sb[i2] + (w2 + e) - s_own);
-      E0 = ex ? x0 : 0.0f;
-      E1 = ex ? x1 : 0.0f;
-      E2 = ex ? x2 : 0.0f;
+      const float se = (s_own == -CUDART_INF_F) ? CUDART_INF_F : s_own;
+      E0 = iexp(Sb[i0] + (w0 + e) - se);
+      E1 = iexp(Sb[i1] + (w1 + e) - se);
+      E2 = iexp(Sb[i2] + (w2 + e) - se);
     }
     float* gl = gem + (long long)(T - 1) * C + (has ? t_lab[tid] : 0); // emission gradient of level t
     int i0_ = 0;
@@ -559,14 +559,11 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     g = (Cw[q0] + Cw[q1]) + Cw[q2]; /* node gradient of level t-1: the serial chain */ \
     s_own = s_nxt;                                                                    \
     s_nxt = s_f;                                                                      \
-    { /* off the chain: arc factors of level t-1 */                                   \
-      const bool ex = s_own > -CUDART_INF_F;                                          \
-      const float x0 = iexp(Sw[i0] + (w0 + e_f) - s_own);                             \
-      const float x1 = iexp(Sw[i1] + (w1 + e_f) - s_own);                             \
-      const float x2 = iexp(Sw[i2] + (w2 + e_f) - s_own);                             \
-      E0 = ex ? x0 : 0.0f;                                                            \
-      E1 = ex ? x1 : 0.0f;                                                            \
-      E2 = ex ? x2 : 0.0f;                                                            \
+    { /* arc factors of level t-1; a node that does not exist (score -inf) gets exp(-inf) */ \
+      const float se = (s_own == -CUDART_INF_F) ? CUDART_INF_F : s_own;               \
+      E0 = iexp(Sw[i0] + (w0 + e_f) - se);                                            \
+      E1 = iexp(Sw[i1] + (w1 + e_f) - se);                                            \
+      E2 = iexp(Sw[i2] + (w2 + e_f) - se);                                            \
     }                                                                                 \
   }
     for (; i0_ + 2 * kPf + 1 <= T; i0_ += kPf) {
