@@ -350,6 +350,7 @@ def main():
                        "l2": "flushed between timed iterations (256 MB memset)", "parallelism": "dp%d" % world,
                        "lattice_nodes": sumN, "lattice_arcs": sumA},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "utt/s", "ms_per_step": e2e_ms,
+                    "ms_per_step_median": float(np.median(e2e_times)), "ms_per_step_min": float(np.min(e2e_times)),
                     "h2d_bytes_per_step": int(nbytes + cat.nbytes + lens.nbytes),
                     "d2h_bytes_per_step": int(nbytes + losses.nbytes)},
             "gpu_launches": int(launches),

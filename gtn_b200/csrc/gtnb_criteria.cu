@@ -35,6 +35,7 @@ static int ctc_loss_run(
   float* deltas_dev = nullptr;
   int32_t* small_dev = nullptr; // [targets | offsets | lens | T]
   int32_t* status_dev = nullptr;
+  float* row_scratch = nullptr; // k_linear.cu's per-frame scores, allocated once for all sub-batches
   bool implicit = false;
   int K = 1; // sub-batches (implicit path with host buffers)
   std::vector<int> chunk_lo;
@@ -113,6 +114,7 @@ static int ctc_loss_run(
   TRY(dev_alloc(ctx, &small_dev, tot_t + 3ll * B));
   TRY(composed_alloc(ctx, B, dims.data(), B, 0, Tb.data(), C, e_dev, per, sgn, sga, &lat, implicit));
   if (implicit) {
+    TRY(dev_alloc(ctx, &row_scratch, (long long)B * std::max(maxT, 1)));
     TRY(dev_alloc(ctx, &status_dev, B));
     TRYCUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * B, ctx->stream));
   }
@@ -157,7 +159,7 @@ static int ctc_loss_run(
       TRYCUDA(cudaStreamWaitEvent(ctx->copy_stream, ev_setup, 0));
       ctx->stream = ctx->copy_stream;
       rc = launch_linear_forward(ctx, B, T_dev, maxT, C, e_dev, per, 0, z_dev, g_dev, per, nullptr, 1.0f,
-                                 input_lens ? 0 : 1);
+                                 input_lens ? 0 : 1, row_scratch);
       ctx->stream = main_stream;
       if (rc) goto done;
       TRYCUDA(cudaEventRecord(ev_lin, ctx->copy_stream));
@@ -173,7 +175,7 @@ static int ctc_loss_run(
         ctx->stream = cs;
         rc = launch_linear_forward(ctx, nb, T_dev + b0, maxT, C, e_dev + (long long)b0 * per, per, 0,
                                    z_dev + b0, g_dev ? g_dev + (long long)b0 * per : nullptr, per, nullptr,
-                                   1.0f, input_lens ? 0 : 1);
+                                   1.0f, input_lens ? 0 : 1, row_scratch + (long long)b0 * std::max(maxT, 1));
         if (!rc) rc = launch_implicit_forward(ctx, lat, status_dev, b0, nb);
         if (!rc && grads) rc = launch_implicit_backward(ctx, lat, deltas_dev, g_dev, per, b0, nb);
         ctx->stream = main_stream;
@@ -231,6 +233,7 @@ done:
     for (int k = 0; k < K && k < (int)ctx->side_streams.size(); k++) cudaStreamSynchronize(ctx->side_streams[k]);
   }
   dev_free(ctx, status_dev);
+  dev_free(ctx, row_scratch);
   if (lat) gtnb_lattice_destroy(ctx, lat);
   if (!emissions_on_device) dev_free(ctx, e_dev);
   if (grads && !grads_on_device) dev_free(ctx, g_dev);

@@ -295,7 +295,7 @@ int launch_compose_grad(gtnb_ctx* ctx, gtnb_lattice* lat, float* grad_graph, flo
 int launch_linear_forward(
     gtnb_ctx* ctx, int B, const int32_t* T_dev, int maxT, int C, const float* emis, int64_t stride,
     int tropical, float* scores, float* grad, int64_t grad_stride, const float* deltas, float delta_all,
-    int overwrite = 0);
+    int overwrite = 0, float* scratch = nullptr);
 
 enum { MODE_LOG = 0, MODE_TROPICAL = 1, MODE_PATH = 2 };
 

@@ -104,11 +104,14 @@ __global__ void __launch_bounds__(256) linear_reduce_kernel(
 int launch_linear_forward(
     gtnb_ctx* ctx, int B, const int32_t* T_dev, int maxT, int C, const float* emis, int64_t stride,
     int tropical, float* scores, float* grad, int64_t grad_stride, const float* deltas,
-    float delta_all, int overwrite) {
+    float delta_all, int overwrite, float* scratch) {
   if (B == 0) return GTNB_OK;
-  float* row_score = nullptr;
-  int rc = dev_alloc(ctx, &row_score, (long long)B * std::max(maxT, 1));
-  if (rc) return rc;
+  // per-frame logsumexp, B * maxT floats: the caller's scratch (no allocation on this stream) or ours
+  float* row_score = scratch;
+  if (!scratch) {
+    int rc = dev_alloc(ctx, &row_score, (long long)B * std::max(maxT, 1));
+    if (rc) return rc;
+  }
   if (maxT > 0) {
     dim3 grid((maxT + kRowWarps - 1) / kRowWarps, B);
     if (tropical)
@@ -119,7 +122,7 @@ int launch_linear_forward(
           T_dev, maxT, C, emis, stride, row_score, grad, grad_stride, deltas, delta_all, overwrite));
   }
   GTNB_LAUNCH(ctx, "linear_reduce", linear_reduce_kernel<<<B, 256, 0, ctx->stream>>>(T_dev, maxT, row_score, scores));
-  dev_free(ctx, row_score);
+  if (!scratch) dev_free(ctx, row_score);
   return GTNB_OK;
 }
 
