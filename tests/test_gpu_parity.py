@@ -505,3 +505,39 @@ def test_ctc_implicit_falls_back_on_non_finite_emissions(ctx):
     assert np.allclose(l1[~np.isnan(l1)], l0[~np.isnan(l0)], rtol=1e-5)
     assert np.allclose(np.nan_to_num(g1, posinf=0, neginf=0), np.nan_to_num(g0, posinf=0, neginf=0),
                        rtol=1e-4, atol=1e-5)
+
+
+def test_ctc_host_buffers_sub_batches_match_device_buffers(ctx):
+    """Host buffers above 16 MB are cut into sub-batches that run on their own streams (H2D, sweeps
+    and D2H overlapping); the result must equal the single-launch device-buffer call."""
+    import ctypes as Ct
+    from gtn_b200 import capi
+    L = capi.lib()
+    B, T, C, U = 24, 1000, 192, 60  # 18.4 MB of emissions -> 2 sub-batches
+    e, targets = util.bench_inputs(B, T, C, U, seed=2024)
+    lens = np.asarray([len(t) for t in targets], np.int32)
+    cat = np.ascontiguousarray(np.concatenate(targets), np.int32)
+    il = np.array([T - 7 * (b % 5) for b in range(B)], np.int32)
+    # device buffers, one launch per kernel
+    e_dev = ctx.to_device(e)
+    g_dev = ctx.alloc(e.nbytes)
+    l_dev = np.zeros(B, np.float32)
+    ctx._check(L.gtnb_ctc_loss(ctx.h, B, T, C, e_dev.ptr, 1, il.ctypes.data_as(capi._i32p),
+                               cat.ctypes.data_as(capi._i32p), lens.ctypes.data_as(capi._i32p), 0,
+                               l_dev.ctypes.data_as(capi._f32p), g_dev.ptr, 1))
+    g_from_dev = np.empty_like(e)
+    ctx._check(L.gtnb_memcpy_d2h(ctx.h, g_from_dev.ctypes.data, g_dev.ptr, e.nbytes))
+    ctx.synchronize()
+    # host buffers (pageable numpy arrays): sub-batches
+    ctx.profile(True)
+    ctx.profile_read()
+    l_host, g_host = ctx.ctc_loss(e, targets, input_lens=il)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    assert prof["implicit_forward"][0] == 2 and prof["implicit_backward"][0] == 2, prof
+    assert np.allclose(l_host, l_dev, rtol=1e-6)
+    assert np.allclose(g_host, g_from_dev, rtol=1e-5, atol=1e-6)
+    for b in range(B):
+        assert not g_host[b, il[b]:].any()
+    e_dev.free()
+    g_dev.free()
