@@ -578,12 +578,16 @@ int composed_alloc(
     int C, const float* emissions_dev, int64_t emissions_stride, std::vector<long long>& sgn,
     std::vector<long long>& sga, gtnb_lattice** out, bool implicit_only) {
   *out = nullptr;
-  int maxN = 0, maxA = 0;
+  int maxN = 0, maxA = 0, maxIn = 0, maxOut = 0;
   for (int g = 0; g < n_graphs; g++) {
     maxN = std::max(maxN, dims[g].N);
     maxA = std::max(maxA, dims[g].A);
+    maxIn = std::max(maxIn, dims[g].max_in);
+    maxOut = std::max(maxOut, dims[g].max_out);
   }
   gtnb_lattice* lat = new gtnb_lattice();
+  lat->max_in_deg = maxIn;
+  lat->max_out_deg = maxOut;
   lat->B = B;
   lat->composed = true;
   lat->linear_first = linear_first != 0;
@@ -1147,6 +1151,19 @@ int gtnb_compose_linear(
     gtnb_ctx* ctx, int B, const gtnb_graph_view* graphs, int n_graphs, int linear_first,
     const int32_t* T, int C, const float* emissions_dev, int64_t emissions_stride,
     gtnb_lattice** out) {
+  return gtnb::compose_linear_impl(ctx, B, graphs, n_graphs, linear_first, T, C, emissions_dev,
+                                   emissions_stride, false, out);
+}
+
+} // extern "C"
+
+/* implicit_only: upload the graph operands' tables and allocate the dense score rows, but build no
+ * lattice (the criteria's implicit sweeps, k_implicit.cu); GTNB_ERR_UNSUPPORTED when the operands
+ * do not qualify for them */
+int gtnb::compose_linear_impl(
+    gtnb_ctx* ctx, int B, const gtnb_graph_view* graphs, int n_graphs, int linear_first,
+    const int32_t* T, int C, const float* emissions_dev, int64_t emissions_stride, bool implicit_only,
+    gtnb_lattice** out) {
   if (!ctx || !out || B < 0 || !graphs || !T || C <= 0 || (n_graphs != B && n_graphs != 1))
     return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_compose_linear: bad arguments");
   *out = nullptr;
@@ -1205,14 +1222,27 @@ int gtnb_compose_linear(
 
   std::vector<SgDims> dims(n_graphs);
   for (int g = 0; g < n_graphs; g++) {
-    int all_valid = 1;
-    for (int lab : sg[g].in_label) all_valid &= lab >= 0;
-    dims[g] = SgDims{sg[g].N, sg[g].A, (int)sg[g].acc.size(), all_valid};
+    const SG& s = sg[g];
+    int all_valid = 1, uniform = 1, max_in = 0;
+    for (int lab : s.in_label) all_valid &= lab >= 0;
+    std::vector<int> outdeg(s.N, 0);
+    for (int d = 0; d < s.N; d++) {
+      max_in = std::max(max_in, s.in_ptr[d + 1] - s.in_ptr[d]);
+      for (int k = s.in_ptr[d]; k < s.in_ptr[d + 1]; k++) {
+        uniform &= s.in_label[k] == s.in_label[s.in_ptr[d]];
+        outdeg[s.in_src[k]]++;
+      }
+    }
+    int max_out = 0;
+    for (int n = 0; n < s.N; n++) max_out = std::max(max_out, outdeg[n]);
+    dims[g] = SgDims{s.N, s.A, (int)s.acc.size(), all_valid, uniform, max_in, max_out};
   }
+  if (implicit_only && !implicit_dims_supported(dims.data(), n_graphs))
+    return fail(ctx, GTNB_ERR_UNSUPPORTED, "graph operand does not qualify for the implicit sweeps");
   std::vector<long long> sgn, sga;
   gtnb_lattice* lat = nullptr;
   int rc = composed_alloc(ctx, B, dims.data(), n_graphs, linear_first, T, C, emissions_dev,
-                          emissions_stride, sgn, sga, &lat);
+                          emissions_stride, sgn, sga, &lat, implicit_only);
   if (rc) return rc;
   const long long tc = lat->tot_acc;
 #define TRY(x)              \
@@ -1249,7 +1279,7 @@ int gtnb_compose_linear(
     }
     TRY(upload(ctx, lat->meta, lat->meta_h.data(), B));
     TRY(upload(ctx, lat->acc_nodes, acc_stage.data(), tc));
-    TRY(launch_compose(ctx, lat));
+    if (!implicit_only) TRY(launch_compose(ctx, lat));
   }
   *out = lat;
   return GTNB_OK;
@@ -1259,6 +1289,8 @@ bad:
   return rc;
 #undef TRY
 }
+
+extern "C" {
 
 int gtnb_compose_grad(
     gtnb_ctx* ctx, gtnb_lattice* lat, float* grad_graph_dev, float* grad_emissions_dev,

@@ -60,7 +60,7 @@ static int ctc_loss_run(
     for (int u = 1; u < U; u++) skips += tg[u] != tg[u - 1];
     for (int u = 0; u < U; u++) all_valid &= tg[u] >= 0 && tg[u] < C;
     const int L = 2 * U + 1;
-    dims[b] = SgDims{L, L + (L - 1) + skips, L >= 2 ? 2 : 1, all_valid, /*uniform=*/1};
+    dims[b] = SgDims{L, L + (L - 1) + skips, L >= 2 ? 2 : 1, all_valid, /*uniform=*/1, /*max_in=*/3, /*max_out=*/3};
     tot_t += U;
     Tb[b] = input_lens ? input_lens[b] : T;
     if (Tb[b] < 0 || Tb[b] > T)
@@ -350,6 +350,8 @@ extern "C" int gtnb_asg_loss(
   int rc = GTNB_OK;
   float *e_dev = nullptr, *g_dev = nullptr, *tg_dev = nullptr, *ft_grad = nullptr, *minus1 = nullptr;
   int32_t* ft_map_dev = nullptr;
+  int32_t* status_dev = nullptr;
+  bool implicit = false, needs_exact = false;
   gtnb_lattice *den = nullptr, *num = nullptr;
 
   // transitions graph view (criterion_test.cpp:244-254)
@@ -457,16 +459,48 @@ extern "C" int gtnb_asg_loss(
     TRY(dev_alloc(ctx, &ft_map_dev, std::max<long long>(nFt, 1)));
     TRY(dev_alloc(ctx, &minus1, B));
   }
-  TRY(gtnb_compose_linear(ctx, B, &tview, 1, 1, Tb.data(), C, e_dev, per, &den));
-  TRY(gtnb_compose_linear(ctx, B, fviews.data(), B, 0, Tb.data(), C, e_dev, per, &num));
-  TRY(gtnb_forward(ctx, den, 0, nullptr, nullptr));
-  TRY(gtnb_forward(ctx, num, 0, nullptr, nullptr));
+  // implicit sweeps (k_implicit.cu): neither lattice is built; the dense transitions graph takes
+  // the G-lanes-per-node kernels, the forced-alignment chains the one-node-per-thread kernels
+  implicit = ctx->use_implicit;
+  if (implicit) {
+    rc = compose_linear_impl(ctx, B, &tview, 1, 1, Tb.data(), C, e_dev, per, true, &den);
+    if (!rc) rc = compose_linear_impl(ctx, B, fviews.data(), B, 0, Tb.data(), C, e_dev, per, true, &num);
+    if (rc == GTNB_ERR_UNSUPPORTED) {
+      if (den) gtnb_lattice_destroy(ctx, den);
+      den = nullptr;
+      implicit = false;
+      rc = GTNB_OK;
+    } else if (rc) {
+      goto done;
+    }
+  }
+  if (implicit) {
+    TRY(dev_alloc(ctx, &status_dev, 2ll * B));
+    TRYCUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * 2 * B, ctx->stream));
+    TRY(launch_implicit_forward(ctx, den, status_dev));
+    TRY(launch_implicit_forward(ctx, num, status_dev + B));
+  } else {
+    TRY(gtnb_compose_linear(ctx, B, &tview, 1, 1, Tb.data(), C, e_dev, per, &den));
+    TRY(gtnb_compose_linear(ctx, B, fviews.data(), B, 0, Tb.data(), C, e_dev, per, &num));
+    TRY(gtnb_forward(ctx, den, 0, nullptr, nullptr));
+    TRY(gtnb_forward(ctx, num, 0, nullptr, nullptr));
+  }
   if (want) {
     std::vector<float> m1(B, -1.0f);
-    TRY(gtnb_backward(ctx, den, 0, nullptr)); // +1 (subtract's gradFunc, functions.cpp:53-58)
-    TRY(gtnb_backward(ctx, num, 0, m1.data())); // -1
-    TRY(gtnb_compose_grad(ctx, den, tg_dev, g_dev, per));
-    TRY(gtnb_compose_grad(ctx, num, ft_grad, g_dev, per));
+    if (implicit) {
+      TRY(stage_begin(ctx));
+      TRY(stage_upload(ctx, minus1, m1.data(), sizeof(float) * B));
+      TRY(stage_end(ctx));
+      // +1 / -1: subtract's gradFunc (functions.cpp:53-58); graph-side gradients straight into
+      // the transitions' (shared by the batch) and the forced-alignment chains' slabs
+      TRY(launch_implicit_backward(ctx, den, nullptr, g_dev, per, 0, -1, tg_dev));
+      TRY(launch_implicit_backward(ctx, num, minus1, g_dev, per, 0, -1, ft_grad));
+    } else {
+      TRY(gtnb_backward(ctx, den, 0, nullptr)); // +1 (subtract's gradFunc, functions.cpp:53-58)
+      TRY(gtnb_backward(ctx, num, 0, m1.data())); // -1
+      TRY(gtnb_compose_grad(ctx, den, tg_dev, g_dev, per));
+      TRY(gtnb_compose_grad(ctx, num, ft_grad, g_dev, per));
+    }
     if (nFt) {
       TRY(stage_begin(ctx));
       TRY(stage_upload(ctx, ft_map_dev, ft_map.data(), sizeof(int32_t) * nFt));
@@ -478,16 +512,22 @@ extern "C" int gtnb_asg_loss(
     if (trans_grad_host)
       TRYCUDA(cudaMemcpyAsync(trans_grad_host, tg_dev, sizeof(float) * nTrans, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  TRY(readback_reserve(ctx, 2 * sizeof(float) * B));
+  TRY(readback_reserve(ctx, 4 * sizeof(float) * B));
   {
     float* d = reinterpret_cast<float*>(ctx->readback);
     float* n = d + B;
+    int32_t* st = reinterpret_cast<int32_t*>(n + B);
     TRYCUDA(cudaMemcpyAsync(d, den->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
     TRYCUDA(cudaMemcpyAsync(n, num->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (implicit)
+      TRYCUDA(cudaMemcpyAsync(st, status_dev, sizeof(int32_t) * 2 * B, cudaMemcpyDeviceToHost, ctx->stream));
     TRYCUDA(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < B; b++) losses_host[b] = d[b] - n[b];
+    if (implicit)
+      for (int b = 0; b < 2 * B; b++) needs_exact |= st[b] != 0;
   }
 done:
+  dev_free(ctx, status_dev);
   if (den) gtnb_lattice_destroy(ctx, den);
   if (num) gtnb_lattice_destroy(ctx, num);
   if (!emissions_on_device) dev_free(ctx, e_dev);
@@ -496,6 +536,14 @@ done:
   dev_free(ctx, ft_grad);
   dev_free(ctx, ft_map_dev);
   dev_free(ctx, minus1);
+  if (rc == GTNB_OK && needs_exact) {
+    // a non-finite weight: repeat through the materialised lattices, which reproduce the
+    // reference's inf / NaN propagation arc by arc
+    ctx->use_implicit = false;
+    rc = gtnb_asg_loss(ctx, B, T, C, emissions, emissions_on_device, trans_w_host, targets, target_lens,
+                       losses_host, grads, grads_on_device, trans_grad_host);
+    ctx->use_implicit = true;
+  }
   return rc;
 #undef TRY
 #undef TRYCUDA

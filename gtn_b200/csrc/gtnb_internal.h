@@ -115,6 +115,7 @@ struct gtnb_lattice {
   int forward_mode = -1;
   int C = 0;
   int max_lvl_nodes = 0, max_lvl_arcs = 0; // upper bounds over the batch
+  int max_in_deg = 0, max_out_deg = 0; // of the graph operands (composed lattices)
   int max_T = 0;
   long long tot_N = 0, tot_A = 0, tot_L = 0, tot_acc = 0, tot_bl = 0, tot_bn = 0;
   long long tot_sgN = 0, tot_sgA = 0;
@@ -168,6 +169,7 @@ struct SgDims {
   int N, A, n_acc;
   int all_valid = 0;
   int uniform = 0;
+  int max_in = 0, max_out = 0; // largest in- / out-degree of a node
 };
 int composed_alloc(
     gtnb_ctx* ctx, int B, const SgDims* dims, int n_graphs, int linear_first, const int32_t* T,
@@ -283,7 +285,10 @@ bool implicit_dims_supported(const SgDims* dims, int n_graphs);
 int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0 = 0, int nb = -1);
 int launch_implicit_backward(
     gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride,
-    int b0 = 0, int nb = -1);
+    int b0 = 0, int nb = -1, float* grad_graph = nullptr);
+int compose_linear_impl(
+    gtnb_ctx* ctx, int B, const gtnb_graph_view* graphs, int n_graphs, int linear_first, const int32_t* T,
+    int C, const float* emissions_dev, int64_t emissions_stride, bool implicit_only, gtnb_lattice** out);
 int ensure_side_streams(gtnb_ctx* ctx, int n_streams, int n_events);
 int launch_viterbi_dense(
     gtnb_ctx* ctx, int B, int T_max, int C, const int32_t* T_dev, const float* emis, int64_t stride,

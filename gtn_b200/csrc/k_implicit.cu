@@ -58,11 +58,12 @@ struct ImpLayout {
   int pitch; // floats per score row in shared memory (max over the batch, multiple of 4)
   int tabN, tabA; // table capacities
   int off_S, off_inptr, off_src, off_w, off_lab, off_flags, off_red;
-  int off_outptr, off_outent, off_cursor, off_cur, off_ng; // backward only
+  int off_outptr, off_outent, off_cursor, off_cur, off_ng, off_accg; // backward only
+  int off_sw, off_act, off_erow, off_rows3; // wide kernels
   int total;
 };
 
-ImpLayout make_imp_layout(int maxN, int maxA, bool backward) {
+ImpLayout make_imp_layout(int maxN, int maxA, bool backward, bool wide = false, int C = 0) {
   ImpLayout o;
   o.pitch = (maxN + 3) & ~3;
   o.tabN = maxN + 1;
@@ -80,13 +81,21 @@ ImpLayout make_imp_layout(int maxN, int maxA, bool backward) {
   o.off_lab = take(4 * o.tabN);
   o.off_flags = take(o.tabN);
   o.off_red = take(4 * 16);
-  o.off_outptr = o.off_outent = o.off_cursor = o.off_cur = o.off_ng = 0;
+  o.off_outptr = o.off_outent = o.off_cursor = o.off_cur = o.off_ng = o.off_accg = 0;
+  o.off_sw = o.off_act = o.off_erow = o.off_rows3 = 0;
   if (backward) {
     o.off_outptr = take(4 * (o.tabN + 1));
     o.off_outent = take(4 * o.tabA);
     o.off_cursor = take(4 * o.tabN);
     o.off_cur = take(4 * 2 * std::max(o.tabA, kFastCur));
     o.off_ng = take(4 * o.pitch);
+    o.off_accg = take(4 * o.tabA);
+  }
+  if (wide) {
+    o.off_sw = take(8 * o.tabA);
+    o.off_act = take(4 * 2 * o.tabN);
+    o.off_erow = take(4 * 2 * std::max(C, 4));
+    o.off_rows3 = take(4 * 3 * o.pitch);
   }
   o.total = off;
   return o;
@@ -378,10 +387,42 @@ __global__ void __launch_bounds__(kImpThreads) implicit_forward_kernel(
   if (bad) atomicOr(&status[blockIdx.x], 1);
 }
 
+/* out-arc lists of the graph operand (in-entries grouped by source, ascending): the node
+ * gradients are gathered through them, fixed order, no floating-point atomics */
+__device__ __forceinline__ void build_out_lists(
+    int N1, int A1, const int* t_src, int* t_outptr, int* t_outent, int* t_cursor) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i <= N1; i += kImpThreads) t_outptr[i] = 0;
+  __syncthreads();
+  for (int e = tid; e < A1; e += kImpThreads) atomicAdd(&t_outptr[t_src[e] + 1], 1);
+  __syncthreads();
+  if (tid == 0)
+    for (int u = 0; u < N1; u++) t_outptr[u + 1] += t_outptr[u];
+  __syncthreads();
+  for (int u = tid; u < N1; u += kImpThreads) t_cursor[u] = t_outptr[u];
+  __syncthreads();
+  for (int e = tid; e < A1; e += kImpThreads) t_outent[atomicAdd(&t_cursor[t_src[e]], 1)] = e;
+  __syncthreads();
+  for (int u = tid; u < N1; u += kImpThreads) {
+    const int q0 = t_outptr[u], q1 = t_outptr[u + 1];
+    for (int q = q0 + 1; q < q1; q++) {
+      const int v = t_outent[q];
+      int p = q - 1;
+      while (p >= q0 && t_outent[p] > v) {
+        t_outent[p + 1] = t_outent[p];
+        p--;
+      }
+      t_outent[p + 1] = v;
+    }
+  }
+  __syncthreads();
+}
+
 /* ------------------------------------------------------------------ */
 /* backward                                                            */
 /* ------------------------------------------------------------------ */
 
+template <bool GRAPH_GRAD>
 __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     const GraphMeta* __restrict__ meta,
     const uint8_t* __restrict__ sg_flags,
@@ -389,6 +430,8 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     const int32_t* __restrict__ sg_in_src,
     const int32_t* __restrict__ sg_in_label,
     const float* __restrict__ sg_in_w,
+    const int32_t* __restrict__ sg_in_arc,
+    float* __restrict__ grad_graph,
     const float* __restrict__ emissions,
     const float* __restrict__ scores,
     const float* __restrict__ out_scores,
@@ -414,35 +457,13 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
   int* t_cursor = reinterpret_cast<int*>(smem + lay.off_cursor);
   float* CUR = reinterpret_cast<float*>(smem + lay.off_cur); // [2][tabA]: arc gradients of a level
   float* NG = reinterpret_cast<float*>(smem + lay.off_ng); // node gradients (general path)
+  float* ACCG = reinterpret_cast<float*>(smem + lay.off_accg); // graph-arc gradients (general path)
+  const int32_t* in_arc = sg_in_arc + m.sg_arc_base;
+  float* ggr = GRAPH_GRAD ? grad_graph + m.grad_graph_off : nullptr;
 
   load_tables(m, sg_flags, sg_in_ptr, sg_in_src, sg_in_label, sg_in_w, t_inptr, t_src, t_w, t_lab, t_flags);
 
-  // out-arc lists of the graph operand (in-entries grouped by source, ascending): the node
-  // gradients are gathered through them, fixed order, no floating-point atomics
-  for (int i = tid; i <= N1; i += kImpThreads) t_outptr[i] = 0;
-  __syncthreads();
-  for (int e = tid; e < A1; e += kImpThreads) atomicAdd(&t_outptr[t_src[e] + 1], 1);
-  __syncthreads();
-  if (tid == 0)
-    for (int u = 0; u < N1; u++) t_outptr[u + 1] += t_outptr[u];
-  __syncthreads();
-  for (int u = tid; u < N1; u += kImpThreads) t_cursor[u] = t_outptr[u];
-  __syncthreads();
-  for (int e = tid; e < A1; e += kImpThreads) t_outent[atomicAdd(&t_cursor[t_src[e]], 1)] = e;
-  __syncthreads();
-  for (int u = tid; u < N1; u += kImpThreads) {
-    const int q0 = t_outptr[u], q1 = t_outptr[u + 1];
-    for (int q = q0 + 1; q < q1; q++) {
-      const int v = t_outent[q];
-      int p = q - 1;
-      while (p >= q0 && t_outent[p] > v) {
-        t_outent[p + 1] = t_outent[p];
-        p--;
-      }
-      t_outent[p + 1] = v;
-    }
-  }
-  __syncthreads();
+  build_out_lists(N1, A1, t_src, t_outptr, t_outent, t_cursor);
 
   const float out = out_scores[blockIdx.x];
   if (!finite_f(out) || T < 1) return; // no accepting path (empty lattice): no gradient
@@ -528,6 +549,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
       E2 = iexp(Sb[i2] + (w2 + e) - se);
     }
     float* gl = gem + (long long)(T - 1) * C + (has ? t_lab[tid] : 0); // emission gradient of level t
+    float ga0 = 0.0f, ga1 = 0.0f, ga2 = 0.0f; // gradients of the node's in-arcs of the graph operand
     int i0_ = 0;
     // buffers alternate with the iteration parity: iteration i writes row buffer (i & 1 ? Sb : Sa)
     // and arc-gradient buffer (i & 1 ? CURb : CURa) before its barrier and reads them after it
@@ -540,6 +562,11 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     Cw[a1] = c1;                                                                      \
     Cw[a2] = c2;                                                                      \
     const float acc = (c0 + c1) + c2;                                                 \
+    if (GRAPH_GRAD) {                                                                 \
+      ga0 += c0;                                                                      \
+      ga1 += c1;                                                                      \
+      ga2 += c2;                                                                      \
+    }                                                                                 \
     red_if(acc != 0.0f, gl, acc * delta);                                             \
     gl -= C;                                                                          \
     const float s_f = ps[j]; /* S_{t-2}[u] */                                         \
@@ -578,8 +605,17 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
       }
     }
 #undef GTNB_BWD_STEP
+    if (GRAPH_GRAD && has) {
+      // compose gradFunc, graph side (compose.cpp:500-506): the arc's gradient over all frames
+      const int e0 = t_inptr[tid];
+      atomicAdd(&ggr[in_arc[e0]], ga0 * delta);
+      if (deg > 1) atomicAdd(&ggr[in_arc[e0 + 1]], ga1 * delta);
+      if (deg > 2) atomicAdd(&ggr[in_arc[e0 + 2]], ga2 * delta);
+    }
   } else {
     // ---- general path: several nodes per thread, two barriers per level
+    if (GRAPH_GRAD)
+      for (int a = tid; a < A1; a += kImpThreads) ACCG[a] = 0.0f;
     for (int i = tid; i < N1; i += kImpThreads) {
       const float sT = sc[(long long)T * pitch + i];
       Sa[i] = sT;
@@ -604,6 +640,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
           const float c = ex ? gi * iexp(Sprev[t_src[a]] + (t_w[a] + e) - sn) : 0.0f;
           CURa[a] = c;
           acc += c;
+          if (GRAPH_GRAD) ACCG[a] += c; // entry a belongs to this thread only
         }
         if (acc != 0.0f) atomicAdd(gr + t_lab[i], acc * delta);
       }
@@ -619,7 +656,335 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
       Sprev = ts;
       // the next iteration's first barrier orders NG / Sprev writes before their reads
     }
+    if (GRAPH_GRAD) {
+      __syncthreads();
+      for (int a = tid; a < A1; a += kImpThreads)
+        if (ACCG[a] != 0.0f) atomicAdd(&ggr[in_arc[a]], ACCG[a] * delta);
+    }
   }
+}
+
+
+/* ------------------------------------------------------------------ */
+/* wide graphs (in-/out-degree > 3, e.g. the dense ASG transitions):   */
+/* G lanes per node, each holding up to kWideCap arcs in registers     */
+/* ------------------------------------------------------------------ */
+
+constexpr int kWideCap = 20;
+
+/* packed {source, weight bits} per in-entry; compact lists of the nodes that have in-arcs
+ * (t_act[0..n), n at t_act[N1]) and, for the backward, out-arcs (t_acto likewise) */
+__device__ __forceinline__ void build_wide_tables(
+    int N1, int A1, const int* t_inptr, const int* t_src, const float* t_w, const int* t_outptr, int2* t_sw,
+    int* t_act, int* t_acto) {
+  const int tid = threadIdx.x;
+  for (int a = tid; a < A1; a += kImpThreads) t_sw[a] = make_int2(t_src[a], __float_as_int(t_w[a]));
+  if (tid == 0) {
+    int n = 0;
+    for (int u = 0; u < N1; u++)
+      if (t_inptr[u + 1] > t_inptr[u]) t_act[n++] = u;
+    t_act[N1] = n;
+  }
+  if (tid == 32 && t_outptr) {
+    int n = 0;
+    for (int u = 0; u < N1; u++)
+      if (t_outptr[u + 1] > t_outptr[u]) t_acto[n++] = u;
+    t_acto[N1] = n;
+  }
+  __syncthreads();
+}
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+  return (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+}
+
+template <int G>
+__global__ void __launch_bounds__(kImpThreads) implicit_forward_wide_kernel(
+    const GraphMeta* __restrict__ meta,
+    const uint8_t* __restrict__ sg_flags,
+    const int32_t* __restrict__ sg_in_ptr,
+    const int32_t* __restrict__ sg_in_src,
+    const int32_t* __restrict__ sg_in_label,
+    const float* __restrict__ sg_in_w,
+    const float* __restrict__ emissions,
+    float* __restrict__ scores,
+    float* __restrict__ out_scores,
+    int32_t* __restrict__ status,
+    int C,
+    const ImpLayout lay) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const GraphMeta m = meta[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int N1 = m.sg_N, A1 = m.sg_A, T = m.T;
+  const int pitch = (N1 + 3) & ~3;
+  float* S = reinterpret_cast<float*>(smem + lay.off_S);
+  int* t_inptr = reinterpret_cast<int*>(smem + lay.off_inptr);
+  int* t_src = reinterpret_cast<int*>(smem + lay.off_src);
+  float* t_w = reinterpret_cast<float*>(smem + lay.off_w);
+  int* t_lab = reinterpret_cast<int*>(smem + lay.off_lab);
+  unsigned char* t_flags = smem + lay.off_flags;
+  float* red = reinterpret_cast<float*>(smem + lay.off_red);
+  int2* t_sw = reinterpret_cast<int2*>(smem + lay.off_sw);
+  int* t_act = reinterpret_cast<int*>(smem + lay.off_act);
+  float* E_s = reinterpret_cast<float*>(smem + lay.off_erow); // [2][C]: emission rows, one frame ahead
+
+  bool bad = load_tables(m, sg_flags, sg_in_ptr, sg_in_src, sg_in_label, sg_in_w, t_inptr, t_src, t_w,
+                         t_lab, t_flags);
+  build_wide_tables(N1, A1, t_inptr, t_src, t_w, nullptr, t_sw, t_act, nullptr);
+  float* sc = scores + m.node_base;
+  const float* em = emissions + m.emis_off;
+  float* prev = S;
+  float* cur = S + lay.pitch;
+  for (int i = tid; i < N1; i += kImpThreads) {
+    const float v = (t_flags[i] & 1) ? 0.0f : ninf();
+    prev[i] = v;
+    sc[i] = v;
+  }
+  if (T > 0 && tid < C) {
+    const float e0v = __ldg(em + tid);
+    E_s[tid] = e0v;
+    bad |= !finite_f(e0v);
+  }
+  __syncthreads();
+
+  constexpr int kSlots = kImpThreads / G;
+  const int sub = tid % G, slot0 = tid / G;
+  const unsigned gmask = group_mask<G>();
+  const int n_act = t_act[N1];
+  const int rounds = (n_act + kSlots - 1) / kSlots;
+  for (int t = 1; t <= T; t++) {
+    const float* Ecur = E_s + ((t - 1) & 1) * C;
+    float* Enext = E_s + (t & 1) * C;
+    const bool ld = (t < T) && tid < C; // next frame's emissions: in flight during this level
+    float enext = 0.0f;
+    if (ld) enext = __ldg(em + (long long)t * C + tid);
+    float* srow = sc + (long long)t * pitch;
+    for (int r = 0; r < rounds; r++) {
+      const int slot = r * kSlots + slot0;
+      const bool on = slot < n_act;
+      const int u = on ? t_act[slot] : 0;
+      const int e0 = on ? t_inptr[u] : 0, e1 = on ? t_inptr[u + 1] : 0;
+      const float e = on ? Ecur[t_lab[u]] : 0.0f;
+      float v[kWideCap];
+      float mx = ninf();
+#pragma unroll
+      for (int k = 0; k < kWideCap; k++) {
+        const int a = e0 + sub + k * G;
+        v[k] = ninf();
+        if (a < e1) {
+          const int2 sw = t_sw[a];
+          v[k] = prev[sw.x] + (__int_as_float(sw.y) + e);
+        }
+        mx = fmaxf(mx, v[k]);
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, o));
+      float sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < kWideCap; k++) sum += iexp(v[k] - mx);
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
+      float lg;
+      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(sum));
+      const float sv = (fabsf(mx) == CUDART_INF_F) ? mx : fmaf(lg, 0.6931471805599453f, mx);
+      if (on && sub == 0) {
+        cur[u] = sv;
+        srow[u] = sv;
+      }
+    }
+    // a node without in-arcs does not exist past frame 0
+    for (int i = tid; i < N1; i += kImpThreads)
+      if (t_inptr[i + 1] == t_inptr[i]) {
+        cur[i] = ninf();
+        srow[i] = ninf();
+      }
+    if (ld) {
+      Enext[tid] = enext;
+      bad |= !finite_f(enext);
+    }
+    float* tmp = prev;
+    prev = cur;
+    cur = tmp;
+    __syncthreads();
+  }
+
+  // accept nodes of the last frame (shortest.cpp:147-159); `prev` is the last row written
+  const float* Sf = prev;
+  float mx = ninf();
+  for (int i = tid; i < N1; i += kImpThreads)
+    if (t_flags[i] & 2) mx = fmaxf(mx, Sf[i]);
+  mx = block_max(mx, red);
+  float out = mx;
+  if (mx != CUDART_INF_F && mx != -CUDART_INF_F) {
+    float sum = 0.0f;
+    for (int i = tid; i < N1; i += kImpThreads)
+      if (t_flags[i] & 2) sum += expf(Sf[i] - mx);
+    sum = block_sum(sum, red);
+    out = mx + log1pf(sum - 1.0f);
+  }
+  if (tid == 0) out_scores[blockIdx.x] = out;
+  if (bad) atomicOr(&status[blockIdx.x], 1);
+}
+
+template <int G, bool GRAPH_GRAD>
+__global__ void __launch_bounds__(kImpThreads) implicit_backward_wide_kernel(
+    const GraphMeta* __restrict__ meta,
+    const uint8_t* __restrict__ sg_flags,
+    const int32_t* __restrict__ sg_in_ptr,
+    const int32_t* __restrict__ sg_in_src,
+    const int32_t* __restrict__ sg_in_label,
+    const float* __restrict__ sg_in_w,
+    const int32_t* __restrict__ sg_in_arc,
+    float* __restrict__ grad_graph,
+    const float* __restrict__ emissions,
+    const float* __restrict__ scores,
+    const float* __restrict__ out_scores,
+    const float* __restrict__ deltas,
+    float* __restrict__ grad_emis,
+    long long grad_stride,
+    int C,
+    const ImpLayout lay) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const GraphMeta m = meta[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int N1 = m.sg_N, A1 = m.sg_A, T = m.T;
+  const int pitch = (N1 + 3) & ~3;
+  int* t_inptr = reinterpret_cast<int*>(smem + lay.off_inptr);
+  int* t_src = reinterpret_cast<int*>(smem + lay.off_src);
+  float* t_w = reinterpret_cast<float*>(smem + lay.off_w);
+  int* t_lab = reinterpret_cast<int*>(smem + lay.off_lab);
+  unsigned char* t_flags = smem + lay.off_flags;
+  float* red = reinterpret_cast<float*>(smem + lay.off_red);
+  int* t_outptr = reinterpret_cast<int*>(smem + lay.off_outptr);
+  int* t_outent = reinterpret_cast<int*>(smem + lay.off_outent);
+  int* t_cursor = reinterpret_cast<int*>(smem + lay.off_cursor);
+  float* CUR = reinterpret_cast<float*>(smem + lay.off_cur);
+  float* NG = reinterpret_cast<float*>(smem + lay.off_ng);
+  float* ACCG = reinterpret_cast<float*>(smem + lay.off_accg);
+  int2* t_sw = reinterpret_cast<int2*>(smem + lay.off_sw);
+  int* t_act = reinterpret_cast<int*>(smem + lay.off_act);
+  int* t_acto = t_act + lay.tabN;
+  float* E_s = reinterpret_cast<float*>(smem + lay.off_erow);
+  float* R3 = reinterpret_cast<float*>(smem + lay.off_rows3); // three score rows: t, t-1, staging
+  const int32_t* in_arc = sg_in_arc + m.sg_arc_base;
+  float* ggr = GRAPH_GRAD ? grad_graph + m.grad_graph_off : nullptr;
+
+  load_tables(m, sg_flags, sg_in_ptr, sg_in_src, sg_in_label, sg_in_w, t_inptr, t_src, t_w, t_lab, t_flags);
+  build_out_lists(N1, A1, t_src, t_outptr, t_outent, t_cursor);
+  build_wide_tables(N1, A1, t_inptr, t_src, t_w, t_outptr, t_sw, t_act, t_acto);
+
+  const float out = out_scores[blockIdx.x];
+  if (!finite_f(out) || T < 1) return; // no accepting path (empty lattice): no gradient
+  const float delta = deltas ? deltas[blockIdx.x] : 1.0f;
+  const float* sc = scores + m.node_base;
+  const float* em = emissions + m.emis_off;
+  float* gem = grad_emis + (long long)blockIdx.x * grad_stride;
+
+  float mxa = ninf();
+  for (int i = tid; i < N1; i += kImpThreads)
+    if (t_flags[i] & 2) mxa = fmaxf(mxa, sc[(long long)T * pitch + i]);
+  mxa = block_max(mxa, red);
+  const float denom = expf(out - mxa);
+
+  float* own = R3; // row t
+  float* prv = R3 + lay.pitch; // row t-1
+  float* nxt = R3 + 2 * lay.pitch; // row t-2, staged during level t
+  for (int i = tid; i < N1; i += kImpThreads) {
+    const float sT = sc[(long long)T * pitch + i];
+    own[i] = sT;
+    prv[i] = sc[(long long)(T - 1) * pitch + i];
+    NG[i] = (t_flags[i] & 2) ? expf(sT - mxa) / denom : 0.0f; // shortest.cpp:49-60
+  }
+  if (GRAPH_GRAD)
+    for (int a = tid; a < A1; a += kImpThreads) ACCG[a] = 0.0f;
+  if (tid < C) E_s[((T - 1) & 1) * C + tid] = __ldg(em + (long long)(T - 1) * C + tid);
+  __syncthreads();
+
+  constexpr int kSlots = kImpThreads / G;
+  const int sub = tid % G, slot0 = tid / G;
+  const unsigned gmask = group_mask<G>();
+  const int n_act = t_act[N1], n_acto = t_acto[N1];
+  const int rounds = (n_act + kSlots - 1) / kSlots, rounds_o = (n_acto + kSlots - 1) / kSlots;
+  for (int t = T; t >= 1; t--) {
+    const float* Ecur = E_s + ((t - 1) & 1) * C; // frame t-1
+    float* Enext = E_s + (t & 1) * C; // frame t-2 (same parity as t)
+    const bool more = t >= 2;
+    float snext = ninf(), enext = 0.0f; // in flight during this level
+    if (more && tid < N1) snext = __ldg(sc + (long long)(t - 2) * pitch + tid);
+    if (more && tid < C) enext = __ldg(em + (long long)(t - 2) * C + tid);
+    float* gr = gem + (long long)(t - 1) * C;
+    // phase 1: arc gradients of level t (shortest.cpp:62-80), emission gradient per node
+    for (int r = 0; r < rounds; r++) {
+      const int slot = r * kSlots + slot0;
+      const bool on = slot < n_act;
+      const int u = on ? t_act[slot] : 0;
+      const int e0 = on ? t_inptr[u] : 0, e1 = on ? t_inptr[u + 1] : 0;
+      const int lab = on ? t_lab[u] : 0;
+      const float e = on ? Ecur[lab] : 0.0f;
+      const float g = NG[u], sn = own[u];
+      const float se = (sn == -CUDART_INF_F) ? CUDART_INF_F : sn; // missing node: factors exp(-inf)
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < kWideCap; k++) {
+        const int a = e0 + sub + k * G;
+        if (a < e1) {
+          const int2 sw = t_sw[a];
+          const float c = g * iexp(prv[sw.x] + (__int_as_float(sw.y) + e) - se);
+          CUR[a] = c;
+          acc += c;
+          if (GRAPH_GRAD) ACCG[a] += c; // entry a belongs to this lane only
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+      if (on && sub == 0 && acc != 0.0f) atomicAdd(gr + lab, acc * delta);
+    }
+    __syncthreads();
+    // phase 2: node gradients of frame t-1, gathered over the out-arcs
+    for (int r = 0; r < rounds_o; r++) {
+      const int slot = r * kSlots + slot0;
+      const bool on = slot < n_acto;
+      const int u = on ? t_acto[slot] : 0;
+      const int o0 = on ? t_outptr[u] : 0, o1 = on ? t_outptr[u + 1] : 0;
+      float sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < kWideCap; k++) {
+        const int q = o0 + sub + k * G;
+        if (q < o1) sum += CUR[t_outent[q]];
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
+      if (on && sub == 0) NG[u] = sum;
+    }
+    for (int i = tid; i < N1; i += kImpThreads)
+      if (t_outptr[i + 1] == t_outptr[i]) NG[i] = 0.0f;
+    if (tid < N1) nxt[tid] = snext;
+    if (more && tid < C) Enext[tid] = enext;
+    float* tmp = own;
+    own = prv;
+    prv = nxt;
+    nxt = tmp;
+    __syncthreads();
+  }
+  if (GRAPH_GRAD)
+    for (int a = tid; a < A1; a += kImpThreads)
+      if (ACCG[a] != 0.0f) atomicAdd(&ggr[in_arc[a]], ACCG[a] * delta);
+}
+
+} // namespace
+
+namespace {
+
+/* 0: one node per thread / several nodes per thread (implicit_*_kernel decides per CTA);
+ * otherwise the lanes per node of the wide kernels */
+int wide_lanes(int max_in, int max_out, int maxN, int C, bool backward) {
+  const int deg = backward ? std::max(max_in, max_out) : max_in;
+  if (deg <= 3 || maxN > kImpThreads || C > kImpThreads) return 0;
+  int G = 1;
+  while (G < 32 && (deg + G - 1) / G > kWideCap) G *= 2;
+  if ((deg + G - 1) / G > kWideCap) return 0;
+  return G;
 }
 
 } // namespace
@@ -631,7 +996,7 @@ bool implicit_dims_supported(const SgDims* dims, int n_graphs) {
     maxN = std::max(maxN, dims[g].N);
     maxA = std::max(maxA, dims[g].A);
   }
-  return make_imp_layout(maxN, maxA, true).total <= 200 * 1024;
+  return make_imp_layout(maxN, maxA, true, true, kImpThreads).total <= 200 * 1024;
 }
 
 /* true when every graph of the batch can take the implicit path */
@@ -639,41 +1004,86 @@ bool implicit_supported(const gtnb_lattice* lat) {
   if (!lat->composed) return false;
   for (int b = 0; b < lat->B; b++)
     if (!lat->meta_h[b].sg_uniform || !lat->meta_h[b].sg_all_valid) return false;
-  const ImpLayout lay = make_imp_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, true);
+  const ImpLayout lay = make_imp_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, true, true, kImpThreads);
   return lay.total <= 200 * 1024;
 }
+
+#define GTNB_FWD_ARGS                                                                             \
+  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_w, \
+      lat->emissions, lat->scores, lat->out_scores + b0, status_dev + b0, lat->C, lay
+#define GTNB_BWD_ARGS                                                                             \
+  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_w, \
+      lat->sg_in_arc, grad_graph, lat->emissions, lat->scores, lat->out_scores + b0,             \
+      deltas_dev ? deltas_dev + b0 : nullptr, grad_emis + (long long)b0 * grad_stride,           \
+      (long long)grad_stride, lat->C, lay
 
 /* utterances [b0, b0 + nb) of the batch (nb < 0: all): one CTA each, on ctx->stream */
 int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0, int nb) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
-  const ImpLayout lay = make_imp_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, false);
-  if (lay.total > 48 * 1024) {
-    int rc = ensure_max_smem(ctx, (const void*)implicit_forward_kernel);
-    if (rc) return rc;
+  const int G = wide_lanes(lat->max_in_deg, lat->max_out_deg, lat->max_lvl_nodes, lat->C, false);
+  const ImpLayout lay = make_imp_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, false, G > 0, lat->C);
+#define GTNB_LAUNCH_FWD(K)                                                                \
+  do {                                                                                    \
+    if (lay.total > 48 * 1024) {                                                          \
+      int rc = ensure_max_smem(ctx, (const void*)K);                                      \
+      if (rc) return rc;                                                                  \
+    }                                                                                     \
+    GTNB_LAUNCH(ctx, "implicit_forward", K<<<nb, kImpThreads, lay.total, ctx->stream>>>(GTNB_FWD_ARGS)); \
+  } while (0)
+  switch (G) {
+    case 0: GTNB_LAUNCH_FWD(implicit_forward_kernel); break;
+    case 1: GTNB_LAUNCH_FWD(implicit_forward_wide_kernel<1>); break;
+    case 2: GTNB_LAUNCH_FWD(implicit_forward_wide_kernel<2>); break;
+    case 4: GTNB_LAUNCH_FWD(implicit_forward_wide_kernel<4>); break;
+    case 8: GTNB_LAUNCH_FWD(implicit_forward_wide_kernel<8>); break;
+    case 16: GTNB_LAUNCH_FWD(implicit_forward_wide_kernel<16>); break;
+    default: GTNB_LAUNCH_FWD(implicit_forward_wide_kernel<32>); break;
   }
-  GTNB_LAUNCH(ctx, "implicit_forward",
-              implicit_forward_kernel<<<nb, kImpThreads, lay.total, ctx->stream>>>(
-                  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_w,
-                  lat->emissions, lat->scores, lat->out_scores + b0, status_dev + b0, lat->C, lay));
+#undef GTNB_LAUNCH_FWD
   return GTNB_OK;
 }
 
+/* grad_graph (may be NULL): gradients w.r.t. the graph operands' arc weights, slab of graph b at
+ * meta[b].grad_graph_off (0 for a graph shared by the batch), accumulated with atomics */
 int launch_implicit_backward(
     gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride,
-    int b0, int nb) {
+    int b0, int nb, float* grad_graph) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
-  const ImpLayout lay = make_imp_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, true);
-  if (lay.total > 48 * 1024) {
-    int rc = ensure_max_smem(ctx, (const void*)implicit_backward_kernel);
-    if (rc) return rc;
+  const int G = wide_lanes(lat->max_in_deg, lat->max_out_deg, lat->max_lvl_nodes, lat->C, true);
+  const ImpLayout lay = make_imp_layout(lat->max_lvl_nodes, lat->max_lvl_arcs, true, G > 0, lat->C);
+#define GTNB_LAUNCH_BWD(K)                                                                \
+  do {                                                                                    \
+    if (lay.total > 48 * 1024) {                                                          \
+      int rc = ensure_max_smem(ctx, (const void*)K);                                      \
+      if (rc) return rc;                                                                  \
+    }                                                                                     \
+    GTNB_LAUNCH(ctx, "implicit_backward", K<<<nb, kImpThreads, lay.total, ctx->stream>>>(GTNB_BWD_ARGS)); \
+  } while (0)
+#define GTNB_LAUNCH_BWD_G(GG)                                               \
+  do {                                                                      \
+    if (grad_graph)                                                         \
+      GTNB_LAUNCH_BWD((implicit_backward_wide_kernel<GG, true>));           \
+    else                                                                    \
+      GTNB_LAUNCH_BWD((implicit_backward_wide_kernel<GG, false>));          \
+  } while (0)
+  switch (G) {
+    case 0:
+      if (grad_graph)
+        GTNB_LAUNCH_BWD(implicit_backward_kernel<true>);
+      else
+        GTNB_LAUNCH_BWD(implicit_backward_kernel<false>);
+      break;
+    case 1: GTNB_LAUNCH_BWD_G(1); break;
+    case 2: GTNB_LAUNCH_BWD_G(2); break;
+    case 4: GTNB_LAUNCH_BWD_G(4); break;
+    case 8: GTNB_LAUNCH_BWD_G(8); break;
+    case 16: GTNB_LAUNCH_BWD_G(16); break;
+    default: GTNB_LAUNCH_BWD_G(32); break;
   }
-  GTNB_LAUNCH(ctx, "implicit_backward",
-              implicit_backward_kernel<<<nb, kImpThreads, lay.total, ctx->stream>>>(
-                  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_in_w,
-                  lat->emissions, lat->scores, lat->out_scores + b0, deltas_dev ? deltas_dev + b0 : nullptr,
-                  grad_emis + (long long)b0 * grad_stride, (long long)grad_stride, lat->C, lay));
+#undef GTNB_LAUNCH_BWD_G
+#undef GTNB_LAUNCH_BWD
   return GTNB_OK;
 }
 

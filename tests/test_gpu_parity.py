@@ -541,3 +541,38 @@ def test_ctc_host_buffers_sub_batches_match_device_buffers(ctx):
         assert not g_host[b, il[b]:].any()
     e_dev.free()
     g_dev.free()
+
+
+@pytest.mark.parametrize("shape", [(5, 48, 12, 6), (3, 30, 64, 4), (2, 7, 5, 7)])
+def test_asg_implicit_and_materialised_agree(ctx, oracle, shape):
+    """gtnb_asg_loss without building either lattice (the dense transitions graph through the
+    G-lanes-per-node sweeps, the forced-alignment chains one node per thread) against the
+    materialised lattices and the oracle.  (3, 30, 64, 4): C=64 as in BASELINE configs[2], 65
+    in-arcs per node; (2, 7, 5, 7): T == U, a single feasible alignment."""
+    B, T, C, U = shape
+    rng = np.random.default_rng(100 + T)
+    e = rng.uniform(-5, 5, (B, T, C)).astype(np.float32)
+    tw = rng.uniform(-5, 5, C + C * C).astype(np.float32)
+    targets = [rng.integers(0, C, U).astype(np.int32) for _ in range(B)]
+    targets[-1] = np.full(U, 1, np.int32)  # one label repeated
+    res = {}
+    for imp in (1, 0):
+        ctx.set_flag("implicit", imp)
+        ctx.profile(True)
+        ctx.profile_read()
+        res[imp] = ctx.asg_loss(e, tw, targets)
+        names = set(ctx.profile_read())
+        ctx.profile(False)
+        assert ("implicit_forward" in names) == bool(imp), names
+        assert ("compose_emit" in names) == (not imp), names
+    ctx.set_flag("implicit", 1)
+    assert util.close(res[1][0], res[0][0])
+    tsum = np.zeros_like(res[1][2])
+    for b in range(B):
+        lo, go, tg = oracle.asg_loss(e[b], tw, targets[b])
+        tsum += tg
+        assert util.close(res[1][0][b], lo), (b, res[1][0][b], lo)
+        assert util.grad_close(res[1][1][b], go, 5.0 * T), b
+        assert util.grad_close(res[1][1][b], res[0][1][b], 5.0 * T), b
+    assert util.grad_close(res[1][2], tsum, 5.0 * T * B)
+    assert util.grad_close(res[1][2], res[0][2], 5.0 * T * B)
