@@ -3,10 +3,8 @@
  * same names, argument meaning and error behaviour.  compose / intersect with a
  * gtn::linearGraph operand, forwardScore, viterbiScore, viterbiPath and their
  * gradients run as sm_100a kernels through the C ABI; general (epsilon / non-linear)
- * composition is host graph construction, as in the reference.
- *
- * Rational operations (concat, closure, union_, remove) are outside the scope of
- * this build.
+ * composition and the rational operations (concat, closure, union_, remove:
+ * gtn/rational.cpp) are host graph construction, as in the reference.
  */
 #pragma once
 
@@ -32,6 +30,17 @@ enum class Projection {
 Graph clone(const Graph& g, Projection projection = Projection::NONE);
 Graph projectInput(const Graph& g);
 Graph projectOutput(const Graph& g);
+
+/** Concatenation: accept states of g_i are joined to the start states of g_{i+1} by epsilon arcs (functions.cpp:93-155). */
+Graph concat(const Graph& g1, const Graph& g2);
+Graph concat(const std::vector<Graph>& graphs);
+/** Kleene closure (functions.cpp:157-190). */
+Graph closure(const Graph& g);
+/** Union (functions.cpp:192-223). */
+Graph union_(const std::vector<Graph>& graphs);
+/** Remove arcs labelled `label` (default: epsilon), bridging their end points (functions.cpp:253-318). */
+Graph remove(const Graph& g, int label = epsilon);
+Graph remove(const Graph& g, int ilabel, int olabel);
 
 /** Compose two transducers (functions.cpp:225-237). */
 Graph compose(const Graph& g1, const Graph& g2);

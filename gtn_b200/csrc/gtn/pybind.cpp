@@ -9,7 +9,9 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <sstream>
 
 #include "gtn/gtn.h"
 
@@ -126,6 +128,11 @@ PYBIND11_MODULE(_gtn, m) {
         std::ostringstream os;
         saveTxt(os, g);
         return os.str();
+      })
+      .def("__repr__", [](const Graph& g) {
+        std::ostringstream os;
+        os << g; // abbreviated for large graphs (utils.cpp:378-381)
+        return os.str();
       });
 
   // functions: single graph + list overloads (bindings/python/gtn/_functions.cpp)
@@ -154,6 +161,63 @@ PYBIND11_MODULE(_gtn, m) {
         return clone(g, p);
       },
       "g"_a, "projection"_a = Projection::NONE);
+  m.def("project_input", unaryList(projectInput), "graphs"_a);
+  m.def("project_output", unaryList(projectOutput), "graphs"_a);
+  using G = Graph;
+  using GV = std::vector<Graph>;
+  m.def("concat", binary(static_cast<G (*)(const G&, const G&)>(&concat)), "g1"_a, "g2"_a);
+  m.def("concat", binaryList(static_cast<G (*)(const G&, const G&)>(&concat)), "graphs1"_a, "graphs2"_a);
+  m.def(
+      "concat",
+      [](const GV& graphs) {
+        py::gil_scoped_release release;
+        return concat(graphs);
+      },
+      "graphs"_a);
+  m.def(
+      "concat",
+      [](const std::vector<GV>& graphs) {
+        py::gil_scoped_release release;
+        return parallelMap(static_cast<G (*)(const GV&)>(&concat), graphs);
+      },
+      "graphs"_a);
+  m.def("closure", unary(closure), "g"_a);
+  m.def("closure", unaryList(closure), "graphs"_a);
+  m.def(
+      "union",
+      [](const GV& graphs) {
+        py::gil_scoped_release release;
+        return union_(graphs);
+      },
+      "graphs"_a);
+  m.def(
+      "union",
+      [](const std::vector<GV>& graphs) {
+        py::gil_scoped_release release;
+        return parallelMap(union_, graphs);
+      },
+      "graphs"_a);
+  m.def(
+      "remove",
+      [](const G& g, int label) {
+        py::gil_scoped_release release;
+        return remove(g, label);
+      },
+      "g"_a, "label"_a = epsilon);
+  m.def(
+      "remove",
+      [](const G& g, int ilabel, int olabel) {
+        py::gil_scoped_release release;
+        return remove(g, ilabel, olabel);
+      },
+      "g"_a, "ilabel"_a, "olabel"_a);
+  m.def(
+      "remove",
+      [](const GV& graphs, const std::vector<int>& labels) {
+        py::gil_scoped_release release;
+        return parallelMap(static_cast<G (*)(const G&, int)>(&remove), graphs, labels);
+      },
+      "graphs"_a, "labels"_a = std::vector<int>{epsilon});
 
   // autograd (bindings/python/gtn/_autograd.cpp)
   m.def(
@@ -172,14 +236,19 @@ PYBIND11_MODULE(_gtn, m) {
       "g"_a, "grad"_a, "retain_graph"_a = false);
   m.def(
       "backward",
-      [](const std::vector<Graph>& gs, const std::vector<bool>& retain) {
+      [](std::vector<Graph> graphs, const std::vector<int>& retain) {
         py::gil_scoped_release release;
-        std::vector<int> idx(gs.size());
-        for (size_t i = 0; i < gs.size(); i++) idx[i] = (int)i;
-        auto one = [&](int i) { backward(gs[i], retain.size() == 1 ? retain[0] : (bool)retain[i]); };
-        parallelMap(one, idx);
+        parallelMap([](Graph g, int keep) { backward(g, keep != 0); }, graphs, retain);
       },
-      "graphs"_a, "retain_graph"_a = std::vector<bool>({false}));
+      "graphs"_a, "retain_graphs"_a = std::vector<int>({0}));
+  m.def(
+      "backward",
+      [](std::vector<Graph> graphs, const std::vector<Graph>& grads, const std::vector<int>& retain) {
+        py::gil_scoped_release release;
+        parallelMap([](Graph g, const Graph& grad, int keep) { backward(g, grad, keep != 0); }, graphs, grads,
+                    retain);
+      },
+      "graphs"_a, "grads"_a, "retain_graphs"_a = std::vector<int>({0}));
 
   // creations (bindings/python/gtn/_creations.cpp)
   m.def("scalar_graph", &scalarGraph, "val"_a, "calc_grad"_a = true);
@@ -194,8 +263,50 @@ PYBIND11_MODULE(_gtn, m) {
       },
       "function"_a, "int_list"_a);
 
-  // utils subset
+  // utils (bindings/python/gtn/_utils.cpp) and rand (_rand.cpp)
   m.def("equal", &equal, "g1"_a, "g2"_a);
+  m.def("isomorphic", &isomorphic, "g1"_a, "g2"_a);
+  m.def(
+      "write_dot",
+      [](const Graph& g, const std::string& fileName, const SymbolMap& isymbols, const SymbolMap& osymbols) {
+        draw(g, fileName, isymbols, osymbols);
+      },
+      "g"_a, "file_name"_a, "isymbols"_a = SymbolMap(), "osymbols"_a = SymbolMap());
+  m.def("load", py::overload_cast<const std::string&>(&load), "file_name"_a);
+  m.def("save", py::overload_cast<const std::string&, const Graph&>(&save), "file_name"_a, "graph"_a);
+  m.def("savetxt", py::overload_cast<const std::string&, const Graph&>(&saveTxt), "file_name"_a, "graph"_a);
+  m.def("loadtxt", py::overload_cast<const std::string&>(&loadTxt), "file_name"_a);
+  m.def(
+      "sample",
+      [](const Graph& g, size_t maxLength) {
+        py::gil_scoped_release release;
+        return sample(g, maxLength);
+      },
+      "g"_a, "max_length"_a = 1000);
+  m.def(
+      "rand_equivalent",
+      [](const Graph& g1, const Graph& g2, size_t numSamples, double tol, size_t maxLength) {
+        py::gil_scoped_release release;
+        return randEquivalent(g1, g2, numSamples, tol, maxLength);
+      },
+      "g1"_a, "g2"_a, "num_samples"_a = 1000, "tol"_a = 1e-4, "max_length"_a = 1000);
+  // in-memory forms of the two wire formats (not in the reference: handy for tests and for
+  // shipping graphs between processes without temporary files)
+  m.def("dumps", [](const Graph& g) {
+    std::ostringstream os;
+    saveTxt(os, g);
+    return os.str();
+  });
+  m.def("dumpb", [](const Graph& g) {
+    std::ostringstream os;
+    save(os, g);
+    return py::bytes(os.str());
+  });
+  m.def("loadb", [](const std::string& blob) {
+    std::istringstream in(blob);
+    return load(in);
+  });
+  m.def("srand", [](unsigned seed) { std::srand(seed); }, "seed"_a);
   m.def("loads", [](const std::string& s) {
     std::istringstream in(s);
     return loadTxt(in);

@@ -206,6 +206,14 @@ __device__ __forceinline__ void red_if(bool p, float* dst, float v) {
       : "memory");
 }
 
+/* Barrier over the first `nthreads` threads of the CTA only (a multiple of 32): warps that hold no
+ * graph node leave the frame loop altogether instead of issuing its instruction stream for
+ * nothing (CTC at U=100: 201 nodes = 7 of the 8 warps; the 8th cost 1/8 of the issue slots).
+ * Named barrier 1; __syncthreads() (barrier 0) keeps synchronising the whole CTA elsewhere. */
+__device__ __forceinline__ void bar_nodes(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
 /* three in-arcs, branch-free: absent arcs carry -inf and add exp(-inf) = 0 in arc order
  * (shortest.cpp:102-114); an all--inf (or +inf) maximum is returned as is.  The sum is >= 1
  * (the maximum contributes exp(0)), where lg2.approx has an absolute error <= 2^-22: far
@@ -307,21 +315,28 @@ __global__ void __launch_bounds__(kImpThreads) implicit_forward_kernel(
       }
     }
     const float* eml = em + (has ? t_lab[tid] : 0);
-    float pf[kPf]; // emissions of the next kPf frames (the node's label), loaded kPf frames ahead
+    // Emissions of the node's label reach the thread through two register blocks: pf[] holds
+    // frames f0 .. f0+kPf-1 (complete), nx[] frames f0+kPf .. f0+2kPf-1, in flight since the
+    // previous block boundary.  At a block boundary nx[] is copied to pf[] and the kPf loads of
+    // the block after next are issued into nx[], all together.  ptxas tracks every one of these
+    // loads on ONE scoreboard and waits for it once per block, so a load issued one frame before
+    // that wait (the former one-load-per-frame ring) stalled every block for a full memory
+    // latency: 31 % of this kernel's samples sat on that single wait (profiles/r1h_ncu_summary.txt).
+    // (Where the refill sits matters to ptxas: at the END of the block here -- all loads on one
+    // scoreboard, waited 7 frames later; at the top it spreads them over the scoreboards the
+    // LDS / MUFU results use.  The backward sweep needs it at the top.  Checked in SASS.)
+    float pf[kPf], nx[kPf];
 #pragma unroll
     for (int j = 0; j < kPf; j++) pf[j] = (has && j < T) ? __ldg(eml + (long long)j * C) : 0.0f;
-    const float* epf = eml + (long long)kPf * C;
+#pragma unroll
+    for (int j = 0; j < kPf; j++) nx[j] = (has && kPf + j < T) ? __ldg(eml + (long long)(kPf + j) * C) : 0.0f;
+    const float* epf = eml + (long long)(2 * kPf) * C; // first frame of the next refill
     float* grow = sc + pitch + tid; // this node's score in frame f + 1
     float chk = 0.0f; // becomes NaN when a used emission is not finite
     int f0 = 0;
-#define GTNB_FWD_STEP(j, GUARDED)                                        \
+#define GTNB_FWD_STEP(j)                                                 \
   {                                                                      \
     const float e = has ? pf[j] : 0.0f; /* idle threads load node 0's */ \
-    if (GUARDED)                                                         \
-      ldg_if(has && f0 + (j) + kPf < T, pf[j], epf);                     \
-    else                                                                 \
-      ldg_keep(pf[j], epf);                                              \
-    epf += C;                                                            \
     const float* P = ((j)&1) ? S1 : S0;                                  \
     float* Q = ((j)&1) ? S0 : S1;                                        \
     const float sv = lse3(P[i0] + (w0 + e), P[i1] + (w1 + e), P[i2] + (w2 + e)); \
@@ -329,21 +344,39 @@ __global__ void __launch_bounds__(kImpThreads) implicit_forward_kernel(
     Q[tid] = sv;                                                         \
     if (act) *grow = sv;                                                 \
     grow += pitch;                                                       \
-    __syncthreads();                                                     \
+    bar_nodes(nact);                                                     \
   }
-    for (; f0 + 2 * kPf <= T; f0 += kPf) {
+#define GTNB_FWD_REFILL(GUARDED)                                         \
+  {                                                                      \
+    _Pragma("unroll") for (int j = 0; j < kPf; j++) pf[j] = nx[j];       \
+    _Pragma("unroll") for (int j = 0; j < kPf; j++) {                    \
+      if (GUARDED)                                                       \
+        ldg_if(has && f0 + 2 * kPf + j < T, nx[j], epf + (long long)j * C); \
+      else                                                               \
+        ldg_keep(nx[j], epf + (long long)j * C);                         \
+    }                                                                    \
+    epf += (long long)kPf * C;                                           \
+  }
+    const int nact = (N1 + 31) & ~31; // threads of the warps that hold nodes
+    if (tid < nact) {
+      for (; f0 + 3 * kPf <= T; f0 += kPf) {
 #pragma unroll
-      for (int j = 0; j < kPf; j++) GTNB_FWD_STEP(j, false)
-    }
-    for (; f0 < T; f0 += kPf) {
+        for (int j = 0; j < kPf; j++) GTNB_FWD_STEP(j)
+        GTNB_FWD_REFILL(false)
+      }
+      for (; f0 < T; f0 += kPf) {
 #pragma unroll
-      for (int j = 0; j < kPf; j++) {
-        if (f0 + j >= T) break;
-        GTNB_FWD_STEP(j, true)
+        for (int j = 0; j < kPf; j++) {
+          if (f0 + j >= T) break;
+          GTNB_FWD_STEP(j)
+        }
+        GTNB_FWD_REFILL(true)
       }
     }
+#undef GTNB_FWD_REFILL
 #undef GTNB_FWD_STEP
     bad |= !(chk == 0.0f);
+    __syncthreads(); // the idle warps meet the others again (S rows are read below)
   } else {
     // ---- any graph: several nodes per thread, tables in shared memory
     float* prev = S0;
@@ -520,15 +553,18 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     const float* scu = sc + (act ? tid : 0);
 
     // iteration i handles level t = T - i and prepares level t - 1, for which it needs frame
-    // f = t - 2 = T - 2 - i of the saved scores and of the emissions: ring slot i % kPf
-    float ps[kPf], pe[kPf];
+    // f = t - 2 = T - 2 - i of the saved scores and of the emissions.  Two register blocks as in
+    // the forward sweep: a block of kPf iterations copies nxs/nxe (loaded during the previous
+    // block) to ps/pe and issues all loads of the next block.
+    float ps[kPf], pe[kPf], nxs[kPf], nxe[kPf];
 #pragma unroll
     for (int j = 0; j < kPf; j++) {
       const int f = T - 2 - j;
-      ps[j] = (act && f >= 0) ? __ldg(scu + (long long)f * pitch) : ninf();
-      pe[j] = (has && f >= 0) ? __ldg(eml + (long long)f * C) : 0.0f;
+      nxs[j] = (act && f >= 0) ? __ldg(scu + (long long)f * pitch) : ninf();
+      nxe[j] = (has && f >= 0) ? __ldg(eml + (long long)f * C) : 0.0f;
     }
-    const float* spf = scu + (long long)(T - 2 - kPf) * pitch; // only dereferenced while >= row 0
+    // first frame of the next refill; only dereferenced while >= row 0
+    const float* spf = scu + (long long)(T - 2 - kPf) * pitch;
     const float* epf = eml + (long long)(T - 2 - kPf) * C;
     // prologue: the arc factors of level T need row T-1 in shared memory
     float s_own = act ? __ldg(scu + (long long)T * pitch) : ninf(); // S_T[u]
@@ -553,7 +589,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     int i0_ = 0;
     // buffers alternate with the iteration parity: iteration i writes row buffer (i & 1 ? Sb : Sa)
     // and arc-gradient buffer (i & 1 ? CURb : CURa) before its barrier and reads them after it
-#define GTNB_BWD_STEP(j, GUARDED)                                                     \
+#define GTNB_BWD_STEP(j)                                                              \
   {                                                                                   \
     float* Cw = ((j)&1) ? CURb : CURa;                                                \
     float* Sw = ((j)&1) ? Sb : Sa;                                                    \
@@ -572,17 +608,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     const float s_f = ps[j]; /* S_{t-2}[u] */                                         \
     const float e_f = has ? pe[j] : 0.0f; /* e[t-2][label] */                         \
     Sw[tid] = s_f;                                                                    \
-    if (GUARDED) {                                                                    \
-      const bool inb = T - 2 - (i0_ + (j)) - kPf >= 0;                                \
-      ldg_if(act && inb, ps[j], spf);                                                 \
-      ldg_if(has && inb, pe[j], epf);                                                 \
-    } else {                                                                          \
-      ldg_keep(ps[j], spf);                                                           \
-      ldg_keep(pe[j], epf);                                                           \
-    }                                                                                 \
-    spf -= pitch;                                                                     \
-    epf -= C;                                                                         \
-    __syncthreads();                                                                  \
+    bar_nodes(nact);                                                                  \
     g = (Cw[q0] + Cw[q1]) + Cw[q2]; /* node gradient of level t-1: the serial chain */ \
     s_own = s_nxt;                                                                    \
     s_nxt = s_f;                                                                      \
@@ -593,17 +619,42 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
       E2 = iexp(Sw[i2] + (w2 + e_f) - se);                                            \
     }                                                                                 \
   }
-    for (; i0_ + 2 * kPf + 1 <= T; i0_ += kPf) {
+#define GTNB_BWD_REFILL(GUARDED)                                                      \
+  {                                                                                   \
+    _Pragma("unroll") for (int j = 0; j < kPf; j++) {                                 \
+      ps[j] = nxs[j];                                                                 \
+      pe[j] = nxe[j];                                                                 \
+    }                                                                                 \
+    _Pragma("unroll") for (int j = 0; j < kPf; j++) {                                 \
+      if (GUARDED) {                                                                  \
+        const bool inb = T - 2 - (i0_ + kPf + j) >= 0;                                \
+        ldg_if(act && inb, nxs[j], spf - (long long)j * pitch);                       \
+        ldg_if(has && inb, nxe[j], epf - (long long)j * C);                           \
+      } else {                                                                        \
+        ldg_keep(nxs[j], spf - (long long)j * pitch);                                 \
+        ldg_keep(nxe[j], epf - (long long)j * C);                                     \
+      }                                                                               \
+    }                                                                                 \
+    spf -= (long long)kPf * pitch;                                                    \
+    epf -= (long long)kPf * C;                                                        \
+  }
+    const int nact = (N1 + 31) & ~31; // threads of the warps that hold nodes (see bar_nodes)
+    if (tid < nact) {
+      for (; i0_ + 2 * kPf + 1 <= T; i0_ += kPf) {
+        GTNB_BWD_REFILL(false)
 #pragma unroll
-      for (int j = 0; j < kPf; j++) GTNB_BWD_STEP(j, false)
-    }
-    for (; i0_ < T; i0_ += kPf) {
+        for (int j = 0; j < kPf; j++) GTNB_BWD_STEP(j)
+      }
+      for (; i0_ < T; i0_ += kPf) {
+        GTNB_BWD_REFILL(true)
 #pragma unroll
-      for (int j = 0; j < kPf; j++) {
-        if (i0_ + j >= T) break;
-        GTNB_BWD_STEP(j, true)
+        for (int j = 0; j < kPf; j++) {
+          if (i0_ + j >= T) break;
+          GTNB_BWD_STEP(j)
+        }
       }
     }
+#undef GTNB_BWD_REFILL
 #undef GTNB_BWD_STEP
     if (GRAPH_GRAD && has) {
       // compose gradFunc, graph side (compose.cpp:500-506): the arc's gradient over all frames

@@ -445,6 +445,72 @@ def ref_backward(g, retain=False):
     _rc(libref().ref_backward(g.h, int(retain)))
 
 
+def ref_backward_with(g, seed, retain=False):
+    _rc(libref().ref_backward_with(g.h, seed.h, int(retain)))
+
+
+def _handles(gs):
+    return (C.c_int * len(gs))(*[g.h for g in gs])
+
+
+def ref_concat(gs):
+    return RefGraph(libref().ref_concat(_handles(gs), len(gs)))
+
+
+def ref_union(gs):
+    return RefGraph(libref().ref_union(_handles(gs), len(gs)))
+
+
+def ref_closure(g):
+    return RefGraph(libref().ref_closure(g.h))
+
+
+def ref_remove(g, ilabel=-1, olabel=None):
+    return RefGraph(libref().ref_remove(g.h, ilabel, ilabel if olabel is None else olabel))
+
+
+def ref_clone(g, projection=0):
+    return RefGraph(libref().ref_clone(g.h, projection))
+
+
+def ref_equal(a, b):
+    return bool(_rc(libref().ref_equal(a.h, b.h)))
+
+
+def ref_isomorphic(a, b):
+    return bool(_rc(libref().ref_isomorphic(a.h, b.h)))
+
+
+def ref_serialise(g, kind):
+    """kind: 0 binary save(), 1 saveTxt(), 2 operator<<, 3 draw()."""
+    R = libref()
+    R.ref_serialise.restype = C.c_longlong
+    R.ref_serialise.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_longlong]
+    n = _rc(R.ref_serialise(g.h, kind, None, 0))
+    buf = C.create_string_buffer(max(int(n), 1))
+    _rc(R.ref_serialise(g.h, kind, buf, n))
+    return buf.raw[:n]
+
+
+def ref_parse(blob, kind):
+    """kind: 0 binary load(), 1 loadTxt()."""
+    R = libref()
+    R.ref_parse.argtypes = [C.c_int, C.c_char_p, C.c_longlong]
+    return RefGraph(R.ref_parse(kind, blob, len(blob)))
+
+
+def ref_sample(g, seed, max_length=1000):
+    R = libref()
+    R.ref_sample.argtypes = [C.c_int, C.c_uint, C.c_longlong]
+    return RefGraph(R.ref_sample(g.h, seed, max_length))
+
+
+def ref_rand_equivalent(a, b, seed, num_samples=100):
+    R = libref()
+    R.ref_rand_equivalent.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int]
+    return bool(_rc(R.ref_rand_equivalent(a.h, b.h, seed, num_samples)))
+
+
 def _cat_targets(targets):
     lens = np.asarray([len(t) for t in targets], np.int32)
     cat = np.concatenate([np.asarray(t, np.int32) for t in targets]) if len(targets) else np.zeros(0, np.int32)

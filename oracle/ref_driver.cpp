@@ -12,6 +12,9 @@
  *   gtn::backward                  (gtn/autograd.h:27,37)
  *   gtn::linearGraph / scalarGraph (gtn/creations.h:25,32)
  *   gtn::parallelMap               (gtn/parallel/parallel_map.h:153)
+ *   gtn::concat / closure / union_ / remove / clone (gtn/functions.h:42-104)
+ *   gtn::equal / isomorphic / save / load / saveTxt / loadTxt / draw (gtn/utils.h:23-153)
+ *   gtn::sample / randEquivalent   (gtn/rand.h:22-40)
  *
  * Users: tests/ (to pin oracle/gtn_oracle.c and as the parity checker),
  * tests/golden/make_golden.py (fixture generator) and bench.py's
@@ -24,6 +27,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -304,6 +308,82 @@ int ref_backward_with(int a, int seed, int retain) {
   return guard([&] {
     backward(get(a), get(seed), retain != 0);
     return 0;
+  });
+}
+
+/* ---------------- host API: rational ops, utils, rand ---------------- */
+
+int ref_concat(const int* hs, int n) {
+  return guard([&] {
+    std::vector<Graph> v;
+    for (int i = 0; i < n; i++) v.push_back(get(hs[i]));
+    return put(concat(v));
+  });
+}
+int ref_union(const int* hs, int n) {
+  return guard([&] {
+    std::vector<Graph> v;
+    for (int i = 0; i < n; i++) v.push_back(get(hs[i]));
+    return put(union_(v));
+  });
+}
+int ref_closure(int a) {
+  return guard([&] { return put(closure(get(a))); });
+}
+int ref_remove(int a, int ilabel, int olabel) {
+  return guard([&] { return put(remove(get(a), ilabel, olabel)); });
+}
+int ref_clone(int a, int projection) {
+  return guard([&] { return put(clone(get(a), static_cast<Projection>(projection))); });
+}
+int ref_equal(int a, int b) {
+  return guard([&] { return equal(get(a), get(b)) ? 1 : 0; });
+}
+int ref_isomorphic(int a, int b) {
+  return guard([&] { return isomorphic(get(a), get(b)) ? 1 : 0; });
+}
+
+/* serialisers: kind 0 = binary save(), 1 = saveTxt(), 2 = operator<<, 3 = draw() without symbol
+ * maps.  Returns the byte count (copied into buf when it fits in cap). */
+long long ref_serialise(int h, int kind, char* buf, long long cap) {
+  long long n = -1;
+  int rc = guard([&] {
+    std::ostringstream os;
+    Graph g = get(h);
+    if (kind == 0) {
+      save(os, g);
+    } else if (kind == 1) {
+      saveTxt(os, g);
+    } else if (kind == 2) {
+      os << g;
+    } else {
+      draw(g, os);
+    }
+    std::string str = os.str();
+    n = (long long)str.size();
+    if (buf && n <= cap) std::memcpy(buf, str.data(), str.size());
+    return 0;
+  });
+  return rc < 0 ? rc : n;
+}
+/* kind 0 = binary load(), 1 = loadTxt() */
+int ref_parse(int kind, const char* buf, long long n) {
+  return guard([&] {
+    std::istringstream in(std::string(buf, (size_t)n));
+    return put(kind == 0 ? load(in) : loadTxt(in));
+  });
+}
+/* sample() after std::srand(seed) (rand.cpp:14-72) */
+int ref_sample(int h, unsigned seed, long long maxLength) {
+  return guard([&] {
+    std::srand(seed);
+    return put(sample(get(h), (size_t)maxLength));
+  });
+}
+int ref_rand_equivalent(int a, int b, unsigned seed, int numSamples) {
+  return guard([&] {
+    std::srand(seed);
+    return randEquivalent(get(a), get(b), (size_t)numSamples) ? 1 : 0;
   });
 }
 
