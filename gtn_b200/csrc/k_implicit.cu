@@ -342,9 +342,9 @@ __global__ void __launch_bounds__(kImpThreads) implicit_forward_kernel(
     const float sv = lse3(P[i0] + (w0 + e), P[i1] + (w1 + e), P[i2] + (w2 + e)); \
     chk = fmaf(e, 0.0f, chk);                                            \
     Q[tid] = sv;                                                         \
-    if (act) *grow = sv;                                                 \
-    grow += pitch;                                                       \
     bar_nodes(nact);                                                     \
+    if (act) *grow = sv; /* after the barrier: nothing waits for it */   \
+    grow += pitch;                                                       \
   }
 #define GTNB_FWD_REFILL(GUARDED)                                         \
   {                                                                      \
@@ -603,13 +603,16 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
       ga1 += c1;                                                                      \
       ga2 += c2;                                                                      \
     }                                                                                 \
-    red_if(acc != 0.0f, gl, acc * delta);                                             \
-    gl -= C;                                                                          \
     const float s_f = ps[j]; /* S_{t-2}[u] */                                         \
     const float e_f = has ? pe[j] : 0.0f; /* e[t-2][label] */                         \
     Sw[tid] = s_f;                                                                    \
     bar_nodes(nact);                                                                  \
     g = (Cw[q0] + Cw[q1]) + Cw[q2]; /* node gradient of level t-1: the serial chain */ \
+    /* the emission gradient of level t leaves after the barrier, in the shadow of the gather \
+       (ptxas turns the predicated red into a branch: before the barrier it delayed every   \
+       warp's arrival) */                                                             \
+    red_if(acc != 0.0f, gl, acc * delta);                                             \
+    gl -= C;                                                                          \
     s_own = s_nxt;                                                                    \
     s_nxt = s_f;                                                                      \
     { /* arc factors of level t-1; a node that does not exist (score -inf) gets exp(-inf) */ \
