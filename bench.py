@@ -197,6 +197,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's banner out of stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)

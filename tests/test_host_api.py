@@ -408,3 +408,37 @@ def test_sample_properties_and_gradient(gtn):
         gtn.srand(s)
         r = gtn.sample(d)
         assert (r.num_nodes(), r.num_arcs()) in ((0, 0), (1, 0))
+
+
+# ---------------------------------------------------------------------------------------------
+# general composition (both operands arbitrary: epsilons, cycles, any sortedness) is host graph
+# construction here as in the reference (compose.cpp:377-522); the device takes over when one
+# operand is a gtn::linearGraph (tests/test_gpu_*.py)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(24))
+def test_general_compose_matches_reference_structure_and_gradients(gtn, seed):
+    rng = np.random.default_rng(700 + seed)
+    a = random_graph(rng, int(rng.integers(1, 7)), int(rng.integers(0, 14)), n_labels=3, p_eps=0.2)
+    b = random_graph(rng, int(rng.integers(1, 7)), int(rng.integers(0, 14)), n_labels=3, p_eps=0.2)
+    intersect = seed % 3 == 0
+    if intersect:  # acceptors
+        a = (a[0], a[1], a[2], a[3], a[3].copy(), a[5])
+        b = (b[0], b[1], b[2], b[3], b[3].copy(), b[5])
+    ma, mb, ta, tb = ours_from(gtn, a), ours_from(gtn, b), ref_from(a), ref_from(b)
+    if seed & 1:  # the three matchers: unsorted, singly sorted, doubly sorted (functions.cpp:225-251)
+        ma.arc_sort(True)
+        ta.arc_sort(True)
+    if seed & 2:
+        mb.arc_sort(False)
+        tb.arc_sort(False)
+    mo = gtn.intersect(ma, mb) if intersect else gtn.compose(ma, mb)
+    to = po.ref_op("intersect" if intersect else "compose", ta, tb)
+    assert_same(mo, to, "composed graph: same node and arc numbering as the reference")
+    if mo.num_arcs():
+        seed_m, seed_t = seed_like(gtn, mo, rng)
+        gtn.backward(mo, seed_m)
+        po.ref_backward_with(to, seed_t)
+        for m, t in ((ma, ta), (mb, tb)):
+            assert np.array_equal(np.array(m.grad().weights_to_list(), np.float32).reshape(-1), t.grad().weights())
