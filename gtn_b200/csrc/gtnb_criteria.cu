@@ -149,6 +149,16 @@ static int ctc_loss_run(
   // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
   TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
   if (implicit) {
+    // the sweeps: k_implicit.cu, or (experimental flag) the temporally blocked ones of k_banded.cu
+    const bool banded = ctx->use_banded && banded_supported(lat);
+    auto sweep_forward = [&](int b0, int nb) {
+      return banded ? launch_banded_forward(ctx, lat, status_dev, b0, nb)
+                    : launch_implicit_forward(ctx, lat, status_dev, b0, nb);
+    };
+    auto sweep_backward = [&](int b0, int nb) {
+      return banded ? launch_banded_backward(ctx, lat, deltas_dev, g_dev, per, b0, nb)
+                    : launch_implicit_backward(ctx, lat, deltas_dev, g_dev, per, b0, nb);
+    };
     // everything below only needs what is already enqueued on the main stream (graphs, staging,
     // the memset of the gradients) plus its own slice of the emissions
     cudaEvent_t ev_setup = ctx->side_events[K], ev_lin = ctx->side_events[K + 1];
@@ -163,9 +173,9 @@ static int ctc_loss_run(
       ctx->stream = main_stream;
       if (rc) goto done;
       TRYCUDA(cudaEventRecord(ev_lin, ctx->copy_stream));
-      TRY(launch_implicit_forward(ctx, lat, status_dev));
+      TRY(sweep_forward(0, -1));
       TRYCUDA(cudaStreamWaitEvent(main_stream, ev_lin, 0));
-      if (grads) TRY(launch_implicit_backward(ctx, lat, deltas_dev, g_dev, per));
+      if (grads) TRY(sweep_backward(0, -1));
     } else {
       for (int k = 0; k < K && !rc; k++) {
         const int b0 = chunk_lo[k], nb = chunk_lo[k + 1] - chunk_lo[k];
@@ -176,8 +186,8 @@ static int ctc_loss_run(
         rc = launch_linear_forward(ctx, nb, T_dev + b0, maxT, C, e_dev + (long long)b0 * per, per, 0,
                                    z_dev + b0, g_dev ? g_dev + (long long)b0 * per : nullptr, per, nullptr,
                                    1.0f, input_lens ? 0 : 1, row_scratch + (long long)b0 * std::max(maxT, 1));
-        if (!rc) rc = launch_implicit_forward(ctx, lat, status_dev, b0, nb);
-        if (!rc && grads) rc = launch_implicit_backward(ctx, lat, deltas_dev, g_dev, per, b0, nb);
+        if (!rc) rc = sweep_forward(b0, nb);
+        if (!rc && grads) rc = sweep_backward(b0, nb);
         ctx->stream = main_stream;
         if (rc) goto done;
         if (grads && !grads_on_device)

@@ -3,6 +3,8 @@
 Bit-exact for indices / paths, 1e-4 relative (+1e-5 abs, see tests/util.py) for
 scores and gradients -- BASELINE.json:north_star.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -576,3 +578,42 @@ def test_asg_implicit_and_materialised_agree(ctx, oracle, shape):
         assert util.grad_close(res[1][1][b], res[0][1][b], 5.0 * T), b
     assert util.grad_close(res[1][2], tsum, 5.0 * T * B)
     assert util.grad_close(res[1][2], res[0][2], 5.0 * T * B)
+
+
+# ---------------------------------------------------------------------------
+# EXPERIMENTAL: temporally blocked CTC sweeps (k_banded.cu), opt-in.  Written when round 1 had no GPU
+# time left: run with GTNB_EXPERIMENTAL=1 once a GPU is available, then drop the gate.
+# ---------------------------------------------------------------------------
+
+@pytest.mark.skipif(os.environ.get("GTNB_EXPERIMENTAL") != "1",
+                    reason="k_banded.cu has not been run on a GPU yet (set GTNB_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("shape", [(4, 120, 16, 9), (3, 37, 8, 1), (2, 200, 32, 90), (2, 9, 5, 4), (3, 64, 28, 30),
+                                   (2, 1000, 64, 100)])
+def test_ctc_banded_sweeps_agree_with_implicit_and_oracle(ctx, oracle, shape):
+    """gtnb_ctx_set_flag("banded", 1): K frames per barrier, neighbour scores through warp shuffles
+    (lane arithmetic pinned by scripts/banded_model.py).  Same losses / gradients as k_implicit.cu
+    and the oracle, ragged input lengths included."""
+    B, T, C, U = shape
+    e, targets = util.bench_inputs(B, T, C, U, seed=2468)
+    lens = np.array([T - (3 * b) % max(T // 2, 1) for b in range(B)], np.int32)
+    res = {}
+    for banded in (0, 1):
+        ctx.set_flag("banded", banded)
+        ctx.profile(True)
+        ctx.profile_read()
+        try:
+            res[banded] = ctx.ctc_loss(e, targets, input_lens=lens)
+        finally:
+            ctx.set_flag("banded", 0)
+        names = set(ctx.profile_read())
+        ctx.profile(False)
+        assert ("banded_forward" in names) == bool(banded), names
+        assert "compose_emit" not in names, names  # no fallback to the materialised lattice
+    assert util.close(res[1][0], res[0][0])
+    for b in range(B):
+        lo, go = oracle.ctc_loss(e[b, :lens[b]], targets[b], 0, True)
+        assert util.close(res[1][0][b], lo), (b, res[1][0][b], lo)
+        if np.isfinite(lo):
+            assert util.grad_close(res[1][1][b, :lens[b]], go, 5.0 * T), b
+            assert util.grad_close(res[1][1][b], res[0][1][b], 5.0 * T), b
+        assert not res[1][1][b, lens[b]:].any()
