@@ -29,12 +29,19 @@
  * Not applicable (status bit 2 -> the caller repeats the call through the other kernels): an
  * in-arc from outside the band, two in-arcs from the same source, in-degree > 3.
  */
+#ifdef GTNB_HOST_EMU // the kernels below compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <algorithm>
+
+#include "gtnb_meta.h"
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include <algorithm>
 
 #include "gtnb_internal.h"
+#endif
 
 namespace gtnb {
 
@@ -49,19 +56,32 @@ __device__ __forceinline__ float b_ninf() {
 __device__ __forceinline__ bool b_finite(float x) {
   return fabsf(x) < CUDART_INF_F;
 }
+#ifdef GTNB_HOST_EMU
+__device__ __forceinline__ float b_iexp(float x) {
+  return exp2f(x * 1.4426950408889634f);
+}
+__device__ __forceinline__ float b_lg2(float x) {
+  return log2f(x);
+}
+__device__ __forceinline__ void b_ldg_if(bool p, float& dst, const float* src) {
+  if (p) dst = *src;
+}
+__device__ __forceinline__ void b_ldg_keep(float& dst, const float* src) {
+  dst = *src;
+}
+__device__ __forceinline__ void b_red_if(bool p, float* dst, float v) {
+  if (p) atomicAdd(dst, v);
+}
+#else
 __device__ __forceinline__ float b_iexp(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
   return y;
 }
-/* as lse3 of k_implicit.cu */
-__device__ __forceinline__ float b_lse3(float v0, float v1, float v2) {
-  const float mx = fmaxf(fmaxf(v0, v1), v2);
-  const float sum = (b_iexp(v0 - mx) + b_iexp(v1 - mx)) + b_iexp(v2 - mx);
-  float lg;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(sum));
-  const float r = fmaf(lg, 0.6931471805599453f, mx);
-  return (fabsf(mx) == CUDART_INF_F) ? mx : r;
+__device__ __forceinline__ float b_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void b_ldg_if(bool p, float& dst, const float* src) {
   asm volatile(
@@ -85,6 +105,14 @@ __device__ __forceinline__ void b_red_if(bool p, float* dst, float v) {
       "}\n" ::"l"(dst),
       "f"(v), "r"((int)p)
       : "memory");
+}
+#endif
+/* as lse3 of k_implicit.cu */
+__device__ __forceinline__ float b_lse3(float v0, float v1, float v2) {
+  const float mx = fmaxf(fmaxf(v0, v1), v2);
+  const float sum = (b_iexp(v0 - mx) + b_iexp(v1 - mx)) + b_iexp(v2 - mx);
+  const float r = fmaf(b_lg2(sum), 0.6931471805599453f, mx);
+  return (fabsf(mx) == CUDART_INF_F) ? mx : r;
 }
 
 /* CTA-wide max / sum for any number of warps <= 32; `red` holds 32 floats */
@@ -170,7 +198,7 @@ __global__ void __launch_bounds__(kBandMaxThreads) banded_forward_kernel(
     int row_pitch) {
   static_assert(kBandPf % K == 0, "a prefetch block is a whole number of barrier intervals");
   constexpr int H = 2 * K, OWN = 32 - H;
-  extern __shared__ __align__(16) float b_smem[];
+  GTNB_DYNAMIC_SMEM(float, b_smem);
   float* row0 = b_smem; // exchange rows: scores of all nodes at a block boundary
   float* row1 = b_smem + row_pitch;
   float* red = b_smem + 2 * row_pitch;
@@ -306,7 +334,7 @@ __global__ void __launch_bounds__(kBandMaxThreads) banded_backward_kernel(
     int row_pitch) {
   static_assert(kBandPf % K == 0, "a prefetch block is a whole number of barrier intervals");
   constexpr int H = 2 * K, OWN = 30 - H;
-  extern __shared__ __align__(16) float b_smem[];
+  GTNB_DYNAMIC_SMEM(float, b_smem);
   float* row0 = b_smem; // exchange rows: node gradients at a block boundary
   float* row1 = b_smem + row_pitch;
   float* red = b_smem + 2 * row_pitch;
@@ -427,6 +455,8 @@ constexpr int kBandK = 4; // frames per barrier
 
 } // namespace
 
+#ifndef GTNB_HOST_EMU
+
 /* true when the banded sweeps can take this batch (checked on the host: sizes; the band shape
  * itself is checked by the forward kernel, status bit 2) */
 bool banded_supported(const gtnb_lattice* lat) {
@@ -468,5 +498,7 @@ int launch_banded_backward(
                   (long long)grad_stride, lat->C, row_pitch));
   return GTNB_OK;
 }
+
+#endif // GTNB_HOST_EMU
 
 } // namespace gtnb

@@ -32,12 +32,19 @@
  * reference's NaN / inf propagation arc by arc.  Requires: no epsilon labels, all labels in
  * [0, C), all in-arcs of a graph node carry the same label (CTC, forced alignment, ASG).
  */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <algorithm>
+
+#include "gtnb_meta.h"
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include <algorithm>
 
 #include "gtnb_internal.h"
+#endif
 
 namespace gtnb {
 
@@ -107,15 +114,32 @@ __device__ __forceinline__ float ninf() {
 __device__ __forceinline__ bool finite_f(float x) {
   return fabsf(x) < CUDART_INF_F;
 }
-/* exp / log1p on the SFU, as in k_staged.cu */
-__device__ __forceinline__ float iexp(float x) {
+/* the two SFU primitives (the host emulation of tests/emu substitutes exp2f / log2f) */
+#ifdef GTNB_HOST_EMU
+__device__ __forceinline__ float sfu_ex2(float x) {
+  return exp2f(x);
+}
+__device__ __forceinline__ float sfu_lg2(float x) {
+  return log2f(x);
+}
+#else
+__device__ __forceinline__ float sfu_ex2(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float ilog1p(float x) {
+__device__ __forceinline__ float sfu_lg2(float x) {
   float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(1.0f + x));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#endif
+/* exp / log1p on the SFU, as in k_staged.cu */
+__device__ __forceinline__ float iexp(float x) {
+  return sfu_ex2(x * 1.4426950408889634f);
+}
+__device__ __forceinline__ float ilog1p(float x) {
+  const float y = sfu_lg2(1.0f + x);
   return (x < 1e-3f) ? x * (1.0f - 0.5f * x) : y * 0.6931471805599453f;
 }
 
@@ -176,6 +200,10 @@ __device__ __forceinline__ bool load_tables(
  * block at its end, into temporaries, and copies them to the loop-carried registers at the
  * back edge -- a full-latency stall every kPf frames (ncu: 21 % of all samples on that MOV). */
 __device__ __forceinline__ void ldg_if(bool p, float& dst, const float* src) {
+#ifdef GTNB_HOST_EMU
+  if (p) dst = *src;
+  return;
+#else
   asm volatile(
       "{\n"
       ".reg .pred q;\n"
@@ -184,6 +212,7 @@ __device__ __forceinline__ void ldg_if(bool p, float& dst, const float* src) {
       "}\n"
       : "+f"(dst)
       : "l"(src), "r"((int)p));
+#endif
 }
 /* (Measured alternatives, both slower at B=256: a 2-deep register ring behind prefetch.global.L1
  * issued 8 frames ahead -- 0.33 vs 0.27 ms for the backward; prefetching the three source scores
@@ -192,10 +221,18 @@ __device__ __forceinline__ void ldg_if(bool p, float& dst, const float* src) {
  * (relaxed, CTA scope) load, which ptxas must keep on its side of the bar.sync it was written
  * on, writing the loop-carried ring register directly. */
 __device__ __forceinline__ void ldg_keep(float& dst, const float* src) {
+#ifdef GTNB_HOST_EMU
+  dst = *src;
+#else
   asm volatile("ld.relaxed.cta.global.f32 %0, [%1];" : "=f"(dst) : "l"(src) : "memory");
+#endif
 }
 /* predicated red.global.add.f32 (no branch, no reconvergence point in the frame loop) */
 __device__ __forceinline__ void red_if(bool p, float* dst, float v) {
+#ifdef GTNB_HOST_EMU
+  if (p) atomicAdd(dst, v);
+  return;
+#else
   asm volatile(
       "{\n"
       ".reg .pred q;\n"
@@ -204,6 +241,7 @@ __device__ __forceinline__ void red_if(bool p, float* dst, float v) {
       "}\n" ::"l"(dst),
       "f"(v), "r"((int)p)
       : "memory");
+#endif
 }
 
 /* Barrier over the first `nthreads` threads of the CTA only (a multiple of 32): warps that hold no
@@ -211,7 +249,11 @@ __device__ __forceinline__ void red_if(bool p, float* dst, float v) {
  * nothing (CTC at U=100: 201 nodes = 7 of the 8 warps; the 8th cost 1/8 of the issue slots).
  * Named barrier 1; __syncthreads() (barrier 0) keeps synchronising the whole CTA elsewhere. */
 __device__ __forceinline__ void bar_nodes(int nthreads) {
+#ifdef GTNB_HOST_EMU
+  emu::named_barrier(1, nthreads);
+#else
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+#endif
 }
 
 /* three in-arcs, branch-free: absent arcs carry -inf and add exp(-inf) = 0 in arc order
@@ -221,9 +263,7 @@ __device__ __forceinline__ void bar_nodes(int nthreads) {
 __device__ __forceinline__ float lse3(float v0, float v1, float v2) {
   const float mx = fmaxf(fmaxf(v0, v1), v2);
   const float sum = (iexp(v0 - mx) + iexp(v1 - mx)) + iexp(v2 - mx);
-  float lg;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(sum));
-  const float r = fmaf(lg, 0.6931471805599453f, mx);
+  const float r = fmaf(sfu_lg2(sum), 0.6931471805599453f, mx);
   return (fabsf(mx) == CUDART_INF_F) ? mx : r;
 }
 
@@ -257,7 +297,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_forward_kernel(
     int32_t* __restrict__ status,
     int C,
     const ImpLayout lay) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  GTNB_DYNAMIC_SMEM(unsigned char, smem);
   const GraphMeta m = meta[blockIdx.x];
   const int tid = threadIdx.x;
   const int N1 = m.sg_N, T = m.T;
@@ -473,7 +513,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_kernel(
     long long grad_stride,
     int C,
     const ImpLayout lay) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  GTNB_DYNAMIC_SMEM(unsigned char, smem);
   const GraphMeta m = meta[blockIdx.x];
   const int tid = threadIdx.x;
   const int N1 = m.sg_N, A1 = m.sg_A, T = m.T;
@@ -767,7 +807,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_forward_wide_kernel(
     int32_t* __restrict__ status,
     int C,
     const ImpLayout lay) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  GTNB_DYNAMIC_SMEM(unsigned char, smem);
   const GraphMeta m = meta[blockIdx.x];
   const int tid = threadIdx.x;
   const int N1 = m.sg_N, A1 = m.sg_A, T = m.T;
@@ -839,8 +879,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_forward_wide_kernel(
       for (int k = 0; k < kWideCap; k++) sum += iexp(v[k] - mx);
 #pragma unroll
       for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
-      float lg;
-      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(sum));
+      const float lg = sfu_lg2(sum);
       const float sv = (fabsf(mx) == CUDART_INF_F) ? mx : fmaf(lg, 0.6931471805599453f, mx);
       if (on && sub == 0) {
         cur[u] = sv;
@@ -899,7 +938,7 @@ __global__ void __launch_bounds__(kImpThreads) implicit_backward_wide_kernel(
     long long grad_stride,
     int C,
     const ImpLayout lay) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  GTNB_DYNAMIC_SMEM(unsigned char, smem);
   const GraphMeta m = meta[blockIdx.x];
   const int tid = threadIdx.x;
   const int N1 = m.sg_N, A1 = m.sg_A, T = m.T;
@@ -1043,6 +1082,8 @@ int wide_lanes(int max_in, int max_out, int maxN, int C, bool backward) {
 
 } // namespace
 
+#ifndef GTNB_HOST_EMU
+
 bool implicit_dims_supported(const SgDims* dims, int n_graphs) {
   int maxN = 0, maxA = 0;
   for (int g = 0; g < n_graphs; g++) {
@@ -1140,5 +1181,7 @@ int launch_implicit_backward(
 #undef GTNB_LAUNCH_BWD
   return GTNB_OK;
 }
+
+#endif // GTNB_HOST_EMU
 
 } // namespace gtnb

@@ -1,0 +1,97 @@
+/*
+ * tests/emu/implicit_emu.cpp -- TEST INFRASTRUCTURE: runs the SOURCE of gtn_b200/csrc/k_implicit.cu
+ * (the criterion's implicit-lattice sweeps: the hot kernels of bench.py) on the CPU through
+ * tests/emu/simt_emu.h.  Only the launch geometry and the device tables are restated here.
+ */
+#define GTNB_HOST_EMU 1
+#include "../../gtn_b200/csrc/k_implicit.cu"
+
+#include <vector>
+
+using gtnb::GraphMeta;
+
+namespace {
+
+struct Tables {
+  std::vector<GraphMeta> meta;
+  std::vector<uint8_t> flags;
+  std::vector<int32_t> in_ptr, in_src, in_label, in_arc;
+  std::vector<float> in_w;
+  long long scores_len = 0;
+  int maxN = 0, maxA = 0;
+};
+
+/* graph b given as CSR by destination: ptr[N+1], src, label, w (labels already matched) */
+void add_graph(Tables& t, int b, int T_frames, long long emis_off, int N, const uint8_t* fl, const int32_t* ptr,
+               const int32_t* src, const int32_t* label, const float* w) {
+  GraphMeta m;
+  std::memset(&m, 0, sizeof(m));
+  m.sg_node_base = (long long)t.in_ptr.size();
+  m.sg_arc_base = (long long)t.in_src.size();
+  m.emis_off = emis_off;
+  m.node_base = t.scores_len;
+  m.T = T_frames;
+  m.sg_N = N;
+  m.sg_A = ptr[N];
+  for (int n = 0; n <= N; n++) t.in_ptr.push_back(ptr[n]);
+  for (int n = 0; n < N; n++) t.flags.push_back(fl[n]);
+  t.flags.push_back(0);
+  for (int a = 0; a < ptr[N]; a++) {
+    t.in_src.push_back(src[a]);
+    t.in_label.push_back(label[a]);
+    t.in_w.push_back(w[a]);
+    t.in_arc.push_back(a);
+  }
+  const int pitch = (N + 3) & ~3;
+  t.scores_len += (long long)(T_frames + 1) * pitch;
+  t.maxN = std::max(t.maxN, N);
+  t.maxA = std::max(t.maxA, (int)ptr[N]);
+  t.meta.push_back(m);
+  (void)b;
+}
+
+} // namespace
+
+extern "C" {
+
+/*
+ * forwardScore(intersect(g_b, emissions_b)) and its backward (deltas = -1, as gtnb_ctc_loss seeds
+ * it) for B graphs given as concatenated CSR-by-destination tables:
+ *   n_nodes[B]; node_flags (bit 0 start, bit 1 accept), in_ptr (N_b + 1 entries per graph, arc
+ *   offsets local to the graph), in_src / in_label / in_w per in-entry.
+ *   emissions [B][T][C], input_lens[B]; out_scores[B]; grad [B][T][C] zero on entry; status[B].
+ */
+int emu_implicit(
+    int B, int T, int C, const float* emissions, const int32_t* input_lens, const int32_t* n_nodes,
+    const uint8_t* node_flags, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label,
+    const float* in_w, float* out_scores, float* grad, int32_t* status) {
+  Tables t;
+  long long nb = 0, pb = 0, ab = 0;
+  for (int b = 0; b < B; b++) {
+    const int N = n_nodes[b];
+    add_graph(t, b, input_lens ? input_lens[b] : T, (long long)b * T * C, N, node_flags + nb, in_ptr + pb,
+              in_src + ab, in_label + ab, in_w + ab);
+    ab += in_ptr[pb + N];
+    nb += N;
+    pb += N + 1;
+  }
+  std::vector<float> scores((size_t)t.scores_len + 16, 0.0f);
+  for (int b = 0; b < B; b++) status[b] = 0;
+  const gtnb::ImpLayout lf = gtnb::make_imp_layout(t.maxN, t.maxA, false);
+  emu::launch(B, gtnb::kImpThreads, lf.total, [&] {
+    gtnb::implicit_forward_kernel(t.meta.data(), t.flags.data(), t.in_ptr.data(), t.in_src.data(),
+                                  t.in_label.data(), t.in_w.data(), emissions, scores.data(), out_scores, status,
+                                  C, lf);
+  });
+  std::vector<float> deltas(B, -1.0f);
+  const gtnb::ImpLayout lb = gtnb::make_imp_layout(t.maxN, t.maxA, true);
+  emu::launch(B, gtnb::kImpThreads, lb.total, [&] {
+    gtnb::implicit_backward_kernel<false>(t.meta.data(), t.flags.data(), t.in_ptr.data(), t.in_src.data(),
+                                          t.in_label.data(), t.in_w.data(), t.in_arc.data(), nullptr, emissions,
+                                          scores.data(), out_scores, deltas.data(), grad, (long long)T * C, C,
+                                          lb);
+  });
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,186 @@
+/*
+ * tests/emu/simt_emu.h -- TEST INFRASTRUCTURE: a minimal SIMT emulator, so that the source of a CUDA
+ * kernel (not a restatement of it) can be compiled with g++ and run on the CPU in the `-m "not gpu"`
+ * suite.  One std::thread per CUDA thread, one CTA at a time; __syncthreads() is a std::barrier over
+ * the CTA, warp shuffles exchange through a per-warp slot array between two phases of a per-warp
+ * barrier.  It checks index arithmetic, barrier placement (a misplaced barrier deadlocks or trips the
+ * result), shuffle semantics and tails; it does not model the memory system or timing.
+ *
+ * A kernel file opts in with `#ifdef GTNB_HOST_EMU` around its CUDA includes, its inline PTX
+ * helpers and its launchers (gtn_b200/csrc/k_banded.cu).
+ */
+#pragma once
+
+#include <array>
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(x) alignas(x)
+#define CUDART_INF_F (__builtin_inff())
+
+namespace emu {
+
+struct Dim3 {
+  unsigned x = 1, y = 1, z = 1;
+};
+
+struct Cta {
+  Cta(unsigned nthreads, size_t smem_bytes)
+      : bar(nthreads), smem(smem_bytes + 64), slots((nthreads + 31) / 32) {
+    for (unsigned w = 0; w < (nthreads + 31) / 32; w++) {
+      const unsigned lanes = std::min(32u, nthreads - 32 * w);
+      warp_bar.emplace_back(new std::barrier<>(lanes));
+    }
+  }
+  float* dynamic_smem() {
+    auto p = reinterpret_cast<uintptr_t>(smem.data());
+    return reinterpret_cast<float*>((p + 15) & ~uintptr_t(15));
+  }
+  std::barrier<>& named(int id, int nthreads) {
+    std::lock_guard<std::mutex> l(named_lock);
+    auto& b = named_bars[id];
+    if (!b) b.reset(new std::barrier<>(nthreads));
+    return *b;
+  }
+  std::barrier<> bar;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+  std::vector<unsigned char> smem;
+  std::vector<std::array<uint32_t, 32>> slots;
+  std::mutex named_lock;
+  std::map<int, std::unique_ptr<std::barrier<>>> named_bars; // bar.sync id, n (n fixed per id)
+  std::atomic<int> vote{0};
+};
+
+inline thread_local Cta* g_cta = nullptr;
+
+} // namespace emu
+
+inline thread_local emu::Dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+namespace emu {
+
+/* run `body()` once per thread of a grid x block launch, CTAs one after the other */
+template <class F>
+void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& body) {
+  for (unsigned b = 0; b < grid; b++) {
+    Cta cta(block, smem_bytes);
+    std::vector<std::thread> threads;
+    threads.reserve(block);
+    for (unsigned t = 0; t < block; t++) {
+      threads.emplace_back([&, t] {
+        g_cta = &cta;
+        threadIdx = Dim3{t, 0, 0};
+        blockIdx = Dim3{b, 0, 0};
+        blockDim = Dim3{block, 1, 1};
+        gridDim = Dim3{grid, 1, 1};
+        body();
+        // an exited thread no longer takes part in barriers
+        cta.bar.arrive_and_drop();
+        cta.warp_bar[t / 32]->arrive_and_drop();
+      });
+    }
+    for (auto& th : threads) th.join();
+  }
+}
+
+inline uint32_t exchange(uint32_t v, int src_lane) {
+  Cta& c = *g_cta;
+  const unsigned w = threadIdx.x / 32, l = threadIdx.x % 32;
+  c.slots[w][l] = v;
+  c.warp_bar[w]->arrive_and_wait();
+  const uint32_t r = c.slots[w][src_lane];
+  c.warp_bar[w]->arrive_and_wait();
+  return r;
+}
+template <class T>
+T shfl(T v, int src_lane) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  uint32_t bits;
+  std::memcpy(&bits, &v, 4);
+  bits = exchange(bits, src_lane);
+  std::memcpy(&v, &bits, 4);
+  return v;
+}
+
+/* bar.sync id, nthreads: the first nthreads threads of the CTA (the same count at every use) */
+inline void named_barrier(int id, int nthreads) {
+  g_cta->named(id, nthreads).arrive_and_wait();
+}
+
+} // namespace emu
+
+inline void __syncthreads() {
+  emu::g_cta->bar.arrive_and_wait();
+}
+inline int __syncthreads_or(int pred) {
+  emu::Cta& c = *emu::g_cta;
+  if (pred) c.vote.store(1);
+  c.bar.arrive_and_wait();
+  const int r = c.vote.load();
+  c.bar.arrive_and_wait();
+  if (threadIdx.x == 0) c.vote.store(0);
+  c.bar.arrive_and_wait();
+  return r;
+}
+template <class T>
+T __shfl_up_sync(unsigned, T v, int d) {
+  const int l = threadIdx.x % 32;
+  return emu::shfl(v, l >= d ? l - d : l);
+}
+template <class T>
+T __shfl_down_sync(unsigned, T v, int d) {
+  const int l = threadIdx.x % 32;
+  return emu::shfl(v, l + d < 32 ? l + d : l);
+}
+template <class T>
+T __shfl_xor_sync(unsigned, T v, int m) {
+  const int l = threadIdx.x % 32;
+  return emu::shfl(v, l ^ m);
+}
+template <class T>
+T __ldg(const T* p) {
+  return *p;
+}
+inline int atomicOr(int32_t* p, int v) {
+  return std::atomic_ref<int32_t>(*p).fetch_or(v);
+}
+inline float atomicAdd(float* p, float v) {
+  return std::atomic_ref<float>(*p).fetch_add(v);
+}
+inline int atomicAdd(int* p, int v) {
+  return std::atomic_ref<int>(*p).fetch_add(v);
+}
+struct int2 {
+  int x, y;
+};
+inline int2 make_int2(int x, int y) {
+  return int2{x, y};
+}
+inline int __float_as_int(float f) {
+  int i;
+  std::memcpy(&i, &f, 4);
+  return i;
+}
+inline float __int_as_float(int i) {
+  float f;
+  std::memcpy(&f, &i, 4);
+  return f;
+}
+
+/* dynamic shared memory of the running CTA, 16-byte aligned */
+#define GTNB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_cta->dynamic_smem())

@@ -1,0 +1,141 @@
+"""The SOURCE of gtn_b200/csrc/k_implicit.cu -- the criterion's implicit-lattice forward / backward sweeps,
+the hot kernels of bench.py -- compiled with g++ against the SIMT emulator of tests/emu/simt_emu.h and run
+on the CPU (one std::thread per CUDA thread) against the oracle.
+
+What this pins without a GPU: the one-node-per-thread fast path with its register prefetch blocks, guarded
+tails and the named barrier the idle warps skip; the several-nodes-per-thread general path (more than 256
+graph nodes); ragged input lengths; the non-finite-weight status bit.  The SFU instructions are replaced
+by exp2f / log2f, and nothing is said about speed -- the GPU parity tests (tests/test_gpu_parity.py) stay
+the authority for the compiled kernels."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+SO = os.path.join(EMU, "libimplicit_emu.so")
+f32p, i32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = [os.path.join(EMU, "implicit_emu.cpp"), os.path.join(EMU, "simt_emu.h"),
+           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_implicit.cu")]
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
+        subprocess.check_call(
+            ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I", EMU,
+             "-I", os.path.join(HERE, "..", "gtn_b200", "csrc"), "-I", os.path.join(HERE, "..", "include"),
+             src[0], "-o", SO])
+    lib = C.CDLL(SO)
+    lib.emu_implicit.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, f32p, f32p,
+                                 f32p, i32p]
+    return lib
+
+
+def ctc_tables(target, blank=0):
+    """What k_ctc.cu:ctc_build_kernel writes for one target: CSR by destination, in-arcs of node l in
+    the order skip (l-2), step (l-1), self (l); all weights 0."""
+    U = len(target)
+    L = 2 * U + 1
+    flags = np.zeros(L, np.uint8)
+    flags[0] |= 1
+    flags[L - 1] |= 2
+    if L > 1:
+        flags[L - 2] |= 2
+    ptr, src, lab = [0], [], []
+    for l in range(L):
+        label = int(target[(l - 1) // 2]) if l % 2 else blank
+        if l % 2 and l > 1 and label != int(target[(l - 3) // 2]):
+            src.append(l - 2), lab.append(label)
+        if l > 0:
+            src.append(l - 1), lab.append(label)
+        src.append(l), lab.append(label)
+        ptr.append(len(src))
+    return flags, np.array(ptr, np.int32), np.array(src, np.int32), np.array(lab, np.int32), np.zeros(len(src), np.float32)
+
+
+def run(lib, e, tables, lens):
+    B, T, Cn = e.shape
+    e = np.ascontiguousarray(e, np.float32)
+    nn = np.array([len(t[0]) for t in tables], np.int32)
+    flags = np.ascontiguousarray(np.concatenate([t[0] for t in tables]), np.uint8)
+    ptr = np.ascontiguousarray(np.concatenate([t[1] for t in tables]), np.int32)
+    src = np.ascontiguousarray(np.concatenate([t[2] for t in tables]), np.int32)
+    lab = np.ascontiguousarray(np.concatenate([t[3] for t in tables]), np.int32)
+    w = np.ascontiguousarray(np.concatenate([t[4] for t in tables]), np.float32)
+    lens = np.ascontiguousarray(lens, np.int32)
+    out = np.zeros(B, np.float32)
+    grad = np.zeros((B, T, Cn), np.float32)
+    status = np.zeros(B, np.int32)
+    rc = lib.emu_implicit(B, T, Cn, e.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), nn.ctypes.data_as(i32p),
+                          flags.ctypes.data_as(u8p), ptr.ctypes.data_as(i32p), src.ctypes.data_as(i32p),
+                          lab.ctypes.data_as(i32p), w.ctypes.data_as(f32p), out.ctypes.data_as(f32p),
+                          grad.ctypes.data_as(f32p), status.ctypes.data_as(i32p))
+    assert rc == 0
+    return out, grad, status
+
+
+def float64_gradient(x, target):
+    """d loss / d emissions of the same lattice evaluated in float64 (scripts/banded_model.py): the
+    referee when two fp32 evaluations differ by more than the tolerance -- the oracle's own fp32
+    gradient is 5e-4 off it at T=270, C=8 (tests/golden/README.md has the T=1000 figures)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("banded_model", os.path.join(HERE, "..", "scripts", "banded_model.py"))
+    bm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bm)
+    w, lab, start, accept = bm.ctc_band(target)
+    S = bm.forward_plain(x, w, lab, start)
+    _, g = bm.backward_plain(x, w, lab, accept, S, delta=-1.0)
+    mx = x.max(1, keepdims=True)
+    lse = mx[:, 0] + np.log(np.exp(x - mx).sum(1))
+    return np.exp(x - lse[:, None]) + g
+
+
+def check_against_oracle(oracle, e, targets, lens, out, grad, T):
+    for b in range(e.shape[0]):
+        Tb = int(lens[b])
+        lo, go = oracle.ctc_loss(e[b, :Tb], targets[b], 0, True)
+        x = e[b, :Tb].astype(np.float64)
+        mx = x.max(1, keepdims=True)
+        lse = mx[:, 0] + np.log(np.exp(x - mx).sum(1))
+        if not np.isfinite(lo):
+            assert not np.isfinite(out[b])
+            continue
+        assert util.close(float(lse.sum() - np.float64(out[b])), lo), (b, out[b], lo)
+        g = np.exp(x - lse[:, None]) + grad[b, :Tb]  # normaliser's softmax + (-1) x lattice posterior
+        if not util.grad_close(g, go, 5.0 * T):
+            g64 = float64_gradient(x, targets[b])
+            assert np.abs(g - g64).max() <= np.abs(go - g64).max(), (b, float(np.abs(g - go).max()))
+        assert not grad[b, Tb:].any()
+
+
+# (B, T, C, U).  Fast path: T below / at / above one and three 8-frame prefetch blocks, one to seven node
+# warps (the named barrier), T == 2U+1.  (1, 40, 8, 130): 261 graph nodes > 256 threads -> general path.
+SHAPES = [(2, 5, 4, 1), (3, 13, 6, 3), (2, 9, 5, 4), (2, 31, 8, 12), (2, 40, 16, 18), (1, 57, 28, 26), (1, 24, 5, 11),
+          (1, 230, 64, 100), (1, 270, 8, 130)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_implicit_kernel_source_matches_oracle(emu, oracle, shape):
+    B, T, Cn, U = shape
+    e, targets = util.bench_inputs(B, T, Cn, U, seed=8642)
+    if U > 2:
+        for t in targets:
+            t[1] = t[0]  # a repeated label: no skip arc
+    lens = np.minimum(np.array([max(T - 5 * b, 2 * U) for b in range(B)], np.int32), T)
+    out, grad, status = run(emu, e, [ctc_tables(t) for t in targets], lens)
+    assert not status.any(), status
+    check_against_oracle(oracle, e, targets, lens, out, grad, T)
+
+
+def test_implicit_kernel_reports_non_finite_emissions(emu):
+    B, T, Cn, U = 1, 12, 5, 3
+    e, targets = util.bench_inputs(B, T, Cn, U, seed=5)
+    e[0, 4, int(targets[0][1])] = -np.inf
+    out, grad, status = run(emu, e, [ctc_tables(t) for t in targets], np.array([T], np.int32))
+    assert status[0] & 1
