@@ -26,6 +26,7 @@ constexpr int kAlign = 4; // elements; keeps every per-graph slab 16-byte aligne
 
 /* dynamic shared memory of the CTA (the host-side emulation defines its own) */
 #define GTNB_DYNAMIC_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define GTNB_STATIC_SMEM(type, name, count) __shared__ type name[count]
 
 struct gtnb_ctx {
   int device = 0;

@@ -8,12 +8,18 @@
  * argmax indicator.  Rows are independent, so this is one warp per frame row,
  * fully coalesced, followed by a fixed-order per-utterance reduction.
  */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <cstdint>
+
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include <cstdint>
 
 #include "gtnb_internal.h"
+#endif
 
 namespace gtnb {
 
@@ -184,6 +190,8 @@ __global__ void __launch_bounds__(32 * kRowWarps) linear_rows_vec_kernel(
   }
 }
 
+#ifndef GTNB_HOST_EMU
+
 template <bool TROPICAL, int LPR>
 int launch_rows_vec(
     gtnb_ctx* ctx, int B, const int32_t* T_dev, int maxT, int C, const float* emis, long long stride,
@@ -224,10 +232,12 @@ int try_rows_vec(
 #undef GTNB_ROWS_VEC
 }
 
+#endif // GTNB_HOST_EMU
+
 __global__ void __launch_bounds__(256) linear_reduce_kernel(
     const int32_t* __restrict__ T, int maxT, const float* __restrict__ row_score,
     float* __restrict__ scores) {
-  __shared__ double part[256];
+  GTNB_STATIC_SMEM(double, part, 256);
   const int b = blockIdx.x;
   const int Tb = T[b];
   double s = 0.0;
@@ -242,6 +252,8 @@ __global__ void __launch_bounds__(256) linear_reduce_kernel(
 }
 
 } // namespace
+
+#ifndef GTNB_HOST_EMU
 
 int launch_linear_forward(
     gtnb_ctx* ctx, int B, const int32_t* T_dev, int maxT, int C, const float* emis, int64_t stride,
@@ -273,5 +285,7 @@ int launch_linear_forward(
   if (!scratch) dev_free(ctx, row_score);
   return GTNB_OK;
 }
+
+#endif // GTNB_HOST_EMU
 
 } // namespace gtnb

@@ -61,6 +61,13 @@ struct Cta {
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<unsigned char> smem;
   std::vector<std::array<uint32_t, 32>> slots;
+  void* static_smem(int key, size_t bytes) {
+    std::lock_guard<std::mutex> l(named_lock);
+    auto& v = statics[key];
+    if (v.empty()) v.assign(bytes + 16, 0);
+    return v.data();
+  }
+  std::map<int, std::vector<unsigned char>> statics; // static __shared__ arrays, by source line
   std::mutex named_lock;
   std::map<int, std::unique_ptr<std::barrier<>>> named_bars; // bar.sync id, n (n fixed per id)
   std::atomic<int> vote{0};
@@ -168,6 +175,12 @@ inline int atomicAdd(int* p, int v) {
 struct int2 {
   int x, y;
 };
+struct alignas(16) float4 {
+  float x, y, z, w;
+};
+inline float4 make_float4(float x, float y, float z, float w) {
+  return float4{x, y, z, w};
+}
 inline int2 make_int2(int x, int y) {
   return int2{x, y};
 }
@@ -181,6 +194,10 @@ inline float __int_as_float(int i) {
   std::memcpy(&f, &i, 4);
   return f;
 }
+
+/* a static __shared__ array of the running CTA (one per source line) */
+#define GTNB_STATIC_SMEM(type, name, count) \
+  type* name = reinterpret_cast<type*>(emu::g_cta->static_smem(__LINE__, sizeof(type) * (count)))
 
 /* dynamic shared memory of the running CTA, 16-byte aligned */
 #define GTNB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_cta->dynamic_smem())
