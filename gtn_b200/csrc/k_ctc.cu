@@ -9,11 +9,18 @@
  * (in-arc lists ordered by (source, position in the source's out list), arc ids
  * in the reference's creation order), so no per-utterance host work is left.
  */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <algorithm>
+
+#include "gtnb_meta.h"
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
 
 #include <algorithm>
 
 #include "gtnb_internal.h"
+#endif
 
 namespace gtnb {
 
@@ -35,8 +42,9 @@ __global__ void __launch_bounds__(256) ctc_build_kernel(
     int32_t* __restrict__ sg_ilabel,
     int32_t* __restrict__ sg_olabel,
     int32_t* __restrict__ acc_nodes) {
-  __shared__ int scan[256];
-  __shared__ int carry;
+  GTNB_STATIC_SMEM(int, scan, 256);
+  GTNB_STATIC_SMEM(int, carry_box, 1);
+  int& carry = carry_box[0];
   const int b = blockIdx.x;
   const GraphMeta m = meta[b];
   const int tid = threadIdx.x;
@@ -119,6 +127,8 @@ __global__ void __launch_bounds__(256) ctc_build_kernel(
 
 } // namespace
 
+#ifndef GTNB_HOST_EMU
+
 int launch_ctc_build(
     gtnb_ctx* ctx, gtnb_lattice* lat, const int32_t* targets_dev, const int32_t* tgt_off_dev,
     const int32_t* tgt_len_dev, int blank) {
@@ -130,8 +140,11 @@ int launch_ctc_build(
   return GTNB_OK;
 }
 
+#endif // GTNB_HOST_EMU
+
 } // namespace gtnb
 
+#ifndef GTNB_HOST_EMU
 namespace gtnb {
 namespace {
 __global__ void scatter_add_kernel(float* __restrict__ dst, const int32_t* __restrict__ idx,
@@ -161,3 +174,4 @@ int launch_sub(gtnb_ctx* ctx, const float* a, const float* b, float* out, int n)
   return GTNB_OK;
 }
 } // namespace gtnb
+#endif // GTNB_HOST_EMU

@@ -4,6 +4,7 @@
  * tests/emu/simt_emu.h.  Only the launch geometry and the device tables are restated here.
  */
 #define GTNB_HOST_EMU 1
+#include "../../gtn_b200/csrc/k_ctc.cu"
 #include "../../gtn_b200/csrc/k_implicit.cu"
 
 #include <vector>
@@ -90,6 +91,78 @@ int emu_implicit(
                                           t.in_label.data(), t.in_w.data(), t.in_arc.data(), nullptr, emissions,
                                           scores.data(), out_scores, deltas.data(), grad, (long long)T * C, C,
                                           lb);
+  });
+  return 0;
+}
+
+/*
+ * The CTC criterion's device side as gtnb_ctc_loss runs it: k_ctc.cu's ctc_build_kernel writes the
+ * target-graph tables, k_implicit.cu sweeps them.  targets concatenated, target_lens[B].
+ * Also returns the tables of graph 0 (for a check against the reference's ctcGraph): n_arcs0,
+ * ptr0[N0+1], src0 / label0 (capacity 3 N0).
+ */
+int emu_implicit_ctc(
+    int B, int T, int C, const float* emissions, const int32_t* input_lens, const int32_t* targets,
+    const int32_t* target_lens, int blank, float* out_scores, float* grad, int32_t* status, int32_t* ptr0,
+    int32_t* src0, int32_t* label0) {
+  std::vector<GraphMeta> meta(B);
+  std::vector<int32_t> tgt_off(B);
+  long long nodes = 0, arcs = 0, scores_len = 0, acc = 0, toff = 0;
+  int maxN = 0;
+  for (int b = 0; b < B; b++) {
+    const int L = 2 * target_lens[b] + 1;
+    GraphMeta& m = meta[b];
+    std::memset(&m, 0, sizeof(m));
+    m.sg_node_base = nodes;
+    m.sg_arc_base = arcs;
+    m.acc_base = acc;
+    m.emis_off = (long long)b * T * C;
+    m.node_base = scores_len;
+    m.T = input_lens ? input_lens[b] : T;
+    m.sg_N = L;
+    tgt_off[b] = (int32_t)toff;
+    toff += target_lens[b];
+    nodes += L + 1;
+    arcs += 3 * L;
+    acc += 2;
+    scores_len += (long long)(T + 1) * ((L + 3) & ~3);
+    maxN = std::max(maxN, L);
+  }
+  std::vector<uint8_t> flags(nodes, 0);
+  std::vector<int32_t> in_ptr(nodes, 0), in_src(arcs, 0), in_label(arcs, 0), in_arc(arcs, 0), il(arcs, 0),
+      ol(arcs, 0), acc_nodes(acc, 0);
+  std::vector<float> in_w(arcs, 0.0f);
+  emu::launch(B, 256, 0, [&] {
+    gtnb::ctc_build_kernel(meta.data(), targets, tgt_off.data(), target_lens, blank, C, flags.data(), in_ptr.data(),
+                           in_src.data(), in_label.data(), in_arc.data(), in_w.data(), il.data(), ol.data(),
+                           acc_nodes.data());
+  });
+  int maxA = 0;
+  for (int b = 0; b < B; b++) {
+    meta[b].sg_A = in_ptr[meta[b].sg_node_base + meta[b].sg_N];
+    maxA = std::max(maxA, meta[b].sg_A);
+  }
+  if (ptr0) {
+    const int N0 = meta[0].sg_N;
+    for (int n = 0; n <= N0; n++) ptr0[n] = in_ptr[n];
+    for (int a = 0; a < in_ptr[N0]; a++) {
+      src0[a] = in_src[a];
+      label0[a] = in_label[a];
+    }
+  }
+  std::vector<float> scores((size_t)scores_len + 16, 0.0f);
+  for (int b = 0; b < B; b++) status[b] = 0;
+  const gtnb::ImpLayout lf = gtnb::make_imp_layout(maxN, maxA, false);
+  emu::launch(B, gtnb::kImpThreads, lf.total, [&] {
+    gtnb::implicit_forward_kernel(meta.data(), flags.data(), in_ptr.data(), in_src.data(), in_label.data(),
+                                  in_w.data(), emissions, scores.data(), out_scores, status, C, lf);
+  });
+  std::vector<float> deltas(B, -1.0f);
+  const gtnb::ImpLayout lb = gtnb::make_imp_layout(maxN, maxA, true);
+  emu::launch(B, gtnb::kImpThreads, lb.total, [&] {
+    gtnb::implicit_backward_kernel<false>(meta.data(), flags.data(), in_ptr.data(), in_src.data(), in_label.data(),
+                                          in_w.data(), in_arc.data(), nullptr, emissions, scores.data(),
+                                          out_scores, deltas.data(), grad, (long long)T * C, C, lb);
   });
   return 0;
 }

@@ -25,7 +25,8 @@ f32p, i32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint
 @pytest.fixture(scope="module")
 def emu():
     src = [os.path.join(EMU, "implicit_emu.cpp"), os.path.join(EMU, "simt_emu.h"),
-           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_implicit.cu")]
+           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_implicit.cu"),
+           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_ctc.cu")]
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
         subprocess.check_call(
             ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I", EMU,
@@ -34,6 +35,8 @@ def emu():
     lib = C.CDLL(SO)
     lib.emu_implicit.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, f32p, f32p,
                                  f32p, i32p]
+    lib.emu_implicit_ctc.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, i32p, C.c_int, f32p, f32p, i32p,
+                                     i32p, i32p, i32p]
     return lib
 
 
@@ -139,3 +142,35 @@ def test_implicit_kernel_reports_non_finite_emissions(emu):
     e[0, 4, int(targets[0][1])] = -np.inf
     out, grad, status = run(emu, e, [ctc_tables(t) for t in targets], np.array([T], np.int32))
     assert status[0] & 1
+
+
+@pytest.mark.parametrize("shape", [(3, 21, 7, 4), (2, 40, 16, 18), (1, 30, 64, 100 // 8), (2, 9, 6, 0)])
+def test_ctc_build_kernel_then_sweeps(emu, oracle, shape):
+    """The criterion's device side end to end: k_ctc.cu's ctc_build_kernel (tables of the target graph,
+    benchmarks/ctc.cpp:40-58) feeding the sweeps; graph 0's tables against the restatement above."""
+    B, T, Cn, U = shape
+    e, targets = util.bench_inputs(B, T, Cn, max(U, 1), seed=97)
+    if U == 0:
+        targets = [t[:0] for t in targets]  # empty transcript: the single blank node
+    elif U > 2:
+        targets[0][1] = targets[0][0]
+    lens = np.minimum(np.array([max(T - 3 * b, 2 * U + 1) for b in range(B)], np.int32), T)
+    e = np.ascontiguousarray(e, np.float32)
+    cat = np.ascontiguousarray(np.concatenate(targets) if U else np.zeros(1), np.int32)
+    tl = np.array([len(t) for t in targets], np.int32)
+    out = np.zeros(B, np.float32)
+    grad = np.zeros((B, T, Cn), np.float32)
+    status = np.zeros(B, np.int32)
+    N0 = 2 * len(targets[0]) + 1
+    ptr0 = np.zeros(N0 + 1, np.int32)
+    src0 = np.zeros(3 * N0, np.int32)
+    lab0 = np.zeros(3 * N0, np.int32)
+    rc = emu.emu_implicit_ctc(B, T, Cn, e.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), cat.ctypes.data_as(i32p),
+                              tl.ctypes.data_as(i32p), 0, out.ctypes.data_as(f32p), grad.ctypes.data_as(f32p),
+                              status.ctypes.data_as(i32p), ptr0.ctypes.data_as(i32p), src0.ctypes.data_as(i32p),
+                              lab0.ctypes.data_as(i32p))
+    assert rc == 0 and not status.any()
+    _, ptr, src, lab, _ = ctc_tables(targets[0])
+    assert np.array_equal(ptr0, ptr)
+    assert np.array_equal(src0[:ptr[-1]], src) and np.array_equal(lab0[:ptr[-1]], lab)
+    check_against_oracle(oracle, e, targets, lens, out, grad, T)
