@@ -259,7 +259,7 @@ int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value) {
     return GTNB_OK;
   }
   if (ctx && name && std::string(name) == "banded") {
-    ctx->use_banded = value != 0;
+    ctx->use_banded = value;
     return GTNB_OK;
   }
   return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctx_set_flag: unknown flag");

@@ -150,7 +150,7 @@ static int ctc_loss_run(
   TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
   if (implicit) {
     // the sweeps: k_implicit.cu, or (experimental flag) the temporally blocked ones of k_banded.cu
-    const bool banded = ctx->use_banded && banded_supported(lat);
+    const bool banded = ctx->use_banded != 0 && banded_supported(ctx, lat);
     auto sweep_forward = [&](int b0, int nb) {
       return banded ? launch_banded_forward(ctx, lat, status_dev, b0, nb)
                     : launch_implicit_forward(ctx, lat, status_dev, b0, nb);

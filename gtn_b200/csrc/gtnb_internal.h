@@ -62,7 +62,7 @@ struct gtnb_ctx {
   };
   bool use_staged = true; // gtnb_ctx_set_flag("staged", 0) forces the generic kernels
   bool use_implicit = true; // gtnb_ctx_set_flag("implicit", 0): criteria materialise the lattice
-  bool use_banded = false; // gtnb_ctx_set_flag("banded", 1): EXPERIMENTAL temporally blocked CTC sweeps (k_banded.cu)
+  int use_banded = 0; // gtnb_ctx_set_flag("banded", K): EXPERIMENTAL temporally blocked CTC sweeps (k_banded.cu), K frames per barrier
   bool profiling = false;
   std::vector<ProfEntry> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -249,7 +249,7 @@ bool implicit_supported(const gtnb_lattice* lat);
 bool implicit_dims_supported(const SgDims* dims, int n_graphs);
 int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0 = 0, int nb = -1);
 /* k_banded.cu (experimental): same contract as the implicit sweeps, for band-shaped graph operands */
-bool banded_supported(const gtnb_lattice* lat);
+bool banded_supported(const gtnb_ctx* ctx, const gtnb_lattice* lat);
 int launch_banded_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0 = 0, int nb = -1);
 int launch_banded_backward(
     gtnb_ctx* ctx, gtnb_lattice* lat, const float* deltas_dev, float* grad_emis, int64_t grad_stride,

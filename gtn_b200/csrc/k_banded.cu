@@ -183,7 +183,7 @@ __device__ __forceinline__ BandNode load_band_node(
 /* ------------------------------------------------------------------ */
 
 template <int K>
-__global__ void __launch_bounds__(kBandMaxThreads) banded_forward_kernel(
+__global__ void __launch_bounds__(kBandMaxThreads, 1) banded_forward_kernel(
     const GraphMeta* __restrict__ meta,
     const uint8_t* __restrict__ sg_flags,
     const int32_t* __restrict__ sg_in_ptr,
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kBandMaxThreads) banded_forward_kernel(
 /* ------------------------------------------------------------------ */
 
 template <int K>
-__global__ void __launch_bounds__(kBandMaxThreads) banded_backward_kernel(
+__global__ void __launch_bounds__(kBandMaxThreads, 1) banded_backward_kernel(
     const GraphMeta* __restrict__ meta,
     const uint8_t* __restrict__ sg_flags,
     const int32_t* __restrict__ sg_in_ptr,
@@ -451,17 +451,23 @@ __global__ void __launch_bounds__(kBandMaxThreads) banded_backward_kernel(
 #undef GTNB_BAND_BWD_LEVEL
 }
 
-constexpr int kBandK = 4; // frames per barrier
-
 } // namespace
 
 #ifndef GTNB_HOST_EMU
 
+namespace {
+/* frames per barrier: the value of gtnb_ctx_set_flag("banded", K), K in {1, 2, 4, 8} (else 4) */
+int band_k(const gtnb_ctx* ctx) {
+  const int k = ctx->use_banded;
+  return (k == 1 || k == 2 || k == 4 || k == 8) ? k : 4;
+}
+} // namespace
+
 /* true when the banded sweeps can take this batch (checked on the host: sizes; the band shape
  * itself is checked by the forward kernel, status bit 2) */
-bool banded_supported(const gtnb_lattice* lat) {
+bool banded_supported(const gtnb_ctx* ctx, const gtnb_lattice* lat) {
   if (!lat->composed || lat->max_in_deg > 3) return false;
-  const int own_b = 30 - 2 * kBandK; // the backward sweep has fewer own lanes per warp
+  const int own_b = 30 - 2 * band_k(ctx); // the backward sweep has fewer own lanes per warp
   const int warps = (lat->max_lvl_nodes + own_b - 1) / own_b;
   return warps >= 1 && 32 * warps <= kBandMaxThreads;
 }
@@ -469,15 +475,24 @@ bool banded_supported(const gtnb_lattice* lat) {
 int launch_banded_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0, int nb) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
-  const int own = 32 - 2 * kBandK;
+  const int K = band_k(ctx);
+  const int own = 32 - 2 * K;
   const int warps = std::max(1, (lat->max_lvl_nodes + own - 1) / own);
   const int row_pitch = (warps * own + 3) & ~3;
   const size_t smem = sizeof(float) * (2 * (size_t)row_pitch + 32);
-  GTNB_LAUNCH(ctx, "banded_forward",
-              banded_forward_kernel<kBandK><<<nb, 32 * warps, smem, ctx->stream>>>(
-                  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label,
-                  lat->sg_in_w, lat->emissions, lat->scores, lat->out_scores + b0, status_dev + b0, lat->C,
-                  row_pitch));
+#define GTNB_BAND_FWD(KK)                                                                              \
+  GTNB_LAUNCH(ctx, "banded_forward",                                                                   \
+              banded_forward_kernel<KK><<<nb, 32 * warps, smem, ctx->stream>>>(                        \
+                  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label,     \
+                  lat->sg_in_w, lat->emissions, lat->scores, lat->out_scores + b0, status_dev + b0,    \
+                  lat->C, row_pitch))
+  switch (K) {
+    case 1: GTNB_BAND_FWD(1); break;
+    case 2: GTNB_BAND_FWD(2); break;
+    case 8: GTNB_BAND_FWD(8); break;
+    default: GTNB_BAND_FWD(4); break;
+  }
+#undef GTNB_BAND_FWD
   return GTNB_OK;
 }
 
@@ -486,16 +501,25 @@ int launch_banded_backward(
     int nb) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
-  const int own = 30 - 2 * kBandK;
+  const int K = band_k(ctx);
+  const int own = 30 - 2 * K;
   const int warps = std::max(1, (lat->max_lvl_nodes + own - 1) / own);
   const int row_pitch = (warps * own + 3) & ~3;
   const size_t smem = sizeof(float) * (2 * (size_t)row_pitch + 32);
-  GTNB_LAUNCH(ctx, "banded_backward",
-              banded_backward_kernel<kBandK><<<nb, 32 * warps, smem, ctx->stream>>>(
-                  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label,
-                  lat->sg_in_w, lat->emissions, lat->scores, lat->out_scores + b0,
-                  deltas_dev ? deltas_dev + b0 : nullptr, grad_emis + (long long)b0 * grad_stride,
-                  (long long)grad_stride, lat->C, row_pitch));
+#define GTNB_BAND_BWD(KK)                                                                              \
+  GTNB_LAUNCH(ctx, "banded_backward",                                                                  \
+              banded_backward_kernel<KK><<<nb, 32 * warps, smem, ctx->stream>>>(                       \
+                  lat->meta + b0, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label,     \
+                  lat->sg_in_w, lat->emissions, lat->scores, lat->out_scores + b0,                     \
+                  deltas_dev ? deltas_dev + b0 : nullptr, grad_emis + (long long)b0 * grad_stride,     \
+                  (long long)grad_stride, lat->C, row_pitch))
+  switch (K) {
+    case 1: GTNB_BAND_BWD(1); break;
+    case 2: GTNB_BAND_BWD(2); break;
+    case 8: GTNB_BAND_BWD(8); break;
+    default: GTNB_BAND_BWD(4); break;
+  }
+#undef GTNB_BAND_BWD
   return GTNB_OK;
 }
 

@@ -103,8 +103,9 @@ int64_t gtnb_ctx_launch_count(const gtnb_ctx* ctx);
  * which is how the tests cross-check the two families.  "implicit" (default 1): the
  * criteria (gtnb_ctc_loss) sweep the frames of intersect(target graph, emissions) without
  * materialising the lattice; 0 makes them build it and run the lattice kernels.
- * "banded" (default 0, EXPERIMENTAL): gtnb_ctc_loss's implicit sweeps run K frames per barrier
- * with warp-shuffle neighbour exchange (k_banded.cu) when the target graphs are band shaped.
+ * "banded" (default 0, EXPERIMENTAL): value K in {1, 2, 4, 8}: gtnb_ctc_loss's implicit sweeps run
+ * K frames per barrier with warp-shuffle neighbour exchange (k_banded.cu) when the target graphs
+ * are band shaped.
  */
 int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value);
 

@@ -20,12 +20,12 @@ extern "C" {
  *   out_scores[B]   forwardScore(intersect(ctc, emissions))
  *   grad [B][T][C]  must be zero on entry: receives -d score / d emissions
  *   status[B]       bit 0 non-finite weight, bit 1 (value 2) graph not band shaped
- * Returns 0, or 1 when a graph needs more than 16 warps.
+ * K: frames per barrier (1, 2, 4 or 8).  Returns 0, or 1 when a graph needs more than 16 warps.
  */
 int emu_banded_ctc(
     int B, int T, int C, const float* emissions, const int32_t* input_lens, const int32_t* targets,
-    const int32_t* target_lens, int blank, float* out_scores, float* grad, int32_t* status) {
-  constexpr int K = gtnb::kBandK;
+    const int32_t* target_lens, int blank, int K, float* out_scores, float* grad, int32_t* status) {
+  if (K != 1 && K != 2 && K != 4 && K != 8) return 2;
   std::vector<GraphMeta> meta(B);
   std::vector<uint8_t> flags;
   std::vector<int32_t> in_ptr, in_src, in_label;
@@ -91,16 +91,27 @@ int emu_banded_ctc(
   const int warps_f = std::max(1, (maxN + own_f - 1) / own_f), warps_b = std::max(1, (maxN + own_b - 1) / own_b);
   if (32 * warps_b > gtnb::kBandMaxThreads) return 1;
   const int pitch_f = (warps_f * own_f + 3) & ~3, pitch_b = (warps_b * own_b + 3) & ~3;
-  emu::launch(B, 32 * warps_f, sizeof(float) * (2 * pitch_f + 32), [&] {
-    gtnb::banded_forward_kernel<K>(meta.data(), flags.data(), in_ptr.data(), in_src.data(), in_label.data(),
-                                   in_w.data(), emissions, scores.data(), out_scores, status, C, pitch_f);
-  });
   std::vector<float> deltas(B, -1.0f); // subtract's gradFunc (functions.cpp:53-58)
-  emu::launch(B, 32 * warps_b, sizeof(float) * (2 * pitch_b + 32), [&] {
-    gtnb::banded_backward_kernel<K>(meta.data(), flags.data(), in_ptr.data(), in_src.data(), in_label.data(),
-                                    in_w.data(), emissions, scores.data(), out_scores, deltas.data(), grad,
-                                    (long long)T * C, C, pitch_b);
-  });
+#define RUN_K(KK)                                                                                             \
+  {                                                                                                           \
+    emu::launch(B, 32 * warps_f, sizeof(float) * (2 * pitch_f + 32), [&] {                                    \
+      gtnb::banded_forward_kernel<KK>(meta.data(), flags.data(), in_ptr.data(), in_src.data(),                \
+                                      in_label.data(), in_w.data(), emissions, scores.data(), out_scores,     \
+                                      status, C, pitch_f);                                                    \
+    });                                                                                                       \
+    emu::launch(B, 32 * warps_b, sizeof(float) * (2 * pitch_b + 32), [&] {                                    \
+      gtnb::banded_backward_kernel<KK>(meta.data(), flags.data(), in_ptr.data(), in_src.data(),               \
+                                       in_label.data(), in_w.data(), emissions, scores.data(), out_scores,    \
+                                       deltas.data(), grad, (long long)T * C, C, pitch_b);                    \
+    });                                                                                                       \
+  }
+  switch (K) {
+    case 1: RUN_K(1) break;
+    case 2: RUN_K(2) break;
+    case 8: RUN_K(8) break;
+    default: RUN_K(4) break;
+  }
+#undef RUN_K
   return 0;
 }
 

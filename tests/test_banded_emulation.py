@@ -30,11 +30,11 @@ def emu():
              src[0], "-o", SO])
     lib = C.CDLL(SO)
     f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
-    lib.emu_banded_ctc.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, i32p, C.c_int, f32p, f32p, i32p]
+    lib.emu_banded_ctc.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, i32p, C.c_int, C.c_int, f32p, f32p, i32p]
     return lib
 
 
-def run(lib, e, targets, lens, blank=0):
+def run(lib, e, targets, lens, blank=0, K=4):
     B, T, Cn = e.shape
     e = np.ascontiguousarray(e, np.float32)
     cat = np.ascontiguousarray(np.concatenate(targets) if sum(map(len, targets)) else np.zeros(0), np.int32)
@@ -45,7 +45,7 @@ def run(lib, e, targets, lens, blank=0):
     status = np.zeros(B, np.int32)
     f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
     rc = lib.emu_banded_ctc(B, T, Cn, e.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), cat.ctypes.data_as(i32p),
-                            tl.ctypes.data_as(i32p), blank, out.ctypes.data_as(f32p), grad.ctypes.data_as(f32p),
+                            tl.ctypes.data_as(i32p), blank, K, out.ctypes.data_as(f32p), grad.ctypes.data_as(f32p),
                             status.ctypes.data_as(i32p))
     assert rc == 0
     return out, grad, status
@@ -58,16 +58,19 @@ SHAPES = [(2, 5, 4, 1), (3, 13, 6, 3), (2, 9, 5, 4), (2, 31, 8, 12), (2, 40, 16,
           (1, 24, 5, 11), (1, 70, 9, 34), (1, 230, 64, 100)]
 
 
+@pytest.mark.parametrize("K", [4, 1, 2, 8])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_banded_kernel_source_matches_oracle(emu, oracle, shape):
+def test_banded_kernel_source_matches_oracle(emu, oracle, shape, K):
     B, T, Cn, U = shape
+    if K != 4 and shape not in SHAPES[2:6] + SHAPES[-1:]:
+        pytest.skip("the other barrier intervals run a subset of the shapes")
     e, targets = util.bench_inputs(B, T, Cn, U, seed=1357)
     if U > 2:
         for t in targets:
             t[1] = t[0]  # a repeated label: no skip arc
     lens = np.array([max(T - 5 * b, 2 * U) for b in range(B)], np.int32)  # ragged, still feasible
     lens = np.minimum(lens, T)
-    out, grad, status = run(emu, e, targets, lens)
+    out, grad, status = run(emu, e, targets, lens, K=K)
     assert not status.any(), status
     for b in range(B):
         Tb = int(lens[b])
