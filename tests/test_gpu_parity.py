@@ -477,14 +477,14 @@ def test_ctc_implicit_and_materialised_agree(ctx, oracle, shape):
         assert ("implicit_forward" in names) == bool(imp), names
         assert ("compose_emit" in names) == (not imp), names
     ctx.set_flag("implicit", 1)
-    assert util.close(res[1][0], res[0][0])
+    assert util.close(res[K][0], res[0][0])
     for b in range(B):
         lo, go = oracle.ctc_loss(e[b, :lens[b]], targets[b], 0, True)
-        assert util.close(res[1][0][b], lo), (b, res[1][0][b], lo)
+        assert util.close(res[K][0][b], lo), (b, res[K][0][b], lo)
         if np.isfinite(lo):
-            assert util.grad_close(res[1][1][b, :lens[b]], go, 5.0 * T), b
-            assert util.grad_close(res[1][1][b], res[0][1][b], 5.0 * T), b
-        assert not res[1][1][b, lens[b]:].any()
+            assert util.grad_close(res[K][1][b, :lens[b]], go, 5.0 * T), b
+            assert util.grad_close(res[K][1][b], res[0][1][b], 5.0 * T), b
+        assert not res[K][1][b, lens[b]:].any()
 
 
 def test_ctc_implicit_falls_back_on_non_finite_emissions(ctx):
@@ -589,15 +589,16 @@ def test_asg_implicit_and_materialised_agree(ctx, oracle, shape):
                     reason="k_banded.cu has not been run on a GPU yet (set GTNB_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("shape", [(4, 120, 16, 9), (3, 37, 8, 1), (2, 200, 32, 90), (2, 9, 5, 4), (3, 64, 28, 30),
                                    (2, 1000, 64, 100)])
-def test_ctc_banded_sweeps_agree_with_implicit_and_oracle(ctx, oracle, shape):
-    """gtnb_ctx_set_flag("banded", 1): K frames per barrier, neighbour scores through warp shuffles
+@pytest.mark.parametrize("K", [4, 2, 8, 1])
+def test_ctc_banded_sweeps_agree_with_implicit_and_oracle(ctx, oracle, shape, K):
+    """gtnb_ctx_set_flag("banded", K): K frames per barrier, neighbour scores through warp shuffles
     (lane arithmetic pinned by scripts/banded_model.py).  Same losses / gradients as k_implicit.cu
     and the oracle, ragged input lengths included."""
     B, T, C, U = shape
     e, targets = util.bench_inputs(B, T, C, U, seed=2468)
     lens = np.array([T - (3 * b) % max(T // 2, 1) for b in range(B)], np.int32)
     res = {}
-    for banded in (0, 1):
+    for banded in (0, K):
         ctx.set_flag("banded", banded)
         ctx.profile(True)
         ctx.profile_read()
@@ -609,11 +610,11 @@ def test_ctc_banded_sweeps_agree_with_implicit_and_oracle(ctx, oracle, shape):
         ctx.profile(False)
         assert ("banded_forward" in names) == bool(banded), names
         assert "compose_emit" not in names, names  # no fallback to the materialised lattice
-    assert util.close(res[1][0], res[0][0])
+    assert util.close(res[K][0], res[0][0])
     for b in range(B):
         lo, go = oracle.ctc_loss(e[b, :lens[b]], targets[b], 0, True)
-        assert util.close(res[1][0][b], lo), (b, res[1][0][b], lo)
+        assert util.close(res[K][0][b], lo), (b, res[K][0][b], lo)
         if np.isfinite(lo):
-            assert util.grad_close(res[1][1][b, :lens[b]], go, 5.0 * T), b
-            assert util.grad_close(res[1][1][b], res[0][1][b], 5.0 * T), b
-        assert not res[1][1][b, lens[b]:].any()
+            assert util.grad_close(res[K][1][b, :lens[b]], go, 5.0 * T), b
+            assert util.grad_close(res[K][1][b], res[0][1][b], 5.0 * T), b
+        assert not res[K][1][b, lens[b]:].any()
