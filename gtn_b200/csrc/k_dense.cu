@@ -21,10 +21,14 @@
  * warp shuffles; the next frame's emission row is prefetched while the current frame
  * is evaluated; the traceback runs on one warp with 8 back-pointer rows in flight.
  */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "gtnb_internal.h"
+#endif
 
 namespace gtnb {
 
@@ -43,7 +47,7 @@ __global__ void __launch_bounds__(kDenseThreads) viterbi_dense_kernel(
     uint8_t* __restrict__ bp, // [B][T_max][C]
     int32_t* __restrict__ paths, // [B][T_max]
     float* __restrict__ scores) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GTNB_DYNAMIC_SMEM(unsigned char, smem_raw);
   const int P = C + 32 / G; // padded row stride of the transition tile
   float* s_tr = reinterpret_cast<float*>(smem_raw); // s_tr[j * P + i] = w(j -> i)
   float* s_sc = s_tr + (size_t)C * P; // [2][C]
@@ -172,6 +176,8 @@ __global__ void __launch_bounds__(kDenseThreads) viterbi_dense_kernel(
 
 } // namespace
 
+#ifndef GTNB_HOST_EMU
+
 int launch_viterbi_dense(
     gtnb_ctx* ctx, int B, int T_max, int C, const int32_t* T_dev, const float* emis, int64_t stride,
     const float* trans_dev, uint8_t* bp, int32_t* paths, float* scores) {
@@ -202,5 +208,7 @@ int launch_viterbi_dense(
 #undef LAUNCH_DENSE
   return GTNB_OK;
 }
+
+#endif // GTNB_HOST_EMU
 
 } // namespace gtnb

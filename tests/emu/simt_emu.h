@@ -160,6 +160,23 @@ T __shfl_xor_sync(unsigned, T v, int m) {
   return emu::shfl(v, l ^ m);
 }
 template <class T>
+T __shfl_sync(unsigned, T v, int src_lane) {
+  return emu::shfl(v, src_lane & 31);
+}
+template <class T>
+T __ldcg(const T* p) {
+  return *p;
+}
+inline void __threadfence_block() {
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+inline void __syncwarp(unsigned = 0xffffffffu) {
+  emu::g_cta->warp_bar[threadIdx.x / 32]->arrive_and_wait();
+}
+inline float __fadd_rn(float a, float b) {
+  return a + b;
+}
+template <class T>
 T __ldg(const T* p) {
   return *p;
 }

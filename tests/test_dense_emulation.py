@@ -1,0 +1,51 @@
+"""The SOURCE of gtn_b200/csrc/k_dense.cu (factored dense-trellis Viterbi: viterbiPath / viterbiScore of
+compose(emissions, transitions) without the lattice, BASELINE config 4) run on the CPU through the SIMT
+emulator of tests/emu against the oracle: paths compared with ==, scores bit for bit."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+SO = os.path.join(EMU, "libdense_emu.so")
+f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = [os.path.join(EMU, "dense_emu.cpp"), os.path.join(EMU, "simt_emu.h"),
+           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_dense.cu")]
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
+        subprocess.check_call(
+            ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I", EMU,
+             "-I", os.path.join(HERE, "..", "gtn_b200", "csrc"), "-I", os.path.join(HERE, "..", "include"),
+             src[0], "-o", SO])
+    lib = C.CDLL(SO)
+    lib.emu_viterbi_dense.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, f32p, i32p, f32p]
+    return lib
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 4), (2, 23, 8), (1, 17, 28), (2, 12, 64), (1, 10, 128)])
+@pytest.mark.parametrize("ties", [False, True])
+def test_dense_viterbi_kernel_source_matches_oracle(emu, oracle, shape, ties):
+    B, T, Cn = shape
+    rng = np.random.default_rng(Cn + 1000 * ties)
+    if ties:  # small integers: many equal-score paths, the first-relaxed predecessor must win
+        e = rng.integers(-2, 3, (B, T, Cn)).astype(np.float32)
+        tw = rng.integers(-1, 2, Cn + Cn * Cn).astype(np.float32)
+    else:
+        e = rng.uniform(-5, 5, (B, T, Cn)).astype(np.float32)
+        tw = rng.uniform(-5, 5, Cn + Cn * Cn).astype(np.float32)
+    lens = np.array([T - 2 * b for b in range(B)], np.int32)
+    paths = np.full((B, T), -7, np.int32)
+    scores = np.zeros(B, np.float32)
+    rc = emu.emu_viterbi_dense(B, T, Cn, e.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), tw.ctypes.data_as(f32p),
+                               paths.ctypes.data_as(i32p), scores.ctypes.data_as(f32p))
+    assert rc == 0
+    for b in range(B):
+        want_path, want_score = oracle.viterbi_dense(e[b, :lens[b]], tw)
+        assert np.array_equal(paths[b, :lens[b]], want_path), (b, paths[b, :lens[b]], want_path)
+        assert scores[b] == np.float32(want_score), (b, scores[b], want_score)
