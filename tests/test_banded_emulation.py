@@ -7,28 +7,18 @@ their tails, barrier placement (a wrong one deadlocks or corrupts the exchange r
 The SFU instructions are replaced by exp2f / log2f and nothing is said about speed."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
-from tests import util
+from tests import emu_build, util
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-EMU = os.path.join(HERE, "emu")
-SO = os.path.join(EMU, "libbanded_emu.so")
 
 
 @pytest.fixture(scope="module")
 def emu():
-    src = [os.path.join(EMU, "banded_emu.cpp"), os.path.join(EMU, "simt_emu.h"),
-           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_banded.cu")]
-    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
-        subprocess.check_call(
-            ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I", EMU,
-             "-I", os.path.join(HERE, "..", "gtn_b200", "csrc"), "-I", os.path.join(HERE, "..", "include"),
-             src[0], "-o", SO])
-    lib = C.CDLL(SO)
+    lib = C.CDLL(emu_build.build('banded', ['k_banded.cu']))
     f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
     lib.emu_banded_ctc.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, i32p, C.c_int, C.c_int, f32p, f32p, i32p]
     return lib

@@ -9,30 +9,19 @@ by exp2f / log2f, and nothing is said about speed -- the GPU parity tests (tests
 the authority for the compiled kernels."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
-from tests import util
+from tests import emu_build, util
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-EMU = os.path.join(HERE, "emu")
-SO = os.path.join(EMU, "libimplicit_emu.so")
 f32p, i32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
 
 
 @pytest.fixture(scope="module")
 def emu():
-    src = [os.path.join(EMU, "implicit_emu.cpp"), os.path.join(EMU, "simt_emu.h"),
-           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_implicit.cu"),
-           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_ctc.cu")]
-    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
-        subprocess.check_call(
-            ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I", EMU,
-             "-I", os.path.join(HERE, "..", "gtn_b200", "csrc"), "-I", os.path.join(HERE, "..", "include"),
-             src[0], "-o", SO])
-    lib = C.CDLL(SO)
+    lib = C.CDLL(emu_build.build('implicit', ['k_implicit.cu', 'k_ctc.cu']))
     lib.emu_implicit.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, f32p, f32p,
                                  f32p, i32p]
     lib.emu_implicit_ctc.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, i32p, C.c_int, f32p, f32p, i32p,

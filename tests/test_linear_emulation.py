@@ -3,27 +3,19 @@ emissions chain and its gradient, shortest.cpp:86-188 on creations.cpp:20-33) ru
 SIMT emulator of tests/emu, scalar and float4 kernels, against numpy."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
+from tests import emu_build
+
 HERE = os.path.dirname(os.path.abspath(__file__))
-EMU = os.path.join(HERE, "emu")
-SO = os.path.join(EMU, "liblinear_emu.so")
 f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
 
 
 @pytest.fixture(scope="module")
 def emu():
-    src = [os.path.join(EMU, "linear_emu.cpp"), os.path.join(EMU, "simt_emu.h"),
-           os.path.join(HERE, "..", "gtn_b200", "csrc", "k_linear.cu")]
-    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
-        subprocess.check_call(
-            ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I", EMU,
-             "-I", os.path.join(HERE, "..", "gtn_b200", "csrc"), "-I", os.path.join(HERE, "..", "include"),
-             src[0], "-o", SO])
-    lib = C.CDLL(SO)
+    lib = C.CDLL(emu_build.build('linear', ['k_linear.cu']))
     lib.emu_linear.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, C.c_int, C.c_int, C.c_float, C.c_int, f32p, f32p]
     return lib
 
