@@ -144,7 +144,10 @@ int gtnb_ctx_create(int device, void* cuda_stream, gtnb_ctx** out) {
     return rc;
   }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->total_mem = prop.totalGlobalMem;
+  }
   if (cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
   } else {
@@ -676,9 +679,9 @@ int composed_alloc(
 
   size_t need = (size_t)(tn * 8 + ta * 20 + tl * 8) + (size_t)B * (maxT + 1) * lat->alive_words * 4;
   if (implicit_only) need = (size_t)tn * 4;
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  if (need > total_b) {
+  // the device's capacity, cached at context creation: cudaMemGetInfo is a driver round trip of tens
+  // of microseconds, and this runs once per criterion call, ahead of the first kernel launch
+  if (ctx->total_mem && need > ctx->total_mem) {
     delete lat;
     return fail(ctx, GTNB_ERR_UNSUPPORTED,
                 "gtnb_compose_linear: materialised lattice would not fit in HBM (use the factored path)");

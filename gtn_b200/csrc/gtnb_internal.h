@@ -38,6 +38,7 @@ struct gtnb_ctx {
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   int sm_count = 148;
+  size_t total_mem = 0; // device memory, read once at context creation
   // pinned staging: every small host->device upload of one API call is packed here and
   // copied asynchronously (pageable copies would stall the stream each time)
   unsigned char* stage = nullptr;
