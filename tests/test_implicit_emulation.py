@@ -163,3 +163,55 @@ def test_ctc_build_kernel_then_sweeps(emu, oracle, shape):
     assert np.array_equal(ptr0, ptr)
     assert np.array_equal(src0[:ptr[-1]], src) and np.array_equal(lab0[:ptr[-1]], lab)
     check_against_oracle(oracle, e, targets, lens, out, grad, T)
+
+
+def test_kernel_sources_at_the_benchmark_shape_against_the_reference_golden(emu):
+    """One utterance of BASELINE config 2 (T=1000, C=64, U=100: 201 graph nodes, 7 node warps) through the
+    source of k_ctc.cu + k_implicit.cu, and through k_banded.cu at K=4, against the golden vector generated
+    from the real reference (tests/golden/make_golden.py) and its float64 evaluation."""
+    import ctypes
+    gold = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+    e, tg = util.bench_inputs(1, 1000, 64, 100)
+    T, Cn = 1000, 64
+    x = e[0].astype(np.float64)
+    mx = x.max(1, keepdims=True)
+    lse = mx[:, 0] + np.log(np.exp(x - mx).sum(1))
+    soft = np.exp(x - lse[:, None])
+
+    def check(out, grad, what):
+        loss = float(lse.sum() - np.float64(out[0]))
+        assert util.close(loss, gold["c2_loss"][0]), (what, loss, gold["c2_loss"][0])
+        assert abs(loss - float(gold["c2_loss_f64"])) < 1e-3 * abs(loss)
+        g = soft + grad[0]
+        # two fp32 evaluations of this lattice differ by ~1e-3 (tests/golden/README.md): the float64
+        # gradient is the referee, and the kernel must be no further from it than the reference is
+        err_kernel = np.abs(g - gold["c2_grad_f64"][0]).max()
+        err_reference = np.abs(gold["c2_grad"][0] - gold["c2_grad_f64"][0]).max()
+        assert util.grad_close(g, gold["c2_grad"][0], 5.0 * T) or err_kernel <= err_reference, (what, err_kernel)
+        assert np.allclose(-grad[0].sum(1), 1.0, atol=2e-3)
+
+    # k_ctc.cu + k_implicit.cu
+    cat = np.ascontiguousarray(tg[0], np.int32)
+    tl = np.array([len(tg[0])], np.int32)
+    lens = np.array([T], np.int32)
+    out = np.zeros(1, np.float32)
+    grad = np.zeros((1, T, Cn), np.float32)
+    status = np.zeros(1, np.int32)
+    ee = np.ascontiguousarray(e, np.float32)
+    rc = emu.emu_implicit_ctc(1, T, Cn, ee.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), cat.ctypes.data_as(i32p),
+                              tl.ctypes.data_as(i32p), 0, out.ctypes.data_as(f32p), grad.ctypes.data_as(f32p),
+                              status.ctypes.data_as(i32p), None, None, None)
+    assert rc == 0 and not status.any()
+    check(out, grad, "implicit")
+
+    # k_banded.cu, K = 4
+    lib = ctypes.CDLL(emu_build.build("banded", ["k_banded.cu"]))
+    lib.emu_banded_ctc.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, i32p, C.c_int, C.c_int, f32p, f32p, i32p]
+    out2 = np.zeros(1, np.float32)
+    grad2 = np.zeros((1, T, Cn), np.float32)
+    status2 = np.zeros(1, np.int32)
+    rc = lib.emu_banded_ctc(1, T, Cn, ee.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), cat.ctypes.data_as(i32p),
+                            tl.ctypes.data_as(i32p), 0, 4, out2.ctypes.data_as(f32p), grad2.ctypes.data_as(f32p),
+                            status2.ctypes.data_as(i32p))
+    assert rc == 0 and not status2.any()
+    check(out2, grad2, "banded")
