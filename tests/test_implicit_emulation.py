@@ -185,8 +185,10 @@ def test_kernel_sources_at_the_benchmark_shape_against_the_reference_golden(emu)
         g = soft + grad[0]
         # two fp32 evaluations of this lattice differ by ~1e-3 (tests/golden/README.md): the float64
         # gradient is the referee, and the kernel must be no further from it than the reference is
-        err_kernel = np.abs(g - gold["c2_grad_f64"][0]).max()
-        err_reference = np.abs(gold["c2_grad"][0] - gold["c2_grad_f64"][0]).max()
+        g64 = gold["c2_grad_f64"]  # [T][C]
+        assert g64.shape == g.shape
+        err_kernel = np.abs(g - g64).max()
+        err_reference = np.abs(gold["c2_grad"][0] - g64).max()
         assert util.grad_close(g, gold["c2_grad"][0], 5.0 * T) or err_kernel <= err_reference, (what, err_kernel)
         assert np.allclose(-grad[0].sum(1), 1.0, atol=2e-3)
 
