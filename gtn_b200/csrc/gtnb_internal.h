@@ -13,20 +13,12 @@
 
 #include "gtn_b200.h"
 
-namespace gtnb {
-
-constexpr uint32_t kRowMask = 0x3FFFFFFFu; // low 30 bits of a row_ptr entry
-constexpr uint32_t kStartBit = 0x40000000u; // node is a start node
-constexpr uint32_t kAcceptBit = 0x80000000u; // node is an accept node
-constexpr int kAlign = 4; // elements; keeps every per-graph slab 16-byte aligned
-
-} // namespace gtnb
-
-#include "gtnb_meta.h" // GraphMeta: plain struct, shared with the host-side kernel emulation (tests/emu)
+#include "gtnb_meta.h" // GraphMeta + layout constants: plain data, shared with the host-side kernel emulation (tests/emu)
 
 /* dynamic shared memory of the CTA (the host-side emulation defines its own) */
 #define GTNB_DYNAMIC_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #define GTNB_STATIC_SMEM(type, name, count) __shared__ type name[count]
+#define GTNB_STATIC_SMEM_2D(type, name, d0, d1) __shared__ type name[d0][d1]
 
 struct gtnb_ctx {
   int device = 0;

@@ -5,7 +5,14 @@
  */
 #pragma once
 
+#include <cstdint>
+
 namespace gtnb {
+
+constexpr uint32_t kRowMask = 0x3FFFFFFFu; // low 30 bits of a row_ptr entry
+constexpr uint32_t kStartBit = 0x40000000u; // node is a start node
+constexpr uint32_t kAcceptBit = 0x80000000u; // node is an accept node
+constexpr int kAlign = 4; // elements; keeps every per-graph slab 16-byte aligned
 
 /*
  * Per-graph descriptor, one per batch entry, resident in HBM.  All bases are

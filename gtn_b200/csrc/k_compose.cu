@@ -23,9 +23,16 @@
  *
  *   compose_grad_kernel = compose's gradFunc (compose.cpp:496-518).
  */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <algorithm>
+
+#include "gtnb_meta.h"
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
 
 #include "gtnb_internal.h"
+#endif
 
 namespace gtnb {
 
@@ -35,9 +42,13 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kMaxWords = 256; // graphs of up to 8192 nodes
 
 __device__ __forceinline__ unsigned lanemask_lt() {
+#ifdef GTNB_HOST_EMU
+  return (1u << (threadIdx.x & 31)) - 1u;
+#else
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+#endif
 }
 
 /* ---- k1: per-frame alive sets ------------------------------------- */
@@ -51,8 +62,8 @@ __global__ void __launch_bounds__(256) compose_alive_kernel(
     uint32_t* __restrict__ alive,
     int W,
     int maxT) {
-  __shared__ uint32_t cur[kMaxWords];
-  __shared__ uint32_t nxt[kMaxWords];
+  GTNB_STATIC_SMEM(uint32_t, cur, kMaxWords);
+  GTNB_STATIC_SMEM(uint32_t, nxt, kMaxWords);
   const GraphMeta m = meta[blockIdx.x];
   const int tid = threadIdx.x;
   const int N1 = m.sg_N, T = m.T;
@@ -210,8 +221,8 @@ __global__ void __launch_bounds__(1024) compose_scan_kernel(
     int32_t* __restrict__ lvl_node_ptr,
     int32_t* __restrict__ lvl_arc_ptr,
     int32_t* __restrict__ acc_nodes) {
-  __shared__ int sn[1024];
-  __shared__ int sa[1024];
+  GTNB_STATIC_SMEM(int, sn, 1024);
+  GTNB_STATIC_SMEM(int, sa, 1024);
   const int b = blockIdx.x;
   const GraphMeta m = meta[b];
   const int tid = threadIdx.x;
@@ -294,7 +305,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) compose_emit_kernel(
     uint32_t* __restrict__ row_ptr,
     int2* __restrict__ arcs,
     int2* __restrict__ gi) {
-  __shared__ int pre[kWarpsPerBlock][kMaxWords]; // popcount prefix of alive[t-1]
+  GTNB_STATIC_SMEM_2D(int, pre, kWarpsPerBlock, kMaxWords); // popcount prefix of alive[t-1]
   const int b = blockIdx.y;
   const GraphMeta m = meta[b];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -460,6 +471,8 @@ __global__ void __launch_bounds__(256) compose_grad_kernel(
 
 } // namespace
 
+#ifndef GTNB_HOST_EMU
+
 int launch_compose(gtnb_ctx* ctx, gtnb_lattice* lat, cudaEvent_t emissions_ready) {
   if (lat->B == 0) return GTNB_OK;
   const int W = lat->alive_words;
@@ -497,5 +510,7 @@ int launch_compose_grad(
       (long long)grad_stride));
   return GTNB_OK;
 }
+
+#endif // GTNB_HOST_EMU
 
 } // namespace gtnb

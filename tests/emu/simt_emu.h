@@ -186,6 +186,28 @@ inline int atomicOr(int32_t* p, int v) {
 inline float atomicAdd(float* p, float v) {
   return std::atomic_ref<float>(*p).fetch_add(v);
 }
+inline int min(int a, int b) {
+  return a < b ? a : b;
+}
+inline int max(int a, int b) {
+  return a > b ? a : b;
+}
+inline unsigned atomicOr(uint32_t* p, uint32_t v) {
+  return std::atomic_ref<uint32_t>(*p).fetch_or(v);
+}
+inline int __popc(unsigned x) {
+  return __builtin_popcount(x);
+}
+inline int __syncthreads_and(int pred) {
+  emu::Cta& c = *emu::g_cta;
+  if (!pred) c.vote.store(1);
+  c.bar.arrive_and_wait();
+  const int r = !c.vote.load();
+  c.bar.arrive_and_wait();
+  if (threadIdx.x == 0) c.vote.store(0);
+  c.bar.arrive_and_wait();
+  return r;
+}
 inline int atomicAdd(int* p, int v) {
   return std::atomic_ref<int>(*p).fetch_add(v);
 }
@@ -215,6 +237,9 @@ inline float __int_as_float(int i) {
 /* a static __shared__ array of the running CTA (one per source line) */
 #define GTNB_STATIC_SMEM(type, name, count) \
   type* name = reinterpret_cast<type*>(emu::g_cta->static_smem(__LINE__, sizeof(type) * (count)))
+
+#define GTNB_STATIC_SMEM_2D(type, name, d0, d1) \
+  type(*name)[d1] = reinterpret_cast<type(*)[d1]>(emu::g_cta->static_smem(__LINE__, sizeof(type) * (d0) * (d1)))
 
 /* dynamic shared memory of the running CTA, 16-byte aligned */
 #define GTNB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_cta->dynamic_smem())

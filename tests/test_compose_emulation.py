@@ -1,0 +1,179 @@
+"""The SOURCE of gtn_b200/csrc/k_compose.cu (frame-synchronous device composition with a
+gtn::linearGraph operand: alive sets, counts, scans, CSR emission, and compose's gradFunc) run on the CPU
+through the SIMT emulator of tests/emu against the oracle's compose (which is pinned to the reference's,
+tests/test_oracle.py).
+
+The device numbers the lattice frame-major; the reference numbers it in BFS discovery order and leaves
+that unspecified (test/functions_test.cpp:137-227 check isomorphism only).  So the comparison is by
+provenance: every composed arc is identified by gradInfo = (arc of the graph operand, arc of the
+emissions chain) (compose.cpp:445), which is unique; the two lattices must hold the same set of
+(provenance, weight) with bit-identical weights, the same node count, and the device lattice must be
+consistent with its own CSR (an arc's end points sit in consecutive frames and correspond to the graph
+arc's end points)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests import emu_build, util
+
+f32p, i32p, u8p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = C.CDLL(emu_build.build("compose", ["k_compose.cu"]))
+    lib.emu_compose.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p, f32p, i32p, i32p,
+                                i32p, i32p, u32p, i32p, f32p, i32p, i32p, i32p, i32p, i32p, f32p, f32p, f32p]
+    return lib
+
+
+def tables_of(og, Cn):
+    """What gtnb_compose_linear uploads for a graph operand: CSR by destination, in-arcs of a node
+    ordered by (source, arc id), matched label = ilabel or -1 when it cannot match an emission."""
+    a = og.arrays()
+    N = len(a["flags"])
+    ptr, src, lab, arc, w = [0], [], [], [], []
+    for d in range(N):
+        ins = sorted(np.nonzero(a["dst"] == d)[0].tolist(), key=lambda k: (int(a["src"][k]), k))
+        for k in ins:
+            l = int(a["ilabel"][k])
+            src.append(int(a["src"][k])), lab.append(l if 0 <= l < Cn else -1), arc.append(k), w.append(float(a["w"][k]))
+        ptr.append(len(src))
+    return dict(flags=a["flags"].astype(np.uint8), ptr=np.array(ptr, np.int32), src=np.array(src, np.int32),
+                lab=np.array(lab, np.int32), arc=np.array(arc, np.int32), w=np.array(w, np.float32),
+                acc=a["accept"].astype(np.int32), g_src=a["src"], g_dst=a["dst"])
+
+
+def cat(xs, dt):
+    xs = [np.asarray(x, dt) for x in xs]
+    return np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0, dt), dt)
+
+
+def run(lib, e, lens, tabs, arc_grads=None):
+    B, T, Cn = e.shape
+    e = np.ascontiguousarray(e, np.float32)
+    lens = np.ascontiguousarray(lens, np.int32)
+    nn = np.array([len(t["flags"]) for t in tabs], np.int32)
+    capN = [int((lens[b] + 1) * nn[b] + 1) for b in range(B)]
+    capA = [max(int(lens[b]) * len(tabs[b]["src"]), 1) for b in range(B)]
+    outN, outA, nacc_out = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    row_ptr = np.zeros(sum(capN), np.uint32)
+    arc_src, gi_g, gi_e = (np.zeros(sum(capA), np.int32) for _ in range(3))
+    arc_w = np.zeros(sum(capA), np.float32)
+    lvl = np.zeros(int(sum(lens + 2)), np.int32)
+    acc_out = np.zeros(max(sum(len(t["acc"]) for t in tabs), 1), np.int32)
+    n_acc = np.array([len(t["acc"]) for t in tabs], np.int32)
+    gg = np.zeros(max(sum(len(t["src"]) for t in tabs), 1), np.float32)
+    ge = np.zeros((B, T, Cn), np.float32)
+    ag = None
+    if arc_grads is not None:
+        ag = np.zeros(sum(capA), np.float32)
+        off = 0
+        for b in range(B):
+            ag[off:off + len(arc_grads[b])] = arc_grads[b]
+            off += capA[b]
+    P = lambda a, t: a.ctypes.data_as(t)
+    flags, ptr = cat([t["flags"] for t in tabs], np.uint8), cat([t["ptr"] for t in tabs], np.int32)
+    src, lab = cat([t["src"] for t in tabs], np.int32), cat([t["lab"] for t in tabs], np.int32)
+    arc, w, acc = cat([t["arc"] for t in tabs], np.int32), cat([t["w"] for t in tabs], np.float32), cat([t["acc"] for t in tabs], np.int32)
+    rc = lib.emu_compose(B, T, Cn, P(e, f32p), P(lens, i32p), P(nn, i32p), P(flags, u8p), P(ptr, i32p), P(src, i32p),
+                         P(lab, i32p), P(arc, i32p), P(w, f32p), P(n_acc, i32p), P(acc, i32p), P(outN, i32p), P(outA, i32p),
+                         P(row_ptr, u32p), P(arc_src, i32p), P(arc_w, f32p), P(gi_g, i32p), P(gi_e, i32p), P(lvl, i32p),
+                         P(acc_out, i32p), P(nacc_out, i32p), None if ag is None else P(ag, f32p), P(gg, f32p), P(ge, f32p))
+    assert rc == 0
+    res, no, ao, lo, co, go = [], 0, 0, 0, 0, 0
+    for b in range(B):
+        N, A = int(outN[b]), int(outA[b])
+        res.append(dict(N=N, A=A, row_ptr=row_ptr[no:no + N + 1].copy(), src=arc_src[ao:ao + A].copy(),
+                        w=arc_w[ao:ao + A].copy(), gi_g=gi_g[ao:ao + A].copy(), gi_e=gi_e[ao:ao + A].copy(),
+                        lvl=lvl[lo:lo + int(lens[b]) + 2].copy(), acc=acc_out[co:co + int(nacc_out[b])].copy(),
+                        grad_graph=gg[go:go + len(tabs[b]["src"])].copy(), grad_emis=ge[b].copy()))
+        no, ao, lo, co, go = no + capN[b], ao + capA[b], lo + int(lens[b]) + 2, co + len(tabs[b]["acc"]), go + len(tabs[b]["src"])
+    return res
+
+
+def check_lattice(r, tab, og, e_b, Tb, Cn):
+    lin = po.Graph.linear(Tb, Cn, e_b[:Tb])
+    want = po.compose(og, lin)
+    g1, g2 = want.gradinfo()
+    wa = want.arrays()
+    assert r["N"] == len(wa["flags"]) and r["A"] == len(wa["src"]), (r["N"], len(wa["flags"]), r["A"], len(wa["src"]))
+    # same arcs by provenance, bit-identical weights (compose.cpp:435: first.weight + second.weight)
+    mine = sorted(zip(r["gi_g"].tolist(), r["gi_e"].tolist(), r["w"].view(np.int32).tolist()))
+    ref = sorted(zip(g1.tolist(), g2.tolist(), wa["w"].view(np.int32).tolist()))
+    assert mine == ref
+    # CSR consistency: level = frame, node identity = (graph node, frame)
+    rp = (r["row_ptr"] & 0x3FFFFFFF).astype(np.int64)
+    assert rp[0] == 0 and rp[r["N"]] == r["A"] and (np.diff(rp) >= 0).all()
+    lvl = r["lvl"]
+    assert lvl[0] == 0 and lvl[Tb + 1] == r["N"]
+    level_of = np.searchsorted(lvl[1:], np.arange(r["N"]), side="right")
+    ident = {}
+    for n in range(r["N"]):
+        for a in range(rp[n], rp[n + 1]):
+            i, j = int(r["gi_g"][a]), int(r["gi_e"][a])
+            t = j // Cn + 1
+            assert level_of[n] == t and level_of[r["src"][a]] == t - 1
+            assert ident.setdefault(n, int(tab["g_dst"][i])) == int(tab["g_dst"][i])
+            assert ident.setdefault(int(r["src"][a]), int(tab["g_src"][i])) == int(tab["g_src"][i])
+    # start / accept bits
+    starts = [n for n in range(r["N"]) if r["row_ptr"][n] & 0x40000000]
+    assert all(level_of[n] == 0 for n in starts) and len(starts) == int((wa["flags"] & 1).sum())
+    accepts = sorted(n for n in range(r["N"]) if r["row_ptr"][n] & 0x80000000)
+    assert accepts == sorted(r["acc"].tolist()) and len(accepts) == int(((wa["flags"] & 2) > 0).sum())
+    assert all(level_of[n] == Tb for n in accepts)
+    return want
+
+
+@pytest.mark.parametrize("shape", [(3, 14, 6, 3), (2, 9, 5, 4), (2, 40, 8, 12), (1, 3, 4, 0), (1, 25, 40, 9)])
+def test_compose_kernels_ctc_lattices(emu, shape):
+    """CTC target graphs x emissions; ragged T (the cone at both ends and the all-alive steady state of
+    compose_count / compose_emit both occur), T == 2U+1, an empty transcript."""
+    B, T, Cn, U = shape
+    e, targets = util.bench_inputs(B, T, Cn, max(U, 1), seed=31)
+    if U == 0:
+        targets = [t[:0] for t in targets]
+    lens = np.minimum(np.array([max(T - 4 * b, 2 * U + 1) for b in range(B)], np.int32), T)
+    ogs = [po.Graph.ctc(t, 0, True) for t in targets]
+    tabs = [tables_of(g, Cn) for g in ogs]
+    rng = np.random.default_rng(5)
+    res = run(emu, e, lens, tabs)
+    grads = [rng.integers(-3, 4, r["A"]).astype(np.float32) for r in res]
+    res = run(emu, e, lens, tabs, arc_grads=grads)
+    for b in range(B):
+        check_lattice(res[b], tabs[b], ogs[b], e[b], int(lens[b]), Cn)
+        # compose's gradFunc (compose.cpp:496-518): scatter-add by provenance
+        gg = np.zeros(len(tabs[b]["src"]), np.float32)
+        np.add.at(gg, res[b]["gi_g"], grads[b])
+        ge = np.zeros(T * Cn, np.float32)
+        np.add.at(ge, res[b]["gi_e"], grads[b])
+        assert np.array_equal(res[b]["grad_graph"], gg)
+        assert np.array_equal(res[b]["grad_emis"].reshape(-1), ge)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_compose_kernels_general_graph_operand(emu, seed):
+    """Any epsilon-free graph operand: cycles, several start / accept nodes, dead ends, mixed labels per
+    node, labels that no emission carries (they can never match, compose.cpp:211-374)."""
+    rng = np.random.default_rng(900 + seed)
+    Cn, T, B = 5, int(rng.integers(1, 9)), 2
+    ogs, tabs = [], []
+    for _ in range(B):
+        n = int(rng.integers(1, 40 if seed == 5 else 9))
+        flags = np.zeros(n, np.uint8)
+        flags[rng.integers(0, n, max(1, n // 3))] |= 1
+        flags[rng.integers(0, n, max(1, n // 3))] |= 2
+        na = int(rng.integers(0, 3 * n + 1))
+        src, dst = rng.integers(0, n, na), rng.integers(0, n, na)
+        lab = rng.integers(0, Cn + 2, na)  # Cn, Cn+1: no such emission
+        w = rng.integers(-3, 4, na).astype(np.float32)
+        og = po.Graph.from_arrays(flags, src, dst, lab, lab, w)
+        ogs.append(og)
+        tabs.append(tables_of(og, Cn))
+    e = rng.integers(-4, 5, (B, T, Cn)).astype(np.float32)
+    lens = np.array([T, max(T - 1, 0)], np.int32)
+    res = run(emu, e, lens, tabs)
+    for b in range(B):
+        check_lattice(res[b], tabs[b], ogs[b], e[b], int(lens[b]), Cn)
