@@ -266,6 +266,5 @@ int launch_linear_forward(
     int tropical, float* scores, float* grad, int64_t grad_stride, const float* deltas, float delta_all,
     int overwrite = 0, float* scratch = nullptr);
 
-enum { MODE_LOG = 0, MODE_TROPICAL = 1, MODE_PATH = 2 };
 
 } // namespace gtnb

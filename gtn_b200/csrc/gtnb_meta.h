@@ -14,6 +14,9 @@ constexpr uint32_t kStartBit = 0x40000000u; // node is a start node
 constexpr uint32_t kAcceptBit = 0x80000000u; // node is an accept node
 constexpr int kAlign = 4; // elements; keeps every per-graph slab 16-byte aligned
 
+/* semiring / output of the shortest-distance kernels */
+enum { MODE_LOG = 0, MODE_TROPICAL = 1, MODE_PATH = 2 };
+
 /*
  * Per-graph descriptor, one per batch entry, resident in HBM.  All bases are
  * ELEMENT offsets into the batch-wide arrays of gtnb_lattice.

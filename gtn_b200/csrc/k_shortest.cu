@@ -20,12 +20,20 @@
  * the running sum started at -1 (shortest.cpp:102-114).  score + weight is a
  * single fp32 add (no FMA can be contracted into it: there is no multiply).
  */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <cstdlib>
+
+#include "gtn_b200.h"
+#include "gtnb_meta.h"
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include <cstdlib>
 
 #include "gtnb_internal.h"
+#endif
 
 namespace gtnb {
 
@@ -332,6 +340,8 @@ __global__ void gather_prov_kernel(
 
 } // namespace
 
+#ifndef GTNB_HOST_EMU
+
 static bool use_staged(const gtnb_ctx* ctx, const gtnb_lattice* lat) {
   return ctx->use_staged && staged_supported(lat);
 }
@@ -390,5 +400,7 @@ int launch_gather_prov(
       lat->meta, lat->gi, lat->arcs, max_len, path_dev, len_dev, pg, pl, pw));
   return GTNB_OK;
 }
+
+#endif // GTNB_HOST_EMU
 
 } // namespace gtnb

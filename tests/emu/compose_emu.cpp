@@ -1,11 +1,13 @@
 /*
  * tests/emu/compose_emu.cpp -- TEST INFRASTRUCTURE: the SOURCE of gtn_b200/csrc/k_compose.cu
  * (frame-synchronous device composition: alive sets, counts, scans, CSR emission, and compose's
- * gradFunc) on the CPU through tests/emu/simt_emu.h.  The slab layout of gtnb_capi.cu's
- * composed_alloc and the launch geometry of launch_compose are restated here.
+ * gradFunc) and of k_shortest.cu's generic shortest-distance kernels on the CPU through
+ * tests/emu/simt_emu.h.  The slab layout of gtnb_capi.cu's composed_alloc and the launch geometry
+ * of launch_compose / launch_forward / launch_backward are restated here.
  */
 #define GTNB_HOST_EMU 1
 #include "../../gtn_b200/csrc/k_compose.cu"
+#include "../../gtn_b200/csrc/k_shortest.cu"
 
 #include <vector>
 
@@ -15,35 +17,32 @@ namespace {
 long long align_up(long long x, long long a) {
   return (x + a - 1) / a * a;
 }
-} // namespace
 
-extern "C" {
 
-/*
- * compose(g_b, linearGraph(T_b, C) with the given emissions) for B graphs given as concatenated
- * CSR-by-destination tables (n_nodes[B], in_ptr with N_b + 1 entries per graph, offsets local):
- * flags bit 0 start / bit 1 accept, in_src / in_label (-1: cannot match) / in_arc (Graph arc id) / in_w,
- * accept lists acc (n_acc[B]).  Outputs per graph b (capacities (T+1) N_b + 1 nodes, T A_b arcs,
- * concatenated at node_off[b] / arc_off[b] which the caller computes the same way):
- *   out_N[b], out_A[b], row_ptr, arc_src, arc_w, gi_graph, gi_emis, lvl_node_ptr (T_b + 2 per graph at
- *   lvl_off[b]), accept nodes of the lattice (acc_out, n_acc_out[b]).
- * arc_grad (nullable, indexed like the arcs): if given, compose's gradFunc is run into grad_graph
- * (A_b per graph, concatenated) and grad_emis [B][T][C] (both zero on entry).
- */
-int emu_compose(
-    int B, int T, int C, const float* emissions, const int32_t* lens, const int32_t* n_nodes, const uint8_t* flags,
-    const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label, const int32_t* in_arc, const float* in_w,
-    const int32_t* n_acc, const int32_t* acc, int32_t* out_N, int32_t* out_A, uint32_t* row_ptr, int32_t* arc_src,
-    float* arc_w, int32_t* gi_graph, int32_t* gi_emis, int32_t* lvl_node_ptr, int32_t* acc_out, int32_t* n_acc_out,
-    const float* arc_grad, float* grad_graph, float* grad_emis) {
-  using namespace gtnb;
-  std::vector<GraphMeta> meta(B);
+/* the packed batch as composed_alloc lays it out + the four compose launches */
+struct Lat {
+  int B = 0, W = 0, maxT = 0;
+  long long tn = 0, ta = 0, tl = 0, tc = 0;
+  std::vector<GraphMeta> meta;
   std::vector<uint8_t> sg_flags;
-  std::vector<int32_t> sg_ptr, sg_src, sg_lab, sg_arc;
+  std::vector<int32_t> sg_ptr, sg_src, sg_lab, sg_arc, acc_stage, lnp, lap;
   std::vector<float> sg_w;
+  std::vector<uint32_t> alive, rp;
+  std::vector<int2> arcs, gi;
+};
+
+int build_lattice(
+    Lat& L, int B, int T, int C, const float* emissions, const int32_t* lens, const int32_t* n_nodes,
+    const uint8_t* flags, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label, const int32_t* in_arc,
+    const float* in_w, const int32_t* n_acc, const int32_t* acc) {
+  using namespace gtnb;
+  auto& meta = L.meta;
+  auto& sg_flags = L.sg_flags;
+  auto &sg_ptr = L.sg_ptr, &sg_src = L.sg_src, &sg_lab = L.sg_lab, &sg_arc = L.sg_arc, &acc_stage = L.acc_stage;
+  auto& sg_w = L.sg_w;
+  meta.assign(B, GraphMeta{});
   long long tn = 0, ta = 0, tl = 0, tc = 0, gg = 0, nb = 0, pb = 0, ab = 0, accb = 0;
   int maxN = 0, maxT = 0;
-  std::vector<int32_t> acc_stage;
   for (int b = 0; b < B; b++) {
     const int N = n_nodes[b], A = in_ptr[pb + N], Tb = lens ? lens[b] : T;
     GraphMeta& m = meta[b];
@@ -101,9 +100,15 @@ int emu_compose(
   }
   const int W = (maxN + 31) / 32;
   if (W > kMaxWords) return 1;
-  std::vector<uint32_t> alive((size_t)B * (maxT + 1) * W + 16, 0), rp((size_t)tn + 16, 0);
-  std::vector<int32_t> lnp((size_t)tl + 16, 0), lap((size_t)tl + 16, 0);
-  std::vector<int2> arcs((size_t)ta + 16), gi((size_t)ta + 16);
+  L.alive.assign((size_t)B * (maxT + 1) * W + 16, 0);
+  L.rp.assign((size_t)tn + 16, 0);
+  L.lnp.assign((size_t)tl + 16, 0);
+  L.lap.assign((size_t)tl + 16, 0);
+  L.arcs.assign((size_t)ta + 16, int2{0, 0});
+  L.gi.assign((size_t)ta + 16, int2{0, 0});
+  auto &alive = L.alive, &rp = L.rp;
+  auto &lnp = L.lnp, &lap = L.lap;
+  auto &arcs = L.arcs, &gi = L.gi;
 
   emu::launch(B, 256, 0, [&] {
     compose_alive_kernel(meta.data(), sg_flags.data(), sg_ptr.data(), sg_src.data(), sg_lab.data(), alive.data(), W, maxT);
@@ -130,6 +135,46 @@ int emu_compose(
                             arcs.data(), gi.data());
       });
 
+  L.B = B;
+  L.W = W;
+  L.maxT = maxT;
+  L.tn = tn;
+  L.ta = ta;
+  L.tl = tl;
+  L.tc = tc;
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+/*
+ * compose(g_b, linearGraph(T_b, C) with the given emissions) for B graphs given as concatenated
+ * CSR-by-destination tables (n_nodes[B], in_ptr with N_b + 1 entries per graph, offsets local):
+ * flags bit 0 start / bit 1 accept, in_src / in_label (-1: cannot match) / in_arc (Graph arc id) / in_w,
+ * accept lists acc (n_acc[B]).  Outputs per graph b (capacities (T+1) N_b + 1 nodes, T A_b arcs,
+ * concatenated at node_off[b] / arc_off[b] which the caller computes the same way):
+ *   out_N[b], out_A[b], row_ptr, arc_src, arc_w, gi_graph, gi_emis, lvl_node_ptr (T_b + 2 per graph at
+ *   lvl_off[b]), accept nodes of the lattice (acc_out, n_acc_out[b]).
+ * arc_grad (nullable, indexed like the arcs): if given, compose's gradFunc is run into grad_graph
+ * (A_b per graph, concatenated) and grad_emis [B][T][C] (both zero on entry).
+ */
+int emu_compose(
+    int B, int T, int C, const float* emissions, const int32_t* lens, const int32_t* n_nodes, const uint8_t* flags,
+    const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label, const int32_t* in_arc, const float* in_w,
+    const int32_t* n_acc, const int32_t* acc, int32_t* out_N, int32_t* out_A, uint32_t* row_ptr, int32_t* arc_src,
+    float* arc_w, int32_t* gi_graph, int32_t* gi_emis, int32_t* lvl_node_ptr, int32_t* acc_out, int32_t* n_acc_out,
+    const float* arc_grad, float* grad_graph, float* grad_emis) {
+  using namespace gtnb;
+  Lat L;
+  if (int rc = build_lattice(L, B, T, C, emissions, lens, n_nodes, flags, in_ptr, in_src, in_label, in_arc, in_w, n_acc, acc))
+    return rc;
+  auto& meta = L.meta;
+  auto &rp = L.rp;
+  auto &lnp = L.lnp, &acc_stage = L.acc_stage;
+  auto &arcs = L.arcs, &gi = L.gi;
+  const long long ta = L.ta;
   // hand the lattices back, graph by graph, in the caller's (unaligned) capacities
   long long no = 0, ao = 0, lo = 0, co = 0;
   for (int b = 0; b < B; b++) {
@@ -169,6 +214,74 @@ int emu_compose(
           gridDim.x = ggx;
           compose_grad_kernel(meta.data(), rp.data(), ag.data(), gi.data(), grad_graph, grad_emis, (long long)T * C);
         });
+  }
+  return 0;
+}
+
+/*
+ * The materialised criterion path end to end, as gtnb_ctc_loss runs it with the "implicit" and
+ * "staged" flags off: compose -> sd_forward_generic (log semiring) -> sd_backward_generic (deltas)
+ * -> compose's gradFunc.  Graph tables as in emu_compose.  out_scores[B] = forwardScore of the
+ * lattice; grad_emis [B][T][C] (zero on entry) receives deltas[b] * d score / d emissions; grad_graph
+ * likewise per graph arc.  With viterbi != 0 additionally: viterbiScore into vit_scores[B] and the best
+ * path's emission labels into vit_labels [B][T] (MODE_PATH forward + traceback + gather_prov).
+ */
+int emu_materialised(
+    int B, int T, int C, const float* emissions, const int32_t* lens, const int32_t* n_nodes, const uint8_t* flags,
+    const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label, const int32_t* in_arc, const float* in_w,
+    const int32_t* n_acc, const int32_t* acc, const float* deltas, float* out_scores, float* grad_graph,
+    float* grad_emis, int viterbi, float* vit_scores, int32_t* vit_labels) {
+  using namespace gtnb;
+  Lat L;
+  if (int rc = build_lattice(L, B, T, C, emissions, lens, n_nodes, flags, in_ptr, in_src, in_label, in_arc, in_w, n_acc, acc))
+    return rc;
+  std::vector<float> scores((size_t)L.tn + 16, 0.0f), node_grad((size_t)L.tn + 16, 0.0f), arc_grad((size_t)L.ta + 16, 0.0f);
+  std::vector<int32_t> back_ptr((size_t)L.tn + 16, -1), best(B, -1);
+  emu::launch(B, kThreads, 0, [&] {
+    sd_forward_generic<MODE_LOG>(L.meta.data(), L.lnp.data(), L.rp.data(), L.arcs.data(), nullptr, L.acc_stage.data(),
+                                 scores.data(), back_ptr.data(), out_scores, best.data());
+  });
+  emu::launch(B, kThreads, 0, [&] {
+    sd_backward_generic<false>(L.meta.data(), L.lnp.data(), nullptr, nullptr, L.rp.data(), L.arcs.data(),
+                               L.acc_stage.data(), scores.data(), out_scores, best.data(), deltas, node_grad.data(),
+                               arc_grad.data());
+  });
+  int capN = 1;
+  for (int b = 0; b < B; b++) capN = std::max(capN, L.meta[b].cap_N);
+  const int ggx = std::min((capN + 255) / 256, 4096);
+  for (int by = 0; by < B; by++)
+    for (int bx = 0; bx < ggx; bx++)
+      emu::launch(1, 256, 0, [&] {
+        blockIdx.x = bx;
+        blockIdx.y = by;
+        gridDim.x = ggx;
+        compose_grad_kernel(L.meta.data(), L.rp.data(), arc_grad.data(), L.gi.data(), grad_graph, grad_emis,
+                            (long long)T * C);
+      });
+  if (viterbi) {
+    emu::launch(B, kThreads, 0, [&] {
+      sd_forward_generic<MODE_PATH>(L.meta.data(), L.lnp.data(), L.rp.data(), L.arcs.data(), nullptr, L.acc_stage.data(),
+                                    scores.data(), back_ptr.data(), vit_scores, best.data());
+    });
+    std::vector<int32_t> path((size_t)B * std::max(T, 1), -1), plen(B, 0), pg((size_t)B * std::max(T, 1), -1),
+        pl((size_t)B * std::max(T, 1), -1);
+    emu::launch((B + 63) / 64, 64, 0, [&] {
+      traceback_kernel(L.meta.data(), L.arcs.data(), back_ptr.data(), best.data(), B, T, path.data(), plen.data());
+    });
+    if (T > 0)
+      for (int by = 0; by < B; by++)
+        for (int bx = 0; bx < (T + 127) / 128; bx++)
+          emu::launch(1, 128, 0, [&] {
+            blockIdx.x = bx;
+            blockIdx.y = by;
+            gather_prov_kernel(L.meta.data(), L.gi.data(), L.arcs.data(), T, path.data(), plen.data(), pg.data(),
+                               pl.data(), nullptr);
+          });
+    for (int b = 0; b < B; b++)
+      for (int t = 0; t < T; t++) {
+        const int32_t j = t < plen[b] ? pl[(size_t)b * T + t] : -1; // arc of the emissions chain: frame * C + label
+        vit_labels[(size_t)b * T + t] = j >= 0 ? j % C : -1;
+      }
   }
   return 0;
 }

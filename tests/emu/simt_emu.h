@@ -32,6 +32,7 @@
 #define __launch_bounds__(...)
 #define __align__(x) alignas(x)
 #define CUDART_INF_F (__builtin_inff())
+#define CUDART_NAN_F (__builtin_nanf(""))
 
 namespace emu {
 

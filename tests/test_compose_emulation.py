@@ -177,3 +177,86 @@ def test_compose_kernels_general_graph_operand(emu, seed):
     res = run(emu, e, lens, tabs)
     for b in range(B):
         check_lattice(res[b], tabs[b], ogs[b], e[b], int(lens[b]), Cn)
+
+
+def run_materialised(lib, e, lens, tabs, deltas, viterbi=False):
+    B, T, Cn = e.shape
+    e = np.ascontiguousarray(e, np.float32)
+    lens = np.ascontiguousarray(lens, np.int32)
+    deltas = np.ascontiguousarray(deltas, np.float32)
+    nn = np.array([len(t["flags"]) for t in tabs], np.int32)
+    n_acc = np.array([len(t["acc"]) for t in tabs], np.int32)
+    out = np.zeros(B, np.float32)
+    gg = np.zeros(max(sum(len(t["src"]) for t in tabs), 1), np.float32)
+    ge = np.zeros((B, T, Cn), np.float32)
+    vs = np.zeros(B, np.float32)
+    vl = np.full((B, max(T, 1)), -9, np.int32)
+    P = lambda a, t: a.ctypes.data_as(t)
+    flags, ptr = cat([t["flags"] for t in tabs], np.uint8), cat([t["ptr"] for t in tabs], np.int32)
+    src, lab = cat([t["src"] for t in tabs], np.int32), cat([t["lab"] for t in tabs], np.int32)
+    arc, w, acc = cat([t["arc"] for t in tabs], np.int32), cat([t["w"] for t in tabs], np.float32), cat([t["acc"] for t in tabs], np.int32)
+    lib.emu_materialised.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p, f32p, i32p,
+                                     i32p, f32p, f32p, f32p, f32p, C.c_int, f32p, i32p]
+    rc = lib.emu_materialised(B, T, Cn, P(e, f32p), P(lens, i32p), P(nn, i32p), P(flags, u8p), P(ptr, i32p), P(src, i32p),
+                              P(lab, i32p), P(arc, i32p), P(w, f32p), P(n_acc, i32p), P(acc, i32p), P(deltas, f32p),
+                              P(out, f32p), P(gg, f32p), P(ge, f32p), int(viterbi), P(vs, f32p), P(vl, i32p))
+    assert rc == 0
+    return out, gg, ge, vs, vl
+
+
+@pytest.mark.parametrize("shape", [(3, 14, 6, 3), (2, 9, 5, 4), (2, 40, 8, 12), (1, 25, 40, 9)])
+def test_materialised_ctc_path_end_to_end(emu, oracle, shape):
+    """compose -> sd_forward_generic -> sd_backward_generic -> compose gradFunc (k_compose.cu + k_shortest.cu):
+    the CSR formulation of the north star, as gtnb_ctc_loss runs it with the implicit and staged flags off."""
+    B, T, Cn, U = shape
+    e, targets = util.bench_inputs(B, T, Cn, U, seed=77)
+    lens = np.minimum(np.array([max(T - 4 * b, 2 * U + 1) for b in range(B)], np.int32), T)
+    ogs = [po.Graph.ctc(t, 0, True) for t in targets]
+    tabs = [tables_of(g, Cn) for g in ogs]
+    out, gg, ge, _, _ = run_materialised(emu, e, lens, tabs, -np.ones(B, np.float32))
+    for b in range(B):
+        Tb = int(lens[b])
+        lo, go = oracle.ctc_loss(e[b, :Tb], targets[b], 0, True)
+        x = e[b, :Tb].astype(np.float64)
+        mx = x.max(1, keepdims=True)
+        lse = mx[:, 0] + np.log(np.exp(x - mx).sum(1))
+        assert util.close(float(lse.sum() - np.float64(out[b])), lo), (b, out[b], lo)
+        g = np.exp(x - lse[:, None]) + ge[b, :Tb]
+        assert util.grad_close(g, go, 5.0 * T), (b, float(np.abs(g - go).max()))
+        assert not ge[b, Tb:].any()
+    # the graph-side gradient (compose.cpp:500-506): minus the expected count of each target-graph arc; the
+    # arcs into one graph node are used once per frame the node is occupied, so per utterance they sum to -T
+    off = 0
+    for b in range(B):
+        A = len(tabs[b]["src"])
+        assert np.isclose(gg[off:off + A].sum(), -float(lens[b]), rtol=1e-4)
+        off += A
+
+
+@pytest.mark.parametrize("ties", [False, True])
+def test_materialised_viterbi_path(emu, oracle, ties):
+    """viterbiPath(intersect(ctc, emissions)): MODE_PATH forward + traceback + label provenance; the score
+    bit for bit, the path with == when nothing ties exactly."""
+    B, T, Cn, U = 3, 18, 6, 4
+    rng = np.random.default_rng(21 + ties)
+    e = (rng.integers(-2, 3, (B, T, Cn)) if ties else rng.uniform(-5, 5, (B, T, Cn))).astype(np.float32)
+    targets = [rng.integers(1, Cn, U).astype(np.int32) for _ in range(B)]
+    lens = np.array([T, T - 3, T - 7], np.int32)
+    ogs = [po.Graph.ctc(t, 0, True) for t in targets]
+    tabs = [tables_of(g, Cn) for g in ogs]
+    _, _, _, vs, vl = run_materialised(emu, e, lens, tabs, np.ones(B, np.float32), viterbi=True)
+    for b in range(B):
+        Tb = int(lens[b])
+        want_path, want_score = oracle.viterbi_ctc(e[b, :Tb], targets[b], 0, True)
+        assert vs[b] == np.float32(want_score)
+        got = vl[b, :Tb]
+        if not ties:
+            assert np.array_equal(got, want_path), (b, got, want_path)
+            continue
+        # exact ties: the reference keeps the first-RELAXED predecessor, which follows compose's BFS
+        # numbering of the product states; the device lattice is numbered frame-major, so an equally
+        # optimal alignment may come back (DESIGN.md section 4).  It must be one: a valid CTC
+        # alignment of the target with the same total score.
+        collapsed = [int(l) for k, l in enumerate(got) if l != 0 and (k == 0 or l != got[k - 1])]
+        assert collapsed == targets[b].tolist(), (b, got, targets[b])
+        assert np.float32(sum(float(e[b, t, got[t]]) for t in range(Tb))) == np.float32(want_score)
