@@ -4,6 +4,10 @@
  */
 #pragma once
 
+#ifdef GTNB_HOST_EMU
+#error "GTNB_HOST_EMU is for tests/emu only (kernel sources compiled by g++ for the CPU test suite): the product library is never built with it, and this header is not part of that build"
+#endif
+
 #include <cuda_runtime.h>
 
 #include <cstdint>

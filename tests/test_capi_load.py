@@ -41,3 +41,15 @@ def test_no_cpu_fallback():
     with pytest.raises(capi.GtnbError) as ei:
         capi.Ctx(0)
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_library_contains_no_emulation_code():
+    """tests/emu compiles kernel SOURCES with g++ (-DGTNB_HOST_EMU) for CPU-side logic tests; none of that
+    may reach the product: the Makefile never defines the macro (gtnb_internal.h refuses it) and the
+    library exports no emulator symbol."""
+    import subprocess
+    mk = open(os.path.join(ROOT, "gtn_b200", "csrc", "Makefile")).read()
+    assert "GTNB_HOST_EMU" not in mk
+    so = os.path.join(ROOT, "gtn_b200", "lib", "libgtn_b200.so")
+    syms = subprocess.run(["nm", "-DC", "--defined-only", so], capture_output=True, text=True).stdout
+    assert "emu::" not in syms and "simt" not in syms.lower()
