@@ -112,6 +112,7 @@ int emu_banded_ctc(
     default: RUN_K(4) break;
   }
 #undef RUN_K
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }
 

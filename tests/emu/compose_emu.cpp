@@ -142,6 +142,7 @@ int build_lattice(
   L.ta = ta;
   L.tl = tl;
   L.tc = tc;
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }
 
@@ -215,6 +216,7 @@ int emu_compose(
           compose_grad_kernel(meta.data(), rp.data(), ag.data(), gi.data(), grad_graph, grad_emis, (long long)T * C);
         });
   }
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }
 
@@ -283,6 +285,7 @@ int emu_materialised(
         vit_labels[(size_t)b * T + t] = j >= 0 ? j % C : -1;
       }
   }
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }
 

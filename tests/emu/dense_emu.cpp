@@ -32,6 +32,7 @@ int emu_viterbi_dense(int B, int T, int C, const float* emissions, const int32_t
     default: RUN(32); break;
   }
 #undef RUN
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }
 

@@ -92,6 +92,7 @@ int emu_implicit(
                                           scores.data(), out_scores, deltas.data(), grad, (long long)T * C, C,
                                           lb);
   });
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }
 
@@ -164,6 +165,7 @@ int emu_implicit_ctc(
                                           in_w.data(), in_arc.data(), nullptr, emissions, scores.data(),
                                           out_scores, deltas.data(), grad, (long long)T * C, C, lb);
   });
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }
 

@@ -59,6 +59,7 @@ int emu_linear(int B, int T, int C, const float* emissions, const int32_t* lens,
         });
   }
   emu::launch(B, 256, 0, [&] { linear_reduce_kernel(lens, T, row.data(), scores); });
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }
 

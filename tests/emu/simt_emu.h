@@ -16,10 +16,12 @@
 #include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -82,26 +84,44 @@ inline thread_local emu::Dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace emu {
 
+/* set when the host refused to create the threads of a CTA: the drivers return kEmuNoThreads and the
+ * tests skip instead of failing (a sandbox with a low thread limit must not turn the suite red) */
+inline std::atomic<bool> g_launch_failed{false};
+constexpr int kEmuNoThreads = 77;
+
 /* run `body()` once per thread of a grid x block launch, CTAs one after the other */
 template <class F>
 void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& body) {
-  for (unsigned b = 0; b < grid; b++) {
+  for (unsigned b = 0; b < grid && !g_launch_failed.load(); b++) {
     Cta cta(block, smem_bytes);
     std::vector<std::thread> threads;
     threads.reserve(block);
+    // the threads park on `go` until all of them exist: if the host refuses one, none runs the body
+    std::atomic<int> go{0}; // 0 wait, 1 run, -1 abandon
+    // GTNB_EMU_MAX_THREADS=n simulates a host that refuses the (n+1)-th thread (tests/test_dense_emulation.py)
+    const char* cap = std::getenv("GTNB_EMU_MAX_THREADS");
     for (unsigned t = 0; t < block; t++) {
-      threads.emplace_back([&, t] {
-        g_cta = &cta;
-        threadIdx = Dim3{t, 0, 0};
-        blockIdx = Dim3{b, 0, 0};
-        blockDim = Dim3{block, 1, 1};
-        gridDim = Dim3{grid, 1, 1};
-        body();
-        // an exited thread no longer takes part in barriers
-        cta.bar.arrive_and_drop();
-        cta.warp_bar[t / 32]->arrive_and_drop();
-      });
+      try {
+        if (cap && t >= (unsigned)std::atoi(cap)) throw std::system_error(std::make_error_code(std::errc::resource_unavailable_try_again));
+        threads.emplace_back([&, t] {
+          while (go.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+          if (go.load() < 0) return;
+          g_cta = &cta;
+          threadIdx = Dim3{t, 0, 0};
+          blockIdx = Dim3{b, 0, 0};
+          blockDim = Dim3{block, 1, 1};
+          gridDim = Dim3{grid, 1, 1};
+          body();
+          // an exited thread no longer takes part in barriers
+          cta.bar.arrive_and_drop();
+          cta.warp_bar[t / 32]->arrive_and_drop();
+        });
+      } catch (const std::system_error&) {
+        g_launch_failed.store(true);
+        break;
+      }
     }
+    go.store(g_launch_failed.load() ? -1 : 1, std::memory_order_release);
     for (auto& th : threads) th.join();
   }
 }

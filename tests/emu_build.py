@@ -23,3 +23,11 @@ def build(name, kernels):
     if r.returncode != 0:
         pytest.skip("cannot build the kernel emulation with this g++: " + r.stderr.strip().splitlines()[-1][:200])
     return so
+
+
+def check(rc):
+    """Return code of an emulation driver: 0 ok; 77 = the host refused to create the threads of a CTA
+    (sandbox thread limit) -> skip, do not fail."""
+    if rc == 77:
+        pytest.skip("the host refused to create the emulator's threads (thread limit)")
+    assert rc == 0, rc

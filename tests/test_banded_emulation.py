@@ -37,7 +37,7 @@ def run(lib, e, targets, lens, blank=0, K=4):
     rc = lib.emu_banded_ctc(B, T, Cn, e.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), cat.ctypes.data_as(i32p),
                             tl.ctypes.data_as(i32p), blank, K, out.ctypes.data_as(f32p), grad.ctypes.data_as(f32p),
                             status.ctypes.data_as(i32p))
-    assert rc == 0
+    emu_build.check(rc)
     return out, grad, status
 
 

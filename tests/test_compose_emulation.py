@@ -82,7 +82,7 @@ def run(lib, e, lens, tabs, arc_grads=None):
                          P(lab, i32p), P(arc, i32p), P(w, f32p), P(n_acc, i32p), P(acc, i32p), P(outN, i32p), P(outA, i32p),
                          P(row_ptr, u32p), P(arc_src, i32p), P(arc_w, f32p), P(gi_g, i32p), P(gi_e, i32p), P(lvl, i32p),
                          P(acc_out, i32p), P(nacc_out, i32p), None if ag is None else P(ag, f32p), P(gg, f32p), P(ge, f32p))
-    assert rc == 0
+    emu_build.check(rc)
     res, no, ao, lo, co, go = [], 0, 0, 0, 0, 0
     for b in range(B):
         N, A = int(outN[b]), int(outA[b])
@@ -200,7 +200,7 @@ def run_materialised(lib, e, lens, tabs, deltas, viterbi=False):
     rc = lib.emu_materialised(B, T, Cn, P(e, f32p), P(lens, i32p), P(nn, i32p), P(flags, u8p), P(ptr, i32p), P(src, i32p),
                               P(lab, i32p), P(arc, i32p), P(w, f32p), P(n_acc, i32p), P(acc, i32p), P(deltas, f32p),
                               P(out, f32p), P(gg, f32p), P(ge, f32p), int(viterbi), P(vs, f32p), P(vl, i32p))
-    assert rc == 0
+    emu_build.check(rc)
     return out, gg, ge, vs, vl
 
 

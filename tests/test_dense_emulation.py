@@ -36,8 +36,27 @@ def test_dense_viterbi_kernel_source_matches_oracle(emu, oracle, shape, ties):
     scores = np.zeros(B, np.float32)
     rc = emu.emu_viterbi_dense(B, T, Cn, e.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), tw.ctypes.data_as(f32p),
                                paths.ctypes.data_as(i32p), scores.ctypes.data_as(f32p))
-    assert rc == 0
+    emu_build.check(rc)
     for b in range(B):
         want_path, want_score = oracle.viterbi_dense(e[b, :lens[b]], tw)
         assert np.array_equal(paths[b, :lens[b]], want_path), (b, paths[b, :lens[b]], want_path)
         assert scores[b] == np.float32(want_score), (b, scores[b], want_score)
+
+
+def test_emulator_skips_when_the_host_refuses_threads(emu, monkeypatch):
+    """A sandbox with a low thread limit must skip the emulation tests, not abort the suite: the CTA's
+    threads park until all of them exist, and the driver reports 77 when one could not be created."""
+    monkeypatch.setenv("GTNB_EMU_MAX_THREADS", "100")
+    e = np.zeros((1, 4, 8), np.float32)
+    tw = np.zeros(8 + 64, np.float32)
+    paths = np.zeros((1, 4), np.int32)
+    scores = np.zeros(1, np.float32)
+    rc = emu.emu_viterbi_dense(1, 4, 8, e.ctypes.data_as(f32p), None, tw.ctypes.data_as(f32p), paths.ctypes.data_as(i32p),
+                               scores.ctypes.data_as(f32p))
+    assert rc == 77
+    with pytest.raises(pytest.skip.Exception):
+        emu_build.check(rc)
+    monkeypatch.delenv("GTNB_EMU_MAX_THREADS")
+    rc = emu.emu_viterbi_dense(1, 4, 8, e.ctypes.data_as(f32p), None, tw.ctypes.data_as(f32p), paths.ctypes.data_as(i32p),
+                               scores.ctypes.data_as(f32p))
+    assert rc == 0  # and the next launch works again

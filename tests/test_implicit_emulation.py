@@ -68,7 +68,7 @@ def run(lib, e, tables, lens):
                           flags.ctypes.data_as(u8p), ptr.ctypes.data_as(i32p), src.ctypes.data_as(i32p),
                           lab.ctypes.data_as(i32p), w.ctypes.data_as(f32p), out.ctypes.data_as(f32p),
                           grad.ctypes.data_as(f32p), status.ctypes.data_as(i32p))
-    assert rc == 0
+    emu_build.check(rc)
     return out, grad, status
 
 
@@ -158,7 +158,8 @@ def test_ctc_build_kernel_then_sweeps(emu, oracle, shape):
                               tl.ctypes.data_as(i32p), 0, out.ctypes.data_as(f32p), grad.ctypes.data_as(f32p),
                               status.ctypes.data_as(i32p), ptr0.ctypes.data_as(i32p), src0.ctypes.data_as(i32p),
                               lab0.ctypes.data_as(i32p))
-    assert rc == 0 and not status.any()
+    emu_build.check(rc)
+    assert not status.any()
     _, ptr, src, lab, _ = ctc_tables(targets[0])
     assert np.array_equal(ptr0, ptr)
     assert np.array_equal(src0[:ptr[-1]], src) and np.array_equal(lab0[:ptr[-1]], lab)
@@ -203,7 +204,8 @@ def test_kernel_sources_at_the_benchmark_shape_against_the_reference_golden(emu)
     rc = emu.emu_implicit_ctc(1, T, Cn, ee.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), cat.ctypes.data_as(i32p),
                               tl.ctypes.data_as(i32p), 0, out.ctypes.data_as(f32p), grad.ctypes.data_as(f32p),
                               status.ctypes.data_as(i32p), None, None, None)
-    assert rc == 0 and not status.any()
+    emu_build.check(rc)
+    assert not status.any()
     check(out, grad, "implicit")
 
     # k_banded.cu, K = 4
@@ -215,5 +217,6 @@ def test_kernel_sources_at_the_benchmark_shape_against_the_reference_golden(emu)
     rc = lib.emu_banded_ctc(1, T, Cn, ee.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), cat.ctypes.data_as(i32p),
                             tl.ctypes.data_as(i32p), 0, 4, out2.ctypes.data_as(f32p), grad2.ctypes.data_as(f32p),
                             status2.ctypes.data_as(i32p))
-    assert rc == 0 and not status2.any()
+    emu_build.check(rc)
+    assert not status2.any()
     check(out2, grad2, "banded")

@@ -54,7 +54,7 @@ def test_normaliser_kernels_match_numpy(emu, C_, tropical):
     vec_ok = C_ in (4, 8, 16, 32, 64, 128)
     for vec in ((0, 1) if vec_ok else (0,)):
         rc, s, grad = run(emu, e, lens, tropical, vec, delta=0.5)
-        assert rc == 0
+        emu_build.check(rc)
         assert np.allclose(s, want_s, rtol=1e-6), (vec, s, want_s)
         for b in range(B):
             assert np.allclose(grad[b, :lens[b]], 0.5 * g[b, :lens[b]], rtol=1e-5, atol=1e-7), (vec, b)
