@@ -97,6 +97,75 @@ int emu_implicit(
 }
 
 /*
+ * As emu_implicit, with the kernel family picked the way launch_implicit_forward / _backward do (one
+ * node per thread, several nodes per thread, or the G-lanes-per-node "wide" kernels for in- / out-degrees
+ * above three: dense ASG transitions), the graph-arc gradients included (grad_graph: A_b floats per graph,
+ * concatenated, zero on entry; in_arc maps in-entries to Graph arc ids) and caller-chosen deltas.
+ * Returns the lanes per node used (0 = the narrow kernels), negative on error.
+ */
+int emu_implicit_general(
+    int B, int T, int C, const float* emissions, const int32_t* input_lens, const int32_t* n_nodes,
+    const uint8_t* node_flags, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label,
+    const int32_t* in_arc, const float* in_w, const float* deltas, float* out_scores, float* grad, float* grad_graph,
+    int32_t* status) {
+  using namespace gtnb;
+  Tables t;
+  long long nb = 0, pb = 0, ab = 0;
+  int max_in = 0, max_out = 0;
+  for (int b = 0; b < B; b++) {
+    const int N = n_nodes[b];
+    add_graph(t, b, input_lens ? input_lens[b] : T, (long long)b * T * C, N, node_flags + nb, in_ptr + pb,
+              in_src + ab, in_label + ab, in_w + ab);
+    const int A = in_ptr[pb + N];
+    std::vector<int> outdeg(N, 0);
+    for (int n = 0; n < N; n++) max_in = std::max(max_in, in_ptr[pb + n + 1] - in_ptr[pb + n]);
+    for (int a = 0; a < A; a++) max_out = std::max(max_out, ++outdeg[in_src[ab + a]]);
+    for (int a = 0; a < A; a++) t.in_arc[t.meta[b].sg_arc_base + a] = in_arc[ab + a];
+    t.meta[b].grad_graph_off = ab;
+    ab += A;
+    nb += N;
+    pb += N + 1;
+  }
+  std::vector<float> scores((size_t)t.scores_len + 16, 0.0f);
+  for (int b = 0; b < B; b++) status[b] = 0;
+  const int Gf = wide_lanes(max_in, max_out, t.maxN, C, false), Gb = wide_lanes(max_in, max_out, t.maxN, C, true);
+  const ImpLayout lf = make_imp_layout(t.maxN, t.maxA, false, Gf > 0, C);
+  const ImpLayout lb = make_imp_layout(t.maxN, t.maxA, true, Gb > 0, C);
+#define FWD_ARGS                                                                                            \
+  t.meta.data(), t.flags.data(), t.in_ptr.data(), t.in_src.data(), t.in_label.data(), t.in_w.data(), emissions, \
+      scores.data(), out_scores, status, C, lf
+#define BWD_ARGS                                                                                            \
+  t.meta.data(), t.flags.data(), t.in_ptr.data(), t.in_src.data(), t.in_label.data(), t.in_w.data(),        \
+      t.in_arc.data(), grad_graph, emissions, scores.data(), out_scores, deltas, grad, (long long)T * C, C, lb
+#define RUN_FWD(K) emu::launch(B, kImpThreads, lf.total, [&] { K(FWD_ARGS); })
+#define RUN_BWD(K) emu::launch(B, kImpThreads, lb.total, [&] { K(BWD_ARGS); })
+  switch (Gf) {
+    case 0: RUN_FWD(implicit_forward_kernel); break;
+    case 1: RUN_FWD(implicit_forward_wide_kernel<1>); break;
+    case 2: RUN_FWD(implicit_forward_wide_kernel<2>); break;
+    case 4: RUN_FWD(implicit_forward_wide_kernel<4>); break;
+    case 8: RUN_FWD(implicit_forward_wide_kernel<8>); break;
+    case 16: RUN_FWD(implicit_forward_wide_kernel<16>); break;
+    default: RUN_FWD(implicit_forward_wide_kernel<32>); break;
+  }
+  switch (Gb) {
+    case 0: RUN_BWD(implicit_backward_kernel<true>); break;
+    case 1: RUN_BWD((implicit_backward_wide_kernel<1, true>)); break;
+    case 2: RUN_BWD((implicit_backward_wide_kernel<2, true>)); break;
+    case 4: RUN_BWD((implicit_backward_wide_kernel<4, true>)); break;
+    case 8: RUN_BWD((implicit_backward_wide_kernel<8, true>)); break;
+    case 16: RUN_BWD((implicit_backward_wide_kernel<16, true>)); break;
+    default: RUN_BWD((implicit_backward_wide_kernel<32, true>)); break;
+  }
+#undef RUN_FWD
+#undef RUN_BWD
+#undef FWD_ARGS
+#undef BWD_ARGS
+  if (emu::g_launch_failed.exchange(false)) return -emu::kEmuNoThreads;
+  return Gb;
+}
+
+/*
  * The CTC criterion's device side as gtnb_ctc_loss runs it: k_ctc.cu's ctc_build_kernel writes the
  * target-graph tables, k_implicit.cu sweeps them.  targets concatenated, target_lens[B].
  * Also returns the tables of graph 0 (for a check against the reference's ctcGraph): n_arcs0,

@@ -220,3 +220,65 @@ def test_kernel_sources_at_the_benchmark_shape_against_the_reference_golden(emu)
     emu_build.check(rc)
     assert not status2.any()
     check(out2, grad2, "banded")
+
+
+def general_tables(og, Cn):
+    """CSR by destination of an oracle graph, in-arcs ordered by (source, arc id) like gtnb_compose_linear."""
+    a = og.arrays()
+    N = len(a["flags"])
+    ptr, src, lab, arc, w = [0], [], [], [], []
+    for d in range(N):
+        for k in sorted(np.nonzero(a["dst"] == d)[0].tolist(), key=lambda k: (int(a["src"][k]), k)):
+            src.append(int(a["src"][k])), lab.append(int(a["ilabel"][k])), arc.append(k), w.append(float(a["w"][k]))
+        ptr.append(len(src))
+    return (a["flags"].astype(np.uint8), np.array(ptr, np.int32), np.array(src, np.int32), np.array(lab, np.int32),
+            np.array(w, np.float32), np.array(arc, np.int32))
+
+
+@pytest.mark.parametrize("Cn,T", [(6, 9), (20, 7), (40, 5), (64, 4)])
+def test_wide_kernels_on_asg_transitions(emu, Cn, T):
+    """forwardScore(compose(transitions, emissions)) and its backward for the dense ASG transitions graph
+    (start -> c and c' -> c for every pair, test/criterion_test.cpp:244-254): in- / out-degrees above three take
+    the G-lanes-per-node kernels, arc gradients of the graph operand included (the ASG denominator of
+    BASELINE config 3).  Oracle: its own compose + shortest-distance gradient + compose gradFunc."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(Cn)
+    tw = rng.uniform(-2, 2, Cn + Cn * Cn).astype(np.float32)
+    B = 2
+    e = rng.uniform(-3, 3, (B, T, Cn)).astype(np.float32)
+    lens = np.array([T, T - 2], np.int32)
+    og = po.Graph.transitions(Cn, tw)
+    tab = general_tables(og, Cn)
+    A = len(tab[2])
+    nn = np.array([len(tab[0])] * B, np.int32)
+    catb = lambda k, dt: np.ascontiguousarray(np.concatenate([tab[k]] * B), dt)
+    flags, ptr, src, lab, w, arc = catb(0, np.uint8), catb(1, np.int32), catb(2, np.int32), catb(3, np.int32), catb(4, np.float32), catb(5, np.int32)
+    out = np.zeros(B, np.float32)
+    grad = np.zeros((B, T, Cn), np.float32)
+    gg = np.zeros(B * A, np.float32)
+    status = np.zeros(B, np.int32)
+    deltas = np.array([1.0, -0.5], np.float32)
+    ee = np.ascontiguousarray(e)
+    emu.emu_implicit_general.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p, f32p,
+                                         f32p, f32p, f32p, f32p, i32p]
+    G = emu.emu_implicit_general(B, T, Cn, ee.ctypes.data_as(f32p), lens.ctypes.data_as(i32p), nn.ctypes.data_as(i32p),
+                                 flags.ctypes.data_as(u8p), ptr.ctypes.data_as(i32p), src.ctypes.data_as(i32p),
+                                 lab.ctypes.data_as(i32p), arc.ctypes.data_as(i32p), w.ctypes.data_as(f32p),
+                                 deltas.ctypes.data_as(f32p), out.ctypes.data_as(f32p), grad.ctypes.data_as(f32p),
+                                 gg.ctypes.data_as(f32p), status.ctypes.data_as(i32p))
+    if G == -77:
+        pytest.skip("the host refused to create the emulator's threads")
+    assert G > 0, G  # the wide kernels were used
+    assert not status.any()
+    for b in range(B):
+        Tb = int(lens[b])
+        lin = po.Graph.linear(Tb, Cn, e[b, :Tb])
+        comp = po.compose(og, lin)
+        score, arc_grads = po.forward_score_and_grad(comp, False, float(deltas[b]))
+        g1, g2 = po.compose_grad(comp, arc_grads, len(og.arrays()["src"]), Tb * Cn)
+        assert util.close(out[b], score), (b, out[b], score)
+        assert util.grad_close(grad[b, :Tb].reshape(-1), g2, 5.0 * T), b
+        assert not grad[b, Tb:].any()
+        mine = np.zeros(A, np.float32)
+        mine[:] = gg[b * A:(b + 1) * A]  # indexed by Graph arc id through in_arc
+        assert util.grad_close(mine, g1, 5.0 * T), (b, float(np.abs(mine - g1).max()))
