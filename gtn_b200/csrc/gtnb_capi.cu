@@ -261,6 +261,10 @@ int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value) {
     ctx->use_implicit = value != 0;
     return GTNB_OK;
   }
+  if (ctx && name && std::string(name) == "exact_ties") {
+    ctx->exact_ties = value != 0;
+    return GTNB_OK;
+  }
   if (ctx && name && std::string(name) == "banded") {
     ctx->use_banded = value;
     return GTNB_OK;
@@ -550,6 +554,8 @@ void free_lattice_device(gtnb_ctx* ctx, gtnb_lattice* lat) {
   dev_free(ctx, lat->sg_in_w);
   dev_free(ctx, lat->sg_ilabel);
   dev_free(ctx, lat->sg_olabel);
+  dev_free(ctx, lat->sg_out_pos);
+  dev_free(ctx, lat->sg_start_rank);
   dev_free(ctx, lat->alive);
 }
 
@@ -1078,6 +1084,11 @@ int gtnb_viterbi_path(
   int bad = first_bad_status(ctx, lat, status_host);
   int rc;
   if (!lat->back_ptr && (rc = dev_alloc(ctx, &lat->back_ptr, lat->tot_N))) return rc;
+  if (lat->composed && lat->sg_out_pos && !lat->relax_rank) {
+    // exact_ties: the reference's relaxation ranks and accept order, once per lattice (k_order.cu)
+    if ((rc = dev_alloc(ctx, &lat->relax_rank, lat->tot_A))) return rc;
+    if ((rc = launch_relax_order(ctx, lat))) return rc;
+  }
   if ((rc = launch_forward(ctx, lat, MODE_PATH))) return rc;
   lat->forward_done = false; // scores now hold the path recursion, not shortestDistance
   int B = lat->B;
@@ -1181,6 +1192,7 @@ int gtnb::compose_linear_impl(
     int N = 0, A = 0;
     std::vector<uint8_t> flags;
     std::vector<int32_t> in_ptr, in_src, in_label, in_arc, il, ol, acc;
+    std::vector<int32_t> in_out_pos, start_rank; // exact_ties only (k_order.cu)
     std::vector<float> in_w;
   };
   std::vector<SG> sg(n_graphs);
@@ -1220,8 +1232,13 @@ int gtnb::compose_linear_impl(
         s.in_label.push_back((lab >= 0 && lab < C) ? lab : -1);
         s.in_arc.push_back(a);
         s.in_w.push_back(v.weights ? v.weights[a] : 0.0f);
+        if (ctx->exact_ties) s.in_out_pos.push_back(out_pos[a]);
       }
       s.in_ptr[d + 1] = (int)s.in_src.size();
+    }
+    if (ctx->exact_ties) {
+      s.start_rank.assign(s.N, -1);
+      for (size_t k = 0; k < adj.start.size(); k++) s.start_rank[adj.start[k]] = (int32_t)k;
     }
     maxN = std::max(maxN, s.N);
     maxA = std::max(maxA, s.A);
@@ -1277,6 +1294,14 @@ int gtnb::compose_linear_impl(
     TRY(upload_slabs(ctx, lat->sg_ilabel, sga, pi));
     for (int g = 0; g < n_graphs; g++) pi[g] = &sg[g].ol;
     TRY(upload_slabs(ctx, lat->sg_olabel, sga, pi));
+    if (ctx->exact_ties) {
+      TRY(dev_alloc(ctx, &lat->sg_out_pos, lat->tot_sgA));
+      TRY(dev_alloc(ctx, &lat->sg_start_rank, lat->tot_sgN));
+      for (int g = 0; g < n_graphs; g++) pi[g] = &sg[g].in_out_pos;
+      TRY(upload_slabs(ctx, lat->sg_out_pos, sga, pi));
+      for (int g = 0; g < n_graphs; g++) pi[g] = &sg[g].start_rank;
+      TRY(upload_slabs(ctx, lat->sg_start_rank, sgn, pi));
+    }
     // accept lists in g.accept() order: the kernel turns them into lattice nodes
     std::vector<int32_t> acc_stage((size_t)tc, 0);
     std::vector<int32_t> nacc(B);

@@ -59,6 +59,7 @@ struct gtnb_ctx {
   };
   bool use_staged = true; // gtnb_ctx_set_flag("staged", 0) forces the generic kernels
   bool use_implicit = true; // gtnb_ctx_set_flag("implicit", 0): criteria materialise the lattice
+  bool exact_ties = false; // gtnb_ctx_set_flag("exact_ties", 1): EXPERIMENTAL, viterbiPath on composed lattices breaks exact ties like the reference (k_order.cu)
   int use_banded = 0; // gtnb_ctx_set_flag("banded", K): EXPERIMENTAL temporally blocked CTC sweeps (k_banded.cu), K frames per barrier
   bool profiling = false;
   std::vector<ProfEntry> prof;
@@ -117,6 +118,9 @@ struct gtnb_lattice {
   float* sg_in_w = nullptr;
   int32_t* sg_ilabel = nullptr; // by arc id
   int32_t* sg_olabel = nullptr;
+  // exact_ties only (else NULL): per in-entry the arc's position in its source's out list; per node its index in g.start()
+  int32_t* sg_out_pos = nullptr;
+  int32_t* sg_start_rank = nullptr;
   uint32_t* alive = nullptr; // [B][max_T+1][W] bitmasks
   int alive_words = 0;
 
@@ -245,6 +249,8 @@ int launch_backward_fused(
 bool implicit_supported(const gtnb_lattice* lat);
 bool implicit_dims_supported(const SgDims* dims, int n_graphs);
 int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0 = 0, int nb = -1);
+/* k_order.cu (experimental): relax_rank + accept order of a composed lattice as the reference's shortestPath sees them */
+int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat);
 /* k_banded.cu (experimental): same contract as the implicit sweeps, for band-shaped graph operands */
 bool banded_supported(const gtnb_ctx* ctx, const gtnb_lattice* lat);
 int launch_banded_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0 = 0, int nb = -1);

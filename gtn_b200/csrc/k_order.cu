@@ -1,0 +1,194 @@
+/*
+ * k_order.cu -- EXPERIMENTAL (gtnb_ctx_set_flag("exact_ties", 1) before gtnb_compose_linear; off by
+ * default; checked on the CPU through tests/emu, not yet run on a GPU): the reference's tie-breaking
+ * order on a device-composed lattice.
+ *
+ * detail::shortestPath (shortest.cpp:190-245) keeps, for every node, the FIRST-RELAXED predecessor
+ * among those that reach the maximum, and the first strictly greatest accept node in g.accept()
+ * order.  On compose(g, linearGraph) both orders are structural:
+ *
+ *   discovery  compose's BFS (compose.cpp:389-470) creates the product states of frame t+1 while it
+ *              explores those of frame t in creation order, their matched arcs in matcher order; a
+ *              state is created by the first arc that reaches it.  g.accept() of the composed graph
+ *              is the creation order of its accepting states.
+ *   relaxation shortestPath pops frame t's states in the order they became ready; state (v, t+1)
+ *              becomes ready when the LAST of its in-arcs has been relaxed.
+ *
+ * With pos_D / pos_P the position of a frame-t state in the two orders and o(e) the position of
+ * graph arc e in its source's out-arc list (the matcher enumerates a state's arcs in that order when
+ * the graph operand is the query side: unsorted and singly-sorted matchers always, the doubly-sorted
+ * one while out-degree <= C, compose.cpp:211-374):
+ *
+ *   key_D(v) = min over in-arcs e: u -> v of  pos_D[u] * K + o(e)      pos_D'[v] = rank of key_D
+ *   key_P(v) = max over in-arcs e: u -> v of  pos_P[u] * K + o(e)      pos_P'[v] = rank of key_P
+ *
+ * and the relaxation rank of lattice arc (u, t) -> (v, t+1) is pos_P[u] * K + o(e): the per-arc
+ * `relax_rank` sd_forward_generic<MODE_PATH> already breaks ties with (host-packed graphs use it).
+ * One CTA per utterance walks the frames; ranks are counted (O(N^2 / threads) per frame: fine for
+ * criterion-sized graphs, this is a decode-time option, not a training path).
+ */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <algorithm>
+
+#include "gtn_b200.h"
+#include "gtnb_meta.h"
+#include "simt_emu.h"
+#else
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "gtnb_internal.h"
+#endif
+
+namespace gtnb {
+
+namespace {
+
+constexpr int kOrderThreads = 256;
+constexpr int kNoKey = 0x7fffffff;
+
+__device__ __forceinline__ bool bit_of(const uint32_t* words, int n) {
+  return (words[n >> 5] >> (n & 31)) & 1u;
+}
+
+/* number of set bits below position n */
+__device__ __forceinline__ int rank_of(const uint32_t* words, int n) {
+  int r = 0;
+  for (int c = 0; c < (n >> 5); c++) r += __popc(words[c]);
+  return r + __popc(words[n >> 5] & ((1u << (n & 31)) - 1u));
+}
+
+__global__ void __launch_bounds__(kOrderThreads) lattice_relax_order_kernel(
+    const GraphMeta* __restrict__ meta,
+    const uint8_t* __restrict__ sg_flags,
+    const int32_t* __restrict__ sg_in_ptr,
+    const int32_t* __restrict__ sg_in_src,
+    const int32_t* __restrict__ sg_in_label,
+    const int32_t* __restrict__ sg_out_pos, // per in-entry: position of the arc in its source's out list
+    const int32_t* __restrict__ sg_start_rank, // per graph node: index in g.start(), -1 if not a start node
+    const uint32_t* __restrict__ alive,
+    int W,
+    int maxT,
+    int K, // > every out-arc position
+    const int32_t* __restrict__ lvl_node_ptr,
+    const uint32_t* __restrict__ row_ptr,
+    int32_t* __restrict__ relax_rank, // out, per lattice arc
+    int32_t* __restrict__ acc_nodes) { // in / out: reordered to the composed graph's accept order
+  GTNB_DYNAMIC_SMEM(int, o_smem);
+  const GraphMeta m = meta[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int N1 = m.sg_N, T = m.T;
+  int* posD = o_smem; // positions of the current frame's states
+  int* posP = o_smem + N1;
+  int* keyD = o_smem + 2 * N1; // keys of the next frame's states
+  int* keyP = o_smem + 3 * N1;
+  const int32_t* ip = sg_in_ptr + m.sg_node_base;
+  const int32_t* is = sg_in_src + m.sg_arc_base;
+  const int32_t* il = sg_in_label + m.sg_arc_base;
+  const int32_t* op = sg_out_pos + m.sg_arc_base;
+  const int32_t* sr = sg_start_rank + m.sg_node_base;
+  const uint8_t* fl = sg_flags + m.sg_node_base;
+  const uint32_t* al = alive + (size_t)blockIdx.x * (maxT + 1) * W;
+  const int32_t* lp = lvl_node_ptr + m.lvl_base;
+  const uint32_t* rp = row_ptr + m.node_base;
+  int32_t* rr = relax_rank + m.arc_base;
+
+  // frame 0: the start states, in g.start() order, are both created and popped in that order
+  for (int u = tid; u < N1; u += kOrderThreads) keyD[u] = (bit_of(al, u) && sr[u] >= 0) ? sr[u] : kNoKey;
+  __syncthreads();
+  for (int u = tid; u < N1; u += kOrderThreads) {
+    int r = -1;
+    if (keyD[u] != kNoKey) {
+      r = 0;
+      for (int w = 0; w < N1; w++) r += keyD[w] < keyD[u];
+    }
+    posD[u] = r;
+    posP[u] = r;
+  }
+  __syncthreads();
+
+  for (int t = 0; t < T; t++) {
+    const uint32_t* at = al + (size_t)t * W; // frame t
+    const uint32_t* an = at + W; // frame t + 1
+    for (int v = tid; v < N1; v += kOrderThreads) {
+      int kd = kNoKey, kp = -1;
+      if (bit_of(an, v)) {
+        // the row of lattice node (v, t+1): its arcs are the in-entries of v whose source is alive in
+        // frame t, in in-entry order (compose_emit_kernel)
+        int pos = (int)(rp[lp[t + 1] + rank_of(an, v)] & kRowMask);
+        for (int e = ip[v]; e < ip[v + 1]; e++) {
+          const int u = is[e];
+          if (il[e] >= 0 && bit_of(at, u)) {
+            kd = min(kd, posD[u] * K + op[e]);
+            const int rk = posP[u] * K + op[e];
+            kp = max(kp, rk);
+            rr[pos++] = rk;
+          }
+        }
+      }
+      keyD[v] = kd;
+      keyP[v] = kp;
+    }
+    __syncthreads();
+    for (int v = tid; v < N1; v += kOrderThreads) {
+      int rd = -1, rq = -1;
+      if (keyD[v] != kNoKey) {
+        rd = 0;
+        rq = 0;
+        for (int w = 0; w < N1; w++) {
+          rd += keyD[w] < keyD[v]; // states that are not alive carry kNoKey: never smaller
+          rq += (keyP[w] >= 0) && (keyP[w] < keyP[v]);
+        }
+      }
+      posD[v] = rd;
+      posP[v] = rq;
+    }
+    __syncthreads();
+  }
+
+  // g.accept() of the composed graph: its accepting states in creation order
+  if (tid == 0) {
+    const uint32_t* aT = al + (size_t)T * W;
+    int32_t* acc = acc_nodes + m.acc_base;
+    int k = 0;
+    for (int u = 0; u < N1; u++)
+      if (bit_of(aT, u) && (fl[u] & 2)) k++;
+    for (int u = 0; u < N1; u++) {
+      if (!(bit_of(aT, u) && (fl[u] & 2))) continue;
+      int before = 0; // accepting states created earlier
+      for (int w = 0; w < N1; w++) before += bit_of(aT, w) && (fl[w] & 2) && posD[w] < posD[u];
+      acc[before] = lp[T] + rank_of(aT, u);
+    }
+    (void)k;
+  }
+}
+
+} // namespace
+
+#ifndef GTNB_HOST_EMU
+
+/* relax_rank (tot_A ints) and the accept order of a composed lattice; needs the tables the
+ * "exact_ties" flag makes gtnb_compose_linear upload */
+int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat) {
+  if (lat->B == 0) return GTNB_OK;
+  if (!lat->sg_out_pos || !lat->sg_start_rank || !lat->alive)
+    return fail(ctx, GTNB_ERR_LOGIC, "exact_ties: the lattice was composed without the flag");
+  const size_t smem = sizeof(int) * 4 * (size_t)std::max(lat->max_lvl_nodes, 1);
+  if (smem > (size_t)kMaxDynamicSmem)
+    return fail(ctx, GTNB_ERR_UNSUPPORTED, "exact_ties: graph operand too large");
+  if (smem > 48 * 1024) {
+    int rc = ensure_max_smem(ctx, (const void*)lattice_relax_order_kernel);
+    if (rc) return rc;
+  }
+  GTNB_LAUNCH(ctx, "relax_order",
+              lattice_relax_order_kernel<<<lat->B, kOrderThreads, smem, ctx->stream>>>(
+                  lat->meta, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_out_pos,
+                  lat->sg_start_rank, lat->alive, lat->alive_words, lat->max_T, lat->max_out_deg + 1,
+                  lat->lvl_node_ptr, lat->row_ptr, lat->relax_rank, lat->acc_nodes));
+  return GTNB_OK;
+}
+
+#endif // GTNB_HOST_EMU
+
+} // namespace gtnb

@@ -105,7 +105,8 @@ int64_t gtnb_ctx_launch_count(const gtnb_ctx* ctx);
  * materialising the lattice; 0 makes them build it and run the lattice kernels.
  * "banded" (default 0, EXPERIMENTAL): value K in {1, 2, 4, 8}: gtnb_ctc_loss's implicit sweeps run
  * K frames per barrier with warp-shuffle neighbour exchange (k_banded.cu) when the target graphs
- * are band shaped.
+ * are band shaped.  "exact_ties" (default 0, EXPERIMENTAL; set before gtnb_compose_linear): gtnb_viterbi_path
+ * on a composed lattice breaks exact score ties like the reference's shortestPath (k_order.cu).
  */
 int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value);
 

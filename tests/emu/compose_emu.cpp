@@ -8,6 +8,7 @@
 #define GTNB_HOST_EMU 1
 #include "../../gtn_b200/csrc/k_compose.cu"
 #include "../../gtn_b200/csrc/k_shortest.cu"
+#include "../../gtn_b200/csrc/k_order.cu"
 
 #include <vector>
 
@@ -285,6 +286,70 @@ int emu_materialised(
         vit_labels[(size_t)b * T + t] = j >= 0 ? j % C : -1;
       }
   }
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
+  return 0;
+}
+
+/*
+ * viterbiPath through the materialised lattice with the reference's tie-breaking order (k_order.cu, the
+ * "exact_ties" option): compose -> lattice_relax_order_kernel -> sd_forward_generic<MODE_PATH> with the
+ * per-arc relax ranks -> traceback -> label provenance.  out_pos: per in-entry, the position of the arc in
+ * its source's out-arc list; start_rank: per node, its index in g.start() or -1 (concatenated like flags).
+ */
+int emu_viterbi_exact(
+    int B, int T, int C, const float* emissions, const int32_t* lens, const int32_t* n_nodes, const uint8_t* flags,
+    const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label, const int32_t* in_arc, const float* in_w,
+    const int32_t* out_pos, const int32_t* start_rank, int max_out, const int32_t* n_acc, const int32_t* acc,
+    float* vit_scores, int32_t* vit_labels, int32_t* vit_graph_arcs) {
+  using namespace gtnb;
+  Lat L;
+  if (int rc = build_lattice(L, B, T, C, emissions, lens, n_nodes, flags, in_ptr, in_src, in_label, in_arc, in_w, n_acc, acc))
+    return rc;
+  // the two extra tables, in the slab layout build_lattice gave the others
+  std::vector<int32_t> sg_out_pos(L.sg_src.size(), 0), sg_start_rank(L.sg_ptr.size(), -1);
+  long long nb = 0, pb = 0, ab = 0;
+  int maxN = 0;
+  for (int b = 0; b < B; b++) {
+    const int N = n_nodes[b], A = in_ptr[pb + N];
+    for (int a = 0; a < A; a++) sg_out_pos[L.meta[b].sg_arc_base + a] = out_pos[ab + a];
+    for (int n = 0; n < N; n++) sg_start_rank[L.meta[b].sg_node_base + n] = start_rank[nb + n];
+    maxN = std::max(maxN, N);
+    nb += N;
+    pb += N + 1;
+    ab += A;
+  }
+  std::vector<int32_t> relax((size_t)L.ta + 16, 0);
+  emu::launch(B, kOrderThreads, sizeof(int) * 4 * std::max(maxN, 1), [&] {
+    lattice_relax_order_kernel(L.meta.data(), L.sg_flags.data(), L.sg_ptr.data(), L.sg_src.data(), L.sg_lab.data(),
+                               sg_out_pos.data(), sg_start_rank.data(), L.alive.data(), L.W, L.maxT, max_out + 1,
+                               L.lnp.data(), L.rp.data(), relax.data(), L.acc_stage.data());
+  });
+  std::vector<float> scores((size_t)L.tn + 16, 0.0f);
+  std::vector<int32_t> back_ptr((size_t)L.tn + 16, -1), best(B, -1);
+  emu::launch(B, kThreads, 0, [&] {
+    sd_forward_generic<MODE_PATH>(L.meta.data(), L.lnp.data(), L.rp.data(), L.arcs.data(), relax.data(),
+                                  L.acc_stage.data(), scores.data(), back_ptr.data(), vit_scores, best.data());
+  });
+  std::vector<int32_t> path((size_t)B * std::max(T, 1), -1), plen(B, 0), pg((size_t)B * std::max(T, 1), -1),
+      pl((size_t)B * std::max(T, 1), -1);
+  emu::launch((B + 63) / 64, 64, 0, [&] {
+    traceback_kernel(L.meta.data(), L.arcs.data(), back_ptr.data(), best.data(), B, T, path.data(), plen.data());
+  });
+  if (T > 0)
+    for (int by = 0; by < B; by++)
+      for (int bx = 0; bx < (T + 127) / 128; bx++)
+        emu::launch(1, 128, 0, [&] {
+          blockIdx.x = bx;
+          blockIdx.y = by;
+          gather_prov_kernel(L.meta.data(), L.gi.data(), L.arcs.data(), T, path.data(), plen.data(), pg.data(),
+                             pl.data(), nullptr);
+        });
+  for (int b = 0; b < B; b++)
+    for (int t = 0; t < T; t++) {
+      const bool on = t < plen[b];
+      vit_labels[(size_t)b * T + t] = on ? pl[(size_t)b * T + t] % C : -1;
+      vit_graph_arcs[(size_t)b * T + t] = on ? pg[(size_t)b * T + t] : -1;
+    }
   if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }

@@ -23,7 +23,7 @@ f32p, i32p, u8p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.
 
 @pytest.fixture(scope="module")
 def emu():
-    lib = C.CDLL(emu_build.build("compose", ["k_compose.cu"]))
+    lib = C.CDLL(emu_build.build("compose", ["k_compose.cu", "k_shortest.cu", "k_order.cu"]))
     lib.emu_compose.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p, f32p, i32p, i32p,
                                 i32p, i32p, u32p, i32p, f32p, i32p, i32p, i32p, i32p, i32p, f32p, f32p, f32p]
     return lib
@@ -260,3 +260,131 @@ def test_materialised_viterbi_path(emu, oracle, ties):
         collapsed = [int(l) for k, l in enumerate(got) if l != 0 and (k == 0 or l != got[k - 1])]
         assert collapsed == targets[b].tolist(), (b, got, targets[b])
         assert np.float32(sum(float(e[b, t, got[t]]) for t in range(Tb))) == np.float32(want_score)
+
+
+def tables_with_out_pos(og, Cn):
+    """tables_of + the two tables the exact-ties option uploads: per in-entry the position of the arc in its
+    source's out-arc list (the reference's per-node order, after any arcSort), per node its index in g.start()."""
+    a = og.arrays()
+    ip, ia, op, oa = og.adjacency()
+    N = len(a["flags"])
+    out_pos = np.zeros(len(a["src"]), np.int32)
+    for n in range(N):
+        for k in range(op[n], op[n + 1]):
+            out_pos[oa[k]] = k - op[n]
+    t = tables_of(og, Cn)
+    # in-arcs of a node ordered by (source, position in the source's out list), as gtnb_compose_linear does
+    ptr, src, lab, arc, w, opos = [0], [], [], [], [], []
+    for d in range(N):
+        ins = sorted(np.nonzero(a["dst"] == d)[0].tolist(), key=lambda k: (int(a["src"][k]), int(out_pos[k])))
+        for k in ins:
+            l = int(a["ilabel"][k])
+            src.append(int(a["src"][k])), lab.append(l if 0 <= l < Cn else -1), arc.append(k)
+            w.append(float(a["w"][k])), opos.append(int(out_pos[k]))
+        ptr.append(len(src))
+    t.update(ptr=np.array(ptr, np.int32), src=np.array(src, np.int32), lab=np.array(lab, np.int32),
+             arc=np.array(arc, np.int32), w=np.array(w, np.float32), out_pos=np.array(opos, np.int32))
+    sr = np.full(N, -1, np.int32)
+    for k, s in enumerate(a["start"]):
+        sr[s] = k
+    t["start_rank"] = sr
+    t["max_out"] = int(max([op[n + 1] - op[n] for n in range(N)] + [0]))
+    return t
+
+
+def run_exact(lib, e, lens, tabs):
+    B, T, Cn = e.shape
+    e = np.ascontiguousarray(e, np.float32)
+    lens = np.ascontiguousarray(lens, np.int32)
+    nn = np.array([len(t["flags"]) for t in tabs], np.int32)
+    n_acc = np.array([len(t["acc"]) for t in tabs], np.int32)
+    vs = np.zeros(B, np.float32)
+    vl = np.full((B, max(T, 1)), -9, np.int32)
+    vg = np.full((B, max(T, 1)), -9, np.int32)
+    P = lambda a, t: a.ctypes.data_as(t)
+    flags, ptr = cat([t["flags"] for t in tabs], np.uint8), cat([t["ptr"] for t in tabs], np.int32)
+    src, lab = cat([t["src"] for t in tabs], np.int32), cat([t["lab"] for t in tabs], np.int32)
+    arc, w, acc = cat([t["arc"] for t in tabs], np.int32), cat([t["w"] for t in tabs], np.float32), cat([t["acc"] for t in tabs], np.int32)
+    opos, sr = cat([t["out_pos"] for t in tabs], np.int32), cat([t["start_rank"] for t in tabs], np.int32)
+    lib.emu_viterbi_exact.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p, f32p, i32p,
+                                      i32p, C.c_int, i32p, i32p, f32p, i32p, i32p]
+    rc = lib.emu_viterbi_exact(B, T, Cn, P(e, f32p), P(lens, i32p), P(nn, i32p), P(flags, u8p), P(ptr, i32p), P(src, i32p),
+                               P(lab, i32p), P(arc, i32p), P(w, f32p), P(opos, i32p), P(sr, i32p),
+                               max(t["max_out"] for t in tabs), P(n_acc, i32p), P(acc, i32p), P(vs, f32p), P(vl, i32p),
+                               P(vg, i32p))
+    emu_build.check(rc)
+    return vs, vl, vg
+
+
+def reference_path(og, e_b, Tb, Cn):
+    """The oracle's shortestPath (pinned to the reference's, ties included: tests/test_oracle.py) on its own
+    compose: (graph arc ids, emission labels) along the path, and the score."""
+    lin = po.Graph.linear(Tb, Cn, e_b[:Tb])
+    comp = po.compose(og, lin)
+    arcs = po.shortest_path(comp)
+    if arcs is None:
+        return None, None, None
+    g1, g2 = comp.gradinfo()
+    w = comp.arrays()["w"]
+    score = np.float32(0.0)
+    for k in arcs:
+        score = np.float32(score + w[k])
+    return [int(g1[k]) for k in arcs], [int(g2[k]) % Cn for k in arcs], score
+
+
+@pytest.mark.parametrize("blank_last", [False, True])
+def test_exact_ties_option_reproduces_the_reference_path_on_ctc_lattices(emu, blank_last):
+    """k_order.cu: with the reference's relaxation ranks and accept order, viterbiPath through the device
+    lattice returns the reference's path on integer-valued emissions (ties at nearly every node), for blank
+    first and blank last (where compose's discovery order is not the node order)."""
+    B, T, Cn, U = 4, 16, 5, 3
+    rng = np.random.default_rng(11 + blank_last)
+    e = rng.integers(-1, 2, (B, T, Cn)).astype(np.float32)
+    blank = Cn - 1 if blank_last else 0
+    labels = [l for l in range(Cn) if l != blank]
+    targets = [rng.choice(labels, U).astype(np.int32) for _ in range(B)]
+    targets[1][1] = targets[1][0]
+    lens = np.array([T, T - 2, T - 5, 2 * U + 1], np.int32)
+    ogs = [po.Graph.ctc(t, blank, True) for t in targets]
+    tabs = [tables_with_out_pos(g, Cn) for g in ogs]
+    vs, vl, vg = run_exact(emu, e, lens, tabs)
+    for b in range(B):
+        Tb = int(lens[b])
+        want_arcs, want_labels, want_score = reference_path(ogs[b], e[b], Tb, Cn)
+        assert vg[b, :Tb].tolist() == want_arcs, (b, vg[b, :Tb], want_arcs)
+        assert vl[b, :Tb].tolist() == want_labels
+        assert vs[b] == want_score
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_exact_ties_option_on_general_graph_operands(emu, seed):
+    """Any epsilon-free graph operand, sorted or not (unsorted / singly / doubly sorted matchers), integer
+    weights: same path, arc for arc, as the reference."""
+    rng = np.random.default_rng(4000 + seed)
+    Cn, T, B = 4, int(rng.integers(2, 8)), 2
+    ogs, tabs = [], []
+    for _ in range(B):
+        n = int(rng.integers(2, 8))
+        flags = np.zeros(n, np.uint8)
+        flags[rng.integers(0, n, max(1, n // 3))] |= 1
+        flags[rng.integers(0, n, max(1, n // 2))] |= 2
+        na = int(rng.integers(n, 3 * n + 1))
+        src, dst = rng.integers(0, n, na), rng.integers(0, n, na)
+        lab = rng.integers(0, Cn, na)
+        w = rng.integers(-1, 2, na).astype(np.float32)
+        og = po.Graph.from_arrays(flags, src, dst, lab, lab, w)
+        if seed % 2:
+            og.arc_sort(False)
+        ogs.append(og)
+        tabs.append(tables_with_out_pos(og, Cn))
+    e = rng.integers(-1, 2, (B, T, Cn)).astype(np.float32)
+    lens = np.array([T, T - 1], np.int32)
+    vs, vl, vg = run_exact(emu, e, lens, tabs)
+    for b in range(B):
+        Tb = int(lens[b])
+        want_arcs, want_labels, want_score = reference_path(ogs[b], e[b], Tb, Cn)
+        if want_arcs is None:
+            assert not np.isfinite(vs[b]) or (vg[b, :Tb] < 0).all()
+            continue
+        assert vg[b, :Tb].tolist() == want_arcs, (b, vg[b, :Tb], want_arcs)
+        assert vs[b] == want_score

@@ -618,3 +618,37 @@ def test_ctc_banded_sweeps_agree_with_implicit_and_oracle(ctx, oracle, shape, K)
             assert util.grad_close(res[K][1][b, :lens[b]], go, 5.0 * T), b
             assert util.grad_close(res[K][1][b], res[0][1][b], 5.0 * T), b
         assert not res[K][1][b, lens[b]:].any()
+
+
+# ---------------------------------------------------------------------------
+# EXPERIMENTAL: exact score ties in viterbiPath on device lattices (k_order.cu), opt-in.  The kernel's
+# logic is covered on the CPU by tests/test_compose_emulation.py; this is its first GPU run.
+# ---------------------------------------------------------------------------
+
+@pytest.mark.skipif(os.environ.get("GTNB_EXPERIMENTAL") != "1",
+                    reason="k_order.cu has not been run on a GPU yet (set GTNB_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("blank_last", [False, True])
+def test_viterbi_exact_ties_option_vs_oracle(ctx, oracle, blank_last):
+    """gtnb_ctx_set_flag("exact_ties", 1) before compose: integer-valued emissions make nearly every lattice
+    node a tie; the path through the lattice API must then be the reference's, label for label."""
+    B, T, C, U = 6, 40, 6, 7
+    rng = np.random.default_rng(5 + blank_last)
+    e = rng.integers(-1, 2, (B, T, C)).astype(np.float32)
+    blank = C - 1 if blank_last else 0
+    labels = [l for l in range(C) if l != blank]
+    targets = [rng.choice(labels, U).astype(np.int32) for _ in range(B)]
+    lens = [T - 3 * b for b in range(B)]
+    ctx.set_flag("exact_ties", 1)
+    try:
+        e_dev = ctx.to_device(e)
+        views = [util.view_of(oracle.Graph.ctc(t, blank, True)) for t in targets]
+        lat = ctx.compose_linear(views, lens, C, e_dev, T * C)
+        out = lat.viterbi_path(T)
+    finally:
+        ctx.set_flag("exact_ties", 0)
+    for b in range(B):
+        p, s = oracle.viterbi_ctc(e[b, :lens[b]], targets[b], blank, True)
+        assert out["lens"][b] == lens[b]
+        assert np.array_equal(out["ilabels"][b][:lens[b]], p), (b, out["ilabels"][b][:lens[b]], p)
+    lat.free()
+    e_dev.free()
