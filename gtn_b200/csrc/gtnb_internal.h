@@ -21,6 +21,7 @@
 
 /* dynamic shared memory of the CTA (the host-side emulation defines its own) */
 #define GTNB_DYNAMIC_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define GTNB_DYNAMIC_SMEM_128(type, name) extern __shared__ __align__(128) type name[]
 #define GTNB_STATIC_SMEM(type, name, count) __shared__ type name[count]
 #define GTNB_STATIC_SMEM_2D(type, name, d0, d1) __shared__ type name[d0][d1]
 

@@ -30,10 +30,18 @@
  * the 8-byte arc records; per-graph slabs start on 4-element boundaries and
  * every array has 16 elements of slack, so the extra elements are always mapped.
  */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <algorithm>
+
+#include "gtn_b200.h"
+#include "gtnb_meta.h"
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "gtnb_internal.h"
+#endif
 
 namespace gtnb {
 
@@ -51,11 +59,67 @@ constexpr int kMaxStages = 8;
 __device__ __forceinline__ float neg_inf() {
   return -CUDART_INF_F;
 }
+#ifdef GTNB_HOST_EMU
+/* the PTX below, restated for the host emulation (tests/emu/simt_emu.h): shared-window addresses are
+ * offsets into the CTA's emulated shared memory, mbarriers and the bulk copy are emu:: objects */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return emu::shared_window(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  emu::mbar_init(bar, count);
+}
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  emu::mbar_expect_tx(bar, bytes);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  emu::mbar_arrive(bar);
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  emu::mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  emu::mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  emu::bulk_g2s(dst, src, bytes, bar);
+}
+template <int NC>
+__device__ __forceinline__ void consumer_bar() {
+  emu::named_barrier(1, NC);
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  return *emu::shared_ptr<uint32_t>(addr);
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  return *emu::shared_ptr<float>(addr);
+}
+__device__ __forceinline__ int2 lds_v2(uint32_t addr) {
+  return *emu::shared_ptr<int2>(addr);
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  *emu::shared_ptr<float>(addr) = v;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, float v) {
+  atomicAdd(emu::shared_ptr<float>(addr), v);
+}
+__device__ __forceinline__ float fexp(float x) {
+  return exp2f(x * 1.4426950408889634f);
+}
+__device__ __forceinline__ float flog1p(float x) {
+  const float y = log2f(1.0f + x);
+  return (x < 1e-3f) ? x * (1.0f - 0.5f * x) : y * 0.6931471805599453f;
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+/* makes the mbarrier.init of the elected thread visible to the async proxy */
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -142,6 +206,8 @@ __device__ __forceinline__ float flog1p(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(1.0f + x));
   return (x < 1e-3f) ? x * (1.0f - 0.5f * x) : y * 0.6931471805599453f;
 }
+
+#endif // GTNB_HOST_EMU
 
 /* Shared-memory carve-up, computed on the host and passed by value. */
 struct Layout {
@@ -258,7 +324,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_forward_staged
     float* __restrict__ out_scores,
     int32_t* __restrict__ best_accept,
     const Layout lay) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  GTNB_DYNAMIC_SMEM_128(unsigned char, smem);
   constexpr int kConsumers = 32 * consumer_warps(G);
   constexpr int kStagedThreads = kConsumers + 32;
   const GraphMeta m = meta[blockIdx.x];
@@ -279,7 +345,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_forward_staged
       mbar_init(sbase + 8 * s, 1);
       mbar_init(sbase + 8 * (kMaxStages + s), 1);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init_fence();
   }
   __syncthreads();
 
@@ -541,7 +607,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_backward_stage
     const float* __restrict__ deltas,
     float* __restrict__ arc_grad,
     const Layout lay) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  GTNB_DYNAMIC_SMEM_128(unsigned char, smem);
   constexpr int kConsumers = 32 * consumer_warps(G);
   constexpr int kStagedThreads = kConsumers + 32;
   const GraphMeta m = meta[blockIdx.x];
@@ -564,7 +630,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(G) + 32) sd_backward_stage
       mbar_init(sbase + 8 * s, 1);
       mbar_init(sbase + 8 * (kMaxStages + s), 1);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init_fence();
   }
   __syncthreads();
 
@@ -866,7 +932,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(1) + 32) sd_backward_fused
     long long grad_stride,
     int C,
     const Layout lay) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  GTNB_DYNAMIC_SMEM_128(unsigned char, smem);
   constexpr int kConsumers = 32 * consumer_warps(1);
   constexpr int kStagedThreads = kConsumers + 32;
   const GraphMeta m = meta[blockIdx.x];
@@ -894,7 +960,7 @@ __global__ void __launch_bounds__(32 * consumer_warps(1) + 32) sd_backward_fused
       mbar_init(sbase + 8 * s, 1);
       mbar_init(sbase + 8 * (kMaxStages + s), consumer_warps(1)); // every consumer warp releases
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init_fence();
   }
   __syncthreads();
 
@@ -1100,6 +1166,10 @@ __global__ void __launch_bounds__(32 * consumer_warps(1) + 32) sd_backward_fused
   }
 }
 
+#ifdef GTNB_HOST_EMU
+} // namespace
+#else
+
 struct StagedPlan {
   bool ok;
   int G, max_L;
@@ -1240,5 +1310,7 @@ int launch_backward_staged(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const
     DISPATCH_G_BWD(false);
   return GTNB_OK;
 }
+
+#endif // GTNB_HOST_EMU
 
 } // namespace gtnb

@@ -9,6 +9,10 @@
 #include "../../gtn_b200/csrc/k_compose.cu"
 #include "../../gtn_b200/csrc/k_shortest.cu"
 #include "../../gtn_b200/csrc/k_order.cu"
+// k_shortest.cu and k_staged.cu each keep a file-local neg_inf(): one translation unit here
+#define neg_inf staged_neg_inf
+#include "../../gtn_b200/csrc/k_staged.cu"
+#undef neg_inf
 
 #include <vector>
 
@@ -350,6 +354,107 @@ int emu_viterbi_exact(
       vit_labels[(size_t)b * T + t] = on ? pl[(size_t)b * T + t] % C : -1;
       vit_graph_arcs[(size_t)b * T + t] = on ? pg[(size_t)b * T + t] : -1;
     }
+  if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
+  return 0;
+}
+
+/*
+ * The materialised criterion path through the TMA-staged persistent kernels (k_staged.cu; G = 1, the
+ * CTC-degree family): compose -> sd_forward_staged -> either sd_backward_staged + compose's gradFunc
+ * (fused == 0) or sd_backward_fused (fused != 0).  cp.async.bulk / mbarrier are emulated (simt_emu.h).
+ * Tables as in emu_compose; out_scores[B]; grad_emis [B][T][C] zero on entry; viterbi != 0 additionally
+ * runs the MODE_PATH sweep + traceback (labels into vit_labels [B][T], scores into vit_scores).
+ * Returns 0, or 3 when the staged plan does not apply (mean degree > 4 or too large).
+ */
+int emu_materialised_staged(
+    int B, int T, int C, const float* emissions, const int32_t* lens, const int32_t* n_nodes, const uint8_t* flags,
+    const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label, const int32_t* in_arc, const float* in_w,
+    const int32_t* n_acc, const int32_t* acc, const float* deltas, int fused, float* out_scores, float* grad_emis,
+    int viterbi, float* vit_scores, int32_t* vit_labels) {
+  using namespace gtnb;
+  Lat L;
+  if (int rc = build_lattice(L, B, T, C, emissions, lens, n_nodes, flags, in_ptr, in_src, in_label, in_arc, in_w, n_acc, acc))
+    return rc;
+  // plan() of k_staged.cu, restated: stages, layouts, lanes per node
+  int max_L = 0, maxN = 0, maxA = 0;
+  long long sumA = 0, sumN = 0;
+  for (int b = 0; b < B; b++) {
+    max_L = std::max(max_L, L.meta[b].L);
+    sumA += L.meta[b].sg_A;
+    sumN += L.meta[b].sg_N;
+    maxN = std::max(maxN, L.meta[b].sg_N);
+    maxA = std::max(maxA, L.meta[b].sg_A);
+  }
+  const double deg = sumN ? (double)sumA / (double)sumN : 0.0;
+  if (deg > 4.0 || max_L + 1 > kMaxLevelsInSmem) return 3;
+  Layout lf{}, lb{};
+  bool ok = false;
+  for (int ls = 3; ls >= 1 && !ok; ls--) {
+    lf = make_layout(maxN, maxA, max_L, ls, 2, false);
+    lb = make_layout(maxN, maxA, max_L, ls, 4, true);
+    const int cap = (lb.total <= 100 * 1024 || ls == 1) ? 200 * 1024 : 100 * 1024;
+    ok = lb.total <= cap && lf.total <= cap;
+  }
+  if (!ok) return 3;
+  constexpr int kT = 32 * consumer_warps(1) + 32;
+  std::vector<float> scores((size_t)L.tn + 16, 0.0f), arc_grad((size_t)L.ta + 16, 0.0f);
+  std::vector<int32_t> back_ptr((size_t)L.tn + 16, -1), best(B, -1);
+  emu::launch(B, kT, lf.total, [&] {
+    sd_forward_staged<MODE_LOG, 1>(L.meta.data(), L.lnp.data(), L.lap.data(), L.rp.data(), L.arcs.data(),
+                                   L.acc_stage.data(), scores.data(), back_ptr.data(), out_scores, best.data(), lf);
+  });
+  if (fused) {
+    Layout lay = lb;
+    lay.tab_nodes = maxN;
+    lay.tab_arcs = maxA;
+    lay.off_tab = (lay.total + 15) / 16 * 16;
+    lay.total = lay.off_tab + 4 * (3 * lay.tab_nodes + 2 + 3 * lay.tab_arcs) + 16;
+    emu::launch(B, kT, lay.total, [&] {
+      sd_backward_fused(L.meta.data(), L.lnp.data(), L.lap.data(), L.rp.data(), L.arcs.data(), L.gi.data(),
+                        L.acc_stage.data(), scores.data(), out_scores, deltas, L.sg_ptr.data(), L.sg_src.data(),
+                        L.sg_lab.data(), grad_emis, (long long)T * C, C, lay);
+    });
+  } else {
+    emu::launch(B, kT, lb.total, [&] {
+      sd_backward_staged<false, 1>(L.meta.data(), L.lnp.data(), L.lap.data(), L.rp.data(), L.arcs.data(),
+                                   L.acc_stage.data(), scores.data(), out_scores, best.data(), deltas,
+                                   arc_grad.data(), lb);
+    });
+    int capN = 1;
+    for (int b = 0; b < B; b++) capN = std::max(capN, L.meta[b].cap_N);
+    const int ggx = std::min((capN + 255) / 256, 4096);
+    for (int by = 0; by < B; by++)
+      for (int bx = 0; bx < ggx; bx++)
+        emu::launch(1, 256, 0, [&] {
+          blockIdx.x = bx;
+          blockIdx.y = by;
+          gridDim.x = ggx;
+          compose_grad_kernel(L.meta.data(), L.rp.data(), arc_grad.data(), L.gi.data(), nullptr, grad_emis,
+                              (long long)T * C);
+        });
+  }
+  if (viterbi) {
+    emu::launch(B, kT, lf.total, [&] {
+      sd_forward_staged<MODE_PATH, 1>(L.meta.data(), L.lnp.data(), L.lap.data(), L.rp.data(), L.arcs.data(),
+                                      L.acc_stage.data(), scores.data(), back_ptr.data(), vit_scores, best.data(), lf);
+    });
+    std::vector<int32_t> path((size_t)B * std::max(T, 1), -1), plen(B, 0), pg((size_t)B * std::max(T, 1), -1),
+        pl((size_t)B * std::max(T, 1), -1);
+    emu::launch((B + 63) / 64, 64, 0, [&] {
+      traceback_kernel(L.meta.data(), L.arcs.data(), back_ptr.data(), best.data(), B, T, path.data(), plen.data());
+    });
+    if (T > 0)
+      for (int by = 0; by < B; by++)
+        for (int bx = 0; bx < (T + 127) / 128; bx++)
+          emu::launch(1, 128, 0, [&] {
+            blockIdx.x = bx;
+            blockIdx.y = by;
+            gather_prov_kernel(L.meta.data(), L.gi.data(), L.arcs.data(), T, path.data(), plen.data(), pg.data(),
+                               pl.data(), nullptr);
+          });
+    for (int b = 0; b < B; b++)
+      for (int t = 0; t < T; t++) vit_labels[(size_t)b * T + t] = t < plen[b] ? pl[(size_t)b * T + t] % C : -1;
+  }
   if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads; // the host refused the threads
   return 0;
 }

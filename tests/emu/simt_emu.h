@@ -44,7 +44,7 @@ struct Dim3 {
 
 struct Cta {
   Cta(unsigned nthreads, size_t smem_bytes)
-      : bar(nthreads), smem(smem_bytes + 64), slots((nthreads + 31) / 32) {
+      : bar(nthreads), smem(smem_bytes + 256), slots((nthreads + 31) / 32) {
     for (unsigned w = 0; w < (nthreads + 31) / 32; w++) {
       const unsigned lanes = std::min(32u, nthreads - 32 * w);
       warp_bar.emplace_back(new std::barrier<>(lanes));
@@ -52,7 +52,7 @@ struct Cta {
   }
   float* dynamic_smem() {
     auto p = reinterpret_cast<uintptr_t>(smem.data());
-    return reinterpret_cast<float*>((p + 15) & ~uintptr_t(15));
+    return reinterpret_cast<float*>((p + 127) & ~uintptr_t(127));
   }
   std::barrier<>& named(int id, int nthreads) {
     std::lock_guard<std::mutex> l(named_lock);
@@ -71,6 +71,15 @@ struct Cta {
     return v.data();
   }
   std::map<int, std::vector<unsigned char>> statics; // static __shared__ arrays, by source line
+  /* mbarrier objects by shared-window address: arrival count per phase, pending arrivals, outstanding
+   * transaction bytes, phase parity (mbarrier.init / arrive / arrive.expect_tx / complete_tx /
+   * try_wait.parity) */
+  struct MBar {
+    int count = 0, pending = 0, phase = 0;
+    long long tx = 0;
+  };
+  std::mutex mbar_lock;
+  std::map<uint32_t, MBar> mbars;
   std::mutex named_lock;
   std::map<int, std::unique_ptr<std::barrier<>>> named_bars; // bar.sync id, n (n fixed per id)
   std::atomic<int> vote{0};
@@ -145,6 +154,61 @@ T shfl(T v, int src_lane) {
   return v;
 }
 
+/* 32-bit shared-window addresses (cvta.to.shared): offsets into the CTA's dynamic shared memory, biased so
+ * that 0 is never a valid address */
+constexpr uint32_t kWindowBias = 1024;
+inline uint32_t shared_window(const void* p) {
+  return (uint32_t)(reinterpret_cast<const unsigned char*>(p) -
+                    reinterpret_cast<const unsigned char*>(g_cta->dynamic_smem())) + kWindowBias;
+}
+template <class T>
+T* shared_ptr(uint32_t addr) {
+  return reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(g_cta->dynamic_smem()) + (addr - kWindowBias));
+}
+inline void mbar_complete_locked(Cta::MBar& b) {
+  if (b.pending == 0 && b.tx == 0) {
+    b.phase ^= 1;
+    b.pending = b.count;
+  }
+}
+inline void mbar_init(uint32_t bar, int count) {
+  std::lock_guard<std::mutex> l(g_cta->mbar_lock);
+  Cta::MBar& b = g_cta->mbars[bar];
+  b.count = b.pending = count;
+  b.phase = 0;
+  b.tx = 0;
+}
+inline void mbar_arrive(uint32_t bar) {
+  std::lock_guard<std::mutex> l(g_cta->mbar_lock);
+  Cta::MBar& b = g_cta->mbars[bar];
+  b.pending--;
+  mbar_complete_locked(b);
+}
+inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) { // mbarrier.arrive.expect_tx
+  std::lock_guard<std::mutex> l(g_cta->mbar_lock);
+  Cta::MBar& b = g_cta->mbars[bar];
+  b.tx += bytes;
+  b.pending--;
+  mbar_complete_locked(b);
+}
+inline void mbar_wait(uint32_t bar, uint32_t parity) { // try_wait.parity in a loop
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> l(g_cta->mbar_lock);
+      if ((uint32_t)g_cta->mbars[bar].phase != parity) return; // the phase with that parity has completed
+    }
+    std::this_thread::yield();
+  }
+}
+/* cp.async.bulk global -> shared with mbarrier complete_tx: the copy, then the transaction bytes */
+inline void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  std::memcpy(shared_ptr<unsigned char>(dst), src, bytes);
+  std::lock_guard<std::mutex> l(g_cta->mbar_lock);
+  Cta::MBar& b = g_cta->mbars[bar];
+  b.tx -= bytes;
+  mbar_complete_locked(b);
+}
+
 /* bar.sync id, nthreads: the first nthreads threads of the CTA (the same count at every use) */
 inline void named_barrier(int id, int nthreads) {
   g_cta->named(id, nthreads).arrive_and_wait();
@@ -193,6 +257,9 @@ inline void __threadfence_block() {
 }
 inline void __syncwarp(unsigned = 0xffffffffu) {
   emu::g_cta->warp_bar[threadIdx.x / 32]->arrive_and_wait();
+}
+inline void __nanosleep(unsigned) {
+  std::this_thread::yield();
 }
 inline float __fadd_rn(float a, float b) {
   return a + b;
@@ -262,5 +329,6 @@ inline float __int_as_float(int i) {
 #define GTNB_STATIC_SMEM_2D(type, name, d0, d1) \
   type(*name)[d1] = reinterpret_cast<type(*)[d1]>(emu::g_cta->static_smem(__LINE__, sizeof(type) * (d0) * (d1)))
 
-/* dynamic shared memory of the running CTA, 16-byte aligned */
+/* dynamic shared memory of the running CTA, 128-byte aligned */
 #define GTNB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_cta->dynamic_smem())
+#define GTNB_DYNAMIC_SMEM_128(type, name) GTNB_DYNAMIC_SMEM(type, name)

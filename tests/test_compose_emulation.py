@@ -23,7 +23,7 @@ f32p, i32p, u8p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.
 
 @pytest.fixture(scope="module")
 def emu():
-    lib = C.CDLL(emu_build.build("compose", ["k_compose.cu", "k_shortest.cu", "k_order.cu"]))
+    lib = C.CDLL(emu_build.build("compose", ["k_compose.cu", "k_shortest.cu", "k_order.cu", "k_staged.cu"]))
     lib.emu_compose.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p, f32p, i32p, i32p,
                                 i32p, i32p, u32p, i32p, f32p, i32p, i32p, i32p, i32p, i32p, f32p, f32p, f32p]
     return lib
@@ -388,3 +388,66 @@ def test_exact_ties_option_on_general_graph_operands(emu, seed):
             continue
         assert vg[b, :Tb].tolist() == want_arcs, (b, vg[b, :Tb], want_arcs)
         assert vs[b] == want_score
+
+
+def run_staged(lib, e, lens, tabs, deltas, fused, viterbi=False):
+    B, T, Cn = e.shape
+    e = np.ascontiguousarray(e, np.float32)
+    lens = np.ascontiguousarray(lens, np.int32)
+    deltas = np.ascontiguousarray(deltas, np.float32)
+    nn = np.array([len(t["flags"]) for t in tabs], np.int32)
+    n_acc = np.array([len(t["acc"]) for t in tabs], np.int32)
+    out = np.zeros(B, np.float32)
+    ge = np.zeros((B, T, Cn), np.float32)
+    vs = np.zeros(B, np.float32)
+    vl = np.full((B, max(T, 1)), -9, np.int32)
+    P = lambda a, t: a.ctypes.data_as(t)
+    flags, ptr = cat([t["flags"] for t in tabs], np.uint8), cat([t["ptr"] for t in tabs], np.int32)
+    src, lab = cat([t["src"] for t in tabs], np.int32), cat([t["lab"] for t in tabs], np.int32)
+    arc, w, acc = cat([t["arc"] for t in tabs], np.int32), cat([t["w"] for t in tabs], np.float32), cat([t["acc"] for t in tabs], np.int32)
+    lib.emu_materialised_staged.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p, f32p,
+                                            i32p, i32p, f32p, C.c_int, f32p, f32p, C.c_int, f32p, i32p]
+    rc = lib.emu_materialised_staged(B, T, Cn, P(e, f32p), P(lens, i32p), P(nn, i32p), P(flags, u8p), P(ptr, i32p),
+                                     P(src, i32p), P(lab, i32p), P(arc, i32p), P(w, f32p), P(n_acc, i32p), P(acc, i32p),
+                                     P(deltas, f32p), int(fused), P(out, f32p), P(ge, f32p), int(viterbi), P(vs, f32p),
+                                     P(vl, i32p))
+    emu_build.check(rc)
+    return out, ge, vs, vl
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("shape", [(3, 14, 6, 3), (2, 9, 5, 4), (2, 40, 8, 12), (1, 25, 40, 9), (1, 70, 16, 30)])
+def test_tma_staged_kernels_end_to_end(emu, oracle, shape, fused):
+    """k_staged.cu -- the warp-specialised persistent kernels of the materialised path (producer warp:
+    cp.async.bulk + mbarrier ring; eight consumer warps) -- with the bulk copies and mbarriers emulated:
+    sd_forward_staged, then sd_backward_staged + compose's gradFunc, or the fused criterion backward."""
+    B, T, Cn, U = shape
+    e, targets = util.bench_inputs(B, T, Cn, U, seed=123)
+    lens = np.minimum(np.array([max(T - 4 * b, 2 * U + 1) for b in range(B)], np.int32), T)
+    ogs = [po.Graph.ctc(t, 0, True) for t in targets]
+    tabs = [tables_of(g, Cn) for g in ogs]
+    out, ge, _, _ = run_staged(emu, e, lens, tabs, -np.ones(B, np.float32), fused)
+    for b in range(B):
+        Tb = int(lens[b])
+        lo, go = oracle.ctc_loss(e[b, :Tb], targets[b], 0, True)
+        x = e[b, :Tb].astype(np.float64)
+        mx = x.max(1, keepdims=True)
+        lse = mx[:, 0] + np.log(np.exp(x - mx).sum(1))
+        assert util.close(float(lse.sum() - np.float64(out[b])), lo), (b, out[b], lo)
+        g = np.exp(x - lse[:, None]) + ge[b, :Tb]
+        assert util.grad_close(g, go, 5.0 * T), (b, float(np.abs(g - go).max()))
+        assert not ge[b, Tb:].any()
+
+
+def test_tma_staged_viterbi_path(emu, oracle):
+    B, T, Cn, U = 3, 18, 6, 4
+    rng = np.random.default_rng(8)
+    e = rng.uniform(-5, 5, (B, T, Cn)).astype(np.float32)
+    targets = [rng.integers(1, Cn, U).astype(np.int32) for _ in range(B)]
+    lens = np.array([T, T - 3, T - 7], np.int32)
+    tabs = [tables_of(po.Graph.ctc(t, 0, True), Cn) for t in targets]
+    _, _, vs, vl = run_staged(emu, e, lens, tabs, np.ones(B, np.float32), False, viterbi=True)
+    for b in range(B):
+        Tb = int(lens[b])
+        want_path, want_score = oracle.viterbi_ctc(e[b, :Tb], targets[b], 0, True)
+        assert np.array_equal(vl[b, :Tb], want_path) and vs[b] == np.float32(want_score)
