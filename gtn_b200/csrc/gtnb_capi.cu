@@ -1084,11 +1084,6 @@ int gtnb_viterbi_path(
   int bad = first_bad_status(ctx, lat, status_host);
   int rc;
   if (!lat->back_ptr && (rc = dev_alloc(ctx, &lat->back_ptr, lat->tot_N))) return rc;
-  if (lat->composed && lat->sg_out_pos && !lat->relax_rank) {
-    // exact_ties: the reference's relaxation ranks and accept order, once per lattice (k_order.cu)
-    if ((rc = dev_alloc(ctx, &lat->relax_rank, lat->tot_A))) return rc;
-    if ((rc = launch_relax_order(ctx, lat))) return rc;
-  }
   if ((rc = launch_forward(ctx, lat, MODE_PATH))) return rc;
   lat->forward_done = false; // scores now hold the path recursion, not shortestDistance
   int B = lat->B;
@@ -1312,6 +1307,8 @@ int gtnb::compose_linear_impl(
     TRY(upload(ctx, lat->meta, lat->meta_h.data(), B));
     TRY(upload(ctx, lat->acc_nodes, acc_stage.data(), tc));
     if (!implicit_only) TRY(launch_compose(ctx, lat));
+    // exact_ties: rows and accept list in the reference's relaxation / creation order (k_order.cu)
+    if (!implicit_only && ctx->exact_ties) TRY(launch_relax_order(ctx, lat));
   }
   *out = lat;
   return GTNB_OK;

@@ -250,7 +250,7 @@ int launch_backward_fused(
 bool implicit_supported(const gtnb_lattice* lat);
 bool implicit_dims_supported(const SgDims* dims, int n_graphs);
 int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0 = 0, int nb = -1);
-/* k_order.cu (experimental): relax_rank + accept order of a composed lattice as the reference's shortestPath sees them */
+/* k_order.cu (experimental): a composed lattice's rows and accept list in the order the reference's shortestPath relaxes / creates them */
 int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat);
 /* k_banded.cu (experimental): same contract as the implicit sweeps, for band-shaped graph operands */
 bool banded_supported(const gtnb_ctx* ctx, const gtnb_lattice* lat);

@@ -22,8 +22,10 @@
  *   key_D(v) = min over in-arcs e: u -> v of  pos_D[u] * K + o(e)      pos_D'[v] = rank of key_D
  *   key_P(v) = max over in-arcs e: u -> v of  pos_P[u] * K + o(e)      pos_P'[v] = rank of key_P
  *
- * and the relaxation rank of lattice arc (u, t) -> (v, t+1) is pos_P[u] * K + o(e): the per-arc
- * `relax_rank` sd_forward_generic<MODE_PATH> already breaks ties with (host-packed graphs use it).
+ * and the relaxation rank of lattice arc (u, t) -> (v, t+1) is pos_P[u] * K + o(e).  Every lattice row's
+ * arcs (and their provenance) are then sorted by that rank, so that "first maximum in in-arc order" --
+ * what every MODE_PATH kernel, staged or generic, already implements -- IS the reference's rule, and the
+ * lattice's accept list is put in the composed graph's accept order.
  * One CTA per utterance walks the frames; ranks are counted (O(N^2 / threads) per frame: fine for
  * criterion-sized graphs, this is a decode-time option, not a training path).
  */
@@ -151,16 +153,45 @@ __global__ void __launch_bounds__(kOrderThreads) lattice_relax_order_kernel(
   if (tid == 0) {
     const uint32_t* aT = al + (size_t)T * W;
     int32_t* acc = acc_nodes + m.acc_base;
-    int k = 0;
-    for (int u = 0; u < N1; u++)
-      if (bit_of(aT, u) && (fl[u] & 2)) k++;
     for (int u = 0; u < N1; u++) {
       if (!(bit_of(aT, u) && (fl[u] & 2))) continue;
       int before = 0; // accepting states created earlier
       for (int w = 0; w < N1; w++) before += bit_of(aT, w) && (fl[w] & 2) && posD[w] < posD[u];
       acc[before] = lp[T] + rank_of(aT, u);
     }
-    (void)k;
+  }
+}
+
+/* sort the arcs of every lattice row by relaxation rank (rows are a handful of arcs: insertion sort,
+ * one thread per lattice node); the provenance moves with the arc */
+__global__ void __launch_bounds__(256) lattice_sort_rows_kernel(
+    const GraphMeta* __restrict__ meta,
+    const uint32_t* __restrict__ row_ptr,
+    int32_t* __restrict__ relax_rank,
+    int2* __restrict__ arcs,
+    int2* __restrict__ gi) {
+  const int b = blockIdx.y;
+  const GraphMeta m = meta[b];
+  const uint32_t* rp = row_ptr + m.node_base;
+  int32_t* rr = relax_rank + m.arc_base;
+  int2* ar = arcs + m.arc_base;
+  int2* gp = gi + m.arc_base;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < m.N; n += gridDim.x * blockDim.x) {
+    const int r0 = (int)(rp[n] & kRowMask), r1 = (int)(rp[n + 1] & kRowMask);
+    for (int a = r0 + 1; a < r1; a++) {
+      const int key = rr[a];
+      const int2 av = ar[a], gv = gp[a];
+      int p = a - 1;
+      while (p >= r0 && rr[p] > key) {
+        rr[p + 1] = rr[p];
+        ar[p + 1] = ar[p];
+        gp[p + 1] = gp[p];
+        p--;
+      }
+      rr[p + 1] = key;
+      ar[p + 1] = av;
+      gp[p + 1] = gv;
+    }
   }
 }
 
@@ -168,11 +199,11 @@ __global__ void __launch_bounds__(kOrderThreads) lattice_relax_order_kernel(
 
 #ifndef GTNB_HOST_EMU
 
-/* relax_rank (tot_A ints) and the accept order of a composed lattice; needs the tables the
- * "exact_ties" flag makes gtnb_compose_linear upload */
+/* put a freshly composed lattice in the reference's relaxation order (rows) and accept order; needs the
+ * tables the "exact_ties" flag makes gtnb_compose_linear upload */
 int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat) {
   if (lat->B == 0) return GTNB_OK;
-  if (!lat->sg_out_pos || !lat->sg_start_rank || !lat->alive)
+  if (!lat->sg_out_pos || !lat->sg_start_rank || !lat->alive || !lat->gi)
     return fail(ctx, GTNB_ERR_LOGIC, "exact_ties: the lattice was composed without the flag");
   const size_t smem = sizeof(int) * 4 * (size_t)std::max(lat->max_lvl_nodes, 1);
   if (smem > (size_t)kMaxDynamicSmem)
@@ -181,11 +212,20 @@ int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat) {
     int rc = ensure_max_smem(ctx, (const void*)lattice_relax_order_kernel);
     if (rc) return rc;
   }
+  int32_t* rank = nullptr; // per lattice arc, only needed until the rows are sorted
+  int rc = dev_alloc(ctx, &rank, lat->tot_A);
+  if (rc) return rc;
   GTNB_LAUNCH(ctx, "relax_order",
               lattice_relax_order_kernel<<<lat->B, kOrderThreads, smem, ctx->stream>>>(
                   lat->meta, lat->sg_flags, lat->sg_in_ptr, lat->sg_in_src, lat->sg_in_label, lat->sg_out_pos,
                   lat->sg_start_rank, lat->alive, lat->alive_words, lat->max_T, lat->max_out_deg + 1,
-                  lat->lvl_node_ptr, lat->row_ptr, lat->relax_rank, lat->acc_nodes));
+                  lat->lvl_node_ptr, lat->row_ptr, rank, lat->acc_nodes));
+  int capN = 1;
+  for (int b = 0; b < lat->B; b++) capN = std::max(capN, lat->meta_h[b].cap_N);
+  dim3 grid(std::min((capN + 255) / 256, 4096), lat->B);
+  GTNB_LAUNCH(ctx, "sort_rows",
+              lattice_sort_rows_kernel<<<grid, 256, 0, ctx->stream>>>(lat->meta, lat->row_ptr, rank, lat->arcs, lat->gi));
+  dev_free(ctx, rank);
   return GTNB_OK;
 }
 

@@ -348,10 +348,7 @@ static bool use_staged(const gtnb_ctx* ctx, const gtnb_lattice* lat) {
 
 int launch_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int mode) {
   if (lat->B == 0) return GTNB_OK;
-  // a composed lattice that carries relax ranks (exact_ties) takes the generic path kernel: the staged one
-  // breaks ties by in-arc position only
-  const bool ranked_path = mode == MODE_PATH && lat->composed && lat->relax_rank;
-  if (use_staged(ctx, lat) && !ranked_path) return launch_forward_staged(ctx, lat, mode);
+  if (use_staged(ctx, lat)) return launch_forward_staged(ctx, lat, mode);
   dim3 grid(lat->B), block(kThreads);
 #define ARGS                                                                           \
   lat->meta, lat->lvl_node_ptr, lat->row_ptr, lat->arcs,                        \

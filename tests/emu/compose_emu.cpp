@@ -295,16 +295,17 @@ int emu_materialised(
 }
 
 /*
- * viterbiPath through the materialised lattice with the reference's tie-breaking order (k_order.cu, the
- * "exact_ties" option): compose -> lattice_relax_order_kernel -> sd_forward_generic<MODE_PATH> with the
- * per-arc relax ranks -> traceback -> label provenance.  out_pos: per in-entry, the position of the arc in
- * its source's out-arc list; start_rank: per node, its index in g.start() or -1 (concatenated like flags).
+ * viterbiPath through the materialised lattice put in the reference's tie-breaking order (k_order.cu, the
+ * "exact_ties" option): compose -> lattice_relax_order_kernel -> lattice_sort_rows_kernel -> the MODE_PATH
+ * sweep (staged != 0: sd_forward_staged of k_staged.cu, else sd_forward_generic) -> traceback -> label
+ * provenance.  out_pos: per in-entry, the position of the arc in its source's out-arc list; start_rank: per
+ * node, its index in g.start() or -1 (concatenated like flags).
  */
 int emu_viterbi_exact(
     int B, int T, int C, const float* emissions, const int32_t* lens, const int32_t* n_nodes, const uint8_t* flags,
     const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_label, const int32_t* in_arc, const float* in_w,
     const int32_t* out_pos, const int32_t* start_rank, int max_out, const int32_t* n_acc, const int32_t* acc,
-    float* vit_scores, int32_t* vit_labels, int32_t* vit_graph_arcs) {
+    int staged, float* vit_scores, int32_t* vit_labels, int32_t* vit_graph_arcs) {
   using namespace gtnb;
   Lat L;
   if (int rc = build_lattice(L, B, T, C, emissions, lens, n_nodes, flags, in_ptr, in_src, in_label, in_arc, in_w, n_acc, acc))
@@ -328,12 +329,39 @@ int emu_viterbi_exact(
                                sg_out_pos.data(), sg_start_rank.data(), L.alive.data(), L.W, L.maxT, max_out + 1,
                                L.lnp.data(), L.rp.data(), relax.data(), L.acc_stage.data());
   });
+  {
+    int capN = 1;
+    for (int b = 0; b < B; b++) capN = std::max(capN, L.meta[b].cap_N);
+    const int ggx = std::min((capN + 255) / 256, 4096);
+    for (int by = 0; by < B; by++)
+      for (int bx = 0; bx < ggx; bx++)
+        emu::launch(1, 256, 0, [&] {
+          blockIdx.x = bx;
+          blockIdx.y = by;
+          gridDim.x = ggx;
+          lattice_sort_rows_kernel(L.meta.data(), L.rp.data(), relax.data(), L.arcs.data(), L.gi.data());
+        });
+  }
   std::vector<float> scores((size_t)L.tn + 16, 0.0f);
   std::vector<int32_t> back_ptr((size_t)L.tn + 16, -1), best(B, -1);
-  emu::launch(B, kThreads, 0, [&] {
-    sd_forward_generic<MODE_PATH>(L.meta.data(), L.lnp.data(), L.rp.data(), L.arcs.data(), relax.data(),
-                                  L.acc_stage.data(), scores.data(), back_ptr.data(), vit_scores, best.data());
-  });
+  if (staged) {
+    int max_L = 0, mN = 0, mA = 0;
+    for (int b = 0; b < B; b++) {
+      max_L = std::max(max_L, L.meta[b].L);
+      mN = std::max(mN, L.meta[b].sg_N);
+      mA = std::max(mA, L.meta[b].sg_A);
+    }
+    const Layout lf = make_layout(mN, mA, max_L, 1, 2, false);
+    emu::launch(B, 32 * consumer_warps(1) + 32, lf.total, [&] {
+      sd_forward_staged<MODE_PATH, 1>(L.meta.data(), L.lnp.data(), L.lap.data(), L.rp.data(), L.arcs.data(),
+                                      L.acc_stage.data(), scores.data(), back_ptr.data(), vit_scores, best.data(), lf);
+    });
+  } else {
+    emu::launch(B, kThreads, 0, [&] {
+      sd_forward_generic<MODE_PATH>(L.meta.data(), L.lnp.data(), L.rp.data(), L.arcs.data(), nullptr,
+                                    L.acc_stage.data(), scores.data(), back_ptr.data(), vit_scores, best.data());
+    });
+  }
   std::vector<int32_t> path((size_t)B * std::max(T, 1), -1), plen(B, 0), pg((size_t)B * std::max(T, 1), -1),
       pl((size_t)B * std::max(T, 1), -1);
   emu::launch((B + 63) / 64, 64, 0, [&] {

@@ -292,7 +292,7 @@ def tables_with_out_pos(og, Cn):
     return t
 
 
-def run_exact(lib, e, lens, tabs):
+def run_exact(lib, e, lens, tabs, staged=False):
     B, T, Cn = e.shape
     e = np.ascontiguousarray(e, np.float32)
     lens = np.ascontiguousarray(lens, np.int32)
@@ -307,11 +307,11 @@ def run_exact(lib, e, lens, tabs):
     arc, w, acc = cat([t["arc"] for t in tabs], np.int32), cat([t["w"] for t in tabs], np.float32), cat([t["acc"] for t in tabs], np.int32)
     opos, sr = cat([t["out_pos"] for t in tabs], np.int32), cat([t["start_rank"] for t in tabs], np.int32)
     lib.emu_viterbi_exact.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, u8p, i32p, i32p, i32p, i32p, f32p, i32p,
-                                      i32p, C.c_int, i32p, i32p, f32p, i32p, i32p]
+                                      i32p, C.c_int, i32p, i32p, C.c_int, f32p, i32p, i32p]
     rc = lib.emu_viterbi_exact(B, T, Cn, P(e, f32p), P(lens, i32p), P(nn, i32p), P(flags, u8p), P(ptr, i32p), P(src, i32p),
                                P(lab, i32p), P(arc, i32p), P(w, f32p), P(opos, i32p), P(sr, i32p),
-                               max(t["max_out"] for t in tabs), P(n_acc, i32p), P(acc, i32p), P(vs, f32p), P(vl, i32p),
-                               P(vg, i32p))
+                               max(t["max_out"] for t in tabs), P(n_acc, i32p), P(acc, i32p), int(staged), P(vs, f32p),
+                               P(vl, i32p), P(vg, i32p))
     emu_build.check(rc)
     return vs, vl, vg
 
@@ -332,11 +332,13 @@ def reference_path(og, e_b, Tb, Cn):
     return [int(g1[k]) for k in arcs], [int(g2[k]) % Cn for k in arcs], score
 
 
+@pytest.mark.parametrize("staged", [False, True])
 @pytest.mark.parametrize("blank_last", [False, True])
-def test_exact_ties_option_reproduces_the_reference_path_on_ctc_lattices(emu, blank_last):
-    """k_order.cu: with the reference's relaxation ranks and accept order, viterbiPath through the device
-    lattice returns the reference's path on integer-valued emissions (ties at nearly every node), for blank
-    first and blank last (where compose's discovery order is not the node order)."""
+def test_exact_ties_option_reproduces_the_reference_path_on_ctc_lattices(emu, blank_last, staged):
+    """k_order.cu: with every lattice row sorted by the reference's relaxation rank and the accept list in
+    creation order, viterbiPath through the device lattice -- generic or TMA-staged path kernel -- returns the
+    reference's path on integer-valued emissions (ties at nearly every node), for blank first and blank last
+    (where compose's discovery order is not the node order)."""
     B, T, Cn, U = 4, 16, 5, 3
     rng = np.random.default_rng(11 + blank_last)
     e = rng.integers(-1, 2, (B, T, Cn)).astype(np.float32)
@@ -347,7 +349,7 @@ def test_exact_ties_option_reproduces_the_reference_path_on_ctc_lattices(emu, bl
     lens = np.array([T, T - 2, T - 5, 2 * U + 1], np.int32)
     ogs = [po.Graph.ctc(t, blank, True) for t in targets]
     tabs = [tables_with_out_pos(g, Cn) for g in ogs]
-    vs, vl, vg = run_exact(emu, e, lens, tabs)
+    vs, vl, vg = run_exact(emu, e, lens, tabs, staged)
     for b in range(B):
         Tb = int(lens[b])
         want_arcs, want_labels, want_score = reference_path(ogs[b], e[b], Tb, Cn)
