@@ -45,6 +45,7 @@ SYMBOLS = [
     ("gtnb_last_error", C.c_char_p, [_vp]),
     ("gtnb_ctx_synchronize", C.c_int, [_vp]),
     ("gtnb_ctx_stream", _vp, [_vp]),
+    ("gtnb_ctx_device", C.c_int, [_vp]),
     ("gtnb_ctx_launch_count", C.c_int64, [_vp]),
     ("gtnb_ctx_set_flag", C.c_int, [_vp, C.c_char_p, C.c_int]),
     ("gtnb_device_alloc", C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -329,6 +330,27 @@ class Ctx:
         self._check(lib().gtnb_ctc_loss(
             self.h, B, T, Cn, e.ctypes.data, 0, _p(il, _i32p), _p(cat, _i32p), _p(lens, _i32p),
             blank, _p(losses, _f32p), None if grads is None else grads.ctypes.data, 0))
+        return losses, grads
+
+    def ctc_loss_dev(self, emissions, targets, blank=0, input_lens=None):
+        """Device-buffer entry point: uploads once, runs gtnb_ctc_loss on device pointers (emissions
+        in HBM in, gradients in HBM out), downloads the gradients afterwards -> (losses, grads)."""
+        e = np.ascontiguousarray(emissions, dtype=np.float32)
+        B, T, Cn = e.shape
+        lens = np.asarray([len(t) for t in targets], np.int32)
+        cat = np.ascontiguousarray(np.concatenate([np.asarray(t, np.int32) for t in targets]), np.int32)
+        il = None if input_lens is None else np.ascontiguousarray(input_lens, np.int32)
+        losses = np.zeros(B, np.float32)
+        e_dev = self.to_device(e)
+        g_dev = self.alloc(e.nbytes)
+        try:
+            self._check(lib().gtnb_ctc_loss(
+                self.h, B, T, Cn, e_dev.ptr, 1, _p(il, _i32p), _p(cat, _i32p), _p(lens, _i32p),
+                blank, _p(losses, _f32p), g_dev.ptr, 1))
+            grads = g_dev.download(e.shape)
+        finally:
+            e_dev.free()
+            g_dev.free()
         return losses, grads
 
 

@@ -13,7 +13,7 @@ Graph scalarGraph(float val, bool calcGrad) {
 
 Graph linearGraph(int M, int N, bool calcGrad /* = true */) {
   Graph g(calcGrad);
-  g.addNode(true, M == 0);
+  g.addNode(true); // not accepting, even for M == 0 (creations.cpp:22): forwardScore(linearGraph(0, N)) is -inf
   for (int m = 1; m <= M; ++m) {
     g.addNode(false, m == M);
     for (int n = 0; n < N; ++n) {
@@ -23,8 +23,11 @@ Graph linearGraph(int M, int N, bool calcGrad /* = true */) {
   g.markArcSorted();
   g.markArcSorted(true);
   // remember the structure: compose / forwardScore take the frame-synchronous device path
-  g.sharedGraph_->linearFrames = M;
-  g.sharedGraph_->linearLabels = N;
+  // (M == 0 has no accept node: it takes the generic path like any other graph)
+  if (M > 0) {
+    g.sharedGraph_->linearFrames = M;
+    g.sharedGraph_->linearLabels = N;
+  }
   return g;
 }
 

@@ -60,8 +60,8 @@ struct ViewStorage {
 };
 void makeView(const Graph& g, ViewStorage& s);
 
-/** True if `p` points to device memory. */
-bool isDevicePointer(const void* p);
+/** True if `p` points to device memory; `*device` (optional) receives the GPU it lives on. */
+bool isDevicePointer(const void* p, int* device = nullptr);
 
 } // namespace detail
 } // namespace gtn

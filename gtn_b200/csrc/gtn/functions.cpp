@@ -479,8 +479,8 @@ Graph shortestDistanceDevice(const Graph& g, bool tropical) {
   if (g.isLinear() && g.linearLabels() > 0 && !g.isDeviceResident()) return shortestDistanceLinear(g, tropical);
   std::shared_ptr<LatticeHandle> handle;
   bool latticeEntry = false;
-  if (g.lattice() && g.lattice()->composed) {
-    handle = g.lattice();
+  if (g.scoringLattice() && g.scoringLattice()->composed) {
+    handle = g.scoringLattice();
     latticeEntry = true;
   } else {
     auto c = threadContext();
@@ -563,8 +563,8 @@ Graph viterbiScore(const Graph& g) {
 Graph viterbiPath(const Graph& g) {
   using namespace detail;
   std::shared_ptr<LatticeHandle> handle;
-  if (g.lattice() && g.lattice()->composed) {
-    handle = g.lattice();
+  if (g.scoringLattice() && g.scoringLattice()->composed) {
+    handle = g.scoringLattice();
   } else {
     auto c = threadContext();
     ViewStorage vs;

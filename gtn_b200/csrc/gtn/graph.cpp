@@ -73,12 +73,13 @@ LatticeHandle::~LatticeHandle() {
   }
 }
 
-bool isDevicePointer(const void* p) {
+bool isDevicePointer(const void* p, int* device) {
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
+  if (device) *device = attr.device;
   return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
@@ -159,6 +160,23 @@ Graph Graph::fromLattice(
   g.sharedGraph_->lattice = std::move(lattice);
   g.sharedGraph_->latticeIndex = index;
   g.sharedGraph_->hostReady = false;
+  // The arc weights belong to THIS handle's SharedWeights only: gradient graphs share sharedGraph_
+  // (addGrad) but own their weights, so materialising the topology through one of them must never
+  // write the lattice's forward weights over a gradient (round-1 advisor finding).
+  auto lat = g.sharedGraph_->lattice;
+  g.sharedWeights_->latticeWeights = true;
+  g.sharedWeights_->lazyFetch = [lat, index](std::vector<float>& host) {
+    std::vector<int32_t> nn(lat->B), na(lat->B);
+    std::lock_guard<std::mutex> cl(lat->owner->lock);
+    detail::check(lat->owner, gtnb_lattice_sizes(lat->owner->ctx, lat->lat, nn.data(), na.data()));
+    host.assign(std::max(na[index], 1), 0.0f);
+    detail::check(
+        lat->owner,
+        gtnb_lattice_download(
+            lat->owner->ctx, lat->lat, index, nullptr, nullptr, nullptr, nullptr, nullptr, host.data(),
+            nullptr, nullptr));
+    host.resize(na[index]);
+  };
   return g;
 }
 
@@ -187,14 +205,14 @@ void Graph::materialize() const {
   const int N = nn[sg.latticeIndex], A = na[sg.latticeIndex];
   std::vector<uint8_t> flags(std::max(N, 1));
   std::vector<int32_t> src(std::max(A, 1)), dst(std::max(A, 1)), il(std::max(A, 1)), ol(std::max(A, 1));
-  std::vector<float> w(std::max(A, 1));
   {
+    // topology only: the weights are fetched by the owning handle's SharedWeights (fromLattice)
     std::lock_guard<std::mutex> cl(lat->owner->lock);
     detail::check(
         lat->owner,
         gtnb_lattice_download(
             lat->owner->ctx, lat->lat, sg.latticeIndex, flags.data(), src.data(), dst.data(),
-            il.data(), ol.data(), w.data(), nullptr, nullptr));
+            il.data(), ol.data(), nullptr, nullptr, nullptr));
   }
   sg.nodes.clear();
   sg.arcs.clear();
@@ -207,7 +225,6 @@ void Graph::materialize() const {
     if (flags[n] & 1) sg.start.push_back(n);
     if (flags[n] & 2) sg.accept.push_back(n);
   }
-  if (sharedWeights_) sharedWeights_->host.assign(w.begin(), w.begin() + A);
   for (int a = 0; a < A; a++) {
     sg.arcs.emplace_back(src[a], dst[a], il[a], ol[a]);
     sg.nodes[src[a]].out.push_back(a);
@@ -250,7 +267,7 @@ int Graph::addNode(bool start /* = false */, bool accept /* = false */) {
   if (accept) sg.accept.push_back(idx);
   sg.ilabelSorted = false;
   sg.olabelSorted = false;
-  sg.linearFrames = sg.linearLabels = -1;
+  topologyEdited();
   return idx;
 }
 
@@ -268,7 +285,7 @@ size_t Graph::addArc(size_t srcNode, size_t dstNode, int ilabel, int olabel, flo
   sg.nodes[dstNode].in.push_back(idx);
   sg.ilabelSorted = false;
   sg.olabelSorted = false;
-  sg.linearFrames = sg.linearLabels = -1;
+  topologyEdited();
   return idx;
 }
 
@@ -337,8 +354,10 @@ std::vector<float>& Graph::hostWeights() const {
 float* Graph::weights() {
   host();
   auto& hw = hostWeights();
-  // the caller may write through the pointer: the device copy can no longer be trusted
+  // the caller may write through the pointer: neither the device copy nor a device lattice built
+  // from the old values can be trusted any longer
   sharedWeights_->device.reset();
+  sharedWeights_->latticeWeights = false;
   return hw.data();
 }
 
@@ -356,6 +375,7 @@ void Graph::setWeight(size_t i, float weight) {
   host();
   hostWeights()[i] = weight;
   sharedWeights_->device.reset();
+  sharedWeights_->latticeWeights = false;
 }
 
 std::shared_ptr<detail::DeviceBuffer> Graph::deviceWeights() const {
@@ -373,18 +393,36 @@ void Graph::cacheDeviceWeights(std::shared_ptr<detail::DeviceBuffer> buf) const 
 void Graph::setWeights(const float* weights) {
   const size_t n = numArcs();
   auto& sw = *sharedWeights_;
-  if (n > 0 && detail::isDevicePointer(weights)) {
+  int ptrDevice = -1;
+  if (n > 0 && detail::isDevicePointer(weights, &ptrDevice)) {
     auto c = detail::threadContext();
+    if (ptrDevice != gtnb_ctx_device(c->ctx))
+      throw std::invalid_argument(
+          "[Graph::setWeights] device pointer lives on GPU " + std::to_string(ptrDevice) +
+          ", this thread's context on GPU " + std::to_string(gtnb_ctx_device(c->ctx)));
     auto buf = std::make_shared<detail::DeviceBuffer>(c, n);
     {
       std::lock_guard<std::mutex> cl(c->lock);
       cudaStream_t st = (cudaStream_t)gtnb_ctx_stream(c->ctx);
-      if (cudaMemcpyAsync(buf->ptr, weights, sizeof(float) * n, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      // Order the copy after the producer of `weights`.  The context's stream is non-blocking, so
+      // nothing orders it after e.g. a torch kernel still writing the tensor: wait for everything
+      // queued so far on the legacy default stream (torch's default) and on the per-thread default
+      // stream.  A producer on any other stream must synchronise before calling.
+      cudaEvent_t ev;
+      bool ok = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+      for (cudaStream_t prod : {cudaStreamLegacy, cudaStreamPerThread}) {
+        ok = ok && cudaEventRecord(ev, prod) == cudaSuccess && cudaStreamWaitEvent(st, ev, 0) == cudaSuccess;
+      }
+      if (ok) cudaEventDestroy(ev);
+      if (!ok ||
+          cudaMemcpyAsync(buf->ptr, weights, sizeof(float) * n, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         throw std::runtime_error("[Graph::setWeights] device copy failed");
     }
     std::lock_guard<std::mutex> l(sw.lock);
     sw.device = buf;
     sw.hostStale = true;
+    sw.lazyFetch = nullptr;
+    sw.latticeWeights = false;
     return;
   }
   std::lock_guard<std::mutex> l(sw.lock);
@@ -392,6 +430,8 @@ void Graph::setWeights(const float* weights) {
   std::copy(weights, weights + n, sw.host.data());
   sw.device.reset();
   sw.hostStale = false;
+  sw.lazyFetch = nullptr;
+  sw.latticeWeights = false;
 }
 
 void Graph::labelsToArray(int* out, bool ilabel) {

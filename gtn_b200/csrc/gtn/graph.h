@@ -141,6 +141,7 @@ class Graph {
     if (!n.accept) {
       sharedGraph_->accept.push_back(static_cast<int>(i));
       n.accept = true;
+      topologyEdited();
     }
   };
   size_t numOut(size_t i) const {
@@ -200,6 +201,16 @@ class Graph {
   std::shared_ptr<detail::LatticeHandle> lattice() const {
     return sharedGraph_->lattice;
   }
+  /**
+   * The lattice, but only while it still IS this graph: null once the topology was edited (the
+   * edit drops it) or this handle's weights are no longer the lattice's (setWeights, setWeight, a
+   * write through weights(), or a gradient graph that merely shares the topology).  The device
+   * shortest-distance / path ops use this one and otherwise re-pack the host view.
+   */
+  std::shared_ptr<detail::LatticeHandle> scoringLattice() const {
+    if (!sharedWeights_ || !sharedWeights_->latticeWeights) return nullptr;
+    return sharedGraph_->lattice;
+  }
   int latticeIndex() const {
     return sharedGraph_->latticeIndex;
   }
@@ -250,7 +261,8 @@ class Graph {
     std::vector<float> host;
     std::shared_ptr<detail::DeviceBuffer> device; // set by setWeights(device pointer)
     bool hostStale{false}; // device holds the truth, host not yet filled
-    std::function<void(std::vector<float>&)> lazyFetch; // see addLazyGrad
+    std::function<void(std::vector<float>&)> lazyFetch; // see addLazyGrad, fromLattice
+    bool latticeWeights{false}; // these ARE the (unmodified) arc weights of sharedGraph_->lattice
     std::mutex lock;
   };
 
@@ -261,6 +273,12 @@ class Graph {
     bool calcGrad;
   };
 
+  // after any topology edit: the device forms no longer describe this graph
+  void topologyEdited() {
+    sharedGraph_->linearFrames = sharedGraph_->linearLabels = -1;
+    sharedGraph_->lattice.reset();
+    if (sharedWeights_) sharedWeights_->latticeWeights = false;
+  }
   // host topology, materialising it from the device lattice on first use
   const SharedGraph& host() const;
   SharedGraph& host();

@@ -207,6 +207,10 @@ void* gtnb_ctx_stream(gtnb_ctx* ctx) {
   return (void*)ctx->stream;
 }
 
+int gtnb_ctx_device(const gtnb_ctx* ctx) {
+  return ctx ? ctx->device : -1;
+}
+
 int64_t gtnb_ctx_launch_count(const gtnb_ctx* ctx) {
   return ctx->launches;
 }

@@ -60,7 +60,7 @@ struct gtnb_ctx {
   };
   bool use_staged = true; // gtnb_ctx_set_flag("staged", 0) forces the generic kernels
   bool use_implicit = true; // gtnb_ctx_set_flag("implicit", 0): criteria materialise the lattice
-  bool exact_ties = false; // gtnb_ctx_set_flag("exact_ties", 1): EXPERIMENTAL, viterbiPath on composed lattices breaks exact ties like the reference (k_order.cu)
+  bool exact_ties = true; // gtnb_ctx_set_flag("exact_ties", 0) turns it off: composed lattices are put in the reference's relaxation order so that viterbiPath breaks exact ties like shortest.cpp:212-218 (k_order.cu)
   int use_banded = 0; // gtnb_ctx_set_flag("banded", K): EXPERIMENTAL temporally blocked CTC sweeps (k_banded.cu), K frames per barrier
   bool profiling = false;
   std::vector<ProfEntry> prof;

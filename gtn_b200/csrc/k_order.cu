@@ -1,7 +1,8 @@
 /*
- * k_order.cu -- EXPERIMENTAL (gtnb_ctx_set_flag("exact_ties", 1) before gtnb_compose_linear; off by
- * default; checked on the CPU through tests/emu, not yet run on a GPU): the reference's tie-breaking
- * order on a device-composed lattice.
+ * k_order.cu -- the reference's tie-breaking order on a device-composed lattice (on by default;
+ * gtnb_ctx_set_flag("exact_ties", 0) before gtnb_compose_linear skips it).  GPU-validated in round 2
+ * (tests/test_gpu_parity.py::test_viterbi_exact_ties_vs_oracle,
+ * tests/test_gpu_config_parity.py::test_forced_alignment_config4_vs_reference).
  *
  * detail::shortestPath (shortest.cpp:190-245) keeps, for every node, the FIRST-RELAXED predecessor
  * among those that reach the maximum, and the first strictly greatest accept node in g.accept()

@@ -93,6 +93,8 @@ void gtnb_ctx_destroy(gtnb_ctx* ctx);
 const char* gtnb_last_error(const gtnb_ctx* ctx);
 int gtnb_ctx_synchronize(gtnb_ctx* ctx);
 void* gtnb_ctx_stream(gtnb_ctx* ctx);
+/* the CUDA device ordinal the context was created on */
+int gtnb_ctx_device(const gtnb_ctx* ctx);
 int gtnb_version(void);
 /* number of kernels this context has launched so far (bench bookkeeping) */
 int64_t gtnb_ctx_launch_count(const gtnb_ctx* ctx);

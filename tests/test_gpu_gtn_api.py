@@ -368,3 +368,69 @@ def test_cpp_api_example_matches_batched_criterion():
     assert out.returncode == 0, out.stdout + out.stderr
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["max_rel_loss_diff"] < 1e-4
+
+
+# ---------------------------------------------------------------------------
+# round-1 advisor findings: gradient graphs sharing a device-resident topology, edits
+# after compose, linearGraph edits
+# ---------------------------------------------------------------------------
+
+def test_backward_through_viterbi_path_of_device_lattice(gtn, oracle):
+    """backward(viterbi_path(compose(ctc, emissions))): the path's gradFunc adds a host gradient to the
+    still device-resident composed graph; materialising the shared topology must not overwrite it with
+    the lattice's forward weights.  emissions.grad = 1 on the arcs (t, label_t) of the best path."""
+    T, C, target = 30, 6, [2, 4, 4, 1]
+    rng = np.random.default_rng(3)
+    e = rng.uniform(-5, 5, (T, C)).astype(np.float32)
+    ctc = ctc_graph(gtn, target, 0)
+    em = gtn.linear_graph(T, C)
+    em.set_weights(e.ravel())
+    lat = gtn.compose(ctc, em)
+    assert lat.is_device_resident()
+    path = gtn.viterbi_path(lat)
+    labels = path.labels_to_list()
+    p, _ = oracle.viterbi_ctc(e, np.asarray(target, np.int32), 0, False)
+    assert labels == list(p)
+    gtn.backward(path)
+    want = np.zeros((T, C), np.float32)
+    want[np.arange(T), p] = 1.0
+    assert np.array_equal(em.grad().weights_to_numpy().reshape(T, C), want)
+    # the composed graph's own weights are still the lattice's (w_ctc + e), not the gradient
+    w = lat.weights_to_numpy()
+    assert np.all(np.isin(np.round(w, 4), np.round(e.ravel(), 4)))
+    g = lat.grad().weights_to_numpy()
+    assert g.sum() == T and set(np.unique(g)) <= {0.0, 1.0}
+
+
+def test_edits_after_compose_are_scored(gtn):
+    """forwardScore must see set_weights / add_arc done on a composed graph after the fact
+    (the reference scores the edited graph; the stale device lattice must not be used)."""
+    T, C = 6, 4
+    rng = np.random.default_rng(8)
+    e = rng.uniform(-2, 2, (T, C)).astype(np.float32)
+    ctc = ctc_graph(gtn, [1, 2], 0)
+    em = gtn.linear_graph(T, C)
+    em.set_weights(e.ravel())
+    lat = gtn.compose(ctc, em)
+    s0 = gtn.forward_score(lat).item()
+    w = lat.weights_to_numpy().copy()
+    lat.set_weights(w + 1.0)  # every accepting path has T arcs
+    assert abs(gtn.forward_score(lat).item() - (s0 + T)) < 1e-4
+    lat2 = gtn.compose(ctc, em)
+    n = lat2.add_node(False, True)
+    lat2.add_arc(0, n, 0, 0, 100.0)  # node 0 = (ctc start, frame 0)
+    assert gtn.forward_score(lat2).item() > 99.0
+    assert gtn.viterbi_score(lat2).item() >= 100.0
+
+
+def test_linear_graph_edits_and_empty(gtn):
+    """linearGraph(0, N) has no accept node (creations.cpp:22): forwardScore is -inf; make_accept on a
+    linear graph makes it an ordinary graph (an early exit), scored as the reference would."""
+    g0 = gtn.linear_graph(0, 3)
+    assert g0.num_nodes() == 1 and g0.num_arcs() == 0 and g0.num_accept() == 0
+    assert gtn.forward_score(g0).item() == -math.inf
+    g = gtn.linear_graph(3, 2)
+    g.set_weights([0.0] * 6)
+    g.make_accept(1)
+    # paths: 2 of length 1 (node 1 accepts) + 8 of length 3
+    assert abs(gtn.forward_score(g).item() - math.log(10.0)) < 1e-5

@@ -581,12 +581,10 @@ def test_asg_implicit_and_materialised_agree(ctx, oracle, shape):
 
 
 # ---------------------------------------------------------------------------
-# EXPERIMENTAL: temporally blocked CTC sweeps (k_banded.cu), opt-in.  Written when round 1 had no GPU
-# time left: run with GTNB_EXPERIMENTAL=1 once a GPU is available, then drop the gate.
+# temporally blocked CTC sweeps (k_banded.cu), opt-in through gtnb_ctx_set_flag("banded", K); first GPU
+# run in round 2: parity green for every K, K=2 measured 0.152 / 0.184 ms fwd / bwd at config 2.
 # ---------------------------------------------------------------------------
 
-@pytest.mark.skipif(os.environ.get("GTNB_EXPERIMENTAL") != "1",
-                    reason="k_banded.cu has not been run on a GPU yet (set GTNB_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("shape", [(4, 120, 16, 9), (3, 37, 8, 1), (2, 200, 32, 90), (2, 9, 5, 4), (3, 64, 28, 30),
                                    (2, 1000, 64, 100)])
 @pytest.mark.parametrize("K", [4, 2, 8, 1])
@@ -621,15 +619,13 @@ def test_ctc_banded_sweeps_agree_with_implicit_and_oracle(ctx, oracle, shape, K)
 
 
 # ---------------------------------------------------------------------------
-# EXPERIMENTAL: exact score ties in viterbiPath on device lattices (k_order.cu), opt-in.  The kernel's
-# logic is covered on the CPU by tests/test_compose_emulation.py; this is its first GPU run.
+# exact score ties in viterbiPath on device lattices (k_order.cu): on by default since round 2 (first GPU
+# run green, gpurun_out/r2a_tests.log); gtnb_ctx_set_flag("exact_ties", 0) skips the ordering pass.
 # ---------------------------------------------------------------------------
 
-@pytest.mark.skipif(os.environ.get("GTNB_EXPERIMENTAL") != "1",
-                    reason="k_order.cu has not been run on a GPU yet (set GTNB_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("blank_last", [False, True])
-def test_viterbi_exact_ties_option_vs_oracle(ctx, oracle, blank_last):
-    """gtnb_ctx_set_flag("exact_ties", 1) before compose: integer-valued emissions make nearly every lattice
+def test_viterbi_exact_ties_vs_oracle(ctx, oracle, blank_last):
+    """Integer-valued emissions make nearly every lattice
     node a tie; the path through the lattice API must then be the reference's, label for label."""
     B, T, C, U = 6, 40, 6, 7
     rng = np.random.default_rng(5 + blank_last)
@@ -638,14 +634,10 @@ def test_viterbi_exact_ties_option_vs_oracle(ctx, oracle, blank_last):
     labels = [l for l in range(C) if l != blank]
     targets = [rng.choice(labels, U).astype(np.int32) for _ in range(B)]
     lens = [T - 3 * b for b in range(B)]
-    ctx.set_flag("exact_ties", 1)
-    try:
-        e_dev = ctx.to_device(e)
-        views = [util.view_of(oracle.Graph.ctc(t, blank, True)) for t in targets]
-        lat = ctx.compose_linear(views, lens, C, e_dev, T * C)
-        out = lat.viterbi_path(T)
-    finally:
-        ctx.set_flag("exact_ties", 0)
+    e_dev = ctx.to_device(e)
+    views = [util.view_of(oracle.Graph.ctc(t, blank, True)) for t in targets]
+    lat = ctx.compose_linear(views, lens, C, e_dev, T * C)
+    out = lat.viterbi_path(T)
     for b in range(B):
         p, s = oracle.viterbi_ctc(e[b, :lens[b]], targets[b], blank, True)
         assert out["lens"][b] == lens[b]
