@@ -331,10 +331,14 @@ def main():
         "linear_rows": 8 * TC * B,
         # implicit-lattice criterion kernels (k_implicit.cu): SURVEY.md 8(d) "B_io" -- emissions in,
         # dense per-frame node scores out (forward) / in (backward), emission gradients out
+        # the bidirectional kernel (k_bidir.cu): the WHOLE criterion -- SURVEY.md 8(d) B_io = emissions in
+        # (4TC), gradients out (4TC), per-frame node scores written once and read once (2 * 4 * T * S)
+        "bidir_ctc": 4 * TC * B + 4 * TC * B + 2 * 4 * T * pitch * B,
         "implicit_forward": 4 * TC * B + 4 * (T + 1) * pitch * B,
         "implicit_backward": 4 * TC * B + 4 * (T + 1) * pitch * B + 4 * TC * B,
     }
-    formulation = {"implicit_forward": "B_io (lattice never materialised)",
+    formulation = {"bidir_ctc": "B_io (lattice never materialised; SURVEY.md 8(d) secondary figure, whole criterion)",
+                   "implicit_forward": "B_io (lattice never materialised)",
                    "implicit_backward": "B_io (lattice never materialised)"}
     b_csr = 32 * sumA + 28 * sumN + 12 * TC * B
 

@@ -269,6 +269,10 @@ int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value) {
     ctx->exact_ties = value != 0;
     return GTNB_OK;
   }
+  if (ctx && name && std::string(name) == "bidir") {
+    ctx->use_bidir = value < 0 ? kBidirDefault : value != 0; // -1: back to the default
+    return GTNB_OK;
+  }
   if (ctx && name && std::string(name) == "banded") {
     ctx->use_banded = value;
     return GTNB_OK;

@@ -36,7 +36,10 @@ static int ctc_loss_run(
   int32_t* small_dev = nullptr; // [targets | offsets | lens | T]
   int32_t* status_dev = nullptr;
   float* row_scratch = nullptr; // k_linear.cu's per-frame scores, allocated once for all sub-batches
+  float* zparts_dev = nullptr; // k_bidir.cu: forwardScore(emissions) as two partial sums per utterance
+  float* boff_dev = nullptr; // k_bidir.cu: per-block score offsets of the two CTAs of every utterance
   bool implicit = false;
+  bool bidir = false;
   int K = 1; // sub-batches (implicit path with host buffers)
   std::vector<int> chunk_lo;
   cudaStream_t main_stream = ctx->stream;
@@ -113,8 +116,14 @@ static int ctc_loss_run(
   TRY(dev_alloc(ctx, &deltas_dev, B));
   TRY(dev_alloc(ctx, &small_dev, tot_t + 3ll * B));
   TRY(composed_alloc(ctx, B, dims.data(), B, 0, Tb.data(), C, e_dev, per, sgn, sga, &lat, implicit));
+  // the whole criterion in one launch per sub-batch (k_bidir.cu) when the batch qualifies
+  bidir = implicit && ctx->use_bidir && ctx->use_banded == 0 && bidir_supported(lat, e_dev, per, g_dev, per);
+  if (bidir) {
+    TRY(dev_alloc(ctx, &zparts_dev, 2ll * B));
+    TRY(dev_alloc(ctx, &boff_dev, 8ll * B * bidir_blocks(maxT)));
+  }
   if (implicit) {
-    TRY(dev_alloc(ctx, &row_scratch, (long long)B * std::max(maxT, 1)));
+    if (!bidir) TRY(dev_alloc(ctx, &row_scratch, (long long)B * std::max(maxT, 1)));
     TRY(dev_alloc(ctx, &status_dev, B));
     TRYCUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * B, ctx->stream));
   }
@@ -164,7 +173,25 @@ static int ctc_loss_run(
     cudaEvent_t ev_setup = ctx->side_events[K], ev_lin = ctx->side_events[K + 1];
     const int32_t* T_dev = small_dev + tot_t + 2ll * B;
     TRYCUDA(cudaEventRecord(ev_setup, main_stream));
-    if (K == 1 && !h2d_event && !(grads && !grads_on_device)) {
+    if (bidir && K == 1 && !h2d_event && !(grads && !grads_on_device)) {
+      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1));
+    } else if (bidir) {
+      for (int k = 0; k < K && !rc; k++) {
+        const int b0 = chunk_lo[k], nb = chunk_lo[k + 1] - chunk_lo[k];
+        cudaStream_t cs = ctx->side_streams[k];
+        TRYCUDA(cudaStreamWaitEvent(cs, ev_setup, 0));
+        if (h2d_event) TRYCUDA(cudaStreamWaitEvent(cs, ctx->side_events[k], 0));
+        ctx->stream = cs;
+        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb);
+        ctx->stream = main_stream;
+        if (rc) goto done;
+        if (grads && !grads_on_device)
+          TRYCUDA(cudaMemcpyAsync(grads + (long long)b0 * per, g_dev + (long long)b0 * per,
+                                  sizeof(float) * per * nb, cudaMemcpyDeviceToHost, cs));
+        TRYCUDA(cudaEventRecord(ctx->side_events[k], cs));
+        TRYCUDA(cudaStreamWaitEvent(main_stream, ctx->side_events[k], 0));
+      }
+    } else if (K == 1 && !h2d_event && !(grads && !grads_on_device)) {
       // forwardScore(emissions) and its +1 gradient beside the forward sweep
       TRYCUDA(cudaStreamWaitEvent(ctx->copy_stream, ev_setup, 0));
       ctx->stream = ctx->copy_stream;
@@ -219,17 +246,21 @@ static int ctc_loss_run(
     if (!grads_on_device)
       TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  TRY(readback_reserve(ctx, 3 * sizeof(float) * B));
+  TRY(readback_reserve(ctx, 4 * sizeof(float) * B));
   {
-    float* z = reinterpret_cast<float*>(ctx->readback);
-    float* s = z + B;
+    float* z = reinterpret_cast<float*>(ctx->readback); // [2B]: bidir's two partial sums, else z in [0, B)
+    float* s = z + 2 * B;
     int32_t* st = reinterpret_cast<int32_t*>(s + B);
-    TRYCUDA(cudaMemcpyAsync(z, z_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bidir)
+      TRYCUDA(cudaMemcpyAsync(z, zparts_dev, sizeof(float) * 2 * B, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+      TRYCUDA(cudaMemcpyAsync(z, z_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
     TRYCUDA(cudaMemcpyAsync(s, lat->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
     if (implicit)
       TRYCUDA(cudaMemcpyAsync(st, status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->stream));
     TRYCUDA(cudaStreamSynchronize(ctx->stream));
-    for (int b = 0; b < B; b++) losses_host[b] = z[b] - s[b]; // subtract, functions.cpp:52
+    for (int b = 0; b < B; b++) // subtract, functions.cpp:52
+      losses_host[b] = bidir ? (z[2 * b] + z[2 * b + 1]) - s[b] : z[b] - s[b];
     if (implicit)
       for (int b = 0; b < B; b++)
         if (st[b]) *needs_exact = true;
@@ -244,6 +275,8 @@ done:
   }
   dev_free(ctx, status_dev);
   dev_free(ctx, row_scratch);
+  dev_free(ctx, zparts_dev);
+  dev_free(ctx, boff_dev);
   if (lat) gtnb_lattice_destroy(ctx, lat);
   if (!emissions_on_device) dev_free(ctx, e_dev);
   if (grads && !grads_on_device) dev_free(ctx, g_dev);

@@ -25,6 +25,10 @@
 #define GTNB_STATIC_SMEM(type, name, count) __shared__ type name[count]
 #define GTNB_STATIC_SMEM_2D(type, name, d0, d1) __shared__ type name[d0][d1]
 
+// k_bidir.cu as gtnb_ctc_loss's default path: off until it beats the two sweeps of k_implicit.cu on the B200
+// (round 2, first measurements: 0.54 ms against 0.41 + 0.09 ms -- the helper warps' issue slots)
+constexpr bool kBidirDefault = false;
+
 struct gtnb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -60,6 +64,7 @@ struct gtnb_ctx {
   };
   bool use_staged = true; // gtnb_ctx_set_flag("staged", 0) forces the generic kernels
   bool use_implicit = true; // gtnb_ctx_set_flag("implicit", 0): criteria materialise the lattice
+  bool use_bidir = kBidirDefault; // gtnb_ctx_set_flag("bidir", 0): the CTC criterion takes the two sweeps of k_implicit.cu instead of the bidirectional kernel (k_bidir.cu)
   bool exact_ties = true; // gtnb_ctx_set_flag("exact_ties", 0) turns it off: composed lattices are put in the reference's relaxation order so that viterbiPath breaks exact ties like shortest.cpp:212-218 (k_order.cu)
   int use_banded = 0; // gtnb_ctx_set_flag("banded", K): EXPERIMENTAL temporally blocked CTC sweeps (k_banded.cu), K frames per barrier
   bool profiling = false;
@@ -250,6 +255,12 @@ int launch_backward_fused(
 bool implicit_supported(const gtnb_lattice* lat);
 bool implicit_dims_supported(const SgDims* dims, int n_graphs);
 int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, int b0 = 0, int nb = -1);
+/* k_bidir.cu: the CTC criterion in one launch (two-CTA clusters meeting in the middle), normaliser included */
+bool bidir_supported(const gtnb_lattice* lat, const float* emissions, int64_t stride, const float* grad, int64_t grad_stride);
+int bidir_blocks(int max_T);
+int launch_bidir_ctc(
+    gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
+    int64_t grad_stride, int b0 = 0, int nb = -1);
 /* k_order.cu (experimental): a composed lattice's rows and accept list in the order the reference's shortestPath relaxes / creates them */
 int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat);
 /* k_banded.cu (experimental): same contract as the implicit sweeps, for band-shaped graph operands */

@@ -87,6 +87,14 @@ struct Cta {
 
 inline thread_local Cta* g_cta = nullptr;
 
+/* a thread-block cluster: its CTAs run concurrently and share one barrier (barrier.cluster) */
+struct Cluster {
+  explicit Cluster(unsigned nthreads) : bar(nthreads) {}
+  std::barrier<> bar;
+};
+inline thread_local Cluster* g_cluster = nullptr;
+inline thread_local unsigned g_cluster_rank = 0;
+
 } // namespace emu
 
 inline thread_local emu::Dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -133,6 +141,63 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& body) {
     go.store(g_launch_failed.load() ? -1 : 1, std::memory_order_release);
     for (auto& th : threads) th.join();
   }
+}
+
+/* the same for a launch with cluster dimension `csize`: the CTAs of one cluster run concurrently
+ * (csize * block host threads), clusters one after the other */
+template <class F>
+void launch_clusters(unsigned grid, unsigned csize, unsigned block, size_t smem_bytes, F&& body) {
+  for (unsigned b0 = 0; b0 < grid && !g_launch_failed.load(); b0 += csize) {
+    std::vector<std::unique_ptr<Cta>> ctas;
+    for (unsigned k = 0; k < csize; k++) ctas.emplace_back(new Cta(block, smem_bytes));
+    Cluster cluster(csize * block);
+    std::vector<std::thread> threads;
+    threads.reserve(csize * block);
+    std::atomic<int> go{0};
+    for (unsigned k = 0; k < csize && !g_launch_failed.load(); k++)
+      for (unsigned t = 0; t < block; t++) {
+        try {
+          threads.emplace_back([&, k, t] {
+            while (go.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+            if (go.load() < 0) return;
+            Cta& cta = *ctas[k];
+            g_cta = &cta;
+            g_cluster = &cluster;
+            g_cluster_rank = k;
+            threadIdx = Dim3{t, 0, 0};
+            blockIdx = Dim3{b0 + k, 0, 0};
+            blockDim = Dim3{block, 1, 1};
+            gridDim = Dim3{grid, 1, 1};
+            body();
+            cta.bar.arrive_and_drop();
+            cta.warp_bar[t / 32]->arrive_and_drop();
+            g_cluster = nullptr;
+          });
+        } catch (const std::system_error&) {
+          g_launch_failed.store(true);
+          break;
+        }
+      }
+    go.store(g_launch_failed.load() ? -1 : 1, std::memory_order_release);
+    for (auto& th : threads) th.join();
+  }
+}
+/* barrier.cluster.arrive + barrier.cluster.wait: every thread of the cluster exactly once per phase */
+inline void cluster_sync() {
+  g_cluster->bar.arrive_and_wait();
+}
+/* the split form: arrive now (non-blocking), wait later */
+inline thread_local std::barrier<>::arrival_token* g_cluster_token = nullptr;
+inline void cluster_arrive() {
+  g_cluster_token = new std::barrier<>::arrival_token(g_cluster->bar.arrive());
+}
+inline void cluster_wait() {
+  g_cluster->bar.wait(std::move(*g_cluster_token));
+  delete g_cluster_token;
+  g_cluster_token = nullptr;
+}
+inline unsigned cluster_ctarank() {
+  return g_cluster_rank;
 }
 
 inline uint32_t exchange(uint32_t v, int src_lane) {
@@ -182,6 +247,12 @@ inline void mbar_arrive(uint32_t bar) {
   std::lock_guard<std::mutex> l(g_cta->mbar_lock);
   Cta::MBar& b = g_cta->mbars[bar];
   b.pending--;
+  mbar_complete_locked(b);
+}
+inline void mbar_arrive_n(uint32_t bar, int n) { // mbarrier.arrive with a count
+  std::lock_guard<std::mutex> l(g_cta->mbar_lock);
+  Cta::MBar& b = g_cta->mbars[bar];
+  b.pending -= n;
   mbar_complete_locked(b);
 }
 inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) { // mbarrier.arrive.expect_tx
@@ -282,6 +353,18 @@ inline int max(int a, int b) {
 }
 inline unsigned atomicOr(uint32_t* p, uint32_t v) {
   return std::atomic_ref<uint32_t>(*p).fetch_or(v);
+}
+inline int __float2int_rn(float x) { // cvt.rni.s32.f32: saturating
+  if (!(x > -2147483648.0f)) return -2147483647 - 1;
+  if (x >= 2147483648.0f) return 2147483647;
+  return (int)lrintf(x);
+}
+inline int __reduce_max_sync(unsigned, int v) { // redux.sync.max.s32 over the full warp
+  for (int o = 16; o > 0; o >>= 1) {
+    const int w = emu::shfl(v, (int)((threadIdx.x % 32) ^ o));
+    v = w > v ? w : v;
+  }
+  return v;
 }
 inline int __popc(unsigned x) {
   return __builtin_popcount(x);

@@ -467,16 +467,20 @@ def test_ctc_implicit_and_materialised_agree(ctx, oracle, shape):
     e, targets = util.bench_inputs(B, T, C, U, seed=4321)
     lens = np.array([T - (3 * b) % max(T // 2, 1) for b in range(B)], np.int32)
     res = {}
-    for imp in (1, 0):
-        ctx.set_flag("implicit", imp)
-        ctx.profile(True)
-        ctx.profile_read()
-        res[imp] = ctx.ctc_loss(e, targets, input_lens=lens)
-        names = set(ctx.profile_read())
-        ctx.profile(False)
-        assert ("implicit_forward" in names) == bool(imp), names
-        assert ("compose_emit" in names) == (not imp), names
-    ctx.set_flag("implicit", 1)
+    ctx.set_flag("bidir", 0)  # the two sweeps of k_implicit.cu (k_bidir.cu has its own tests below)
+    try:
+        for imp in (1, 0):
+            ctx.set_flag("implicit", imp)
+            ctx.profile(True)
+            ctx.profile_read()
+            res[imp] = ctx.ctc_loss(e, targets, input_lens=lens)
+            names = set(ctx.profile_read())
+            ctx.profile(False)
+            assert ("implicit_forward" in names) == bool(imp), names
+            assert ("compose_emit" in names) == (not imp), names
+    finally:
+        ctx.set_flag("implicit", 1)
+        ctx.set_flag("bidir", -1)
     assert util.close(res[1][0], res[0][0])
     for b in range(B):
         lo, go = oracle.ctc_loss(e[b, :lens[b]], targets[b], 0, True)
@@ -578,6 +582,93 @@ def test_asg_implicit_and_materialised_agree(ctx, oracle, shape):
         assert util.grad_close(res[1][1][b], res[0][1][b], 5.0 * T), b
     assert util.grad_close(res[1][2], tsum, 5.0 * T * B)
     assert util.grad_close(res[1][2], res[0][2], 5.0 * T * B)
+
+
+# ---------------------------------------------------------------------------
+# the bidirectional meet-in-the-middle kernel (k_bidir.cu): gtnb_ctc_loss's default since round 2
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", [(4, 120, 16, 9), (3, 37, 8, 1), (2, 9, 4, 4), (1, 100, 28, 10), (3, 64, 28, 30),
+                                   (2, 300, 128, 127), (2, 1000, 64, 100), (5, 1, 8, 0)])
+@pytest.mark.parametrize("want_grad", [True, False])
+def test_ctc_bidir_agrees_with_two_sweeps_and_oracle(ctx, oracle, shape, want_grad):
+    """gtnb_ctc_loss through k_bidir.cu (one launch: alpha from the front and beta from the back in a
+    two-CTA cluster, posteriors on the fly, normaliser fused) against the two sweeps of k_implicit.cu
+    (flag "bidir" 0), the oracle and the float64 referee; ragged input lengths; loss only.
+    (2, 300, 128, 127): 255 graph nodes = 8 node warps, C = 128; (5, 1, 8, 0): T = 1, empty targets."""
+    from oracle import f64
+    B, T, C, U = shape
+    e, targets = util.bench_inputs(B, T, C, U, seed=555)
+    lens = np.array([T - (5 * b) % max(T // 2, 1) for b in range(B)], np.int32)
+    res = {}
+    for bidir in (1, 0):
+        ctx.set_flag("bidir", bidir)
+        ctx.profile(True)
+        ctx.profile_read()
+        try:
+            res[bidir] = ctx.ctc_loss(e, targets, input_lens=lens, want_grad=want_grad)
+        finally:
+            ctx.set_flag("bidir", -1)
+        names = set(ctx.profile_read())
+        ctx.profile(False)
+        assert ("bidir_ctc" in names) == bool(bidir), names
+        assert ("implicit_forward" in names) == (not bidir), names
+        assert "compose_emit" not in names, names
+    assert util.close(res[1][0], res[0][0])
+    for b in range(B):
+        lo, go = oracle.ctc_loss(e[b, :lens[b]], targets[b], 0, want_grad)
+        assert util.close(res[1][0][b], lo), (b, res[1][0][b], lo)
+        if want_grad and np.isfinite(lo):
+            _, g64 = f64.ctc_f64(e[b, :lens[b]], targets[b])
+            mine = res[1][1][b, :lens[b]]
+            oracle_err = np.abs(go - g64).max()
+            assert np.abs(mine - g64).max() <= 2.0 * oracle_err + 2e-6, b
+            # the distance to the oracle's fp32 gradient is the oracle's own distance to the exact one
+            assert np.abs(mine - go).max() <= 1.5 * oracle_err + 1e-5, b
+            assert not res[1][1][b, lens[b]:].any()
+
+
+def test_ctc_bidir_falls_back_on_non_finite_emissions(ctx):
+    """a non-finite emission raises the status bit and the call is repeated materialised, like the
+    two-sweep path (C = 8: bidir eligible)."""
+    B, T, C, U = 3, 40, 8, 5
+    e, targets = util.bench_inputs(B, T, C, U, seed=98)
+    e[1, 7, int(targets[1][2])] = -np.inf
+    ctx.profile(True)
+    ctx.profile_read()
+    ctx.set_flag("bidir", 1)
+    try:
+        l1, g1 = ctx.ctc_loss(e, targets)
+    finally:
+        ctx.set_flag("bidir", -1)
+    names = set(ctx.profile_read())
+    ctx.profile(False)
+    assert "bidir_ctc" in names and "compose_emit" in names, names
+    ctx.set_flag("implicit", 0)
+    l0, g0 = ctx.ctc_loss(e, targets)
+    ctx.set_flag("implicit", 1)
+    assert np.array_equal(np.isnan(l1), np.isnan(l0)) and np.array_equal(np.isnan(g1), np.isnan(g0))
+    assert np.allclose(l1[~np.isnan(l1)], l0[~np.isnan(l0)], rtol=1e-5)
+
+
+def test_ctc_bidir_host_buffers_sub_batches(ctx):
+    """host buffers above 16 MB: sub-batches on their own streams, one bidir launch each."""
+    B, T, C, U = 40, 1000, 128, 60  # 20.5 MB of emissions -> 2 sub-batches
+    e, targets = util.bench_inputs(B, T, C, U, seed=2025)
+    il = np.array([T - 7 * (b % 5) for b in range(B)], np.int32)
+    ctx.set_flag("bidir", 1)
+    try:
+        l_dev, g_dev = ctx.ctc_loss_dev(e, targets, input_lens=il)
+        ctx.profile(True)
+        ctx.profile_read()
+        l_host, g_host = ctx.ctc_loss(e, targets, input_lens=il)
+    finally:
+        ctx.set_flag("bidir", -1)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    assert prof["bidir_ctc"][0] == 2, prof
+    assert np.array_equal(l_host, l_dev)
+    assert np.array_equal(g_host, g_dev)
 
 
 # ---------------------------------------------------------------------------
