@@ -40,6 +40,7 @@ static int ctc_loss_run(
   float* boff_dev = nullptr; // k_bidir.cu: per-block score offsets of the two CTAs of every utterance
   bool implicit = false;
   bool bidir = false;
+  int zp = 1;
   int K = 1; // sub-batches (implicit path with host buffers)
   std::vector<int> chunk_lo;
   cudaStream_t main_stream = ctx->stream;
@@ -119,7 +120,7 @@ static int ctc_loss_run(
   // the whole criterion in one launch per sub-batch (k_bidir.cu) when the batch qualifies
   bidir = implicit && ctx->use_bidir && ctx->use_banded == 0 && bidir_supported(lat, e_dev, per, g_dev, per);
   if (bidir) {
-    TRY(dev_alloc(ctx, &zparts_dev, 2ll * B));
+    TRY(dev_alloc(ctx, &zparts_dev, 2ll * B * bidir_zparts()));
     TRY(dev_alloc(ctx, &boff_dev, 8ll * B * bidir_blocks(maxT)));
   }
   if (implicit) {
@@ -174,7 +175,7 @@ static int ctc_loss_run(
     const int32_t* T_dev = small_dev + tot_t + 2ll * B;
     TRYCUDA(cudaEventRecord(ev_setup, main_stream));
     if (bidir && K == 1 && !h2d_event && !(grads && !grads_on_device)) {
-      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1));
+      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1));
     } else if (bidir) {
       for (int k = 0; k < K && !rc; k++) {
         const int b0 = chunk_lo[k], nb = chunk_lo[k + 1] - chunk_lo[k];
@@ -182,7 +183,7 @@ static int ctc_loss_run(
         TRYCUDA(cudaStreamWaitEvent(cs, ev_setup, 0));
         if (h2d_event) TRYCUDA(cudaStreamWaitEvent(cs, ctx->side_events[k], 0));
         ctx->stream = cs;
-        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb);
+        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1);
         ctx->stream = main_stream;
         if (rc) goto done;
         if (grads && !grads_on_device)
@@ -246,21 +247,25 @@ static int ctc_loss_run(
     if (!grads_on_device)
       TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  TRY(readback_reserve(ctx, 4 * sizeof(float) * B));
+  zp = bidir ? 2 * bidir_zparts() : 1; // partial sums of forwardScore(emissions) per utterance
+  TRY(readback_reserve(ctx, (zp + 2) * sizeof(float) * B));
   {
-    float* z = reinterpret_cast<float*>(ctx->readback); // [2B]: bidir's two partial sums, else z in [0, B)
-    float* s = z + 2 * B;
+    float* z = reinterpret_cast<float*>(ctx->readback);
+    float* s = z + (long long)zp * B;
     int32_t* st = reinterpret_cast<int32_t*>(s + B);
     if (bidir)
-      TRYCUDA(cudaMemcpyAsync(z, zparts_dev, sizeof(float) * 2 * B, cudaMemcpyDeviceToHost, ctx->stream));
+      TRYCUDA(cudaMemcpyAsync(z, zparts_dev, sizeof(float) * zp * B, cudaMemcpyDeviceToHost, ctx->stream));
     else
       TRYCUDA(cudaMemcpyAsync(z, z_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
     TRYCUDA(cudaMemcpyAsync(s, lat->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
     if (implicit)
       TRYCUDA(cudaMemcpyAsync(st, status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->stream));
     TRYCUDA(cudaStreamSynchronize(ctx->stream));
-    for (int b = 0; b < B; b++) // subtract, functions.cpp:52
-      losses_host[b] = bidir ? (z[2 * b] + z[2 * b + 1]) - s[b] : z[b] - s[b];
+    for (int b = 0; b < B; b++) { // subtract, functions.cpp:52
+      float zb = 0.0f;
+      for (int k = 0; k < zp; k++) zb += z[(long long)zp * b + k];
+      losses_host[b] = zb - s[b];
+    }
     if (implicit)
       for (int b = 0; b < B; b++)
         if (st[b]) *needs_exact = true;

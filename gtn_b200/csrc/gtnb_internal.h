@@ -25,9 +25,9 @@
 #define GTNB_STATIC_SMEM(type, name, count) __shared__ type name[count]
 #define GTNB_STATIC_SMEM_2D(type, name, d0, d1) __shared__ type name[d0][d1]
 
-// k_bidir.cu as gtnb_ctc_loss's default path: off until it beats the two sweeps of k_implicit.cu on the B200
-// (round 2, first measurements: 0.54 ms against 0.41 + 0.09 ms -- the helper warps' issue slots)
-constexpr bool kBidirDefault = false;
+// k_bidir.cu is gtnb_ctc_loss's default path (gtnb_ctx_set_flag("bidir", 0): the two sweeps of k_implicit.cu):
+// 0.39 ms in one launch against 0.17 + 0.24 ms (+ k_linear.cu beside them), and 4-5x closer to float64
+constexpr bool kBidirDefault = true;
 
 struct gtnb_ctx {
   int device = 0;
@@ -258,9 +258,10 @@ int launch_implicit_forward(gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_de
 /* k_bidir.cu: the CTC criterion in one launch (two-CTA clusters meeting in the middle), normaliser included */
 bool bidir_supported(const gtnb_lattice* lat, const float* emissions, int64_t stride, const float* grad, int64_t grad_stride);
 int bidir_blocks(int max_T);
+int bidir_zparts(); // partial sums of forwardScore(emissions) per CTA
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
-    int64_t grad_stride, int b0 = 0, int nb = -1);
+    int64_t grad_stride, int b0 = 0, int nb = -1, int zero_w = 0);
 /* k_order.cu (experimental): a composed lattice's rows and accept list in the order the reference's shortestPath relaxes / creates them */
 int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat);
 /* k_banded.cu (experimental): same contract as the implicit sweeps, for band-shaped graph operands */

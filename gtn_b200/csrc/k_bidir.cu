@@ -23,28 +23,39 @@
  * at the meeting level equals forwardScore of the lattice.  The dependent chain is T steps instead of
  * 2T, and HBM traffic does not grow: each half of the saved scores is written once and read once.
  *
- * Inside a CTA (warp-specialised):
- *   node warps    one graph node per thread; per level 3 LDS of the neighbours' scores (absent arcs read
- *                 a slot that holds a large negative finite number, so there is no -inf / NaN special
- *                 casing on the chain), max, 3 ex2, lg2, one STS, one named barrier.  Scores are kept in
- *                 log2 units (emissions and arc weights are multiplied by log2(e) on the way in), which
- *                 removes the multiply from every exp and log.
- *   producer warp cp.async.bulk (TMA 1-D bulk copies, mbarrier complete_tx) of 8 emission frames at a
- *                 time into a 3-stage ring.
- *   helper warps  (2) per block of 8 frames: row logsumexp of the emissions (forwardScore(emissions)
- *                 and its softmax gradient, k_linear.cu's job before), the posteriors summed by label
- *                 through per-label node lists (no floating-point atomics anywhere), and the finished
- *                 gradient rows written with coalesced 16-byte stores.  They also issue the bulk loads of
- *                 the partner's saved scores; the node threads turn those rows into posteriors in place.
+ * Inside a CTA (warp-specialised, 12 warps at 40 registers so that the four CTAs of two utterances share an SM):
+ *   node warps    (<= 7) one graph node per thread; per level 3 LDS of the neighbours' scores (absent arcs read
+ *                 a slot that holds a large negative finite number, so there is no -inf / NaN special casing on
+ *                 the chain), FMNMX3, 3 ex2, lg2, one STS, one named barrier: 22 SASS instructions per level in
+ *                 phase 1, 27 in phase 2.  Scores are kept in log2 units (emissions are multiplied by log2(e)
+ *                 on the way in), which removes the multiply from every exp and log, and are RENORMALISED every
+ *                 8 levels by an integer (see publish_block_max): the posteriors come out 4-5x closer to a
+ *                 float64 evaluation than the reference's own fp32 gradient.
+ *   producer warp cp.async.bulk (TMA 1-D bulk copies, mbarrier complete_tx) of 8 emission frames at a time into
+ *                 a 4-stage ring and, in phase 2, of the partner's 8 saved score rows (+ that block's offset)
+ *                 into a 2-stage ring.
+ *   helper warps  (4) own two rows of a block each: row logsumexp of the emissions (forwardScore(emissions) and
+ *                 its softmax gradient, k_linear.cu's job before) with LDS.128 and half-warp shuffles, the
+ *                 posteriors summed by label -- the node threads write theirs into 4 slots per label of a
+ *                 separate block, so a label's mass is one LDS.128; labels carried by more nodes (CTC: blank)
+ *                 sit behind the slots and are summed by the row's 16 lanes together; no floating-point
+ *                 atomics anywhere -- and the finished gradient row leaves as one 16-byte store per lane.
  *
- * Numerics: gamma's exponent is evaluated as ((x - Zh) + y) - Zl with x the larger of alpha/beta: both
+ * What bounds it (profiles/r2_bidir_notes.md, scripts/ubench/chain*.cu): the SFU.  A level costs 4 MUFU per
+ * node (+1 for the posterior) and the B200 retires 16 per clock and SM: 0.35 cycles per node-level measured at
+ * saturation whatever the CTA shape, i.e. >= 0.14 ms for config 2.  The two sweeps of k_implicit.cu spend 7
+ * MUFU per node and frame, this kernel 9 -- it halves the dependent chain but does MORE SFU work, which is
+ * why it lands at 0.39 ms against 0.17 + 0.24 (+ 0.085 of k_linear.cu beside them) and not at half.
+ *
+ * Numerics: gamma's exponent is evaluated as ((x - Zh) + y) - zsub with x the larger of alpha/beta: both
  * subtractions are exact or nearly so (Sterbenz), so the posterior carries only the rounding error the
- * recursions themselves accumulated -- like the reference's own chain of arc-factor products.  Measured
- * against a float64 evaluation it is closer than the reference's fp32 result (DESIGN.md "Tolerances").
+ * recursions themselves accumulated -- and those run on renormalised scores (|score| < ~100, ulp 8e-6
+ * instead of 5e-4).  Measured against a float64 evaluation: max abs 6e-4 / mean 8e-7 where the reference's
+ * fp32 gradient has 2.8e-3 / 4.0e-5 (DESIGN.md "Tolerances").
  *
  * Valid when every weight is finite (|x| < 1e29): otherwise a status bit is raised and the caller repeats
  * the batch through the materialised path, which reproduces the reference's inf / NaN propagation arc by
- * arc.  Requires: <= 256 graph nodes, in- and out-degree <= 3, one label per node (CTC, forced alignment),
+ * arc.  Requires: <= 224 graph nodes, in- and out-degree <= 3, one label per node (CTC, forced alignment),
  * C a multiple of 4 and <= 128, 16-byte aligned emissions.  Anything else takes k_implicit.cu.
  */
 #ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
@@ -66,16 +77,20 @@ namespace gtnb {
 
 namespace bidir {
 
-constexpr int kMaxNodes = 256; // graph nodes per utterance (one per thread)
+constexpr int kMaxNodes = 256; // table capacity
+constexpr int kMaxNodeWarps = 7; // graph nodes per utterance: at most 224, one per thread (4 CTAs of 12 warps per SM at 40 registers)
 constexpr int kRowF = 264; // floats per chain row in shared memory
 constexpr int kDummy = 256; // slot of every chain row that holds kNeg (absent arcs point here)
 constexpr int kBlk = 8; // frames per block (one TMA copy, one helper pass, one renormalisation)
-constexpr int kSE = 4; // emission stages
-constexpr int kSO = 3; // stages of the partner's saved scores
+constexpr int kSE = 4; // emission stages (kSE, kSO, kSG are powers of two: stage = v & (k - 1), parity = (v / k) & 1)
+constexpr int kSO = 2; // stages of the partner's saved scores
 constexpr int kSG = 2; // posterior blocks between the node warps and the helper warps
-constexpr int kHelpers = 2; // helper warps
-constexpr int kHeavyLen = 8; // labels carried by more nodes than this are summed cooperatively
-constexpr int kMaxHeavy = 4;
+constexpr int kHelpers = 4; // helper warps
+// (Tried and dropped: gathering the nodes with <= 2 neighbours -- every CTC blank -- in warps of their own that take a
+// two-score logsumexp with half the SFU work.  Measured slower on the B200, 0.179 vs 0.132 ms for the loss-only sweep at
+// config 2: strided saves / stage reads and a branch per level cost more than the SFU cycles saved.)
+constexpr int kSlots = 4; // posterior slots per label in a row of the helpers' block (one LDS.128)
+constexpr int kMaxHeavy = 4; // labels carried by more than kSlots nodes that get the cooperative sum
 constexpr float kNeg = -1.0e30f; // "this node does not exist" (finite: absorbs every later add)
 constexpr float kHuge = 1.0e29f; // inputs at or above this magnitude take the exact (materialised) path
 constexpr float kLog2e = 1.4426950408889634f;
@@ -83,9 +98,10 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kIntMin = -2147483647 - 1;
 
 struct Layout {
-  int off_ring, off_e, off_o, off_g, off_od, off_out, off_seg, off_perm, off_nlab, off_hlist, off_xch, off_red, off_redi,
+  int off_ring, off_e, off_o, off_g, off_od, off_seg, off_perm, off_nlab, off_hlist, off_red, off_redi,
       off_bar;
-  int e_stage_bytes, o_stage_bytes;
+  int e_stage_bytes, o_stage_bytes, g_block_bytes;
+  int pg; // floats per row of a posterior block: kSlots per label, then the overflow positions
   int total;
 };
 
@@ -103,14 +119,14 @@ inline Layout make_layout(int C, int max_pitch) {
   L.o_stage_bytes = kBlk * max_pitch * 4;
   // the out-arc scratch of CTA B's set-up (cnt[256] + dst[768] + w[768]) aliases the score stages
   L.off_o = take(std::max(kSO * L.o_stage_bytes, (kMaxNodes + 6 * kMaxNodes) * 4));
-  L.off_g = take(kSG * L.o_stage_bytes);
+  L.pg = kSlots * C + max_pitch;
+  L.g_block_bytes = kBlk * L.pg * 4;
+  L.off_g = take(kSG * L.g_block_bytes);
   L.off_od = take(kSO * 16);
-  L.off_out = take(kBlk * C * 4);
   L.off_seg = take(C * 4);
   L.off_perm = take(kMaxNodes * 4);
   L.off_nlab = take(kMaxNodes * 4);
-  L.off_hlist = take((kMaxHeavy + 1) * 4);
-  L.off_xch = take(kHelpers * kBlk * (2 + kMaxHeavy) * 4);
+  L.off_hlist = take((kMaxHeavy + 1) * 4 + kMaxHeavy * 12);
   L.off_red = take(32 * 4);
   L.off_redi = take(8 * 4);
   L.off_bar = take((2 * kSE + 2 * kSO + 2 * kSG + 1) * 8);
@@ -129,13 +145,14 @@ struct Params {
   float* saved; // [node_base + f * pitch + u]: alpha_{f+1} for f < M (written by A), beta_{f+1} for f >= M (by B)
   float* boff; // [utterance][2][nblk_cap][4]: the score offset in effect for the rows of each block, per CTA
   float* out_scores; // [B] forwardScore of the lattice (natural log)
-  float* zparts; // [2B] forwardScore(emissions): the part each CTA of the pair summed
+  float* zparts; // [2B * kHelpers] forwardScore(emissions): the part each helper warp of the pair of CTAs summed
   int32_t* status; // [B] bit 0: a weight was not finite
   float* grad; // [B][grad_stride] or NULL (loss only)
   long long grad_stride;
   int C;
   int nwn; // node warps in the launch (ceil(max nodes / 32))
   int nblk_cap;
+  int zero_w; // every arc weight of every graph is 0 (host knowledge: CTC / forced alignment targets)
   Layout lay;
 };
 
@@ -185,6 +202,12 @@ __device__ __forceinline__ void sts_u(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return *emu::shared_ptr<float4>(addr);
+}
+__device__ __forceinline__ void smem_max_s32(uint32_t addr, int v) {
+  std::atomic_ref<int32_t> a(*emu::shared_ptr<int32_t>(addr));
+  int32_t cur = a.load();
+  while (cur < v && !a.compare_exchange_weak(cur, v)) {
+  }
 }
 __device__ __forceinline__ void stg_v4(float* p, float4 v) {
   *reinterpret_cast<float4*>(p) = v;
@@ -258,7 +281,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(100);
+    __nanosleep(400);
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -290,6 +313,9 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void smem_max_s32(uint32_t addr, int v) { // native ATOMS.MAX.S32
+  asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void stg_v4(float* p, float4 v) {
   asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -351,16 +377,22 @@ struct NodeState {
   uint32_t pc, qc; // chain rows: read / write (swapped every level)
   uint32_t ea; // this node's emission in the current stage row
   uint32_t oa; // this node's slot in the current stage row of the partner's scores
-  uint32_t pdelta; // where the posterior goes, relative to oa: (posterior block - score stage) + (label-sorted position - node id) * 4
-  int estep, ostep; // +-(C * 4), +-(pitch * 4)
+  uint32_t ga; // where this node's posterior of the current level goes (its label's slot in the helpers' block)
   float* gs; // where this node's score of the current level is saved (phase 1)
-  long long gstep; // +-pitch
   float adj; // renormalisation: subtracted from every score at the first level of a block (an integer)
   float D; // sum of the adjustments so far: true score = kept score + D (exact: integers below 2^24)
   float Zh, zsub; // phase 2: posterior = ex2(((own - Zh) + other) - zsub)
-  float Zl, D0, Do0; // the pieces of Z: Z = D0 + Do0 + Zh + Zl (log2 units)
-  uint32_t redi; // per-warp maxima of the block's last level (ints), 8 slots
-  bool act;
+  float Zl, Dc; // Z = Dc + Zh + Zl (log2 units); Dc: both CTAs' offsets at the meeting level (an integer)
+  uint32_t redi; // the word (of an 8-byte aligned pair) the current block's maximum is published into
+};
+
+/* What is the same for every node thread of the CTA (kept in uniform registers / the constant bank, not in
+ * per-thread registers: the node warps run at 40 registers).  Threads of the last node warp beyond the
+ * utterance's nodes CLONE the last node -- same addresses, same values, harmless duplicate stores -- so
+ * that the level code needs no "is this thread a node" state at all; `act` only matters where a thread's
+ * value enters a reduction. */
+struct NodeUni {
+  int c4, p4, g4, pitch; // bytes per emission row / score-stage row / posterior row; floats per saved row
   int nact; // threads of the node warps of this CTA
 };
 
@@ -373,15 +405,18 @@ struct NodeState {
  * subtracts it from every score.  Integers subtract exactly and their sum D stays exact in fp32, so the
  * kept scores stay within a few hundred of zero (ulp ~ 3e-5) and nothing is lost: true = kept + D.
  */
-__device__ __forceinline__ void publish_block_max(const NodeState& st, float stored) {
-  const int iv = st.act ? __float2int_rn(fmaxf(stored, -2.0e9f)) : kIntMin;
+__device__ __forceinline__ void publish_block_max(NodeState& st, float stored) {
+  const int iv = __float2int_rn(fmaxf(stored, -2.0e9f));
   const int wm = __reduce_max_sync(0xffffffffu, iv);
-  if ((threadIdx.x & 31) == 0) sts_u(st.redi + 4u * (threadIdx.x >> 5), (uint32_t)wm);
+  // two words, used alternately: the one the NEXT block will publish into is reset here (every thread
+  // has read it at the start of this block, many barriers ago)
+  if ((threadIdx.x & 31) == 0) smem_max_s32(st.redi, wm);
+  if (threadIdx.x == 0) sts_u(st.redi ^ 4u, (uint32_t)kIntMin);
 }
 /* at the start of the next block: the adjustment every node thread applies (same value in all of them) */
-__device__ __forceinline__ void fetch_block_adjust(NodeState& st, int nwarps) {
-  int mx = kIntMin;
-  for (int w = 0; w < nwarps; w++) mx = max(mx, (int)lds_u(st.redi + 4u * w));
+__device__ __forceinline__ void fetch_block_adjust(NodeState& st) {
+  const int mx = (int)lds_u(st.redi);
+  st.redi ^= 4u;
   // nothing alive (or nothing published yet): no adjustment
   const float off = (mx <= -2000000000) ? 0.0f : (float)mx;
   st.adj = off;
@@ -390,40 +425,44 @@ __device__ __forceinline__ void fetch_block_adjust(NodeState& st, int nwarps) {
 
 /* one level.  DIR 0: CTA A (alpha), 1: CTA B (beta).  PH 1: save the score; 2: posterior in place.
  * LAST: the block's last level (publishes the maximum for the renormalisation) */
-template <int DIR, int PH>
-__device__ __forceinline__ void node_step(NodeState& st, bool last) {
+template <int DIR, int PH, bool ZW>
+__device__ __forceinline__ void node_step(NodeState& st, const NodeUni& un, bool last) {
   const float x = lds(st.ea);
-  st.ea += st.estep;
-  const float v = lse3(lds(st.pc + st.so0) + st.w0, lds(st.pc + st.so1) + st.w1, lds(st.pc + st.so2) + st.w2);
+  st.ea += DIR ? -un.c4 : un.c4;
+  // ZW: every arc weight of the graph is 0 (CTC, forced alignment): no adds
+  const float v = ZW ? lse3(lds(st.pc + st.so0), lds(st.pc + st.so1), lds(st.pc + st.so2))
+                     : lse3(lds(st.pc + st.so0) + st.w0, lds(st.pc + st.so1) + st.w1, lds(st.pc + st.so2) + st.w2);
   // A: alpha_s = v + e[s-1][label(u)].  B: beta_s = v; what the predecessors read is beta_s + e[s-1][label(u)]
   const float val = DIR == 0 ? v + fmaf(x, kLog2e, -st.adj) : v - st.adj;
   const float stored = DIR == 0 ? val : fmaf(x, kLog2e, val);
   st.adj = 0.0f;
   sts(st.qc + st.u4, stored);
   if (PH == 2) {
-    // the posterior, written at the node's label-sorted position of the helpers' block
-    sts(st.oa + st.pdelta, ex2(((val - st.Zh) + lds(st.oa)) - st.zsub));
-    st.oa += st.ostep;
+    // the posterior, written into the node's slot of the helpers' block
+    sts(st.ga, ex2(((val - st.Zh) + lds(st.oa)) - st.zsub));
+    st.oa += DIR ? -un.p4 : un.p4;
+    st.ga += DIR ? -un.g4 : un.g4;
   }
   if (last) publish_block_max(st, stored);
-  bar_named(1, st.nact);
+  bar_named(1, un.nact);
   if (PH == 1) { // after the barrier: nothing waits for it
-    if (st.act) stg(st.gs, val);
-    st.gs += st.gstep;
+    stg(st.gs, val);
+    st.gs += DIR ? -un.pitch : un.pitch;
   }
   const uint32_t t = st.pc;
   st.pc = st.qc;
   st.qc = t;
 }
 
-template <int DIR, int PH>
-__device__ __forceinline__ void node_rows(NodeState& st, int n) {
+template <int DIR, int PH, bool ZW>
+__device__ __forceinline__ void node_rows(NodeState& st, const NodeUni& un, int n) {
+  // (a rolled loop with the last level peeled was measured slower: 0.419 vs 0.389 ms at config 2)
   if (n == kBlk) {
 #pragma unroll
-    for (int r = 0; r < kBlk; r++) node_step<DIR, PH>(st, r == kBlk - 1);
+    for (int r = 0; r < kBlk; r++) node_step<DIR, PH, ZW>(st, un, r == kBlk - 1);
   } else {
 #pragma unroll 1
-    for (int r = 0; r < n; r++) node_step<DIR, PH>(st, r == n - 1);
+    for (int r = 0; r < n; r++) node_step<DIR, PH, ZW>(st, un, r == n - 1);
   }
 }
 
@@ -457,185 +496,418 @@ __device__ __forceinline__ float node_reduce_sum(float v, uint32_t red, int warp
  * level's posterior follows.  An utterance without any accepting path (Z = kNeg-like) gets Zh = +1e30,
  * which makes every posterior ex2(-huge) = 0.  `doth`: the partner's offset for this block.
  */
-template <int DIR>
+template <int DIR, bool ZW>
 __device__ __forceinline__ void node_first_phase2(
-    NodeState& st, uint32_t red, int warp, int nwarps, float doth, bool last, float* z_out) {
+    NodeState& st, const NodeUni& un, bool act, uint32_t red, int warp, int nwarps, float doth, bool last,
+    float* z_out) {
   const float x = lds(st.ea);
-  st.ea += st.estep;
-  const float v = lse3(lds(st.pc + st.so0) + st.w0, lds(st.pc + st.so1) + st.w1, lds(st.pc + st.so2) + st.w2);
+  st.ea += DIR ? -un.c4 : un.c4;
+  const float v = ZW ? lse3(lds(st.pc + st.so0), lds(st.pc + st.so1), lds(st.pc + st.so2))
+                     : lse3(lds(st.pc + st.so0) + st.w0, lds(st.pc + st.so1) + st.w1, lds(st.pc + st.so2) + st.w2);
   const float val = DIR == 0 ? v + fmaf(x, kLog2e, -st.adj) : v - st.adj;
   const float stored = DIR == 0 ? val : fmaf(x, kLog2e, val);
   st.adj = 0.0f;
   sts(st.qc + st.u4, stored);
-  const float o = st.act ? lds(st.oa) : kNeg;
+  const float o = lds(st.oa);
   // TwoSum (Knuth): hi + lo == val + o exactly
   const float hi = val + o;
   const float bb = hi - val;
   const float lo = (val - (hi - bb)) + (o - bb);
-  const float hv = st.act ? hi : 2.0f * kNeg;
-  const float m = node_reduce_max(hv, red, warp, nwarps, st.nact);
-  const float term = (st.act && m > 1.5f * kNeg) ? ex2((hi - m) + lo) : 0.0f;
-  const float S = node_reduce_sum(term, red, warp, nwarps, st.nact);
+  const float hv = act ? hi : 2.0f * kNeg; // the clones of the last node stay out of the reductions
+  const float m = node_reduce_max(hv, red, warp, nwarps, un.nact);
+  const float term = (act && m > 1.5f * kNeg) ? ex2((hi - m) + lo) : 0.0f;
+  const float S = node_reduce_sum(term, red, warp, nwarps, un.nact);
   const bool feasible = m > kNeg * 0.5f && S > 0.0f;
   st.Zh = feasible ? m : 1.0e30f;
   st.Zl = feasible ? lg2(S) : 0.0f;
-  st.D0 = st.D;
-  st.Do0 = doth;
+  st.Dc = st.D + doth;
   st.zsub = st.Zl;
   if (z_out && threadIdx.x == 0)
-    *z_out = feasible ? (float)((((double)st.D0 + (double)doth) + ((double)m + (double)st.Zl)) * 0.6931471805599453)
-                      : -CUDART_INF_F;
-  sts(st.oa + st.pdelta, ex2(((val - st.Zh) + o) - st.zsub));
-  st.oa += st.ostep;
+    *z_out = feasible ? (float)(((double)st.Dc + ((double)m + (double)st.Zl)) * 0.6931471805599453) : -CUDART_INF_F;
+  sts(st.ga, ex2(((val - st.Zh) + o) - st.zsub));
+  st.oa += DIR ? -un.p4 : un.p4;
+  st.ga += DIR ? -un.g4 : un.g4;
   if (last) publish_block_max(st, stored);
-  bar_named(1, st.nact);
+  bar_named(1, un.nact);
   const uint32_t t = st.pc;
   st.pc = st.qc;
   st.qc = t;
+}
+
+/* everything the node warps' phase loops need that is not per-thread state */
+struct NodeCtx {
+  const uint8_t* fl;
+  float* saved;
+  float* boff_own;
+  float* out_score;
+  uint32_t bars, e_base, o_base, g_base, od_base, perm_a, red_a, spare, lab4;
+  int e_stage_bytes, o_stage_bytes, g_block_bytes, pg, C, T, pitch, nblk, n_ph1, n_ph2, nw_act;
+  bool want_g;
+};
+
+/* barrier addresses (all in one array): */
+__device__ __forceinline__ uint32_t bar_e_full(uint32_t bars, int s) {
+  return bars + 8u * (uint32_t)s;
+}
+__device__ __forceinline__ uint32_t bar_e_empty(uint32_t bars, int s) {
+  return bars + 8u * (uint32_t)(kSE + s);
+}
+__device__ __forceinline__ uint32_t bar_o_full(uint32_t bars, int s) {
+  return bars + 8u * (uint32_t)(2 * kSE + s);
+}
+__device__ __forceinline__ uint32_t bar_o_empty(uint32_t bars, int s) {
+  return bars + 8u * (uint32_t)(2 * kSE + kSO + s);
+}
+__device__ __forceinline__ uint32_t bar_g_full(uint32_t bars, int s) {
+  return bars + 8u * (uint32_t)(2 * kSE + 2 * kSO + s);
+}
+__device__ __forceinline__ uint32_t bar_g_empty(uint32_t bars, int s) {
+  return bars + 8u * (uint32_t)(2 * kSE + 2 * kSO + kSG + s);
+}
+__device__ __forceinline__ uint32_t bar_tbl_ready(uint32_t bars) {
+  return bars + 8u * (uint32_t)(2 * kSE + 2 * kSO + 2 * kSG);
+}
+
+/*
+ * The node warps of one CTA, both phases.  DIR 0: CTA A walks the blocks 0, 1, .. (rows ascending);
+ * DIR 1: CTA B walks nblk-1, nblk-2, .. (rows descending).  Everything that depends only on the
+ * direction is folded into per-thread base addresses up front, so that a block costs its levels plus a
+ * few dozen instructions.
+ */
+template <int DIR, bool ZW>
+__device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool act, int nid) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  NodeUni un;
+  un.c4 = 4 * cx.C;
+  un.p4 = 4 * cx.pitch;
+  un.g4 = 4 * cx.pg;
+  un.pitch = cx.pitch;
+  un.nact = 32 * cx.nw_act;
+  const int nact = un.nact;
+  // the helper warps read the emission blocks of ONE phase (2 when there is a gradient, else 1); for the
+  // other blocks node warp 0 arrives on the stage's "empty" barrier on their behalf
+  const int arr1 = (warp == 0 && cx.want_g) ? 1 + kHelpers : 1;
+  const int arr2 = (warp == 0 && !cx.want_g) ? 1 + kHelpers : 1;
+  // first row of a FULL block in this direction
+  const uint32_t e_row0 = cx.e_base + cx.lab4 + (DIR ? (uint32_t)((kBlk - 1) * cx.C * 4) : 0u);
+  int v = 0; // blocks visited
+  if (DIR == 0) {
+    // level 0: start nodes carry the implicit 0 (shortest.cpp:129-135)
+    if (cx.fl[nid] & 1) sts(st.pc + st.u4, 0.0f);
+    bar_named(1, nact);
+    st.gs = cx.saved + nid;
+    for (; v < cx.n_ph1; v++) {
+      const int s = v & (kSE - 1);
+      mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+      st.ea = e_row0 + (uint32_t)(s * cx.e_stage_bytes);
+      if (v > 0) fetch_block_adjust(st);
+      if (tid == 0) stg(cx.boff_own + 4 * v, st.D);
+      node_rows<0, 1, ZW>(st, un, kBlk); // A's phase-1 blocks are always full
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, s), arr1);
+    }
+  } else if (cx.T > 0) {
+    // level T: accept nodes carry 0; what the predecessors read is beta_T + e[T-1][label]
+    const int j0 = cx.nblk - 1, n0 = min(kBlk, cx.T - kBlk * j0);
+    mbar_wait(bar_e_full(cx.bars, 0), 0);
+    st.ea = cx.e_base + (uint32_t)((n0 - 1) * cx.C * 4) + cx.lab4;
+    if (tid == 0) stg(cx.boff_own + 4 * j0, 0.0f);
+    {
+      const float e2 = lds(st.ea) * kLog2e;
+      st.ea -= un.c4;
+      const float val = (cx.fl[nid] & 2) ? 0.0f : kNeg;
+      sts(st.pc + st.u4, val + e2); // written to the row the first step READS
+      st.gs = cx.saved + (long long)(cx.T - 1) * cx.pitch + nid;
+      if (n0 == 1) publish_block_max(st, val + e2);
+      bar_named(1, nact);
+      stg(st.gs, val);
+      st.gs -= un.pitch;
+    }
+    node_rows<1, 1, ZW>(st, un, n0 - 1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, 0), arr1);
+    for (v = 1; v < cx.n_ph1; v++) {
+      const int s = v & (kSE - 1);
+      mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+      st.ea = e_row0 + (uint32_t)(s * cx.e_stage_bytes);
+      fetch_block_adjust(st);
+      if (tid == 0) stg(cx.boff_own + 4 * (cx.nblk - 1 - v), st.D);
+      node_rows<1, 1, ZW>(st, un, kBlk);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, s), arr1);
+    }
+  }
+  cluster_sync_all();
+  // ---- phase 2
+  if (cx.n_ph2 <= 0) return;
+  // first row of a full block in stage / block 0
+  const uint32_t o_row0 = cx.o_base + 4u * (uint32_t)nid + (DIR ? (uint32_t)((kBlk - 1) * cx.pitch * 4) : 0u);
+  uint32_t g_row0 = cx.spare;
+  int g_stride = 0;
+  if (cx.want_g) {
+    mbar_wait(bar_tbl_ready(cx.bars), 0); // the helper warps' tables
+    g_row0 = cx.g_base + lds_u(cx.perm_a + 4u * (uint32_t)nid) + (DIR ? (uint32_t)((kBlk - 1) * cx.pg * 4) : 0u);
+    g_stride = cx.g_block_bytes;
+  } else {
+    un.g4 = 0; // loss only: the posterior of the one level goes to the spare word
+  }
+  for (int v2 = 0; v2 < cx.n_ph2; v2++, v++) {
+    const int s = v & (kSE - 1), so = v2 & (kSO - 1), sg = v2 & (kSG - 1);
+    // B's phase-2 blocks are full; A's last one may not be, and A's rows start at 0 either way
+    const int nfr = DIR ? kBlk : min(kBlk, cx.T - kBlk * v);
+    mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+    mbar_wait(bar_o_full(cx.bars, so), (v2 / kSO) & 1);
+    if (v2 >= kSG) mbar_wait(bar_g_empty(cx.bars, sg), ((v2 / kSG) - 1) & 1);
+    st.ea = e_row0 + (uint32_t)(s * cx.e_stage_bytes);
+    st.oa = o_row0 + (uint32_t)(so * cx.o_stage_bytes);
+    st.ga = g_row0 + (uint32_t)(sg * g_stride);
+    if (v > 0) fetch_block_adjust(st);
+    const float doth = lds(cx.od_base + 16u * so);
+    if (v2 == 0) {
+      node_first_phase2<DIR, ZW>(st, un, act, cx.red_a, warp, cx.nw_act, doth, nfr == 1,
+                                 DIR == 0 ? cx.out_score : nullptr);
+      if (cx.want_g) node_rows<DIR, 2, ZW>(st, un, nfr - 1);
+    } else {
+      // offsets moved since the meeting level: all integers, the differences are exact
+      st.zsub = st.Zl - ((st.D + doth) - st.Dc);
+      node_rows<DIR, 2, ZW>(st, un, nfr);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive_n(bar_e_empty(cx.bars, s), arr2);
+      mbar_arrive(bar_o_empty(cx.bars, so));
+      mbar_arrive(bar_g_full(cx.bars, sg));
+    }
+  }
 }
 
 /* ------------------------------------------------------------------ */
 /* helper warps                                                        */
 /* ------------------------------------------------------------------ */
 
+/*
+ * Every helper warp owns two rows of a block: lanes 0..15 the row 2 * hw, lanes 16..31 the row
+ * 2 * hw + 1; lane l16 of a half holds the labels 4 * (l16 + 16 i) .. + 3 (one float4 of the emission
+ * row per i), so a row's maximum and sum are four shuffles inside the half-warp and the helper warps
+ * never talk to each other.  The posteriors of a row sit in the block as kSlots floats per label -- the
+ * node threads write theirs into their label's next free slot, unused slots stay 0 -- so the mass on a
+ * label is one LDS.128 and three adds, and the four gradients of a lane leave as one 16-byte store.
+ * Labels carried by more than kSlots nodes (CTC: blank) live behind the slots, contiguously, and are
+ * summed by the 16 lanes of the row together.
+ *
+ * seg[c] = overflow start (10 bits) | number of nodes (10 bits) | (cooperative slot + 1, or 15 = summed by
+ * the owning lane alone) << 20, the last two only when the label has more than kSlots nodes.
+ */
 struct HelperState {
-  int hw, lane, r, part; // helper warp, lane, row of the block, label chunk
-  int C, pitch;
-  uint32_t seg, hlist, xch, out; // shared-window addresses of the tables
-  float zacc; // lanes 0..7 of helper warp 0: sum of the rows' logsumexp
+  int hw, lane, r, l16;
+  int C;
+  uint32_t seg;
+  float zacc; // lanes 0 and 16: sum of their rows' logsumexp
   bool bad;
 };
 
-/* seg[c] = first position (10 bits) | number of nodes (10 bits) | heavy slot + 1 (above): the posteriors
- * of the nodes that carry label c are CONTIGUOUS in a stage row, because the node threads write theirs at
- * the node's label-sorted position */
 __device__ __forceinline__ uint32_t seg_pack(int start, int len, int slot1) {
   return (uint32_t)start | ((uint32_t)len << 10) | ((uint32_t)slot1 << 20);
 }
+__device__ __forceinline__ float half_max(float v) { // over the 16 lanes of a half-warp
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
-/* One block of `nfr` frames (rows 0 .. nfr-1 of the stages).  WANT_G: the posteriors of the block are in
- * the score stage `ostage`; write the gradient rows to `gout` (global, nfr * C floats).  Otherwise only
- * the rows' logsumexp is accumulated.  The emission stage is handed back (e_empty) as soon as its rows
- * are in registers. */
-template <int CH, bool WANT_G>
+/* per-lane constants of the helper warps (NQ float4 chunks of the row per lane) */
+template <int NQ>
+struct HelperConst {
+  uint32_t eoff[NQ]; // byte offset of the chunk in an emission stage (0xffffffff: beyond C)
+  uint32_t goff[NQ]; // byte offset of the chunk's first slot in a posterior block
+  uint32_t hsel[NQ]; // 4 bits per label of the chunk: 0 = slots, h + 1 = cooperative sum h, 15 = own loop
+  uint32_t hoff[kMaxHeavy]; // byte offset of the cooperative label's overflow positions in this lane's row
+  int hlen[kMaxHeavy];
+  uint32_t ovf; // byte offset of the row's overflow area
+};
+
+template <int NQ, bool WANT_G>
 __device__ __forceinline__ void helper_block(
-    HelperState& hs, int nfr, uint32_t estage, uint32_t e_empty_bar, uint32_t ostage, uint32_t g_empty_bar, int nheavy,
-    float* gout) {
-  const int C = hs.C, r = hs.r;
-  const bool row_on = r < nfr;
-  const int c0 = CH * hs.part;
-  float x[CH];
+    HelperState& hs, const HelperConst<NQ>& k, int nfr, uint32_t estage, uint32_t e_empty_bar, uint32_t gblock,
+    uint32_t g_empty_bar, int nheavy, float* gout) {
+  const bool row_on = hs.r < nfr;
+  float4 x[NQ];
   float mx = -3.0e38f;
 #pragma unroll
-  for (int i = 0; i < CH; i++) {
-    const int c = c0 + ((i + r) % CH);
-    const bool ok = row_on && c < C;
-    x[i] = ok ? lds(estage + (uint32_t)(r * C + c) * 4u) : -3.0e38f;
-    if (ok) hs.bad |= !finite_ok(x[i]);
-    mx = fmaxf(mx, x[i]);
+  for (int i = 0; i < NQ; i++) {
+    const bool ok = row_on && k.eoff[i] != 0xffffffffu;
+    x[i] = ok ? lds_v4(estage + k.eoff[i]) : make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
+    const float hi = fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w));
+    const float lo = fminf(fminf(x[i].x, x[i].y), fminf(x[i].z, x[i].w));
+    const float nan_probe = (x[i].x + x[i].y) + (x[i].z + x[i].w); // fmaxf / fminf drop NaNs, a sum keeps them
+    if (ok) hs.bad |= !(hi < kHuge && lo > -kHuge && nan_probe == nan_probe);
+    mx = fmaxf(mx, hi);
   }
   __syncwarp();
-  if (hs.lane == 0) mbar_arrive(e_empty_bar);
-  // the 4 parts of a row sit in lanes r, r + 8, r + 16, r + 24
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  if (hs.lane == 0) mbar_arrive(e_empty_bar); // the emission rows are in registers
+  mx = half_max(mx);
+  const float mxs = mx * kLog2e;
   float sm = 0.0f;
 #pragma unroll
-  for (int i = 0; i < CH; i++) {
-    x[i] = ex2((x[i] - mx) * kLog2e); // invalid entries: ex2(-huge) = 0
-    sm += x[i];
+  for (int i = 0; i < NQ; i++) { // invalid entries: ex2(-huge) = 0
+    x[i].x = ex2(fmaf(x[i].x, kLog2e, -mxs));
+    x[i].y = ex2(fmaf(x[i].y, kLog2e, -mxs));
+    x[i].z = ex2(fmaf(x[i].z, kLog2e, -mxs));
+    x[i].w = ex2(fmaf(x[i].w, kLog2e, -mxs));
+    sm += (x[i].x + x[i].y) + (x[i].z + x[i].w);
   }
-  sm += __shfl_xor_sync(0xffffffffu, sm, 8);
-  sm += __shfl_xor_sync(0xffffffffu, sm, 16);
-  const uint32_t orow = ostage + (uint32_t)(r * hs.pitch) * 4u;
-  // labels carried by many nodes (CTC: blank): this warp's share of the segment, summed over its 4 parts
-  float hp[kMaxHeavy];
-#pragma unroll
-  for (int h = 0; h < kMaxHeavy; h++) {
-    hp[h] = 0.0f;
-    if (WANT_G && h < nheavy) {
-      const uint32_t w = lds_u(hs.seg + 4u * lds_u(hs.hlist + 4u * h));
-      const int start = w & 1023, len = (w >> 10) & 1023;
-      float a0 = 0.0f, a1 = 0.0f;
-      if (row_on) {
-        int k = hs.part;
-        for (; k + 4 * kHelpers < len; k += 8 * kHelpers) {
-          a0 += lds(orow + (uint32_t)(start + k) * 4u);
-          a1 += lds(orow + (uint32_t)(start + k + 4 * kHelpers) * 4u);
-        }
-        if (k < len) a0 += lds(orow + (uint32_t)(start + k) * 4u);
-      }
-      float acc = a0 + a1;
-      acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-      hp[h] = acc;
-    }
-  }
-  // exchange with the other helper warp: (max, sum) of its half of the row, heavy partial sums
-  const uint32_t mine = hs.xch + (uint32_t)((hs.hw * kBlk + r) * (2 + kMaxHeavy)) * 4u;
-  const uint32_t other = hs.xch + (uint32_t)(((1 - hs.hw) * kBlk + r) * (2 + kMaxHeavy)) * 4u;
-  if (hs.lane < kBlk) {
-    sts(mine, mx);
-    sts(mine + 4, sm);
-    if (WANT_G) {
-#pragma unroll
-      for (int h = 0; h < kMaxHeavy; h++) sts(mine + 8 + 4 * h, hp[h]);
-    }
-  }
-  bar_named(2, 32 * kHelpers);
-  const float omx = lds(other), osm = lds(other + 4);
-  const float m = fmaxf(mx, omx);
-  const float sc_mine = ex2((mx - m) * kLog2e);
-  const float S = sm * sc_mine + osm * ex2((omx - m) * kLog2e);
-  if (row_on && hs.hw == 0 && hs.lane < kBlk) hs.zacc += m + lg2(S) * kLn2; // logsumexp of the row
+  sm = half_sum(sm);
+  if (row_on && hs.l16 == 0) hs.zacc += mx + lg2(sm) * kLn2; // logsumexp of the row
   if (WANT_G) {
-    const float scale = sc_mine / S;
+    const float inv = 1.0f / sm;
+    float hsum[kMaxHeavy];
 #pragma unroll
-    for (int h = 0; h < kMaxHeavy; h++)
-      if (h < nheavy) hp[h] += lds(other + 8 + 4 * h);
+    for (int h = 0; h < kMaxHeavy; h++) {
+      hsum[h] = 0.0f;
+      if (h < nheavy) {
+        float a0 = 0.0f, a1 = 0.0f;
+        if (row_on) {
+          const uint32_t a = gblock + k.hoff[h];
+          int q = hs.l16;
+          for (; q + 16 < k.hlen[h]; q += 32) {
+            a0 += lds(a + 4u * q);
+            a1 += lds(a + 4u * (q + 16));
+          }
+          if (q < k.hlen[h]) a0 += lds(a + 4u * q);
+        }
+        hsum[h] = half_sum(a0 + a1);
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < CH; i++) {
-      const int c = c0 + ((i + r) % CH);
-      if (row_on && c < C) {
-        const uint32_t w = lds_u(hs.seg + 4u * c);
-        const int len = (w >> 10) & 1023, slot1 = w >> 20;
-        const uint32_t a = orow + (w & 1023) * 4u;
-        float occ;
-        if (slot1) {
-          occ = hp[0];
+    for (int i = 0; i < NQ; i++) {
+      if (row_on && k.eoff[i] != 0xffffffffu) {
+        const uint32_t a = gblock + k.goff[i];
+        const float4 g0 = lds_v4(a), g1 = lds_v4(a + 16), g2 = lds_v4(a + 32), g3 = lds_v4(a + 48);
+        float o[4] = {(g0.x + g0.y) + (g0.z + g0.w), (g1.x + g1.y) + (g1.z + g1.w), (g2.x + g2.y) + (g2.z + g2.w),
+                      (g3.x + g3.y) + (g3.z + g3.w)};
+        if (k.hsel[i]) { // some label of the chunk has more than kSlots nodes
 #pragma unroll
-          for (int h = 1; h < kMaxHeavy; h++)
-            if (h == slot1 - 1) occ = hp[h];
-        } else {
-          const float g0 = len > 0 ? lds(a) : 0.0f;
-          const float g1 = len > 1 ? lds(a + 4) : 0.0f;
-          const float g2 = len > 2 ? lds(a + 8) : 0.0f;
-          const float g3 = len > 3 ? lds(a + 12) : 0.0f;
-          occ = (g0 + g1) + (g2 + g3);
-          for (int k = 4; k < len; k++) occ += lds(a + 4u * k);
+          for (int j = 0; j < 4; j++) {
+            const int s1 = (k.hsel[i] >> (4 * j)) & 15;
+            if (s1 == 15) { // beyond the cooperative slots: this lane sums the label's positions itself
+              const uint32_t w = lds_u(hs.seg + 4u * (uint32_t)((k.eoff[i] >> 2) - hs.r * hs.C + j));
+              const int len = (w >> 10) & 1023;
+              const uint32_t p = gblock + k.ovf + (w & 1023u) * 4u;
+              float acc = 0.0f;
+              for (int q = 0; q < len; q++) acc += lds(p + 4u * q);
+              o[j] = acc;
+            } else if (s1) {
+#pragma unroll
+              for (int h = 0; h < kMaxHeavy; h++)
+                if (h == s1 - 1) o[j] = hsum[h];
+            }
+          }
         }
         // d(forwardScore(e) - forwardScore(lattice)) / d e[f][c] = softmax - posterior mass on label c
-        sts(hs.out + (uint32_t)(r * C + c) * 4u, x[i] * scale - occ);
+        stg_v4(gout + (k.eoff[i] >> 2), make_float4(fmaf(x[i].x, inv, -o[0]), fmaf(x[i].y, inv, -o[1]),
+                                                    fmaf(x[i].z, inv, -o[2]), fmaf(x[i].w, inv, -o[3])));
       }
     }
     __syncwarp();
     if (hs.lane == 0) mbar_arrive(g_empty_bar); // this warp is done with the posterior block
-    bar_named(2, 32 * kHelpers);
-    // finished rows -> global, 16 bytes per lane
-    const int tid64 = hs.hw * 32 + hs.lane;
-    const int n4 = (nfr * C) >> 2;
-    for (int k = tid64; k < n4; k += 32 * kHelpers) stg_v4(gout + 4 * k, lds_v4(hs.out + 16u * k));
-  } else {
-    bar_named(2, 32 * kHelpers); // xch is rewritten by the next block
   }
+}
+
+/*
+ * The same for the common case, with everything that can be decided once decided once: the emission row is
+ * exactly NQ float4 chunks per lane (C == 64 * NQ), the block is full, and every label with more than kSlots
+ * nodes (CTC: blank, plus the odd label that occurs five times or more) has a cooperative slot.  htab: per
+ * cooperative label {label, overflow start in floats, nodes} in shared memory.  About a third of the generic
+ * version's instructions.
+ */
+template <int NQ>
+__device__ __forceinline__ void helper_block_fast(
+    HelperState& hs, uint32_t ea, uint32_t e_empty_bar, uint32_t ga, uint32_t ovf_row, uint32_t htab, int nheavy,
+    uint32_t g_empty_bar, float* gout) {
+  float4 x[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; i++) x[i] = lds_v4(ea + 256u * i); // chunk i: labels 64 i + 4 l16 .. + 3
+  __syncwarp();
+  if (hs.lane == 0) mbar_arrive(e_empty_bar); // the emission rows are in registers
+  float mx = fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[0].z, x[0].w));
+  float lo = fminf(fminf(x[0].x, x[0].y), fminf(x[0].z, x[0].w));
+#pragma unroll
+  for (int i = 1; i < NQ; i++) {
+    mx = fmaxf(mx, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
+    lo = fminf(lo, fminf(fminf(x[i].x, x[i].y), fminf(x[i].z, x[i].w)));
+  }
+  mx = half_max(mx);
+  const float mxs = mx * kLog2e;
+  float sm = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NQ; i++) {
+    x[i].x = ex2(fmaf(x[i].x, kLog2e, -mxs));
+    x[i].y = ex2(fmaf(x[i].y, kLog2e, -mxs));
+    x[i].z = ex2(fmaf(x[i].z, kLog2e, -mxs));
+    x[i].w = ex2(fmaf(x[i].w, kLog2e, -mxs));
+    sm += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  }
+  sm = half_sum(sm);
+  // a NaN or +inf emission makes the sum NaN, a -inf / huge one trips the range checks
+  hs.bad |= !(lo > -kHuge && mx < kHuge && sm < 3.0e38f);
+  if (hs.l16 == 0) hs.zacc += mx + lg2(sm) * kLn2; // logsumexp of the row
+  float inv;
+#ifdef GTNB_HOST_EMU
+  inv = 1.0f / sm;
+#else
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sm));
+#endif
+  float o[4 * NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; i++) {
+    const uint32_t a = ga + 1024u * i; // 64 labels * kSlots floats further on
+    const float4 g0 = lds_v4(a), g1 = lds_v4(a + 16), g2 = lds_v4(a + 32), g3 = lds_v4(a + 48);
+    o[4 * i + 0] = (g0.x + g0.y) + (g0.z + g0.w);
+    o[4 * i + 1] = (g1.x + g1.y) + (g1.z + g1.w);
+    o[4 * i + 2] = (g2.x + g2.y) + (g2.z + g2.w);
+    o[4 * i + 3] = (g3.x + g3.y) + (g3.z + g3.w);
+  }
+  // the labels carried by many nodes: the row's 16 lanes sum their positions together
+  for (int h = 0; h < nheavy; h++) {
+    const int hc = (int)lds_u(htab + 12u * h), hlen = (int)lds_u(htab + 12u * h + 8);
+    const uint32_t ha = ovf_row + 4u * lds_u(htab + 12u * h + 4);
+    float a0 = 0.0f, a1 = 0.0f;
+    const uint32_t hq = ha + 4u * hs.l16;
+#pragma unroll 1
+    for (int q0 = 0; q0 < hlen; q0 += 32) { // the same trip count in every lane
+      if (q0 + hs.l16 < hlen) a0 += lds(hq + 4u * q0);
+      if (q0 + 16 + hs.l16 < hlen) a1 += lds(hq + 4u * q0 + 64u);
+    }
+    const float hsum = half_sum(a0 + a1);
+    const int rel = hc - 4 * hs.l16; // which of this lane's labels (64 i + 4 l16 + j  ->  4 i + j), if any
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) o[4 * i + j] = rel == 64 * i + j ? hsum : o[4 * i + j];
+    }
+  }
+  // d(forwardScore(e) - forwardScore(lattice)) / d e[f][c] = softmax - posterior mass on label c
+#pragma unroll
+  for (int i = 0; i < NQ; i++) {
+    const float4 gr = make_float4(fmaf(x[i].x, inv, -o[4 * i + 0]), fmaf(x[i].y, inv, -o[4 * i + 1]),
+                                  fmaf(x[i].z, inv, -o[4 * i + 2]), fmaf(x[i].w, inv, -o[4 * i + 3]));
+    stg_v4(gout + 64 * i, gr);
+  }
+  __syncwarp();
+  if (hs.lane == 0) mbar_arrive(g_empty_bar); // this warp is done with the posterior block
 }
 
 /* ------------------------------------------------------------------ */
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
 
-template <int CH>
-__global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(const Params P) {
+template <int NQ, bool ZW>
+__global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_ctc_kernel(const Params P) {
   GTNB_DYNAMIC_SMEM_128(unsigned char, smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x >> 1;
@@ -673,12 +945,6 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
   if (!want_g) n_ph2 = dir == 0 ? (T > 0 ? 1 : 0) : 0;
   const int n_visit = n_ph1 + n_ph2;
   auto block_of = [&](int v) { return dir == 0 ? v : nblk - 1 - v; };
-  // the helper warps read the emission blocks of ONE phase (2 when there is a gradient, else 1); for the
-  // other blocks node warp 0 arrives on the stage's "empty" barrier on their behalf
-  auto helpers_read = [&](int v) { return want_g ? v >= n_ph1 : v < n_ph1; };
-  auto release_e = [&](int v) { // lane 0 of a node warp, after the block's last level
-    mbar_arrive_n(e_empty(v % kSE), (warp == 0 && !helpers_read(v)) ? 1 + kHelpers : 1);
-  };
   auto rows_of = [&](int j) { return min(kBlk, T - kBlk * j); };
   float* boff_own = P.boff + ((long long)(2 * b + dir) * P.nblk_cap) * 4;
   const float* boff_oth = P.boff + ((long long)(2 * b + (1 - dir)) * P.nblk_cap) * 4;
@@ -701,7 +967,10 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
   }
   // chain rows: everything kNeg (the dummy slot stays that way for good)
   for (int i = tid; i < 2 * kRowF; i += blockDim.x) ring[i] = kNeg;
-  if (tid < 8) sts_u(redi_a + 4u * tid, (uint32_t)kIntMin);
+  // posterior blocks: all zero -- the slots no node writes to must read as 0 for good
+  if (want_g)
+    for (int i = tid; i < kSG * (L.g_block_bytes >> 2); i += blockDim.x) sts(g_base + 4u * i, 0.0f);
+  if (tid < 2) sts_u(redi_a + 4u * tid, (uint32_t)kIntMin);
 
   const uint8_t* fl = P.sg_flags + m.sg_node_base;
   const int32_t* ip = P.sg_in_ptr + m.sg_node_base;
@@ -741,28 +1010,26 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
   if (warp < P.nwn) {
     /* ============================ node warps ============================ */
     NodeState st;
-    st.act = tid < N1;
-    st.nact = nact;
-    st.u4 = 4u * (uint32_t)tid;
-    st.so0 = st.so1 = st.so2 = 4u * kDummy;
-    st.w0 = st.w1 = st.w2 = 0.0f;
-    if (st.act) {
-      int nb_[3] = {kDummy, kDummy, kDummy};
-      float wb_[3] = {0.0f, 0.0f, 0.0f};
-      if (dir == 0) {
-        const int e0 = ip[tid];
-        for (int k = 0; k < my_deg && k < 3; k++) {
-          nb_[k] = is[e0 + k];
-          wb_[k] = iw[e0 + k];
-        }
-      } else {
-        const int od = min(o_cnt[tid], 3);
-        for (int k = 0; k < od; k++) {
-          nb_[k] = o_dst[3 * tid + k];
-          wb_[k] = o_w[3 * tid + k];
-        }
-        // the atomics filled the slots in arbitrary order: sort by (node, weight) so that the sum of
-        // the three exponentials is evaluated in a fixed order
+    const bool act = tid < N1;
+    const int nid = min(tid, N1 - 1); // threads beyond the last node clone it (NodeUni)
+    st.u4 = 4u * (uint32_t)nid;
+    int nb_[3] = {kDummy, kDummy, kDummy};
+    float wb_[3] = {0.0f, 0.0f, 0.0f};
+    const int e0n = ip[nid], degn = ip[nid + 1] - e0n;
+    const int labn = degn > 0 ? il[e0n] : 0;
+    if (dir == 0) {
+      for (int k = 0; k < degn && k < 3; k++) {
+        nb_[k] = is[e0n + k];
+        wb_[k] = iw[e0n + k];
+      }
+    } else {
+      const int od = min(o_cnt[nid], 3);
+      for (int k = 0; k < od; k++) {
+        nb_[k] = o_dst[3 * nid + k];
+        wb_[k] = o_w[3 * nid + k];
+      }
+      // the atomics filled the slots in arbitrary order: sort by (node, weight) so that the sum of
+      // the three exponentials is evaluated in a fixed order
 #define GTNB_CSWAP(a, b)                                                          \
   if (nb_[a] > nb_[b] || (nb_[a] == nb_[b] && wb_[a] > wb_[b])) {                \
     const int tn = nb_[a];                                                        \
@@ -772,17 +1039,16 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
     wb_[a] = wb_[b];                                                              \
     wb_[b] = tw;                                                                  \
   }
-        GTNB_CSWAP(0, 1) GTNB_CSWAP(1, 2) GTNB_CSWAP(0, 1)
+      GTNB_CSWAP(0, 1) GTNB_CSWAP(1, 2) GTNB_CSWAP(0, 1)
 #undef GTNB_CSWAP
-      }
-      bad |= !finite_ok(wb_[0]) || !finite_ok(wb_[1]) || !finite_ok(wb_[2]);
-      st.so0 = 4u * (uint32_t)nb_[0];
-      st.so1 = 4u * (uint32_t)nb_[1];
-      st.so2 = 4u * (uint32_t)nb_[2];
-      st.w0 = wb_[0] * kLog2e;
-      st.w1 = wb_[1] * kLog2e;
-      st.w2 = wb_[2] * kLog2e;
     }
+    bad |= !finite_ok(wb_[0]) || !finite_ok(wb_[1]) || !finite_ok(wb_[2]);
+    st.so0 = 4u * (uint32_t)nb_[0];
+    st.so1 = 4u * (uint32_t)nb_[1];
+    st.so2 = 4u * (uint32_t)nb_[2];
+    st.w0 = wb_[0] * kLog2e;
+    st.w1 = wb_[1] * kLog2e;
+    st.w2 = wb_[2] * kLog2e;
     // the scratch is about to be overwritten by the score stages: everybody is done reading it
     __syncthreads(); // (S1) all roles
     if (warp >= nw_act) { // node warp without a node of this utterance
@@ -791,107 +1057,45 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
     }
     st.pc = smem_u32(ring);
     st.qc = smem_u32(ring + kRowF);
-    st.estep = dir == 0 ? 4 * C : -4 * C;
-    // lanes of the last node warp that hold no node must not write a posterior into the stage rows:
-    // they aim at a spare slot of the chain row instead (index kDummy + 1, read by nobody)
-    st.ostep = !st.act ? 0 : dir == 0 ? 4 * pitch : -4 * pitch;
-    const uint32_t spare = smem_u32(ring) + 4u * (kDummy + 1);
-    st.gstep = dir == 0 ? pitch : -pitch;
-    st.Zh = st.zsub = st.Zl = st.D0 = st.Do0 = 0.0f;
+    const uint32_t spare = smem_u32(ring) + 4u * (kDummy + 1); // a word of the chain row nobody reads
+    st.gs = nullptr;
+    st.Zh = st.zsub = st.Zl = st.Dc = 0.0f;
     st.adj = st.D = 0.0f;
-    st.pdelta = 0;
+    st.ea = st.oa = 0;
+    st.ga = spare;
     st.redi = redi_a;
-    const uint32_t lab4 = 4u * (uint32_t)my_lab;
+    const uint32_t lab4 = 4u * (uint32_t)labn;
 
-    int v = 0; // blocks visited
-    if (dir == 0) {
-      // level 0: start nodes carry the implicit 0 (shortest.cpp:129-135)
-      if (st.act && (fl[tid] & 1)) sts(st.pc + st.u4, 0.0f);
-      bar_named(1, nact);
-      st.gs = saved + tid;
-      for (; v < n_ph1; v++) {
-        mbar_wait(e_full(v % kSE), (v / kSE) & 1);
-        st.ea = e_base + (uint32_t)((v % kSE) * L.e_stage_bytes) + lab4;
-        if (v > 0) fetch_block_adjust(st, nw_act);
-        if (tid == 0) stg(boff_own + 4 * v, st.D);
-        node_rows<0, 1>(st, kBlk); // A's phase-1 blocks are always full
-        __syncwarp();
-        if (lane == 0) release_e(v);
-      }
-    } else if (T > 0) {
-      // level T: accept nodes carry 0; what the predecessors read is beta_T + e[T-1][label]
-      const int j0 = nblk - 1, n0 = rows_of(j0);
-      mbar_wait(e_full(0), 0);
-      st.ea = e_base + (uint32_t)((n0 - 1) * C * 4) + lab4;
-      if (tid == 0) stg(boff_own + 4 * j0, 0.0f);
-      {
-        const float e2 = lds(st.ea) * kLog2e;
-        st.ea += st.estep;
-        const float val = (st.act && (fl[tid] & 2)) ? 0.0f : kNeg;
-        sts(st.pc + st.u4, val + e2); // written to the row the first step READS
-        st.gs = saved + (long long)(T - 1) * pitch + tid;
-        if (n0 == 1) publish_block_max(st, val + e2);
-        bar_named(1, nact);
-        if (st.act) stg(st.gs, val);
-        st.gs += st.gstep;
-      }
-      node_rows<1, 1>(st, n0 - 1);
-      __syncwarp();
-      if (lane == 0) release_e(0);
-      for (v = 1; v < n_ph1; v++) {
-        mbar_wait(e_full(v % kSE), (v / kSE) & 1);
-        st.ea = e_base + (uint32_t)((v % kSE) * L.e_stage_bytes + (kBlk - 1) * C * 4) + lab4;
-        fetch_block_adjust(st, nw_act);
-        if (tid == 0) stg(boff_own + 4 * block_of(v), st.D);
-        node_rows<1, 1>(st, kBlk);
-        __syncwarp();
-        if (lane == 0) release_e(v);
-      }
-    }
-    cluster_sync_all();
-    // ---- phase 2
-    uint32_t perm_rel = 0; // (label-sorted position - node id) * 4
-    if (n_ph2 > 0 && want_g) {
-      mbar_wait(tbl_ready, 0); // the helper warps' label-sorted positions
-      if (st.act) perm_rel = lds_u(perm_a + st.u4) - st.u4;
-    }
-    int v2 = 0;
-    for (; v2 < n_ph2; v2++, v++) {
-      const int j = block_of(v), nfr = rows_of(j);
-      const int so = v2 % kSO, sg = v2 % kSG;
-      mbar_wait(e_full(v % kSE), (v / kSE) & 1);
-      mbar_wait(o_full(so), (v2 / kSO) & 1);
-      if (v2 >= kSG) mbar_wait(g_empty(sg), ((v2 / kSG) - 1) & 1);
-      const int r0 = dir == 0 ? 0 : nfr - 1;
-      st.ea = e_base + (uint32_t)((v % kSE) * L.e_stage_bytes + r0 * C * 4) + lab4;
-      st.oa = st.act ? o_base + (uint32_t)(so * L.o_stage_bytes + r0 * pitch * 4) + st.u4 : spare;
-      st.pdelta = st.act ? (g_base + (uint32_t)(sg * L.o_stage_bytes)) - (o_base + (uint32_t)(so * L.o_stage_bytes)) + perm_rel
-                         : 0u;
-      if (v > 0) fetch_block_adjust(st, nw_act);
-      const float doth = lds(od_base + 16u * so);
-      if (v2 == 0) {
-        if (dir == 0) {
-          node_first_phase2<0>(st, red_a, warp, nw_act, doth, nfr == 1, P.out_scores + b);
-          if (want_g) node_rows<0, 2>(st, nfr - 1);
-        } else {
-          node_first_phase2<1>(st, red_a, warp, nw_act, doth, nfr == 1, nullptr);
-          node_rows<1, 2>(st, nfr - 1);
-        }
-      } else {
-        // offsets moved since the meeting level: all integers, the differences are exact
-        st.zsub = st.Zl - ((st.D - st.D0) + (doth - st.Do0));
-        if (dir == 0)
-          node_rows<0, 2>(st, nfr);
-        else
-          node_rows<1, 2>(st, nfr);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        release_e(v);
-        mbar_arrive(o_empty(so));
-        mbar_arrive(g_full(sg));
-      }
-    }
+    NodeCtx cx;
+    cx.fl = fl;
+    cx.saved = saved;
+    cx.boff_own = boff_own;
+    cx.out_score = P.out_scores + b;
+    cx.bars = bars;
+    cx.e_base = e_base;
+    cx.o_base = o_base;
+    cx.g_base = g_base;
+    cx.od_base = od_base;
+    cx.perm_a = perm_a;
+    cx.red_a = red_a;
+    cx.spare = spare;
+    cx.lab4 = lab4;
+    cx.e_stage_bytes = L.e_stage_bytes;
+    cx.o_stage_bytes = L.o_stage_bytes;
+    cx.g_block_bytes = L.g_block_bytes;
+    cx.pg = L.pg;
+    cx.C = C;
+    cx.T = T;
+    cx.pitch = pitch;
+    cx.nblk = nblk;
+    cx.n_ph1 = n_ph1;
+    cx.n_ph2 = n_ph2;
+    cx.nw_act = nw_act;
+    cx.want_g = want_g;
+    if (dir == 0)
+      node_role<0, ZW>(st, cx, act, nid);
+    else
+      node_role<1, ZW>(st, cx, act, nid);
     if (bad) atomicOr(&P.status[b], 1);
     if (T == 0 && dir == 0 && tid == 0) {
       // no frames: the lattice is the graph's start-and-accept nodes, each with score 0
@@ -914,8 +1118,8 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
     bool waited = false;
     for (int v = 0; v < n_visit; v++) {
       const int s = v % kSE, j = block_of(v);
-      if (v >= kSE) mbar_wait_relaxed(e_empty(s), ((v / kSE) - 1) & 1);
       if (lane == 0) {
+        if (v >= kSE) mbar_wait_relaxed(e_empty(s), ((v / kSE) - 1) & 1);
         const uint32_t bytes = (uint32_t)(rows_of(j) * C * 4);
         mbar_expect_tx(e_full(s), bytes);
         bulk_g2s(e_base + (uint32_t)(s * L.e_stage_bytes), em + (long long)j * kBlk * C, bytes, e_full(s));
@@ -930,8 +1134,8 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
           fence_proxy_async();
           waited = true;
         }
-        if (v2 >= kSO) mbar_wait_relaxed(o_empty(so), ((v2 / kSO) - 1) & 1);
         if (lane == 0) {
+          if (v2 >= kSO) mbar_wait_relaxed(o_empty(so), ((v2 / kSO) - 1) & 1);
           const uint32_t bytes = (uint32_t)(rows_of(j) * pitch * 4);
           mbar_expect_tx(o_full(so), bytes + 16u);
           bulk_g2s(o_base + (uint32_t)(so * L.o_stage_bytes), saved + (long long)j * kBlk * pitch, bytes, o_full(so));
@@ -948,80 +1152,124 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
   HelperState hs;
   hs.hw = warp - P.nwn - 1;
   hs.lane = lane;
-  hs.r = lane & 7;
-  hs.part = (lane >> 3) + 4 * hs.hw;
+  hs.r = 2 * hs.hw + (lane >> 4);
+  hs.l16 = lane & 15;
   hs.C = C;
-  hs.pitch = pitch;
   hs.seg = seg_a;
-  hs.hlist = hlist_a;
-  hs.xch = smem_u32(smem + L.off_xch);
-  hs.out = smem_u32(smem + L.off_out);
   hs.zacc = 0.0f;
   hs.bad = false;
-  const int tid64 = hs.hw * 32 + lane;
+  const int ht = hs.hw * 32 + lane; // index among the helper threads
   int nheavy = 0;
   if (want_g) {
-    // Label-sorted positions: the nodes that carry label c get the consecutive positions
-    // [start_c, start_c + n_c), ascending node ids inside (a fixed summation order, no atomics); nodes
-    // without in-arcs (they exist at level 0 only) go behind all of them.
-    for (int c = tid64; c < C; c += 32 * kHelpers) {
+    // Positions in a posterior row.  A label carried by n <= kSlots nodes: its nodes (ascending ids) take the
+    // slots kSlots * c + 0 .. n-1.  A label carried by more: its nodes take consecutive overflow positions
+    // behind the slots.  Nodes without in-arcs (they exist at level 0 only) go behind everything.
+    for (int c = ht; c < C; c += 32 * kHelpers) {
       int n = 0;
       for (int u = 0; u < N1; u++) n += (int)lds_u(nlab_a + 4u * u) == c;
       sts_u(seg_a + 4u * c, (uint32_t)n);
     }
     bar_named(2, 32 * kHelpers);
-    if (tid64 == 0) {
+    if (ht == 0) {
       int nh = 0, at = 0;
       for (int c = 0; c < C; c++) {
         const int n = (int)lds_u(seg_a + 4u * c);
-        int slot1 = 0;
-        if (n > kHeavyLen && nh < kMaxHeavy) {
-          sts_u(hlist_a + 4u * nh, (uint32_t)c);
-          slot1 = ++nh;
+        if (n > kSlots) {
+          int slot1 = 15;
+          if (nh < kMaxHeavy) {
+            sts_u(hlist_a + 4u * nh, (uint32_t)c);
+            slot1 = ++nh;
+          }
+          sts_u(seg_a + 4u * c, seg_pack(at, n, slot1));
+          at += n;
+        } else {
+          sts_u(seg_a + 4u * c, seg_pack(0, n, 0));
         }
-        sts_u(seg_a + 4u * c, seg_pack(at, n, slot1));
-        at += n;
       }
       sts_u(hlist_a + 4u * kMaxHeavy, (uint32_t)nh);
       for (int u = 0; u < N1; u++)
-        if ((int)lds_u(nlab_a + 4u * u) < 0) sts_u(perm_a + 4u * u, 4u * (uint32_t)(at++));
+        if ((int)lds_u(nlab_a + 4u * u) < 0) sts_u(perm_a + 4u * u, 4u * (uint32_t)(kSlots * C + at++));
     }
     bar_named(2, 32 * kHelpers);
     nheavy = (int)lds_u(hlist_a + 4u * kMaxHeavy);
-    for (int c = tid64; c < C; c += 32 * kHelpers) {
-      uint32_t at = lds_u(seg_a + 4u * c) & 1023u;
+    for (int c = ht; c < C; c += 32 * kHelpers) {
+      const uint32_t w = lds_u(seg_a + 4u * c);
+      uint32_t at = (w >> 20) ? (uint32_t)(kSlots * C) + (w & 1023u) : (uint32_t)(kSlots * c);
       for (int u = 0; u < N1; u++)
         if ((int)lds_u(nlab_a + 4u * u) == c) sts_u(perm_a + 4u * u, 4u * (at++));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(tbl_ready);
+    bar_named(2, 32 * kHelpers); // seg is complete before anybody reads other threads' entries below
+  }
+  HelperConst<NQ> hk;
+#pragma unroll
+  for (int i = 0; i < NQ; i++) {
+    const int c = 4 * (hs.l16 + 16 * i);
+    hk.eoff[i] = c < C ? (uint32_t)(hs.r * C + c) * 4u : 0xffffffffu;
+    hk.goff[i] = (uint32_t)(hs.r * L.pg + kSlots * c) * 4u;
+    hk.hsel[i] = 0;
+    if (want_g && c < C)
+      for (int j = 0; j < 4; j++) hk.hsel[i] |= ((lds_u(seg_a + 4u * (c + j)) >> 20) & 15u) << (4 * j);
+  }
+  hk.ovf = (uint32_t)(hs.r * L.pg + kSlots * C) * 4u;
+#pragma unroll
+  for (int h = 0; h < kMaxHeavy; h++) {
+    hk.hoff[h] = 0;
+    hk.hlen[h] = 0;
+    if (want_g && h < nheavy) {
+      const uint32_t w = lds_u(seg_a + 4u * lds_u(hlist_a + 4u * h));
+      hk.hoff[h] = hk.ovf + (w & 1023u) * 4u;
+      hk.hlen[h] = (int)((w >> 10) & 1023u);
+    }
   }
   int v = 0;
   if (!want_g) {
     for (; v < n_ph1; v++) {
       const int s = v % kSE;
       mbar_wait_relaxed(e_full(s), (v / kSE) & 1);
-      helper_block<CH, false>(hs, rows_of(block_of(v)), e_base + (uint32_t)(s * L.e_stage_bytes), e_empty(s), 0, 0, 0,
-                              nullptr);
+      helper_block<NQ, false>(hs, hk, rows_of(block_of(v)), e_base + (uint32_t)(s * L.e_stage_bytes), e_empty(s), 0, 0,
+                              0, nullptr);
     }
   }
   cluster_sync_all();
   if (want_g) {
     v = n_ph1;
+    // the common shape takes helper_block_fast (warp-uniform, in fact CTA-uniform, decision)
+    int n15 = 0;
+    for (int c = 0; c < C; c++) n15 += ((lds_u(seg_a + 4u * c) >> 20) & 15u) == 15u;
+    const bool fast = C == 64 * NQ && n15 == 0;
+    // {label, overflow start, nodes} of the cooperative labels, for helper_block_fast
+    const uint32_t htab = hlist_a + 4u * (kMaxHeavy + 1);
+    if (lane < nheavy) { // (every helper warp writes the same values)
+      const uint32_t hc = lds_u(hlist_a + 4u * lane), w = lds_u(seg_a + 4u * hc);
+      sts_u(htab + 12u * lane, hc);
+      sts_u(htab + 12u * lane + 4, w & 1023u);
+      sts_u(htab + 12u * lane + 8, (w >> 10) & 1023u);
+    }
+    __syncwarp();
+    const uint32_t f_e = (uint32_t)(hs.r * C + 4 * hs.l16) * 4u, f_g = (uint32_t)(hs.r * L.pg + kSlots * 4 * hs.l16) * 4u;
+    float* const f_out = P.grad + (long long)b * P.grad_stride + hs.r * C + 4 * hs.l16;
     for (int v2 = 0; v2 < n_ph2; v2++, v++) {
       const int s = v % kSE, sg = v2 % kSG, j = block_of(v);
-      mbar_wait_relaxed(e_full(s), (v / kSE) & 1);
+      // the node warps arrive on g_full after they are through the block: its emission stage was
+      // complete long before that (they waited for it), so one wait covers both
       mbar_wait_relaxed(g_full(sg), (v2 / kSG) & 1);
-      helper_block<CH, true>(hs, rows_of(j), e_base + (uint32_t)(s * L.e_stage_bytes), e_empty(s),
-                             g_base + (uint32_t)(sg * L.o_stage_bytes), g_empty(sg), nheavy,
+      if (fast && rows_of(j) == kBlk) {
+        const uint32_t gb = g_base + (uint32_t)(sg * L.g_block_bytes);
+        helper_block_fast<NQ>(hs, e_base + (uint32_t)(s * L.e_stage_bytes) + f_e, e_empty(s), gb + f_g, gb + hk.ovf, htab,
+                              nheavy, g_empty(sg), f_out + (long long)j * kBlk * C);
+        continue;
+      }
+      helper_block<NQ, true>(hs, hk, rows_of(j), e_base + (uint32_t)(s * L.e_stage_bytes), e_empty(s),
+                             g_base + (uint32_t)(sg * L.g_block_bytes), g_empty(sg), nheavy,
                              P.grad + (long long)b * P.grad_stride + (long long)j * kBlk * C);
     }
   }
-  // forwardScore(emissions): the rows this CTA summed
-  float z = (hs.hw == 0 && lane < kBlk) ? hs.zacc : 0.0f;
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-  if (tid64 == 0) P.zparts[2 * b + dir] = z;
+  // forwardScore(emissions): the rows this warp summed
+  float z = hs.l16 == 0 ? hs.zacc : 0.0f;
+  z += __shfl_xor_sync(0xffffffffu, z, 16);
+  if (lane == 0) P.zparts[(2 * b + dir) * kHelpers + hs.hw] = z;
   if (hs.bad) atomicOr(&P.status[b], 1);
 }
 
@@ -1032,7 +1280,7 @@ __global__ void __launch_bounds__(32 * (8 + 1 + kHelpers), 4) bidir_ctc_kernel(c
 /* true when every utterance of the batch qualifies for the bidirectional kernel */
 bool bidir_supported(const gtnb_lattice* lat, const float* emissions, int64_t stride, const float* grad, int64_t grad_stride) {
   if (!lat->composed || lat->C % 4 != 0 || lat->C > 128 || lat->C < 4) return false;
-  if (lat->max_lvl_nodes > bidir::kMaxNodes || lat->max_in_deg > 3 || lat->max_out_deg > 3) return false;
+  if (lat->max_lvl_nodes > 32 * bidir::kMaxNodeWarps || lat->max_in_deg > 3 || lat->max_out_deg > 3) return false;
   if (((uintptr_t)emissions & 15) || (stride & 3)) return false;
   if (grad && (((uintptr_t)grad & 15) || (grad_stride & 3))) return false;
   for (int b = 0; b < lat->B; b++)
@@ -1045,10 +1293,13 @@ int bidir_blocks(int max_T) {
   return std::max(1, (max_T + bidir::kBlk - 1) / bidir::kBlk);
 }
 
-/* utterances [b0, b0 + nb): one cluster of two CTAs each, on ctx->stream.  zparts_dev: [2 * B] */
+/* utterances [b0, b0 + nb): one cluster of two CTAs each, on ctx->stream.  zparts_dev: [2 * B * bidir_zparts()] */
+int bidir_zparts() {
+  return bidir::kHelpers;
+}
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
-    int64_t grad_stride, int b0, int nb) {
+    int64_t grad_stride, int b0, int nb, int zero_w) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
   bidir::Params P;
@@ -1063,7 +1314,7 @@ int launch_bidir_ctc(
   P.nblk_cap = bidir_blocks(lat->max_T);
   P.boff = boff_dev + (long long)b0 * 2 * P.nblk_cap * 4;
   P.out_scores = lat->out_scores + b0;
-  P.zparts = zparts_dev + 2ll * b0;
+  P.zparts = zparts_dev + 2ll * b0 * bidir::kHelpers;
   P.status = status_dev + b0;
   P.grad = grad_emis ? grad_emis + (long long)b0 * grad_stride : nullptr;
   P.grad_stride = grad_stride;
@@ -1071,10 +1322,11 @@ int launch_bidir_ctc(
   P.nwn = std::max(1, (lat->max_lvl_nodes + 31) / 32);
   const int max_pitch = (lat->max_lvl_nodes + 3) & ~3;
   P.lay = bidir::make_layout(lat->C, max_pitch);
-  const int CH = (lat->C + 7) / 8;
-  void (*kern)(const bidir::Params) = CH <= 4 ? bidir::bidir_ctc_kernel<4>
-                                      : CH <= 8 ? bidir::bidir_ctc_kernel<8>
-                                                : bidir::bidir_ctc_kernel<16>;
+  // float4 chunks of an emission row per helper lane
+  void (*kern)(const bidir::Params) =
+      lat->C <= 64 ? (zero_w ? bidir::bidir_ctc_kernel<1, true> : bidir::bidir_ctc_kernel<1, false>)
+                   : (zero_w ? bidir::bidir_ctc_kernel<2, true> : bidir::bidir_ctc_kernel<2, false>);
+  P.zero_w = zero_w;
   if (P.lay.total > 48 * 1024) {
     int rc = ensure_max_smem(ctx, (const void*)kern);
     if (rc) return rc;

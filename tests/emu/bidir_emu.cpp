@@ -21,7 +21,7 @@ extern "C" {
  */
 int emu_bidir_ctc(
     int B, int T, int C, const float* emissions, const int32_t* input_lens, const int32_t* targets,
-    const int32_t* target_lens, int blank, float* out_scores, float* znorm, float* grad, int32_t* status) {
+    const int32_t* target_lens, int blank, int zero_w, float* out_scores, float* znorm, float* grad, int32_t* status) {
   using namespace gtnb;
   std::vector<GraphMeta> meta(B);
   std::vector<int32_t> tgt_off(B);
@@ -59,7 +59,7 @@ int emu_bidir_ctc(
   // the bulk copies need 16-byte aligned sources: the vectors' data() is (malloc), T * C * 4 % 16 == 0 is
   // the caller's business (C % 4 == 0)
   std::vector<float> saved((size_t)scores_len + 16, 0.0f);
-  std::vector<float> zparts(2 * (size_t)B, 0.0f);
+  std::vector<float> zparts(2 * (size_t)B * bidir::kHelpers, 0.0f);
   const int nblk_cap = std::max(1, (T + bidir::kBlk - 1) / bidir::kBlk);
   std::vector<float> boff((size_t)B * 2 * nblk_cap * 4 + 16, 0.0f);
   for (int b = 0; b < B; b++) status[b] = 0;
@@ -80,20 +80,23 @@ int emu_bidir_ctc(
   P.grad = grad;
   P.grad_stride = (long long)T * C;
   P.C = C;
+  P.zero_w = zero_w;
   P.nwn = std::max(1, (maxN + 31) / 32);
   P.lay = bidir::make_layout(C, (maxN + 3) & ~3);
-  const int CH = (C + 7) / 8;
   const unsigned block = 32 * (P.nwn + 1 + bidir::kHelpers);
   emu::launch_clusters(2 * B, 2, block, P.lay.total, [&] {
-    if (CH <= 4)
-      bidir::bidir_ctc_kernel<4>(P);
-    else if (CH <= 8)
-      bidir::bidir_ctc_kernel<8>(P);
+    // ctc_build_kernel writes weight 0 on every arc: the zero-weight variant, as gtnb_ctc_loss launches it;
+    // zero_w = 0 exercises the general one on the same graphs
+    if (C <= 64)
+      zero_w ? bidir::bidir_ctc_kernel<1, true>(P) : bidir::bidir_ctc_kernel<1, false>(P);
     else
-      bidir::bidir_ctc_kernel<16>(P);
+      zero_w ? bidir::bidir_ctc_kernel<2, true>(P) : bidir::bidir_ctc_kernel<2, false>(P);
   });
   if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads;
-  for (int b = 0; b < B; b++) znorm[b] = zparts[2 * b] + zparts[2 * b + 1];
+  for (int b = 0; b < B; b++) {
+    znorm[b] = 0.0f;
+    for (int k = 0; k < 2 * bidir::kHelpers; k++) znorm[b] += zparts[2 * bidir::kHelpers * b + k];
+  }
   return 0;
 }
 

@@ -366,6 +366,11 @@ inline int __reduce_max_sync(unsigned, int v) { // redux.sync.max.s32 over the f
   }
   return v;
 }
+inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; i++) r |= (emu::shfl(pred ? 1u : 0u, i) & 1u) << i;
+  return r;
+}
 inline int __popc(unsigned x) {
   return __builtin_popcount(x);
 }

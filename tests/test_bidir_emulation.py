@@ -21,11 +21,11 @@ f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
 @pytest.fixture(scope="module")
 def emu():
     lib = C.CDLL(emu_build.build('bidir', ['k_bidir.cu', 'k_ctc.cu']))
-    lib.emu_bidir_ctc.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, i32p, C.c_int, f32p, f32p, f32p, i32p]
+    lib.emu_bidir_ctc.argtypes = [C.c_int, C.c_int, C.c_int, f32p, i32p, i32p, i32p, C.c_int, C.c_int, f32p, f32p, f32p, i32p]
     return lib
 
 
-def run(lib, e, targets, lens=None, blank=0, want_grad=True):
+def run(lib, e, targets, lens=None, blank=0, want_grad=True, zero_w=1):
     B, T, Cn = e.shape
     e = np.ascontiguousarray(e, np.float32)
     tl = np.asarray([len(t) for t in targets], np.int32)
@@ -36,7 +36,7 @@ def run(lib, e, targets, lens=None, blank=0, want_grad=True):
     grad = np.zeros((B, T, Cn), np.float32) if want_grad else None
     status = np.zeros(B, np.int32)
     rc = lib.emu_bidir_ctc(B, T, Cn, e.ctypes.data_as(f32p), None if il is None else il.ctypes.data_as(i32p),
-                           cat.ctypes.data_as(i32p), tl.ctypes.data_as(i32p), blank, out.ctypes.data_as(f32p),
+                           cat.ctypes.data_as(i32p), tl.ctypes.data_as(i32p), blank, zero_w, out.ctypes.data_as(f32p),
                            zn.ctypes.data_as(f32p), None if grad is None else grad.ctypes.data_as(f32p),
                            status.ctypes.data_as(i32p))
     emu_build.check(rc)
@@ -57,7 +57,7 @@ def test_bidir_kernel_source_matches_oracle(emu, oracle, shape):
     from oracle import f64
     B, T, Cn, U = shape
     e, targets = util.bench_inputs(B, T, Cn, U, seed=77 + T)
-    loss, grad, status = run(emu, e, targets)
+    loss, grad, status = run(emu, e, targets, zero_w=T % 2)  # both weight variants over the shapes
     assert not status.any()
     for b in range(B):
         lo, go = oracle.ctc_loss(e[b], targets[b], 0, True)

@@ -589,13 +589,13 @@ def test_asg_implicit_and_materialised_agree(ctx, oracle, shape):
 # ---------------------------------------------------------------------------
 
 @pytest.mark.parametrize("shape", [(4, 120, 16, 9), (3, 37, 8, 1), (2, 9, 4, 4), (1, 100, 28, 10), (3, 64, 28, 30),
-                                   (2, 300, 128, 127), (2, 1000, 64, 100), (5, 1, 8, 0)])
+                                   (2, 300, 128, 111), (2, 1000, 64, 100), (5, 1, 8, 0)])
 @pytest.mark.parametrize("want_grad", [True, False])
 def test_ctc_bidir_agrees_with_two_sweeps_and_oracle(ctx, oracle, shape, want_grad):
     """gtnb_ctc_loss through k_bidir.cu (one launch: alpha from the front and beta from the back in a
     two-CTA cluster, posteriors on the fly, normaliser fused) against the two sweeps of k_implicit.cu
     (flag "bidir" 0), the oracle and the float64 referee; ragged input lengths; loss only.
-    (2, 300, 128, 127): 255 graph nodes = 8 node warps, C = 128; (5, 1, 8, 0): T = 1, empty targets."""
+    (2, 300, 128, 111): 223 graph nodes = all 7 node warps, C = 128; (5, 1, 8, 0): T = 1, empty targets."""
     from oracle import f64
     B, T, C, U = shape
     e, targets = util.bench_inputs(B, T, C, U, seed=555)
