@@ -175,6 +175,7 @@ void gtnb_ctx_destroy(gtnb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->stage) cudaFreeHost(ctx->stage);
   if (ctx->readback) cudaFreeHost(ctx->readback);
   if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);

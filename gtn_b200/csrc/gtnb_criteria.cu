@@ -38,6 +38,7 @@ static int ctc_loss_run(
   float* row_scratch = nullptr; // k_linear.cu's per-frame scores, allocated once for all sub-batches
   float* zparts_dev = nullptr; // k_bidir.cu: forwardScore(emissions) as two partial sums per utterance
   float* boff_dev = nullptr; // k_bidir.cu: per-block score offsets of the two CTAs of every utterance
+  float* bidir_scores_dev = nullptr; // k_bidir.cu: the lattices' scores, inside the read-back block
   bool implicit = false;
   bool bidir = false;
   int zp = 1;
@@ -120,11 +121,15 @@ static int ctc_loss_run(
   // the whole criterion in one launch per sub-batch (k_bidir.cu) when the batch qualifies
   bidir = implicit && ctx->use_bidir && ctx->use_banded == 0 && bidir_supported(lat, e_dev, per, g_dev, per);
   if (bidir) {
-    TRY(dev_alloc(ctx, &zparts_dev, 2ll * B * bidir_zparts()));
+    // one block for everything that is read back: [partial sums of forwardScore(e) | lattice scores | status]
+    const long long zpb = 2ll * B * bidir_zparts();
+    TRY(dev_alloc(ctx, &zparts_dev, zpb + 2ll * B));
+    bidir_scores_dev = zparts_dev + zpb;
+    status_dev = reinterpret_cast<int32_t*>(zparts_dev + zpb + B);
     TRY(dev_alloc(ctx, &boff_dev, 8ll * B * bidir_blocks(maxT)));
-  }
-  if (implicit) {
-    if (!bidir) TRY(dev_alloc(ctx, &row_scratch, (long long)B * std::max(maxT, 1)));
+    TRYCUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * B, ctx->stream));
+  } else if (implicit) {
+    TRY(dev_alloc(ctx, &row_scratch, (long long)B * std::max(maxT, 1)));
     TRY(dev_alloc(ctx, &status_dev, B));
     TRYCUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * B, ctx->stream));
   }
@@ -132,11 +137,16 @@ static int ctc_loss_run(
   // one pinned staging pass for everything the kernels need from the host
   TRY(stage_begin(ctx));
   TRY(stage_upload(ctx, lat->meta, lat->meta_h.data(), sizeof(GraphMeta) * B));
-  if (tot_t) TRY(stage_upload(ctx, small_dev, targets, sizeof(int32_t) * tot_t));
-  TRY(stage_upload(ctx, small_dev + tot_t, off.data(), sizeof(int32_t) * B));
-  TRY(stage_upload(ctx, small_dev + tot_t + B, target_lens, sizeof(int32_t) * B));
-  TRY(stage_upload(ctx, small_dev + tot_t + 2ll * B, Tb.data(), sizeof(int32_t) * B));
   {
+    // [targets | offsets | lens | T] in ONE copy (each small copy costs microseconds of stream latency)
+    std::vector<int32_t> small_h((size_t)(tot_t + 3ll * B));
+    if (tot_t) std::memcpy(small_h.data(), targets, sizeof(int32_t) * tot_t);
+    std::memcpy(small_h.data() + tot_t, off.data(), sizeof(int32_t) * B);
+    std::memcpy(small_h.data() + tot_t + B, target_lens, sizeof(int32_t) * B);
+    std::memcpy(small_h.data() + tot_t + 2ll * B, Tb.data(), sizeof(int32_t) * B);
+    TRY(stage_upload(ctx, small_dev, small_h.data(), sizeof(int32_t) * small_h.size()));
+  }
+  if (!bidir) {
     std::vector<float> minus1(B, -1.0f); // subtract's gradFunc, functions.cpp:53-58
     TRY(stage_upload(ctx, deltas_dev, minus1.data(), sizeof(float) * B));
   }
@@ -175,7 +185,7 @@ static int ctc_loss_run(
     const int32_t* T_dev = small_dev + tot_t + 2ll * B;
     TRYCUDA(cudaEventRecord(ev_setup, main_stream));
     if (bidir && K == 1 && !h2d_event && !(grads && !grads_on_device)) {
-      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1));
+      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1, bidir_scores_dev));
     } else if (bidir) {
       for (int k = 0; k < K && !rc; k++) {
         const int b0 = chunk_lo[k], nb = chunk_lo[k + 1] - chunk_lo[k];
@@ -183,7 +193,7 @@ static int ctc_loss_run(
         TRYCUDA(cudaStreamWaitEvent(cs, ev_setup, 0));
         if (h2d_event) TRYCUDA(cudaStreamWaitEvent(cs, ctx->side_events[k], 0));
         ctx->stream = cs;
-        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1);
+        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1, bidir_scores_dev);
         ctx->stream = main_stream;
         if (rc) goto done;
         if (grads && !grads_on_device)
@@ -253,13 +263,14 @@ static int ctc_loss_run(
     float* z = reinterpret_cast<float*>(ctx->readback);
     float* s = z + (long long)zp * B;
     int32_t* st = reinterpret_cast<int32_t*>(s + B);
-    if (bidir)
-      TRYCUDA(cudaMemcpyAsync(z, zparts_dev, sizeof(float) * zp * B, cudaMemcpyDeviceToHost, ctx->stream));
-    else
+    if (bidir) { // one copy: the block is laid out like the host buffer
+      TRYCUDA(cudaMemcpyAsync(z, zparts_dev, sizeof(float) * (zp + 2) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
       TRYCUDA(cudaMemcpyAsync(z, z_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
-    TRYCUDA(cudaMemcpyAsync(s, lat->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
-    if (implicit)
-      TRYCUDA(cudaMemcpyAsync(st, status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->stream));
+      TRYCUDA(cudaMemcpyAsync(s, lat->out_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
+      if (implicit)
+        TRYCUDA(cudaMemcpyAsync(st, status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     TRYCUDA(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < B; b++) { // subtract, functions.cpp:52
       float zb = 0.0f;
@@ -278,7 +289,7 @@ done:
     cudaStreamSynchronize(ctx->copy_stream);
     for (int k = 0; k < K && k < (int)ctx->side_streams.size(); k++) cudaStreamSynchronize(ctx->side_streams[k]);
   }
-  dev_free(ctx, status_dev);
+  if (!bidir) dev_free(ctx, status_dev); // (bidir: part of the zparts block)
   dev_free(ctx, row_scratch);
   dev_free(ctx, zparts_dev);
   dev_free(ctx, boff_dev);
@@ -298,8 +309,10 @@ extern "C" int gtnb_ctc_loss(
     const int32_t* input_lens, const int32_t* targets, const int32_t* target_lens, int blank,
     float* losses_host, float* grads, int grads_on_device) {
   bool needs_exact = false;
+  if (ctx) arena_begin(ctx);
   int rc = ctc_loss_run(ctx, B, T, C, emissions, emissions_on_device, input_lens, targets, target_lens, blank,
                         losses_host, grads, grads_on_device, ctx && ctx->use_implicit, &needs_exact);
+  if (ctx) arena_end(ctx);
   if (rc == GTNB_OK && needs_exact)
     // a non-finite emission: the materialised lattice reproduces the reference's inf / NaN
     // propagation arc by arc (shortest.cpp:62-80), the implicit sweep cannot tell a missing

@@ -67,6 +67,12 @@ struct gtnb_ctx {
   bool use_bidir = kBidirDefault; // gtnb_ctx_set_flag("bidir", 0): the CTC criterion takes the two sweeps of k_implicit.cu instead of the bidirectional kernel (k_bidir.cu)
   bool exact_ties = true; // gtnb_ctx_set_flag("exact_ties", 0) turns it off: composed lattices are put in the reference's relaxation order so that viterbiPath breaks exact ties like shortest.cpp:212-218 (k_order.cu)
   int use_banded = 0; // gtnb_ctx_set_flag("banded", K): EXPERIMENTAL temporally blocked CTC sweeps (k_banded.cu), K frames per barrier
+  // Call-scoped device arena (the criteria): while arena_on, dev_alloc bumps a pointer inside one cached
+  // allocation instead of ~25 stream-ordered allocations per call (each a microsecond or two of host time
+  // ahead of the first launch); everything allocated in the scope is released together when it ends.
+  unsigned char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0, arena_need = 0;
+  bool arena_on = false;
   bool profiling = false;
   std::vector<ProfEntry> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -217,14 +223,49 @@ int dev_alloc(gtnb_ctx* ctx, T** p, long long n) {
   *p = nullptr;
   if (n <= 0) n = 1;
   // +16 elements of slack: staged copies round their windows up to 16 bytes
-  GTNB_CUDA(ctx, cudaMallocAsync((void**)p, sizeof(T) * (size_t)(n + 16), ctx->stream));
+  const size_t bytes = sizeof(T) * (size_t)(n + 16);
+  if (ctx->arena_on) {
+    const size_t sz = (bytes + 255) & ~(size_t)255;
+    ctx->arena_need += sz;
+    if (ctx->arena_off + sz <= ctx->arena_cap) {
+      *p = reinterpret_cast<T*>(ctx->arena + ctx->arena_off);
+      ctx->arena_off += sz;
+      return GTNB_OK;
+    }
+  }
+  GTNB_CUDA(ctx, cudaMallocAsync((void**)p, bytes, ctx->stream));
   return GTNB_OK;
 }
 
 template <typename T>
 void dev_free(gtnb_ctx* ctx, T*& p) {
-  if (p) cudaFreeAsync((void*)p, ctx->stream);
+  const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
+  if (p && !(ctx->arena && q >= ctx->arena && q < ctx->arena + ctx->arena_cap)) cudaFreeAsync((void*)p, ctx->stream);
   p = nullptr;
+}
+
+/* the arena scope of one criterion call: begin before the first dev_alloc, end after the last dev_free (and
+ * after the stream was synchronised, which every criterion does to return its losses) */
+inline void arena_begin(gtnb_ctx* ctx) {
+  ctx->arena_on = true;
+  ctx->arena_off = 0;
+  ctx->arena_need = 0;
+}
+inline void arena_end(gtnb_ctx* ctx) {
+  ctx->arena_on = false;
+  if (ctx->arena_need > ctx->arena_cap) { // grow for the next call of this shape
+    if (ctx->arena) cudaFreeAsync(ctx->arena, ctx->stream);
+    ctx->arena = nullptr;
+    ctx->arena_cap = 0;
+    const size_t want = ctx->arena_need + (ctx->arena_need >> 3);
+    void* fresh = nullptr;
+    if (cudaMallocAsync(&fresh, want, ctx->stream) == cudaSuccess) {
+      ctx->arena = static_cast<unsigned char*>(fresh);
+      ctx->arena_cap = want;
+    } else {
+      cudaGetLastError(); // no arena: the plain allocations keep working
+    }
+  }
 }
 
 // Upload through pinned staging is overkill for the small metadata here;
@@ -261,7 +302,7 @@ int bidir_blocks(int max_T);
 int bidir_zparts(); // partial sums of forwardScore(emissions) per CTA
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
-    int64_t grad_stride, int b0 = 0, int nb = -1, int zero_w = 0);
+    int64_t grad_stride, int b0 = 0, int nb = -1, int zero_w = 0, float* out_scores_dev = nullptr);
 /* k_order.cu (experimental): a composed lattice's rows and accept list in the order the reference's shortestPath relaxes / creates them */
 int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat);
 /* k_banded.cu (experimental): same contract as the implicit sweeps, for band-shaped graph operands */

@@ -1299,7 +1299,7 @@ int bidir_zparts() {
 }
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
-    int64_t grad_stride, int b0, int nb, int zero_w) {
+    int64_t grad_stride, int b0, int nb, int zero_w, float* out_scores_dev) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
   bidir::Params P;
@@ -1313,7 +1313,7 @@ int launch_bidir_ctc(
   P.saved = lat->scores;
   P.nblk_cap = bidir_blocks(lat->max_T);
   P.boff = boff_dev + (long long)b0 * 2 * P.nblk_cap * 4;
-  P.out_scores = lat->out_scores + b0;
+  P.out_scores = (out_scores_dev ? out_scores_dev : lat->out_scores) + b0;
   P.zparts = zparts_dev + 2ll * b0 * bidir::kHelpers;
   P.status = status_dev + b0;
   P.grad = grad_emis ? grad_emis + (long long)b0 * grad_stride : nullptr;
