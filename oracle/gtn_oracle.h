@@ -9,7 +9,7 @@
  *   arcSort / linearGraph      gtn/graph.cpp:162-177, gtn/creations.cpp:20-33
  *   CTC / ASG criteria         benchmarks/ctc.cpp:40-58,150-160, test/criterion_test.cpp:244-278
  *
- * Parity pinned: tests/test_oracle_vs_ref.py checks this file against the
+ * Parity pinned: tests/test_oracle.py checks this file against the
  * real reference (oracle/_ref/libgtn_ref.so) on the reference's own known-
  * answer tests (test/criterion_test.cpp, test/functions_test.cpp,
  * test/autograd_test.cpp) and on random graphs; tests/golden/ holds fixtures
