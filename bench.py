@@ -138,6 +138,30 @@ class ClockSampler:
                 "when": "between event-bracketed steps of the timed region"}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node the
+    GPU hangs off.  torchrun does not bind ranks, and round 1's e2e scaling collapsed at N >= 4 because ranks
+    of GPUs 4-7 were copying through the other socket.  Returns a description for the JSON line."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, use)
+        return {"gpu": index, "numa_node": node, "cpus": len(use)}
+    except Exception as ex:  # no sysfs entry (a VM), no NVML: run unbound
+        return {"gpu": index, "numa_node": None, "error": str(ex)[:80]}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -245,6 +269,193 @@ def run_reference(args, rank, world):
     }))
 
 
+# ---------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations: ASG (configs[2]) and dense Viterbi (configs[3])
+# ---------------------------------------------------------------------------------------------------------
+
+def run_other_workload(args, rank, local, world):
+    """One JSON line for --workload asg | viterbi, same contract as the headline: `value` device resident,
+    `e2e` with pinned host buffers, `roofline` for the dominant kernel, `cpu_baseline` = the reference
+    (oracle/_ref) on a bounded sample, in-run `parity` against it.  Weak scaling (B per GPU)."""
+    asg = args.workload == "asg"
+    B = args.batch if args.batch != B_DEF else (128 if asg else 512)
+    T = args.T if args.T != T_DEF else (500 if asg else 2000)
+    C = args.C if args.C != C_DEF else (64 if asg else 128)
+    U = args.U if args.U != U_DEF else 50
+    name = ("ASG loss+grad B=%d/GPU T=%d C=%d U=%d (BASELINE.json configs[2])" % (B, T, C, U)) if asg else \
+           ("dense Viterbi score+path B=%d/GPU T=%d C=%d (BASELINE.json configs[3])" % (B, T, C))
+    metric = "asg_fwd_bwd_utterances_per_s" if asg else "viterbi_decode_utterances_per_s"
+    rngw = np.random.default_rng(7)
+    tw = rngw.uniform(-5, 5, C + C * C).astype(np.float32)
+
+    def inputs(first, count):
+        e = np.empty((count, T, C), np.float32)
+        tg = []
+        for i in range(count):
+            rng = np.random.default_rng(4321 + first + i)
+            e[i] = rng.uniform(-5.0, 5.0, (T, C)).astype(np.float32)
+            tg.append(rng.integers(0, C, U).astype(np.int32))
+        return e, tg
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import pyoracle as po
+        n = min(args.cpu_sample, 16 if asg else 8)
+        e, tg = inputs(0, n)
+        step = (lambda: po.ref_asg_batch(e, tw, tg)[3]) if asg else (lambda: po.ref_viterbi_dense_batch(e, tw)[2])
+        for _ in range(min(args.warmup, 1)):
+            step()
+        secs = [step() for _ in range(max(1, min(args.steps, 3)))]
+        val = n / float(np.mean(secs))
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": val, "unit": "utt/s", "n_gpus": args.gpus,
+            "steps": len(secs), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * float(np.mean(secs)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "parallelism": "dp%d" % world},
+            "cpu_baseline": {"value": val, "unit": "utt/s", "cores": min(po.libref().ref_hardware_threads(), n),
+                             "kind": "reference", "sample": "%d utterances per step (BASELINE.md: the CPU needs seconds "
+                             "and gigabytes per utterance here)" % n},
+            "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import ctypes as Ct
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from gtn_b200 import capi
+    L = capi.lib()
+    ctx = capi.Ctx(local)
+    i32p, f32p = capi._i32p, capi._f32p
+    e, tg = inputs(rank * B, B)
+    lens = np.full(B, U, np.int32)
+    cat = np.ascontiguousarray(np.concatenate(tg), np.int32)
+    e_dev = ctx.to_device(e)
+    hp_e = Ct.c_void_p()
+    ctx._check(L.gtnb_host_alloc(ctx.h, e.nbytes, Ct.byref(hp_e)))
+    Ct.memmove(hp_e.value, e.ctypes.data, e.nbytes)
+    losses = np.zeros(B, np.float32)
+    if asg:
+        g_dev = ctx.alloc(e.nbytes)
+        hp_g = Ct.c_void_p()
+        ctx._check(L.gtnb_host_alloc(ctx.h, e.nbytes, Ct.byref(hp_g)))
+        tgrad = np.zeros(C + C * C, np.float32)
+
+        def call(ep, eon, gp, gon):
+            ctx._check(L.gtnb_asg_loss(ctx.h, B, T, C, ep, eon, tw.ctypes.data_as(f32p), cat.ctypes.data_as(i32p),
+                                       lens.ctypes.data_as(i32p), losses.ctypes.data_as(f32p), gp, gon,
+                                       tgrad.ctypes.data_as(f32p)))
+        step_dev = lambda: call(e_dev.ptr, 1, g_dev.ptr, 1)
+        step_e2e = lambda: call(hp_e.value, 0, hp_g.value, 0)
+        h2d, d2h = e.nbytes + tw.nbytes + cat.nbytes, e.nbytes + losses.nbytes + tgrad.nbytes
+        # SURVEY.md 8(d) B_io on the two factored lattices: emissions in, gradients out, per-frame node scores
+        # (C for the denominator trellis, U for the forced-alignment chain) written once and read once
+        alg = B * (4 * T * C + 4 * T * C + 2 * 4 * T * (C + U))
+    else:
+        paths = np.zeros((B, T), np.int32)
+        scores = np.zeros(B, np.float32)
+
+        def call(ep, eon):
+            ctx._check(L.gtnb_viterbi_dense(ctx.h, B, T, C, ep, eon, None, tw.ctypes.data_as(f32p),
+                                            paths.ctypes.data_as(i32p), scores.ctypes.data_as(f32p)))
+        step_dev = lambda: call(e_dev.ptr, 1)
+        step_e2e = lambda: call(hp_e.value, 0)
+        h2d, d2h = e.nbytes + tw.nbytes, paths.nbytes + scores.nbytes
+        # emissions in, one back-pointer byte per (frame, state) written and read by the traceback, paths out
+        alg = B * (4 * T * C + 2 * T * C + 4 * T)
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    every = max(1, args.steps // 8)
+
+    def region(step, profile):
+        if profile:
+            ctx.profile(True)
+            ctx.profile_read()
+        l0 = ctx.launches
+        barrier()
+        ts, pr = [], {}
+        for i in range(args.steps):
+            ctx.flush_l2()
+            ctx.timer_start()
+            step()
+            ts.append(ctx.timer_stop())
+            if profile:
+                for k, (cnt, ms_) in ctx.profile_read().items():
+                    c0, m0 = pr.get(k, (0, 0.0))
+                    pr[k] = (c0 + cnt, m0 + ms_)
+            if i % every == every // 2:
+                sampler.sample()
+        barrier()
+        if profile:
+            ctx.profile(False)
+        return ts, pr, ctx.launches - l0
+
+    ts, pr, launches = region(step_dev, True)
+    gpu_losses = losses.copy() if asg else scores.copy()
+    gpu_paths = None if asg else paths.copy()
+    for _ in range(2):
+        step_e2e()
+    te, _, _ = region(step_e2e, False)
+    ms, ems = float(np.mean(ts)), float(np.mean(te))
+    if world > 1:
+        t = torch.tensor([ms, ems], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ems = float(t[0]), float(t[1])
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        kern = {k: v[1] / args.steps for k, v in pr.items() if k != "flush_l2"}
+        dom = max(kern.items(), key=lambda kv: kv[1]) if kern else (None, 0.0)
+        out = {
+            "metric": metric, "value": world * B / (ms * 1e-3), "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "ms_per_step_median": float(np.median(ts)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "l2": "flushed between timed iterations (256 MB memset)",
+                       "parallelism": "dp%d" % world},
+            "e2e": {"value": world * B / (ems * 1e-3), "unit": "utt/s", "ms_per_step": ems,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": sampler.result(),
+            # the factored lattices move almost nothing: the sweeps are bound by SFU / issue rate and per-frame
+            # latency (SURVEY.md 8(d)); the HBM figure is reported against the WHOLE step for completeness
+            "roofline": {"bound": "hbm", "kernel": "whole step (dominant kernel by time: %s, %.3f ms)" % dom,
+                         "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": alg,
+                         "note": "factored lattice: issue / SFU and per-frame latency bound, not HBM (SURVEY.md 8(d))"},
+            "kernels_ms_per_step": kern}
+        if not args.no_cpu_baseline:
+            from oracle import pyoracle as po
+            if po.have_ref():
+                n = min(args.cpu_sample, 16 if asg else 8)
+                if asg:
+                    lr, gr, tgr, sec = po.ref_asg_batch(e[:n], tw, tg[:n])
+                    go = g_dev.download((n, T, C))
+                    out["parity"] = {"n": n, "max_rel_loss": float((np.abs(gpu_losses[:n] - lr) / np.abs(lr)).max()),
+                                     "max_abs_grad": float(np.abs(go - gr).max()),
+                                     "against": "oracle/_ref on utterances 0..n-1 of the timed batch (the transition "
+                                                "gradient sums over a different batch and is compared in tests/)"}
+                else:
+                    pr_, sr, sec = po.ref_viterbi_dense_batch(e[:n], tw)
+                    out["parity"] = {"n": n, "paths_equal": bool(np.array_equal(gpu_paths[:n], pr_)),
+                                     "scores_equal": bool(np.array_equal(gpu_losses[:n], sr)),
+                                     "against": "oracle/_ref on utterances 0..n-1 of the timed batch, =="}
+                out["cpu_baseline"] = {"value": n / sec, "unit": "utt/s", "kind": "reference", "seconds": sec,
+                                       "cores": min(po.libref().ref_hardware_threads(), n),
+                                       "sample": "%d utterances on %d threads (BASELINE.md section 3)" % (n, min(po.libref().ref_hardware_threads(), n))}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -256,6 +467,11 @@ def main():
     ap.add_argument("--C", type=int, default=C_DEF)
     ap.add_argument("--U", type=int, default=U_DEF)
     ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--workload", default="ctc", choices=["ctc", "asg", "viterbi"],
+                    help="ctc: BASELINE configs[1] (the headline, what the driver runs); asg: configs[2]; "
+                         "viterbi: configs[3]")
+    ap.add_argument("--strong", action="store_true",
+                    help="ctc only: --batch is the WHOLE job (configs[4]: B=2048 fixed), split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -263,12 +479,21 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.workload != "ctc":
+        run_other_workload(args, rank, local, world)
+        return
+    if args.strong:
+        if args.batch % world:
+            raise SystemExit("--strong: --batch must be a multiple of the number of ranks")
+        args.total_batch = args.batch
+        args.batch //= world
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's banner out of stdout: rank 0 prints ONE JSON line
+    numa = bind_to_gpu_numa_node(local)  # before the first allocation: pinned buffers are first-touch
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
@@ -451,15 +676,19 @@ def main():
         out = {
             "metric": "ctc_fwd_bwd_utterances_per_s", "value": world * B / (ms * 1e-3), "unit": "utt/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": workload_config(B, T, C, U, world),
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, T, C, U, world) if not args.strong else
+            {"workload": "CTC loss+grad B=%d TOTAL (BASELINE.json configs[4]), %d per GPU, T=%d C=%d U=%d"
+                         % (args.total_batch, B, T, C, U),
+             "l2": "flushed between timed iterations (256 MB memset)", "parallelism": "dp%d" % world},
             "lattice": {"nodes": sumN, "arcs": sumA, "note": "per GPU, what compose would materialise"},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "utt/s", "ms_per_step": e2e_ms,
                     "ms_per_step_median": float(np.median(e2e_times)), "ms_per_step_min": float(np.min(e2e_times)),
                     "h2d_bytes_per_step": int(nbytes + cat.nbytes + lens.nbytes),
                     "d2h_bytes_per_step": int(nbytes + losses.nbytes)},
             "gpu_launches": int(launches),
+            "numa": numa,
             "clocks": clocks,
             "ms_per_step_median": float(np.median(times)), "ms_per_step_min": float(np.min(times)),
             "attempts_ms_per_step": {"value": dev_attempts, "e2e": e2e_attempts,

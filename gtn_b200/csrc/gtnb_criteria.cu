@@ -93,7 +93,7 @@ static int ctc_loss_run(
   // Device buffers: K = 1, and the normaliser (k_linear.cu) runs beside the forward sweep.
   if (implicit && (!emissions_on_device || (grads && !grads_on_device))) {
     const long long bytes = (long long)sizeof(float) * per * B;
-    K = (int)std::min<long long>(std::max<long long>(bytes / (8ll << 20), 1), 8);
+    K = (int)std::min<long long>(std::max<long long>(bytes / (4ll << 20), 1), 16);
     K = std::min(K, B);
   }
   TRY(ensure_side_streams(ctx, K, K + 2));

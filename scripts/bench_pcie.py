@@ -35,3 +35,20 @@ run(hp.value, 0, g_dev.ptr, 1, "host->dev ")
 run(e_dev.ptr, 1, hq.value, 0, "dev->host ")
 run(hp.value, 0, hq.value, 0, "host->host")
 run(hp.value, 0, None, 0, "host, no grad")
+# both directions at once (two streams): what full duplex gives on this host
+import torch
+a = torch.empty(n // 4, dtype=torch.float32).pin_memory(); b_ = torch.empty(n // 4, dtype=torch.float32).pin_memory()
+da = torch.empty(n // 4, dtype=torch.float32, device="cuda"); db = torch.empty(n // 4, dtype=torch.float32, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+for rep in range(4):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s1.wait_event(e0); s2.wait_event(e0)
+    with torch.cuda.stream(s1):
+        da.copy_(a, non_blocking=True)
+    with torch.cuda.stream(s2):
+        b_.copy_(db, non_blocking=True)
+    torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+    e1.record(); torch.cuda.synchronize()
+    print("duplex 65.5 MB each way: %.3f ms" % e0.elapsed_time(e1))

@@ -514,12 +514,12 @@ def test_ctc_implicit_falls_back_on_non_finite_emissions(ctx):
 
 
 def test_ctc_host_buffers_sub_batches_match_device_buffers(ctx):
-    """Host buffers above 16 MB are cut into sub-batches that run on their own streams (H2D, sweeps
-    and D2H overlapping); the result must equal the single-launch device-buffer call."""
+    """Host buffers above 8 MB are cut into sub-batches of >= 4 MB that run on their own streams (H2D,
+    sweeps and D2H overlapping); the result must equal the single-launch device-buffer call."""
     import ctypes as Ct
     from gtn_b200 import capi
     L = capi.lib()
-    B, T, C, U = 24, 1000, 192, 60  # 18.4 MB of emissions -> 2 sub-batches
+    B, T, C, U = 24, 1000, 192, 60  # 18.4 MB of emissions -> 4 sub-batches
     e, targets = util.bench_inputs(B, T, C, U, seed=2024)
     lens = np.asarray([len(t) for t in targets], np.int32)
     cat = np.ascontiguousarray(np.concatenate(targets), np.int32)
@@ -540,7 +540,7 @@ def test_ctc_host_buffers_sub_batches_match_device_buffers(ctx):
     l_host, g_host = ctx.ctc_loss(e, targets, input_lens=il)
     prof = ctx.profile_read()
     ctx.profile(False)
-    assert prof["implicit_forward"][0] == 2 and prof["implicit_backward"][0] == 2, prof
+    assert prof["implicit_forward"][0] == 4 and prof["implicit_backward"][0] == 4, prof
     assert np.allclose(l_host, l_dev, rtol=1e-6)
     assert np.allclose(g_host, g_from_dev, rtol=1e-5, atol=1e-6)
     for b in range(B):
@@ -652,8 +652,8 @@ def test_ctc_bidir_falls_back_on_non_finite_emissions(ctx):
 
 
 def test_ctc_bidir_host_buffers_sub_batches(ctx):
-    """host buffers above 16 MB: sub-batches on their own streams, one bidir launch each."""
-    B, T, C, U = 40, 1000, 128, 60  # 20.5 MB of emissions -> 2 sub-batches
+    """host buffers above 8 MB: sub-batches on their own streams, one bidir launch each."""
+    B, T, C, U = 40, 1000, 128, 60  # 20.5 MB of emissions -> 4 sub-batches
     e, targets = util.bench_inputs(B, T, C, U, seed=2025)
     il = np.array([T - 7 * (b % 5) for b in range(B)], np.int32)
     ctx.set_flag("bidir", 1)
@@ -666,7 +666,7 @@ def test_ctc_bidir_host_buffers_sub_batches(ctx):
         ctx.set_flag("bidir", -1)
     prof = ctx.profile_read()
     ctx.profile(False)
-    assert prof["bidir_ctc"][0] == 2, prof
+    assert prof["bidir_ctc"][0] == 4, prof
     assert np.array_equal(l_host, l_dev)
     assert np.array_equal(g_host, g_dev)
 
