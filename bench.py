@@ -206,6 +206,61 @@ def cpu_reference(sample, T, C, U, repeats=1, keep=None):
                       % (sample, T, C, U, min(cores, sample)), "seconds": best}
 
 
+def api_path_leg(e, tg, T, C, steps=5):
+    """The drop-in path a user gets by swapping the import: the reference's Python surface (gtn_b200.gtn), one
+    Graph per utterance, the LIST forms of intersect / forward_score / subtract / backward (bindings/python/
+    gtn/_functions.cpp:69-135), emissions handed over as device pointers of a torch CUDA tensor
+    (docs/source/pytorch.rst's set_weights(data_ptr)), gradients read back per utterance with
+    weights_to_numpy() exactly as bindings/python/examples/pytorch_loss.py:83-102 does.  Target graphs are
+    built once outside the timed region (Python-loop graph construction is interpreter time, not the path).
+    Wall clock with a device synchronise on both sides (the gtn layer runs on its own streams)."""
+    import torch
+    import gtn_b200.gtn as gtn
+    B = e.shape[0]
+    x = torch.tensor(e, device="cuda")
+    ctcs = []
+    for t in tg:
+        L = 2 * len(t) + 1
+        g = gtn.Graph(False)
+        for l in range(L):
+            g.add_node(l == 0, l == L - 1 or l == L - 2)
+            label = int(t[(l - 1) // 2]) if l % 2 else 0
+            g.add_arc(l, l, label)
+            if l > 0:
+                g.add_arc(l - 1, l, label)
+            if l % 2 and l > 1 and label != int(t[(l - 3) // 2]):
+                g.add_arc(l - 2, l, label)
+        g.arc_sort()
+        ctcs.append(g)
+
+    def step():
+        ems = []
+        for b in range(B):
+            em = gtn.linear_graph(T, C)
+            em.set_weights(x[b].data_ptr())
+            ems.append(em)
+        losses = gtn.subtract(gtn.forward_score(ems), gtn.forward_score(gtn.intersect(ctcs, ems)))
+        gtn.backward(losses)
+        grads = [em.grad().weights_to_numpy() for em in ems]
+        return np.array([l.item() for l in losses], np.float32), grads
+
+    step()
+    l0 = gtn.device_launch_count()
+    ts = []
+    for _ in range(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        losses, grads = step()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    launches = (gtn.device_launch_count() - l0) / steps
+    ms = 1e3 * float(np.median(ts))
+    return {"ms_per_step": ms, "utt_per_s": B / (ms * 1e-3), "steps": steps, "kernel_launches_per_step": launches,
+            "what": "gtn_b200.gtn list overloads, B=%d Graphs, device-pointer emissions in, per-utterance host "
+                    "gradients out (weights_to_numpy), target graphs prebuilt" % B,
+            "clock": "wall, median"}, losses, grads
+
+
 def parity_block(ctx, keep, losses_gpu, g_dev, T, C):
     """SURVEY.md 8(d) "parity check in the same run": the reference ran on the first n utterances of the
     very batch that was timed (same seeds); compare the losses and gradients of the LAST TIMED STEP of the
@@ -473,6 +528,7 @@ def main():
     ap.add_argument("--strong", action="store_true",
                     help="ctc only: --batch is the WHOLE job (configs[4]: B=2048 fixed), split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api-path", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -706,6 +762,14 @@ def main():
             out["cpu_baseline"] = cpu_reference(args.cpu_sample, T, C, U, keep=keep)
             if keep:
                 out["parity"] = parity_block(ctx, keep, losses_dev_leg, g_dev, T, C)
+        if not args.no_api_path and world == 1:
+            try:
+                api, al, ag = api_path_leg(e, tg, T, C)
+                api["max_rel_loss_vs_fused"] = float((np.abs(al - losses_dev_leg) / np.abs(losses_dev_leg)).max())
+                api["max_abs_grad_vs_fused"] = float(np.abs(np.stack(ag[:16]).reshape(16, T, C) - g_dev.download((16, T, C))).max())
+                out["api_path"] = api
+            except Exception as ex:  # the line must still print
+                out["api_path"] = {"error": str(ex)[:200]}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -6,6 +6,7 @@
 
 #include <memory>
 #include <mutex>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -20,6 +21,11 @@ namespace detail {
 struct Context {
   gtnb_ctx* ctx{nullptr};
   std::mutex lock; // a lattice may be used from a thread other than its creator
+  // pinned read-back block for the batched list ops (gtn/batched.cpp): the whole batch's emission gradient
+  // comes back in ONE copy and the entries' lazy gradients are host slices of it while `pinnedOwner` says so
+  float* pinned{nullptr};
+  size_t pinnedCount{0};
+  const void* pinnedOwner{nullptr};
   ~Context();
 };
 
@@ -48,7 +54,27 @@ struct LatticeHandle {
   int labels{0}; // C
   bool linearFirst{false};
   int scoreMode{-1}; // semiring of the node scores currently saved in the lattice (-1: none)
+  std::shared_ptr<struct BatchState> batch; // set by the batched list ops (gtn/batched.cpp)
+  std::pair<const std::vector<int32_t>&, const std::vector<int32_t>&> sizes(); // (nodes, arcs) per entry, cached
   ~LatticeHandle();
+
+ private:
+  std::mutex sizesLock;
+  std::vector<int32_t> nn, na;
+};
+
+/* Deferred, batched backward of the B entries of one lattice built by a list op: every entry's gradFunc
+ * only RECORDS its seed; the first read of any resulting gradient runs gtnb_backward + gtnb_compose_grad
+ * once for the whole batch (gtn/batched.cpp). */
+struct BatchState {
+  std::mutex m;
+  int mode{-1}; // semiring of the pending shortest-distance backward (-1: none recorded)
+  std::vector<float> sdDelta; // seeds of the shortest-distance backward, per entry (0: not requested)
+  std::vector<std::vector<float>> hostDeltas; // arc gradients handed in from the host, per entry (rare)
+  bool flushed{false};
+  std::shared_ptr<DeviceBuffer> dLinear, dGraph; // gradients w.r.t. the emissions [B][stride] / the graphs' arcs
+  size_t stride{0};
+  std::vector<size_t> graphOff; // entry b's slab in dGraph
 };
 
 /* Host arrays backing a gtnb_graph_view of a Graph (valid while alive). */

@@ -324,14 +324,14 @@ Graph composeHost(const Graph& first, const Graph& second, bool intersectMode) {
   return ngraph;
 }
 
-namespace {
-
 bool matchedSideHasEpsilon(const Graph& g, bool useIlabel) {
   for (size_t a = 0; a < g.numArcs(); a++) {
     if ((useIlabel ? g.ilabel(a) : g.olabel(a)) == epsilon) return true;
   }
   return false;
 }
+
+namespace {
 
 /* emissions of a linear graph on the device: reuse setWeights(device ptr), else upload */
 std::shared_ptr<DeviceBuffer> emissionsOnDevice(const Graph& linear, const std::shared_ptr<Context>& c) {

@@ -54,9 +54,21 @@ Graph viterbiScore(const Graph& g);
 /** Best path as a chain graph (functions.cpp:328-330). */
 Graph viterbiPath(const Graph& g);
 
+/**
+ * List forms (bindings/python/gtn/_functions.cpp:69-135): one packed launch for the whole list where the graphs
+ * allow it -- every pair a (graph, gtn::linearGraph) composition, every score over the entries of such a batch
+ * or over emission chains -- else parallelMap of the single-graph function.  See gtn/batched.cpp.
+ */
+std::vector<Graph> compose(const std::vector<Graph>& graphs1, const std::vector<Graph>& graphs2);
+std::vector<Graph> intersect(const std::vector<Graph>& graphs1, const std::vector<Graph>& graphs2);
+std::vector<Graph> forwardScore(const std::vector<Graph>& graphs);
+std::vector<Graph> viterbiScore(const std::vector<Graph>& graphs);
+
 namespace detail {
 /** Host graph construction for the general case (epsilons, arbitrary operands). */
 Graph composeHost(const Graph& first, const Graph& second, bool intersectMode);
+/** Does an arc of g carry epsilon on the side matched against a linear graph's labels? */
+bool matchedSideHasEpsilon(const Graph& g, bool useIlabel);
 } // namespace detail
 
 } // namespace gtn

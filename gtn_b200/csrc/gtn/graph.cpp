@@ -21,6 +21,7 @@ namespace gtn {
 namespace detail {
 
 Context::~Context() {
+  if (pinned && ctx) gtnb_host_free(ctx, pinned);
   if (ctx) gtnb_ctx_destroy(ctx);
 }
 
@@ -64,6 +65,19 @@ DeviceBuffer::~DeviceBuffer() {
     std::lock_guard<std::mutex> l(owner->lock);
     gtnb_device_free(owner->ctx, ptr);
   }
+}
+
+/* node / arc counts of every entry, read back once per lattice (a batch of B entries answers B numArcs()
+ * calls with one device round trip) */
+std::pair<const std::vector<int32_t>&, const std::vector<int32_t>&> LatticeHandle::sizes() {
+  std::lock_guard<std::mutex> l(sizesLock);
+  if (nn.empty()) {
+    nn.assign(std::max(B, 1), 0);
+    na.assign(std::max(B, 1), 0);
+    std::lock_guard<std::mutex> cl(owner->lock);
+    check(owner, gtnb_lattice_sizes(owner->ctx, lat, nn.data(), na.data()));
+  }
+  return {nn, na};
 }
 
 LatticeHandle::~LatticeHandle() {
@@ -196,6 +210,30 @@ void Graph::materialize() const {
   auto& sg = *sharedGraph_;
   std::lock_guard<std::mutex> l(sg.materialize_lock);
   if (sg.hostReady) return;
+  if (!sg.lattice) {
+    // a gtn::linearGraph that nobody has looked at yet (creations.cpp): build the chain now
+    const int M = sg.linearFrames, N = sg.linearLabels;
+    sg.nodes.clear();
+    sg.arcs.clear();
+    sg.start.assign(1, 0);
+    sg.accept.assign(1, M);
+    sg.nodes.reserve((size_t)M + 1);
+    sg.arcs.reserve((size_t)M * N);
+    sg.nodes.emplace_back(true, false);
+    for (int m = 1; m <= M; m++) {
+      sg.nodes.emplace_back(false, m == M);
+      sg.nodes[m - 1].out.reserve(N);
+      sg.nodes[m].in.reserve(N);
+      for (int n = 0; n < N; n++) {
+        const int idx = (m - 1) * N + n;
+        sg.arcs.emplace_back(m - 1, m, n, n);
+        sg.nodes[m - 1].out.push_back(idx);
+        sg.nodes[m].in.push_back(idx);
+      }
+    }
+    sg.hostReady = true;
+    return;
+  }
   auto lat = sg.lattice;
   std::vector<int32_t> nn(lat->B), na(lat->B);
   {
@@ -235,25 +273,16 @@ void Graph::materialize() const {
 
 size_t Graph::numArcs() const {
   auto& sg = *sharedGraph_;
-  if (!sg.hostReady) {
-    auto lat = sg.lattice;
-    std::vector<int32_t> nn(lat->B), na(lat->B);
-    std::lock_guard<std::mutex> cl(lat->owner->lock);
-    detail::check(lat->owner, gtnb_lattice_sizes(lat->owner->ctx, lat->lat, nn.data(), na.data()));
-    return (size_t)na[sg.latticeIndex];
-  }
+  if (!sg.hostReady)
+    return sg.lattice ? (size_t)sg.lattice->sizes().second[sg.latticeIndex]
+                      : (size_t)sg.linearFrames * (size_t)sg.linearLabels; // a pending linearGraph
   return sg.arcs.size();
 }
 
 size_t Graph::numNodes() const {
   auto& sg = *sharedGraph_;
-  if (!sg.hostReady) {
-    auto lat = sg.lattice;
-    std::vector<int32_t> nn(lat->B), na(lat->B);
-    std::lock_guard<std::mutex> cl(lat->owner->lock);
-    detail::check(lat->owner, gtnb_lattice_sizes(lat->owner->ctx, lat->lat, nn.data(), na.data()));
-    return (size_t)nn[sg.latticeIndex];
-  }
+  if (!sg.hostReady)
+    return sg.lattice ? (size_t)sg.lattice->sizes().first[sg.latticeIndex] : (size_t)sg.linearFrames + 1;
   return sg.nodes.size();
 }
 
@@ -337,6 +366,16 @@ std::vector<float>& Graph::hostWeights() const {
       sw.lazyFetch = nullptr;
     }
   }
+  if (!sw.lazyAdds.empty()) {
+    std::lock_guard<std::mutex> l(sw.lock);
+    std::vector<float> part;
+    for (auto& f : sw.lazyAdds) {
+      part.assign(sw.host.size(), 0.0f);
+      f(part);
+      for (size_t i = 0; i < sw.host.size() && i < part.size(); i++) sw.host[i] += part[i];
+    }
+    sw.lazyAdds.clear();
+  }
   if (sw.hostStale) {
     std::lock_guard<std::mutex> l(sw.lock);
     if (sw.hostStale) {
@@ -352,29 +391,29 @@ std::vector<float>& Graph::hostWeights() const {
 }
 
 float* Graph::weights() {
-  host();
+  // (no host(): the weights do not need the topology -- a pending linearGraph or a device-resident lattice
+  // stays unmaterialised when only its weights or gradient are read)
   auto& hw = hostWeights();
   // the caller may write through the pointer: neither the device copy nor a device lattice built
   // from the old values can be trusted any longer
   sharedWeights_->device.reset();
+  sharedWeights_->batch.reset();
   sharedWeights_->latticeWeights = false;
   return hw.data();
 }
 
 const float* Graph::weights() const {
-  host();
   return hostWeights().data();
 }
 
 float Graph::weight(size_t i) const {
-  host();
   return hostWeights()[i];
 }
 
 void Graph::setWeight(size_t i, float weight) {
-  host();
   hostWeights()[i] = weight;
   sharedWeights_->device.reset();
+  sharedWeights_->batch.reset();
   sharedWeights_->latticeWeights = false;
 }
 
@@ -382,6 +421,20 @@ std::shared_ptr<detail::DeviceBuffer> Graph::deviceWeights() const {
   if (!sharedWeights_) return nullptr;
   std::lock_guard<std::mutex> l(sharedWeights_->lock);
   return sharedWeights_->device;
+}
+
+std::shared_ptr<detail::DeviceBuffer> Graph::batchSlice(size_t* offset) const {
+  if (!sharedWeights_) return nullptr;
+  std::lock_guard<std::mutex> l(sharedWeights_->lock);
+  if (offset) *offset = sharedWeights_->batchOffset;
+  return sharedWeights_->batch;
+}
+
+void Graph::cacheBatchSlice(std::shared_ptr<detail::DeviceBuffer> buf, size_t offset) const {
+  if (!sharedWeights_) return;
+  std::lock_guard<std::mutex> l(sharedWeights_->lock);
+  sharedWeights_->batch = std::move(buf);
+  sharedWeights_->batchOffset = offset;
 }
 
 void Graph::cacheDeviceWeights(std::shared_ptr<detail::DeviceBuffer> buf) const {
@@ -420,6 +473,7 @@ void Graph::setWeights(const float* weights) {
     }
     std::lock_guard<std::mutex> l(sw.lock);
     sw.device = buf;
+    sw.batch.reset();
     sw.hostStale = true;
     sw.lazyFetch = nullptr;
     sw.latticeWeights = false;
@@ -429,6 +483,7 @@ void Graph::setWeights(const float* weights) {
   sw.host.resize(n);
   std::copy(weights, weights + n, sw.host.data());
   sw.device.reset();
+  sw.batch.reset();
   sw.hostStale = false;
   sw.lazyFetch = nullptr;
   sw.latticeWeights = false;
@@ -488,6 +543,17 @@ void Graph::addLazyGrad(size_t n, std::function<void(std::vector<float>&)> fetch
       sharedGrad_->grad = std::make_unique<Graph>(false);
       sharedGrad_->grad->sharedGraph_ = sharedGraph_;
       sharedGrad_->grad->sharedWeights_->lazyFetch = std::move(fetch);
+      return;
+    }
+  }
+  {
+    // a gradient that itself still lives on the device: queue this contribution behind it instead of
+    // forcing both to the host now (the batched list ops park one per op and entry until somebody reads)
+    std::lock_guard<std::mutex> lock(sharedGraph_->grad_lock);
+    auto& gw = *sharedGrad_->grad->sharedWeights_;
+    if (gw.lazyFetch || !gw.lazyAdds.empty()) {
+      std::lock_guard<std::mutex> l(gw.lock);
+      gw.lazyAdds.push_back(std::move(fetch));
       return;
     }
   }

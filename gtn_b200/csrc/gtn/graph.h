@@ -234,6 +234,9 @@ class Graph {
   bool hasLazyWeights() const {
     return sharedWeights_ && sharedWeights_->lazyFetch != nullptr;
   }
+  /** The slice of a batch-wide device buffer that holds these weights, if a batched list op gathered them. */
+  std::shared_ptr<detail::DeviceBuffer> batchSlice(size_t* offset) const;
+  void cacheBatchSlice(std::shared_ptr<detail::DeviceBuffer> buf, size_t offset) const;
 
  private:
   size_t addArc(size_t srcNode, size_t dstNode, int label, float) = delete;
@@ -262,6 +265,13 @@ class Graph {
     std::shared_ptr<detail::DeviceBuffer> device; // set by setWeights(device pointer)
     bool hostStale{false}; // device holds the truth, host not yet filled
     std::function<void(std::vector<float>&)> lazyFetch; // see addLazyGrad, fromLattice
+    // further device-side contributions that arrived while the first one was still pending: added to the
+    // host vector when somebody reads it (the batched list ops install one per op and entry)
+    std::vector<std::function<void(std::vector<float>&)>> lazyAdds;
+    // a slice of a batch-wide device buffer that holds exactly these weights (gathered by a batched list
+    // op, gtn/batched.cpp); dropped with `device` whenever the weights may change
+    std::shared_ptr<detail::DeviceBuffer> batch;
+    size_t batchOffset{0};
     bool latticeWeights{false}; // these ARE the (unmodified) arc weights of sharedGraph_->lattice
     std::mutex lock;
   };

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "gtn/device.h"
 #include "gtn/gtn.h"
 
 using namespace gtn;
@@ -142,14 +143,38 @@ PYBIND11_MODULE(_gtn, m) {
   m.def("add", binaryList(add), "graphs1"_a, "graphs2"_a);
   m.def("subtract", binary(subtract), "g1"_a, "g2"_a);
   m.def("subtract", binaryList(subtract), "graphs1"_a, "graphs2"_a);
-  m.def("compose", binary(compose), "g1"_a, "g2"_a);
-  m.def("compose", binaryList(compose), "graphs1"_a, "graphs2"_a);
-  m.def("intersect", binary(intersect), "g1"_a, "g2"_a);
-  m.def("intersect", binaryList(intersect), "graphs1"_a, "graphs2"_a);
-  m.def("forward_score", unary(forwardScore), "g"_a);
-  m.def("forward_score", unaryList(forwardScore), "graphs"_a);
-  m.def("viterbi_score", unary(viterbiScore), "g"_a);
-  m.def("viterbi_score", unaryList(viterbiScore), "graphs"_a);
+  m.def("compose", binary(static_cast<Graph (*)(const Graph&, const Graph&)>(&compose)), "g1"_a, "g2"_a);
+  m.def(
+      "compose",
+      [](const std::vector<Graph>& a, const std::vector<Graph>& b) {
+        py::gil_scoped_release release;
+        return compose(a, b); // one packed launch for the whole list where the graphs allow it (gtn/batched.cpp)
+      },
+      "graphs1"_a, "graphs2"_a);
+  m.def("intersect", binary(static_cast<Graph (*)(const Graph&, const Graph&)>(&intersect)), "g1"_a, "g2"_a);
+  m.def(
+      "intersect",
+      [](const std::vector<Graph>& a, const std::vector<Graph>& b) {
+        py::gil_scoped_release release;
+        return intersect(a, b);
+      },
+      "graphs1"_a, "graphs2"_a);
+  m.def("forward_score", unary(static_cast<Graph (*)(const Graph&)>(&forwardScore)), "g"_a);
+  m.def(
+      "forward_score",
+      [](const std::vector<Graph>& gs) {
+        py::gil_scoped_release release;
+        return forwardScore(gs);
+      },
+      "graphs"_a);
+  m.def("viterbi_score", unary(static_cast<Graph (*)(const Graph&)>(&viterbiScore)), "g"_a);
+  m.def(
+      "viterbi_score",
+      [](const std::vector<Graph>& gs) {
+        py::gil_scoped_release release;
+        return viterbiScore(gs);
+      },
+      "graphs"_a);
   m.def("viterbi_path", unary(viterbiPath), "g"_a);
   m.def("viterbi_path", unaryList(viterbiPath), "graphs"_a);
   m.def("project_input", unary(projectInput), "g"_a);
@@ -238,7 +263,12 @@ PYBIND11_MODULE(_gtn, m) {
       "backward",
       [](std::vector<Graph> graphs, const std::vector<int>& retain) {
         py::gil_scoped_release release;
-        parallelMap([](Graph g, int keep) { backward(g, keep != 0); }, graphs, retain);
+        bool uniform = !retain.empty();
+        for (int r : retain) uniform = uniform && (r != 0) == (retain[0] != 0);
+        if (uniform && (retain.size() == 1 || retain.size() == graphs.size()))
+          backward(graphs, retain[0] != 0); // batched tapes are walked in this thread (gtn/batched.cpp)
+        else
+          parallelMap([](Graph g, int keep) { backward(g, keep != 0); }, graphs, retain);
       },
       "graphs"_a, "retain_graphs"_a = std::vector<int>({0}));
   m.def(
@@ -249,6 +279,12 @@ PYBIND11_MODULE(_gtn, m) {
                     retain);
       },
       "graphs"_a, "grads"_a, "retain_graphs"_a = std::vector<int>({0}));
+
+  // B200 addition: kernels launched so far by the calling thread's context (tests / bench bookkeeping)
+  m.def("device_launch_count", []() {
+    auto c = detail::threadContext();
+    return (long long)gtnb_ctx_launch_count(c->ctx);
+  });
 
   // creations (bindings/python/gtn/_creations.cpp)
   m.def("scalar_graph", &scalarGraph, "val"_a, "calc_grad"_a = true);

@@ -8,6 +8,7 @@
  * launch on the context's stream.
  */
 #include <algorithm>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -1201,10 +1202,12 @@ int gtnb::compose_linear_impl(
   };
   std::vector<SG> sg(n_graphs);
   int maxN = 0, maxA = 0;
-  for (int g = 0; g < n_graphs; g++) {
+  const bool exact_ties = ctx->exact_ties;
+  // one graph's tables; independent of the others, so a large batch is spread over host threads (the list
+  // forms of the gtn:: layer hand in B graphs at once: 20 ms of single-threaded table building at B = 256)
+  auto build_one = [&](int g) -> int {
     const gtnb_graph_view& v = graphs[g];
-    int rc = validate_view(ctx, v);
-    if (rc) return rc;
+    if (validate_view(nullptr, v)) return GTNB_ERR_INVALID_ARGUMENT;
     Adj adj;
     build_adj(v, adj);
     SG& s = sg[g];
@@ -1230,22 +1233,41 @@ int gtnb::compose_linear_impl(
         // the label matched against the emissions' labels
         int lab = linear_first ? v.arc_ilabel[a] : v.arc_olabel[a];
         if (lab == GTNB_EPSILON)
-          return fail(ctx, GTNB_ERR_UNSUPPORTED,
-                      "gtnb_compose_linear: epsilon on the matched side (use the host compose)");
+          return GTNB_ERR_UNSUPPORTED;
         s.in_src.push_back(v.arc_src[a]);
         s.in_label.push_back((lab >= 0 && lab < C) ? lab : -1);
         s.in_arc.push_back(a);
         s.in_w.push_back(v.weights ? v.weights[a] : 0.0f);
-        if (ctx->exact_ties) s.in_out_pos.push_back(out_pos[a]);
+        if (exact_ties) s.in_out_pos.push_back(out_pos[a]);
       }
       s.in_ptr[d + 1] = (int)s.in_src.size();
     }
-    if (ctx->exact_ties) {
+    if (exact_ties) {
       s.start_rank.assign(s.N, -1);
       for (size_t k = 0; k < adj.start.size(); k++) s.start_rank[adj.start[k]] = (int32_t)k;
     }
-    maxN = std::max(maxN, s.N);
-    maxA = std::max(maxA, s.A);
+      return GTNB_OK;
+  };
+  {
+    std::vector<int> rcs(n_graphs, GTNB_OK);
+    const int nthr = n_graphs >= 32 ? (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (nthr > 1) {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nthr; t++)
+        pool.emplace_back([&, t] {
+          for (int g = t; g < n_graphs; g += nthr) rcs[g] = build_one(g);
+        });
+      for (auto& th : pool) th.join();
+    } else {
+      for (int g = 0; g < n_graphs; g++) rcs[g] = build_one(g);
+    }
+    for (int g = 0; g < n_graphs; g++) {
+      if (rcs[g] == GTNB_ERR_UNSUPPORTED)
+        return fail(ctx, GTNB_ERR_UNSUPPORTED, "gtnb_compose_linear: epsilon on the matched side (use the host compose)");
+      if (rcs[g]) return validate_view(ctx, graphs[g]) ? GTNB_ERR_INVALID_ARGUMENT : rcs[g]; // (sets the message)
+      maxN = std::max(maxN, sg[g].N);
+      maxA = std::max(maxA, sg[g].A);
+    }
   }
 
   std::vector<SgDims> dims(n_graphs);

