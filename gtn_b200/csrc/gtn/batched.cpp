@@ -104,6 +104,27 @@ std::shared_ptr<DeviceBuffer> gatherEmissions(
   return buf;
 }
 
+/* the gradients of a whole batch come back in ONE copy through a pinned block of the context (caller holds
+ * c->lock); a per-entry read-back costs ~0.2 ms each (measured: 53 ms for 256 utterances) */
+void readBack(const std::shared_ptr<Context>& c, int slot, const void* owner, const float* dev, size_t n) {
+  if (c->pinnedCount[slot] < n) {
+    if (c->pinned[slot]) gtnb_host_free(c->ctx, c->pinned[slot]);
+    c->pinned[slot] = nullptr;
+    c->pinnedCount[slot] = 0;
+    c->pinnedOwner[slot] = nullptr;
+    void* p = nullptr;
+    if (gtnb_host_alloc(c->ctx, sizeof(float) * n, &p) == GTNB_OK) {
+      c->pinned[slot] = static_cast<float*>(p);
+      c->pinnedCount[slot] = n;
+    }
+  }
+  if (c->pinned[slot] && n) {
+    check(c, gtnb_memcpy_d2h(c->ctx, c->pinned[slot], dev, sizeof(float) * n));
+    check(c, gtnb_ctx_synchronize(c->ctx));
+    c->pinnedOwner[slot] = owner;
+  }
+}
+
 /* run the pending backward of a batched lattice once: shortestDistanceGrad for the recorded seeds
  * (shortest.cpp:33-82), host-provided arc gradients on top, then compose's gradFunc (compose.cpp:496-518)
  * for all entries into bs.dLinear / bs.dGraph */
@@ -131,26 +152,14 @@ void flushLattice(const std::shared_ptr<LatticeHandle>& h) {
   check(c, gtnb_memset(c->ctx, bs.dLinear->ptr, 0, sizeof(float) * std::max<size_t>(B * bs.stride, 1)));
   check(c, gtnb_memset(c->ctx, bs.dGraph->ptr, 0, sizeof(float) * std::max<size_t>(graphTotal, 1)));
   check(c, gtnb_compose_grad(c->ctx, h->lat, bs.dGraph->ptr, bs.dLinear->ptr, (int64_t)bs.stride));
-  // the emission gradients of the whole batch come back in one copy through the context's pinned block;
-  // a per-entry read-back costs ~0.2 ms each (measured: 53 ms for 256 utterances)
-  const size_t n = B * bs.stride;
-  if (c->pinnedCount < n) {
-    if (c->pinned) gtnb_host_free(c->ctx, c->pinned);
-    c->pinned = nullptr;
-    c->pinnedCount = 0;
-    void* p = nullptr;
-    if (gtnb_host_alloc(c->ctx, sizeof(float) * n, &p) == GTNB_OK) {
-      c->pinned = static_cast<float*>(p);
-      c->pinnedCount = n;
-    }
-  }
-  if (c->pinned) {
-    check(c, gtnb_memcpy_d2h(c->ctx, c->pinned, bs.dLinear->ptr, sizeof(float) * n));
-    check(c, gtnb_ctx_synchronize(c->ctx));
-    c->pinnedOwner = &bs;
-  }
+  readBack(c, 0, &bs, bs.dLinear->ptr, B * bs.stride);
   bs.flushed = true;
 }
+
+/* one slice of a batch's gradient: a host copy while the context's pinned block still holds that batch's
+ * read-back, a device read otherwise */
+void fetchBatchSlice(const std::shared_ptr<Context>& c, int slot, const void* owner, const float* dev, size_t off,
+                     size_t n, std::vector<float>& out);
 
 void fetchSlice(const std::shared_ptr<Context>& c, const float* dev, size_t n, std::vector<float>& out) {
   out.resize(n);
@@ -266,19 +275,24 @@ std::vector<Graph> composeBatch(const std::vector<Graph>& a, const std::vector<G
       gLinear.addLazyGrad(emisArcs, [handle, bi, emisArcs, c](std::vector<float>& v) {
         flushLattice(handle);
         BatchState& bs = *handle->batch;
-        {
-          std::lock_guard<std::mutex> l(c->lock);
-          if (c->pinnedOwner == &bs) { // still this batch's read-back: a host copy
-            v.assign(c->pinned + (size_t)bi * bs.stride, c->pinned + (size_t)bi * bs.stride + emisArcs);
-            return;
-          }
-        }
-        fetchSlice(c, bs.dLinear->ptr + (size_t)bi * bs.stride, emisArcs, v);
+        fetchBatchSlice(c, 0, &bs, bs.dLinear->ptr, (size_t)bi * bs.stride, emisArcs, v);
       });
     };
     out.push_back(Graph::fromLattice(handle, bi, gradFunc, {a[i], b[i]}));
   }
   return out;
+}
+
+void fetchBatchSlice(const std::shared_ptr<Context>& c, int slot, const void* owner, const float* dev, size_t off,
+                     size_t n, std::vector<float>& out) {
+  {
+    std::lock_guard<std::mutex> l(c->lock);
+    if (c->pinnedOwner[slot] == owner && c->pinned[slot]) {
+      out.assign(c->pinned[slot] + off, c->pinned[slot] + off + n);
+      return;
+    }
+  }
+  fetchSlice(c, dev + off, n, out);
 }
 
 Graph scalarResult(Graph::GradFunc gradFunc, const Graph& input, float score) {
@@ -315,6 +329,7 @@ void flushLinear(const std::shared_ptr<LinearBatch>& lb) {
   check(c, gtnb_linear_forward(c->ctx, (int)B, lb->T.data(), lb->C, lb->emis->ptr, (int64_t)lb->stride,
                                lb->tropical ? 1 : 0, sdev.ptr, lb->grad->ptr, (int64_t)lb->stride, ddev.ptr, 1.0f));
   check(c, gtnb_ctx_synchronize(c->ctx)); // ddev / sdev go out of scope
+  readBack(c, 1, lb.get(), lb->grad->ptr, B * lb->stride);
   lb->flushed = true;
 }
 
@@ -417,7 +432,7 @@ std::vector<Graph> scoreBatch(const std::vector<Graph>& gs, bool tropical) {
           }
           inputs[0].addLazyGrad(n, [lb, bi, n](std::vector<float>& v) {
             flushLinear(lb);
-            fetchSlice(lb->c, lb->grad->ptr + (size_t)bi * lb->stride, n, v);
+            fetchBatchSlice(lb->c, 1, lb.get(), lb->grad->ptr, (size_t)bi * lb->stride, n, v);
           });
         };
         out.push_back(scalarResult(gradFunc, gs[i], scores[i]));

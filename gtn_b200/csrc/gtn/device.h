@@ -23,9 +23,10 @@ struct Context {
   std::mutex lock; // a lattice may be used from a thread other than its creator
   // pinned read-back block for the batched list ops (gtn/batched.cpp): the whole batch's emission gradient
   // comes back in ONE copy and the entries' lazy gradients are host slices of it while `pinnedOwner` says so
-  float* pinned{nullptr};
-  size_t pinnedCount{0};
-  const void* pinnedOwner{nullptr};
+  // slot 0: a batched lattice's emission gradients, slot 1: a batched normaliser's
+  float* pinned[2]{nullptr, nullptr};
+  size_t pinnedCount[2]{0, 0};
+  const void* pinnedOwner[2]{nullptr, nullptr};
   ~Context();
 };
 

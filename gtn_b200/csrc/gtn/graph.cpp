@@ -21,7 +21,8 @@ namespace gtn {
 namespace detail {
 
 Context::~Context() {
-  if (pinned && ctx) gtnb_host_free(ctx, pinned);
+  for (float* p : pinned)
+    if (p && ctx) gtnb_host_free(ctx, p);
   if (ctx) gtnb_ctx_destroy(ctx);
 }
 

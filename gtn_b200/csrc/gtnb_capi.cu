@@ -926,6 +926,11 @@ int gtnb_lattice_download(
     return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_lattice_download: bad arguments");
   int rc = fetch_sizes(ctx, lat);
   if (rc) return rc;
+  if (lat->order_pending && !lat->order_locked) { // hand the arcs out in the reference's order
+    if ((rc = launch_relax_order(ctx, lat))) return rc;
+    lat->order_pending = false;
+  }
+  lat->order_locked = true;
   const GraphMeta& m = lat->meta_h[b];
   std::vector<uint32_t> rp(m.N + 1);
   std::vector<int32_t> src(std::max(m.A, 1)), gg(std::max(m.A, 1), -1), gl(std::max(m.A, 1), -1);
@@ -1030,6 +1035,7 @@ int gtnb_backward(gtnb_ctx* ctx, gtnb_lattice* lat, int tropical, const float* d
   if (!lat->forward_done || lat->forward_mode != (tropical ? MODE_TROPICAL : MODE_LOG))
     return fail(ctx, GTNB_ERR_LOGIC, "gtnb_backward: no matching gtnb_forward on this lattice");
   GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
+  lat->order_locked = true; // arc gradients are indexed by the current arc order
   float* deltas_dev = nullptr;
   int rc;
   if (deltas_host) {
@@ -1078,6 +1084,7 @@ int gtnb_lattice_set_arc_grads(gtnb_ctx* ctx, gtnb_lattice* lat, int b, const fl
   int rc = fetch_sizes(ctx, lat);
   if (rc) return rc;
   if (!lat->arc_grad && (rc = dev_alloc(ctx, &lat->arc_grad, lat->tot_A))) return rc;
+  lat->order_locked = true;
   const GraphMeta& m = lat->meta_h[b];
   GTNB_CUDA(ctx, cudaMemcpyAsync(lat->arc_grad + m.arc_base, grads_host, sizeof(float) * m.A,
                                  cudaMemcpyHostToDevice, ctx->stream));
@@ -1094,6 +1101,10 @@ int gtnb_viterbi_path(
   int bad = first_bad_status(ctx, lat, status_host);
   int rc;
   if (!lat->back_ptr && (rc = dev_alloc(ctx, &lat->back_ptr, lat->tot_N))) return rc;
+  if (lat->order_pending && !lat->order_locked) {
+    if ((rc = launch_relax_order(ctx, lat))) return rc;
+    lat->order_pending = false;
+  }
   if ((rc = launch_forward(ctx, lat, MODE_PATH))) return rc;
   lat->forward_done = false; // scores now hold the path recursion, not shortestDistance
   int B = lat->B;
@@ -1339,7 +1350,9 @@ int gtnb::compose_linear_impl(
     TRY(upload(ctx, lat->acc_nodes, acc_stage.data(), tc));
     if (!implicit_only) TRY(launch_compose(ctx, lat));
     // exact_ties: rows and accept list in the reference's relaxation / creation order (k_order.cu)
-    if (!implicit_only && ctx->exact_ties) TRY(launch_relax_order(ctx, lat));
+    // ... lazily: only Viterbi paths depend on it, and the sort is the most expensive compose kernel, so it
+    // runs before the first gtnb_viterbi_path unless arc ids were handed out first (download / backward)
+    lat->order_pending = !implicit_only && ctx->exact_ties;
   }
   *out = lat;
   return GTNB_OK;

@@ -87,6 +87,8 @@ struct gtnb_lattice {
   bool level_local = false; // every arc goes level l-1 -> l
   bool forward_done = false;
   bool sizes_known = false;
+  bool order_pending = false; // exact_ties: rows still in compose order; sorted by the first viterbi_path
+  bool order_locked = false; // arc ids already handed out (download / backward): the rows stay as they are
   int forward_mode = -1;
   int C = 0;
   int max_lvl_nodes = 0, max_lvl_arcs = 0; // upper bounds over the batch
