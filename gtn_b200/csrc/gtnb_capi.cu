@@ -639,6 +639,8 @@ int composed_alloc(
 
   long long tn = 0, ta = 0, tl = 0, tc = 0, gg_off = 0;
   int maxT = 0;
+  const int fixed_pitch = (implicit_only && maxN <= kImplicitFixedPitch) ? kImplicitFixedPitch : 0;
+  lat->score_pitch = fixed_pitch;
   for (int b = 0; b < B; b++) {
     if (T[b] < 0) {
       delete lat;
@@ -652,7 +654,9 @@ int composed_alloc(
     long long capA = align_up(std::max<long long>((long long)T[b] * s.A, 1), kAlign);
     if (implicit_only) {
       // implicit lattice (k_implicit.cu): only dense per-frame node scores, rows padded to 16 bytes
-      capN = (long long)(T[b] + 1) * align_up(s.N, kAlign) + kAlign;
+      // (graphs of up to 224 nodes: rows of 224, the fixed pitch of k_bidir.cu's FX kernels; the two sweeps of
+      // k_implicit.cu use the first align_up(N) * (T + 1) floats of the same slab)
+      capN = (long long)(T[b] + 1) * (fixed_pitch ? fixed_pitch : align_up(s.N, kAlign)) + kAlign;
       capA = kAlign;
     }
     if (!implicit_only && (capA >= (1ll << 30) || capN >= (1ll << 30))) {

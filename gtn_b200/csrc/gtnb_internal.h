@@ -79,6 +79,9 @@ struct gtnb_ctx {
   std::string prof_text;
 };
 
+// rows of the saved scores of an implicit lattice whose graphs have at most this many nodes (k_bidir.cu's FX kernels)
+constexpr int kImplicitFixedPitch = 224;
+
 struct gtnb_lattice {
   int B = 0;
   bool composed = false;
@@ -87,6 +90,7 @@ struct gtnb_lattice {
   bool level_local = false; // every arc goes level l-1 -> l
   bool forward_done = false;
   bool sizes_known = false;
+  int score_pitch = 0; // implicit lattices: floats per saved-score row when every row has the same (0: the graph's node count rounded up to 4)
   bool order_pending = false; // exact_ties: rows still in compose order; sorted by the first viterbi_path
   bool order_locked = false; // arc ids already handed out (download / backward): the rows stay as they are
   int forward_mode = -1;

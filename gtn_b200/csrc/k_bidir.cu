@@ -96,6 +96,10 @@ constexpr float kHuge = 1.0e29f; // inputs at or above this magnitude take the e
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kIntMin = -2147483647 - 1;
+// FX kernels (C == 64 or 128): the saved-score rows in HBM, the rows of their shared-memory stages and the
+// overflow area of a posterior row all have this many floats, whatever the utterance's node count -- which makes
+// every per-level address of the node warps base + compile-time constant (no pointer arithmetic on the chain)
+constexpr int kFixedPitch = 32 * kMaxNodeWarps;
 
 struct Layout {
   int off_ring, off_e, off_o, off_g, off_od, off_seg, off_perm, off_nlab, off_hlist, off_red, off_redi,
@@ -124,8 +128,8 @@ inline Layout make_layout(int C, int max_pitch) {
   L.off_g = take(kSG * L.g_block_bytes);
   L.off_od = take(kSO * 16);
   L.off_seg = take(C * 4);
-  L.off_perm = take(kMaxNodes * 4);
-  L.off_nlab = take(kMaxNodes * 4);
+  L.off_perm = take(kMaxNodes * 2); // u16: byte offset of a node's posterior word in a row
+  L.off_nlab = take(kMaxNodes); // s8: a node's label (-1: no in-arcs)
   L.off_hlist = take((kMaxHeavy + 1) * 4 + kMaxHeavy * 12);
   L.off_red = take(32 * 4);
   L.off_redi = take(8 * 4);
@@ -203,6 +207,18 @@ __device__ __forceinline__ void sts_u(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return *emu::shared_ptr<float4>(addr);
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  return *emu::shared_ptr<uint16_t>(addr);
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  *emu::shared_ptr<uint16_t>(addr) = (uint16_t)v;
+}
+__device__ __forceinline__ int lds_s8(uint32_t addr) {
+  return *emu::shared_ptr<int8_t>(addr);
+}
+__device__ __forceinline__ void sts_s8(uint32_t addr, int v) {
+  *emu::shared_ptr<int8_t>(addr) = (int8_t)v;
+}
 __device__ __forceinline__ void smem_max_s32(uint32_t addr, int v) {
   std::atomic_ref<int32_t> a(*emu::shared_ptr<int32_t>(addr));
   int32_t cur = a.load();
@@ -267,22 +283,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-/* for the warps that wait a whole block ahead of the math: sleep between polls */
+/* for the warps that wait a whole block ahead of the math: the try_wait suspends the thread in hardware for up
+ * to the hinted time (ns) and wakes it when the phase completes -- no issue slots spent polling (the former
+ * nanosleep loop was 3 % of the kernel's instructions) */
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (;;) {
+  do {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
-    if (done) break;
-    __nanosleep(400);
-  }
+  } while (!done);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -313,6 +329,22 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds_s8(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_s8(uint32_t addr, int v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void smem_max_s32(uint32_t addr, int v) { // native ATOMS.MAX.S32
   asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -423,12 +455,26 @@ __device__ __forceinline__ void fetch_block_adjust(NodeState& st) {
   st.D += off;
 }
 
+/* strides of the per-level accesses: compile-time constants in the FX kernels */
+template <int NQ, bool FX>
+struct Strd {
+  __device__ __forceinline__ static int c4(const NodeUni& un) { return FX ? 256 * NQ : un.c4; }
+  __device__ __forceinline__ static int p4(const NodeUni& un) { return FX ? 4 * kFixedPitch : un.p4; }
+  __device__ __forceinline__ static int g4(const NodeUni& un) {
+    return FX ? 4 * (kSlots * 64 * NQ + kFixedPitch) : un.g4;
+  }
+  __device__ __forceinline__ static int pitch(const NodeUni& un) { return FX ? kFixedPitch : un.pitch; }
+};
+
 /* one level.  DIR 0: CTA A (alpha), 1: CTA B (beta).  PH 1: save the score; 2: posterior in place.
- * LAST: the block's last level (publishes the maximum for the renormalisation) */
-template <int DIR, int PH, bool ZW>
-__device__ __forceinline__ void node_step(NodeState& st, const NodeUni& un, bool last) {
-  const float x = lds(st.ea);
-  st.ea += DIR ? -un.c4 : un.c4;
+ * r: the level's row within the block, counted in the CTA's own direction from the row st.ea / st.oa / st.ga /
+ * st.gs point at (a constant after unrolling: with FX every address is register + immediate).
+ * last: the block's last level (publishes the maximum for the renormalisation) */
+template <int DIR, int PH, bool ZW, int NQ, bool FX>
+__device__ __forceinline__ void node_step(NodeState& st, const NodeUni& un, int r, bool last) {
+  using SD = Strd<NQ, FX>;
+  const int rr = DIR ? -r : r;
+  const float x = lds(st.ea + (uint32_t)(rr * SD::c4(un)));
   // ZW: every arc weight of the graph is 0 (CTC, forced alignment): no adds
   const float v = ZW ? lse3(lds(st.pc + st.so0), lds(st.pc + st.so1), lds(st.pc + st.so2))
                      : lse3(lds(st.pc + st.so0) + st.w0, lds(st.pc + st.so1) + st.w1, lds(st.pc + st.so2) + st.w2);
@@ -439,31 +485,28 @@ __device__ __forceinline__ void node_step(NodeState& st, const NodeUni& un, bool
   sts(st.qc + st.u4, stored);
   if (PH == 2) {
     // the posterior, written into the node's slot of the helpers' block
-    sts(st.ga, ex2(((val - st.Zh) + lds(st.oa)) - st.zsub));
-    st.oa += DIR ? -un.p4 : un.p4;
-    st.ga += DIR ? -un.g4 : un.g4;
+    sts(st.ga + (uint32_t)(rr * SD::g4(un)), ex2(((val - st.Zh) + lds(st.oa + (uint32_t)(rr * SD::p4(un)))) - st.zsub));
   }
   if (last) publish_block_max(st, stored);
   bar_named(1, un.nact);
-  if (PH == 1) { // after the barrier: nothing waits for it
-    stg(st.gs, val);
-    st.gs += DIR ? -un.pitch : un.pitch;
-  }
+  if (PH == 1) stg(st.gs + rr * SD::pitch(un), val); // after the barrier: nothing waits for it
   const uint32_t t = st.pc;
   st.pc = st.qc;
   st.qc = t;
 }
 
-template <int DIR, int PH, bool ZW>
+/* n levels from the rows st.ea / st.oa / st.ga / st.gs point at; st.gs moves on, the others are set per block */
+template <int DIR, int PH, bool ZW, int NQ, bool FX>
 __device__ __forceinline__ void node_rows(NodeState& st, const NodeUni& un, int n) {
   // (a rolled loop with the last level peeled was measured slower: 0.419 vs 0.389 ms at config 2)
   if (n == kBlk) {
 #pragma unroll
-    for (int r = 0; r < kBlk; r++) node_step<DIR, PH, ZW>(st, un, r == kBlk - 1);
+    for (int r = 0; r < kBlk; r++) node_step<DIR, PH, ZW, NQ, FX>(st, un, r, r == kBlk - 1);
   } else {
 #pragma unroll 1
-    for (int r = 0; r < n; r++) node_step<DIR, PH, ZW>(st, un, r == n - 1);
+    for (int r = 0; r < n; r++) node_step<DIR, PH, ZW, NQ, FX>(st, un, r, r == n - 1);
   }
+  if (PH == 1) st.gs += (DIR ? -n : n) * Strd<NQ, FX>::pitch(un);
 }
 
 /* reduction over the node threads of the CTA (named barrier 1): max, then sum */
@@ -496,12 +539,13 @@ __device__ __forceinline__ float node_reduce_sum(float v, uint32_t red, int warp
  * level's posterior follows.  An utterance without any accepting path (Z = kNeg-like) gets Zh = +1e30,
  * which makes every posterior ex2(-huge) = 0.  `doth`: the partner's offset for this block.
  */
-template <int DIR, bool ZW>
+template <int DIR, bool ZW, int NQ, bool FX>
 __device__ __forceinline__ void node_first_phase2(
     NodeState& st, const NodeUni& un, bool act, uint32_t red, int warp, int nwarps, float doth, bool last,
-    float* z_out) {
+    float* z_out, uint32_t feas_a, uint32_t spare) {
+  using SD = Strd<NQ, FX>;
   const float x = lds(st.ea);
-  st.ea += DIR ? -un.c4 : un.c4;
+  st.ea += DIR ? -SD::c4(un) : SD::c4(un);
   const float v = ZW ? lse3(lds(st.pc + st.so0), lds(st.pc + st.so1), lds(st.pc + st.so2))
                      : lse3(lds(st.pc + st.so0) + st.w0, lds(st.pc + st.so1) + st.w1, lds(st.pc + st.so2) + st.w2);
   const float val = DIR == 0 ? v + fmaf(x, kLog2e, -st.adj) : v - st.adj;
@@ -522,11 +566,14 @@ __device__ __forceinline__ void node_first_phase2(
   st.Zl = feasible ? lg2(S) : 0.0f;
   st.Dc = st.D + doth;
   st.zsub = st.Zl;
+  // the posterior mass of a level (1, or 0 without an accepting path): the helper warps take the mass on the
+  // label with the most nodes as this minus the other labels' (visible to them through g_full)
+  if (threadIdx.x == 0) sts(feas_a, feasible ? 1.0f : 0.0f);
   if (z_out && threadIdx.x == 0)
     *z_out = feasible ? (float)(((double)st.Dc + ((double)m + (double)st.Zl)) * 0.6931471805599453) : -CUDART_INF_F;
   sts(st.ga, ex2(((val - st.Zh) + o) - st.zsub));
-  st.oa += DIR ? -un.p4 : un.p4;
-  st.ga += DIR ? -un.g4 : un.g4;
+  st.oa += DIR ? -SD::p4(un) : SD::p4(un);
+  if (st.ga != spare) st.ga += DIR ? -SD::g4(un) : SD::g4(un); // (loss only: the one posterior goes to the spare word)
   if (last) publish_block_max(st, stored);
   bar_named(1, un.nact);
   const uint32_t t = st.pc;
@@ -540,7 +587,7 @@ struct NodeCtx {
   float* saved;
   float* boff_own;
   float* out_score;
-  uint32_t bars, e_base, o_base, g_base, od_base, perm_a, red_a, spare, lab4;
+  uint32_t bars, e_base, o_base, g_base, od_base, perm_a, red_a, spare, lab4, feas_a;
   int e_stage_bytes, o_stage_bytes, g_block_bytes, pg, C, T, pitch, nblk, n_ph1, n_ph2, nw_act;
   bool want_g;
 };
@@ -574,7 +621,7 @@ __device__ __forceinline__ uint32_t bar_tbl_ready(uint32_t bars) {
  * direction is folded into per-thread base addresses up front, so that a block costs its levels plus a
  * few dozen instructions.
  */
-template <int DIR, bool ZW>
+template <int DIR, bool ZW, int NQ, bool FX>
 __device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool act, int nid) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   NodeUni un;
@@ -602,7 +649,7 @@ __device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool
       st.ea = e_row0 + (uint32_t)(s * cx.e_stage_bytes);
       if (v > 0) fetch_block_adjust(st);
       if (tid == 0) stg(cx.boff_own + 4 * v, st.D);
-      node_rows<0, 1, ZW>(st, un, kBlk); // A's phase-1 blocks are always full
+      node_rows<0, 1, ZW, NQ, FX>(st, un, kBlk); // A's phase-1 blocks are always full
       __syncwarp();
       if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, s), arr1);
     }
@@ -623,7 +670,7 @@ __device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool
       stg(st.gs, val);
       st.gs -= un.pitch;
     }
-    node_rows<1, 1, ZW>(st, un, n0 - 1);
+    node_rows<1, 1, ZW, NQ, FX>(st, un, n0 - 1);
     __syncwarp();
     if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, 0), arr1);
     for (v = 1; v < cx.n_ph1; v++) {
@@ -632,7 +679,7 @@ __device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool
       st.ea = e_row0 + (uint32_t)(s * cx.e_stage_bytes);
       fetch_block_adjust(st);
       if (tid == 0) stg(cx.boff_own + 4 * (cx.nblk - 1 - v), st.D);
-      node_rows<1, 1, ZW>(st, un, kBlk);
+      node_rows<1, 1, ZW, NQ, FX>(st, un, kBlk);
       __syncwarp();
       if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, s), arr1);
     }
@@ -646,10 +693,10 @@ __device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool
   int g_stride = 0;
   if (cx.want_g) {
     mbar_wait(bar_tbl_ready(cx.bars), 0); // the helper warps' tables
-    g_row0 = cx.g_base + lds_u(cx.perm_a + 4u * (uint32_t)nid) + (DIR ? (uint32_t)((kBlk - 1) * cx.pg * 4) : 0u);
+    g_row0 = cx.g_base + lds_u16(cx.perm_a + 2u * (uint32_t)nid) + (DIR ? (uint32_t)((kBlk - 1) * cx.pg * 4) : 0u);
     g_stride = cx.g_block_bytes;
   } else {
-    un.g4 = 0; // loss only: the posterior of the one level goes to the spare word
+    // loss only: the posterior of the one level goes to the spare word
   }
   for (int v2 = 0; v2 < cx.n_ph2; v2++, v++) {
     const int s = v & (kSE - 1), so = v2 & (kSO - 1), sg = v2 & (kSG - 1);
@@ -664,13 +711,13 @@ __device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool
     if (v > 0) fetch_block_adjust(st);
     const float doth = lds(cx.od_base + 16u * so);
     if (v2 == 0) {
-      node_first_phase2<DIR, ZW>(st, un, act, cx.red_a, warp, cx.nw_act, doth, nfr == 1,
-                                 DIR == 0 ? cx.out_score : nullptr);
-      if (cx.want_g) node_rows<DIR, 2, ZW>(st, un, nfr - 1);
+      node_first_phase2<DIR, ZW, NQ, FX>(st, un, act, cx.red_a, warp, cx.nw_act, doth, nfr == 1,
+                                         DIR == 0 ? cx.out_score : nullptr, cx.feas_a, cx.spare);
+      if (cx.want_g) node_rows<DIR, 2, ZW, NQ, FX>(st, un, nfr - 1);
     } else {
       // offsets moved since the meeting level: all integers, the differences are exact
       st.zsub = st.Zl - ((st.D + doth) - st.Dc);
-      node_rows<DIR, 2, ZW>(st, un, nfr);
+      node_rows<DIR, 2, ZW, NQ, FX>(st, un, nfr);
     }
     __syncwarp();
     if (lane == 0) {
@@ -734,7 +781,7 @@ struct HelperConst {
 template <int NQ, bool WANT_G>
 __device__ __forceinline__ void helper_block(
     HelperState& hs, const HelperConst<NQ>& k, int nfr, uint32_t estage, uint32_t e_empty_bar, uint32_t gblock,
-    uint32_t g_empty_bar, int nheavy, float* gout) {
+    uint32_t g_empty_bar, int nheavy, bool has_comp, uint32_t feas_a, float* gout) {
   const bool row_on = hs.r < nfr;
   float4 x[NQ];
   float mx = -3.0e38f;
@@ -783,13 +830,19 @@ __device__ __forceinline__ void helper_block(
         hsum[h] = half_sum(a0 + a1);
       }
     }
+    float o[4 * NQ];
+    float part = 0.0f; // this lane's labels' mass, the complement label aside
 #pragma unroll
     for (int i = 0; i < NQ; i++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) o[4 * i + j] = 0.0f;
       if (row_on && k.eoff[i] != 0xffffffffu) {
         const uint32_t a = gblock + k.goff[i];
         const float4 g0 = lds_v4(a), g1 = lds_v4(a + 16), g2 = lds_v4(a + 32), g3 = lds_v4(a + 48);
-        float o[4] = {(g0.x + g0.y) + (g0.z + g0.w), (g1.x + g1.y) + (g1.z + g1.w), (g2.x + g2.y) + (g2.z + g2.w),
-                      (g3.x + g3.y) + (g3.z + g3.w)};
+        o[4 * i + 0] = (g0.x + g0.y) + (g0.z + g0.w);
+        o[4 * i + 1] = (g1.x + g1.y) + (g1.z + g1.w);
+        o[4 * i + 2] = (g2.x + g2.y) + (g2.z + g2.w);
+        o[4 * i + 3] = (g3.x + g3.y) + (g3.z + g3.w);
         if (k.hsel[i]) { // some label of the chunk has more than kSlots nodes
 #pragma unroll
           for (int j = 0; j < 4; j++) {
@@ -800,17 +853,33 @@ __device__ __forceinline__ void helper_block(
               const uint32_t p = gblock + k.ovf + (w & 1023u) * 4u;
               float acc = 0.0f;
               for (int q = 0; q < len; q++) acc += lds(p + 4u * q);
-              o[j] = acc;
+              o[4 * i + j] = acc;
+            } else if (s1 == 14) { // the complement label: nothing was stored for it
+              o[4 * i + j] = 0.0f;
             } else if (s1) {
 #pragma unroll
               for (int h = 0; h < kMaxHeavy; h++)
-                if (h == s1 - 1) o[j] = hsum[h];
+                if (h == s1 - 1) o[4 * i + j] = hsum[h];
             }
           }
         }
+        part += (o[4 * i + 0] + o[4 * i + 1]) + (o[4 * i + 2] + o[4 * i + 3]);
+      }
+    }
+    if (has_comp) { // mass on the label with the most nodes = the level's mass - everybody else's
+      const float cm = lds(feas_a) - half_sum(part);
+#pragma unroll
+      for (int i = 0; i < NQ; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (((k.hsel[i] >> (4 * j)) & 15) == 14) o[4 * i + j] = cm;
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+      if (row_on && k.eoff[i] != 0xffffffffu) {
         // d(forwardScore(e) - forwardScore(lattice)) / d e[f][c] = softmax - posterior mass on label c
-        stg_v4(gout + (k.eoff[i] >> 2), make_float4(fmaf(x[i].x, inv, -o[0]), fmaf(x[i].y, inv, -o[1]),
-                                                    fmaf(x[i].z, inv, -o[2]), fmaf(x[i].w, inv, -o[3])));
+        stg_v4(gout + (k.eoff[i] >> 2), make_float4(fmaf(x[i].x, inv, -o[4 * i + 0]), fmaf(x[i].y, inv, -o[4 * i + 1]),
+                                                    fmaf(x[i].z, inv, -o[4 * i + 2]), fmaf(x[i].w, inv, -o[4 * i + 3])));
       }
     }
     __syncwarp();
@@ -828,7 +897,7 @@ __device__ __forceinline__ void helper_block(
 template <int NQ>
 __device__ __forceinline__ void helper_block_fast(
     HelperState& hs, uint32_t ea, uint32_t e_empty_bar, uint32_t ga, uint32_t ovf_row, uint32_t htab, int nheavy,
-    uint32_t g_empty_bar, float* gout) {
+    bool has_comp, int comp_rel, uint32_t feas_a, uint32_t g_empty_bar, float* gout) {
   float4 x[NQ];
 #pragma unroll
   for (int i = 0; i < NQ; i++) x[i] = lds_v4(ea + 256u * i); // chunk i: labels 64 i + 4 l16 .. + 3
@@ -873,22 +942,34 @@ __device__ __forceinline__ void helper_block_fast(
     o[4 * i + 3] = (g3.x + g3.y) + (g3.z + g3.w);
   }
   // the labels carried by many nodes: the row's 16 lanes sum their positions together
-  for (int h = 0; h < nheavy; h++) {
-    const int hc = (int)lds_u(htab + 12u * h), hlen = (int)lds_u(htab + 12u * h + 8);
-    const uint32_t ha = ovf_row + 4u * lds_u(htab + 12u * h + 4);
-    float a0 = 0.0f, a1 = 0.0f;
-    const uint32_t hq = ha + 4u * hs.l16;
+  // (htab: label | first overflow position << 8 | nodes << 18)
 #pragma unroll 1
-    for (int q0 = 0; q0 < hlen; q0 += 32) { // the same trip count in every lane
+  for (int h = 0; h < nheavy; h++) {
+    const uint32_t w = lds_u(htab + 4u * h);
+    const int hlen = (int)(w >> 18);
+    const uint32_t hq = ovf_row + 4u * ((w >> 8) & 1023u) + 4u * hs.l16;
+    float a0 = hs.l16 < hlen ? lds(hq) : 0.0f;
+    for (int q0 = 16; q0 < hlen; q0 += 16) // (rare: a label on more than 16 nodes that is not the complement label)
       if (q0 + hs.l16 < hlen) a0 += lds(hq + 4u * q0);
-      if (q0 + 16 + hs.l16 < hlen) a1 += lds(hq + 4u * q0 + 64u);
-    }
-    const float hsum = half_sum(a0 + a1);
-    const int rel = hc - 4 * hs.l16; // which of this lane's labels (64 i + 4 l16 + j  ->  4 i + j), if any
+    const float hsum = half_sum(a0);
+    const int rel = (int)(w & 255u) - 4 * hs.l16; // which of this lane's labels (64 i + 4 l16 + j  ->  64 i + j), if any
 #pragma unroll
     for (int i = 0; i < NQ; i++) {
 #pragma unroll
       for (int j = 0; j < 4; j++) o[4 * i + j] = rel == 64 * i + j ? hsum : o[4 * i + j];
+    }
+  }
+  if (has_comp) {
+    // the label with the most nodes (CTC: blank, half of all nodes): its nodes stored nothing; its mass is the
+    // level's mass (1, or 0 for an utterance without an accepting path) minus everybody else's
+    float part = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NQ; i++) part += (o[4 * i + 0] + o[4 * i + 1]) + (o[4 * i + 2] + o[4 * i + 3]);
+    const float cm = lds(feas_a) - half_sum(part);
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) o[4 * i + j] = comp_rel == 64 * i + j ? cm : o[4 * i + j];
     }
   }
   // d(forwardScore(e) - forwardScore(lattice)) / d e[f][c] = softmax - posterior mass on label c
@@ -906,7 +987,7 @@ __device__ __forceinline__ void helper_block_fast(
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
 
-template <int NQ, bool ZW>
+template <int NQ, bool ZW, bool FX>
 __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_ctc_kernel(const Params P) {
   GTNB_DYNAMIC_SMEM_128(unsigned char, smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -914,7 +995,7 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
   const int dir = (int)cluster_rank(); // 0: CTA A (alpha), 1: CTA B (beta)
   const GraphMeta m = P.meta[b];
   const int N1 = m.sg_N, T = m.T, C = P.C;
-  const int pitch = (N1 + 3) & ~3;
+  const int pitch = FX ? kFixedPitch : ((N1 + 3) & ~3); // floats per saved-score row (HBM and stages)
   const bool want_g = P.grad != nullptr;
   const Layout& L = P.lay;
   float* ring = reinterpret_cast<float*>(smem + L.off_ring);
@@ -994,7 +1075,7 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
     my_deg = ip[tid + 1] - e0;
     if (my_deg > 0) my_lab = il[e0];
     // node labels for the helper warps' tables
-    sts_u(nlab_a + 4u * tid, (uint32_t)(my_deg > 0 ? my_lab : -1));
+    sts_s8(nlab_a + (uint32_t)tid, my_deg > 0 ? my_lab : -1);
     if (dir == 1)
       for (int k = 0; k < my_deg; k++) {
         const int s = is[e0 + k];
@@ -1080,6 +1161,7 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
     cx.red_a = red_a;
     cx.spare = spare;
     cx.lab4 = lab4;
+    cx.feas_a = hlist_a + 96u;
     cx.e_stage_bytes = L.e_stage_bytes;
     cx.o_stage_bytes = L.o_stage_bytes;
     cx.g_block_bytes = L.g_block_bytes;
@@ -1093,9 +1175,9 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
     cx.nw_act = nw_act;
     cx.want_g = want_g;
     if (dir == 0)
-      node_role<0, ZW>(st, cx, act, nid);
+      node_role<0, ZW, NQ, FX>(st, cx, act, nid);
     else
-      node_role<1, ZW>(st, cx, act, nid);
+      node_role<1, ZW, NQ, FX>(st, cx, act, nid);
     if (bad) atomicOr(&P.status[b], 1);
     if (T == 0 && dir == 0 && tid == 0) {
       // no frames: the lattice is the graph's start-and-accept nodes, each with score 0
@@ -1166,15 +1248,27 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
     // behind the slots.  Nodes without in-arcs (they exist at level 0 only) go behind everything.
     for (int c = ht; c < C; c += 32 * kHelpers) {
       int n = 0;
-      for (int u = 0; u < N1; u++) n += (int)lds_u(nlab_a + 4u * u) == c;
+      for (int u = 0; u < N1; u++) n += lds_s8(nlab_a + (uint32_t)u) == c;
       sts_u(seg_a + 4u * c, (uint32_t)n);
     }
     bar_named(2, 32 * kHelpers);
     if (ht == 0) {
+      // the label with the most nodes, when it has more than kSlots (CTC: blank): the complement label
+      int comp = -1, cn = kSlots;
+      for (int c = 0; c < C; c++) {
+        const int n = (int)lds_u(seg_a + 4u * c);
+        if (n > cn) {
+          cn = n;
+          comp = c;
+        }
+      }
+      sts_u(hlist_a + 100u, (uint32_t)comp);
       int nh = 0, at = 0;
       for (int c = 0; c < C; c++) {
         const int n = (int)lds_u(seg_a + 4u * c);
-        if (n > kSlots) {
+        if (c == comp) {
+          sts_u(seg_a + 4u * c, seg_pack(0, n, 14));
+        } else if (n > kSlots) {
           int slot1 = 15;
           if (nh < kMaxHeavy) {
             sts_u(hlist_a + 4u * nh, (uint32_t)c);
@@ -1188,15 +1282,18 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
       }
       sts_u(hlist_a + 4u * kMaxHeavy, (uint32_t)nh);
       for (int u = 0; u < N1; u++)
-        if ((int)lds_u(nlab_a + 4u * u) < 0) sts_u(perm_a + 4u * u, 4u * (uint32_t)(kSlots * C + at++));
+        if (lds_s8(nlab_a + (uint32_t)u) < 0) sts_u16(perm_a + 2u * u, 4u * (uint32_t)(kSlots * C + at++));
     }
     bar_named(2, 32 * kHelpers);
     nheavy = (int)lds_u(hlist_a + 4u * kMaxHeavy);
     for (int c = ht; c < C; c += 32 * kHelpers) {
       const uint32_t w = lds_u(seg_a + 4u * c);
-      uint32_t at = (w >> 20) ? (uint32_t)(kSlots * C) + (w & 1023u) : (uint32_t)(kSlots * c);
+      const uint32_t s1 = w >> 20;
+      // the complement label's nodes all store into the row's last word, which nobody reads (with >= 5 of them
+      // out of the overflow area it is never an overflow position)
+      uint32_t at = s1 == 14u ? (uint32_t)(L.pg - 1) : s1 ? (uint32_t)(kSlots * C) + (w & 1023u) : (uint32_t)(kSlots * c);
       for (int u = 0; u < N1; u++)
-        if ((int)lds_u(nlab_a + 4u * u) == c) sts_u(perm_a + 4u * u, 4u * (at++));
+        if (lds_s8(nlab_a + (uint32_t)u) == c) sts_u16(perm_a + 2u * u, 4u * (s1 == 14u ? at : at++));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(tbl_ready);
@@ -1229,7 +1326,7 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
       const int s = v % kSE;
       mbar_wait_relaxed(e_full(s), (v / kSE) & 1);
       helper_block<NQ, false>(hs, hk, rows_of(block_of(v)), e_base + (uint32_t)(s * L.e_stage_bytes), e_empty(s), 0, 0,
-                              0, nullptr);
+                              0, false, 0, nullptr);
     }
   }
   cluster_sync_all();
@@ -1239,15 +1336,17 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
     int n15 = 0;
     for (int c = 0; c < C; c++) n15 += ((lds_u(seg_a + 4u * c) >> 20) & 15u) == 15u;
     const bool fast = C == 64 * NQ && n15 == 0;
-    // {label, overflow start, nodes} of the cooperative labels, for helper_block_fast
+    // label | overflow start << 8 | nodes << 18 of the cooperative labels, for helper_block_fast
     const uint32_t htab = hlist_a + 4u * (kMaxHeavy + 1);
     if (lane < nheavy) { // (every helper warp writes the same values)
       const uint32_t hc = lds_u(hlist_a + 4u * lane), w = lds_u(seg_a + 4u * hc);
-      sts_u(htab + 12u * lane, hc);
-      sts_u(htab + 12u * lane + 4, w & 1023u);
-      sts_u(htab + 12u * lane + 8, (w >> 10) & 1023u);
+      sts_u(htab + 4u * lane, hc | ((w & 1023u) << 8) | (((w >> 10) & 1023u) << 18));
     }
     __syncwarp();
+    const int comp = (int)lds_u(hlist_a + 100u);
+    const bool has_comp = comp >= 0;
+    const int comp_rel = has_comp ? comp - 4 * hs.l16 : -1000;
+    const uint32_t feas_a = hlist_a + 96u;
     const uint32_t f_e = (uint32_t)(hs.r * C + 4 * hs.l16) * 4u, f_g = (uint32_t)(hs.r * L.pg + kSlots * 4 * hs.l16) * 4u;
     float* const f_out = P.grad + (long long)b * P.grad_stride + hs.r * C + 4 * hs.l16;
     for (int v2 = 0; v2 < n_ph2; v2++, v++) {
@@ -1258,11 +1357,11 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
       if (fast && rows_of(j) == kBlk) {
         const uint32_t gb = g_base + (uint32_t)(sg * L.g_block_bytes);
         helper_block_fast<NQ>(hs, e_base + (uint32_t)(s * L.e_stage_bytes) + f_e, e_empty(s), gb + f_g, gb + hk.ovf, htab,
-                              nheavy, g_empty(sg), f_out + (long long)j * kBlk * C);
+                              nheavy, has_comp, comp_rel, feas_a, g_empty(sg), f_out + (long long)j * kBlk * C);
         continue;
       }
       helper_block<NQ, true>(hs, hk, rows_of(j), e_base + (uint32_t)(s * L.e_stage_bytes), e_empty(s),
-                             g_base + (uint32_t)(sg * L.g_block_bytes), g_empty(sg), nheavy,
+                             g_base + (uint32_t)(sg * L.g_block_bytes), g_empty(sg), nheavy, has_comp, feas_a,
                              P.grad + (long long)b * P.grad_stride + (long long)j * kBlk * C);
     }
   }
@@ -1277,6 +1376,8 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
 
 #ifndef GTNB_HOST_EMU
 
+static_assert(bidir::kFixedPitch == kImplicitFixedPitch, "gtnb_compose_linear allocates the rows");
+
 /* true when every utterance of the batch qualifies for the bidirectional kernel */
 bool bidir_supported(const gtnb_lattice* lat, const float* emissions, int64_t stride, const float* grad, int64_t grad_stride) {
   if (!lat->composed || lat->C % 4 != 0 || lat->C > 128 || lat->C < 4) return false;
@@ -1285,6 +1386,8 @@ bool bidir_supported(const gtnb_lattice* lat, const float* emissions, int64_t st
   if (grad && (((uintptr_t)grad & 15) || (grad_stride & 3))) return false;
   for (int b = 0; b < lat->B; b++)
     if (!lat->meta_h[b].sg_uniform || !lat->meta_h[b].sg_all_valid || lat->meta_h[b].sg_N < 1) return false;
+  // the saved-score rows: the graph's node count rounded up to 4, or the fixed pitch of the FX kernels
+  if (lat->score_pitch != 0 && lat->score_pitch != bidir::kFixedPitch) return false;
   return true;
 }
 
@@ -1320,12 +1423,21 @@ int launch_bidir_ctc(
   P.grad_stride = grad_stride;
   P.C = lat->C;
   P.nwn = std::max(1, (lat->max_lvl_nodes + 31) / 32);
-  const int max_pitch = (lat->max_lvl_nodes + 3) & ~3;
+  // FX: the benchmark's shapes (C == 64 or 128) on a lattice whose saved-score rows were allocated with the
+  // fixed pitch (gtnb_compose_linear, implicit lattices): compile-time strides in the node warps
+  const bool fx = (lat->C == 64 || lat->C == 128) && lat->score_pitch == bidir::kFixedPitch;
+  const int max_pitch = fx ? bidir::kFixedPitch : ((lat->max_lvl_nodes + 3) & ~3);
   P.lay = bidir::make_layout(lat->C, max_pitch);
-  // float4 chunks of an emission row per helper lane
-  void (*kern)(const bidir::Params) =
-      lat->C <= 64 ? (zero_w ? bidir::bidir_ctc_kernel<1, true> : bidir::bidir_ctc_kernel<1, false>)
-                   : (zero_w ? bidir::bidir_ctc_kernel<2, true> : bidir::bidir_ctc_kernel<2, false>);
+  // NQ: float4 chunks of an emission row per helper lane
+  void (*kern)(const bidir::Params);
+  if (fx && lat->C == 64)
+    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, true> : bidir::bidir_ctc_kernel<1, false, true>;
+  else if (fx)
+    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, true> : bidir::bidir_ctc_kernel<2, false, true>;
+  else if (lat->C <= 64)
+    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, false> : bidir::bidir_ctc_kernel<1, false, false>;
+  else
+    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, false> : bidir::bidir_ctc_kernel<2, false, false>;
   P.zero_w = zero_w;
   if (P.lay.total > 48 * 1024) {
     int rc = ensure_max_smem(ctx, (const void*)kern);

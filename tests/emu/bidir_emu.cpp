@@ -27,6 +27,7 @@ int emu_bidir_ctc(
   std::vector<int32_t> tgt_off(B);
   long long nodes = 0, arcs = 0, scores_len = 0, acc = 0, toff = 0;
   int maxN = 0;
+  const bool fx = C == 64 || C == 128; // launch_bidir_ctc's rule: fixed row pitch for the FX kernels
   for (int b = 0; b < B; b++) {
     const int L = 2 * target_lens[b] + 1;
     GraphMeta& m = meta[b];
@@ -43,7 +44,7 @@ int emu_bidir_ctc(
     nodes += L + 1;
     arcs += 3 * L;
     acc += 2;
-    scores_len += (long long)(T + 1) * ((L + 3) & ~3);
+    scores_len += (long long)(T + 1) * (fx ? bidir::kFixedPitch : ((L + 3) & ~3));
     maxN = std::max(maxN, L);
   }
   std::vector<uint8_t> flags(nodes, 0);
@@ -82,15 +83,19 @@ int emu_bidir_ctc(
   P.C = C;
   P.zero_w = zero_w;
   P.nwn = std::max(1, (maxN + 31) / 32);
-  P.lay = bidir::make_layout(C, (maxN + 3) & ~3);
+  P.lay = bidir::make_layout(C, fx ? bidir::kFixedPitch : ((maxN + 3) & ~3));
   const unsigned block = 32 * (P.nwn + 1 + bidir::kHelpers);
   emu::launch_clusters(2 * B, 2, block, P.lay.total, [&] {
     // ctc_build_kernel writes weight 0 on every arc: the zero-weight variant, as gtnb_ctc_loss launches it;
     // zero_w = 0 exercises the general one on the same graphs
-    if (C <= 64)
-      zero_w ? bidir::bidir_ctc_kernel<1, true>(P) : bidir::bidir_ctc_kernel<1, false>(P);
+    if (fx && C == 64)
+      zero_w ? bidir::bidir_ctc_kernel<1, true, true>(P) : bidir::bidir_ctc_kernel<1, false, true>(P);
+    else if (fx)
+      zero_w ? bidir::bidir_ctc_kernel<2, true, true>(P) : bidir::bidir_ctc_kernel<2, false, true>(P);
+    else if (C <= 64)
+      zero_w ? bidir::bidir_ctc_kernel<1, true, false>(P) : bidir::bidir_ctc_kernel<1, false, false>(P);
     else
-      zero_w ? bidir::bidir_ctc_kernel<2, true>(P) : bidir::bidir_ctc_kernel<2, false>(P);
+      zero_w ? bidir::bidir_ctc_kernel<2, true, false>(P) : bidir::bidir_ctc_kernel<2, false, false>(P);
   });
   if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads;
   for (int b = 0; b < B; b++) {
