@@ -191,8 +191,28 @@ bool batchComposable(const std::vector<Graph>& a, const std::vector<Graph>& b, b
 
 std::vector<Graph> composeBatch(const std::vector<Graph>& a, const std::vector<Graph>& b, bool intersectMode) {
   bool linearFirst = false;
-  if (!batchComposable(a, b, &linearFirst))
+  if (!batchComposable(a, b, &linearFirst)) {
+    // B arbitrary pairs (no emissions chain among them): one launch of k_gcompose.cu, one CTA per pair
+    const size_t n = std::max(a.size(), b.size());
+    const int policy = detail::composeDevicePolicy();
+    bool general = n >= 2 && policy != 2 && detail::deviceCount() > 0 && (a.size() == n || a.size() == 1) &&
+                   (b.size() == n || b.size() == 1);
+    double states = 0.0;
+    for (size_t i = 0; general && i < n; i++) {
+      const Graph& x = a[a.size() == 1 ? 0 : i];
+      const Graph& y = b[b.size() == 1 ? 0 : i];
+      general = !x.isLinear() && !y.isLinear() && !x.isDeviceResident() && !y.isDeviceResident();
+      states += (double)x.numNodes() * (double)y.numNodes();
+    }
+    if (general && (policy == 1 || states >= 16384.0)) {
+      std::vector<const Graph*> pa(a.size()), pb(b.size());
+      for (size_t i = 0; i < a.size(); i++) pa[i] = &a[i];
+      for (size_t i = 0; i < b.size(); i++) pb[i] = &b[i];
+      std::vector<Graph> out;
+      if (detail::composeGraphsDevice(pa, pb, intersectMode, out)) return out;
+    }
     return parallelMap(intersectMode ? single2(intersect) : single2(compose), a, b);
+  }
   const size_t B = a.size();
   auto c = detail::threadContext();
   std::vector<const Graph*> lin(B), gr(B);

@@ -12,6 +12,7 @@
 #include "gtn/functions.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <limits>
 #include <queue>
@@ -428,12 +429,135 @@ bool composeLinearDevice(const Graph& first, const Graph& second, bool linearFir
   return true;
 }
 
+} // namespace
+
+namespace {
+int g_composePolicy = -1;
+}
+
+int deviceCount() {
+  static const int n = [] {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+      cudaGetLastError();
+      c = 0;
+    }
+    return c;
+  }();
+  return n;
+}
+
+int composeDevicePolicy() {
+  if (g_composePolicy < 0) {
+    const char* e = std::getenv("GTNB_COMPOSE_DEVICE");
+    const std::string v = e ? e : "auto";
+    g_composePolicy = v == "always" ? 1 : (v == "never" ? 2 : 0);
+  }
+  return g_composePolicy;
+}
+
+void setComposeDevicePolicy(int policy) {
+  g_composePolicy = policy;
+}
+
+bool composeGraphsDevice(
+    const std::vector<const Graph*>& first, const std::vector<const Graph*>& second, bool intersectMode,
+    std::vector<Graph>& out) {
+  const size_t B = std::max(first.size(), second.size());
+  if (first.empty() || second.empty() || (first.size() != B && first.size() != 1) ||
+      (second.size() != B && second.size() != 1))
+    return false;
+  auto c = threadContext();
+  std::vector<ViewStorage> v1(first.size()), v2(second.size());
+  std::vector<gtnb_graph_view> w1(first.size()), w2(second.size());
+  for (size_t i = 0; i < first.size(); i++) {
+    makeView(*first[i], v1[i]);
+    w1[i] = v1[i].view;
+  }
+  for (size_t i = 0; i < second.size(); i++) {
+    makeView(*second[i], v2[i]);
+    w2[i] = v2[i].view;
+  }
+  // which matcher the reference would pick (functions.cpp:225-251)
+  std::vector<int32_t> kind(B);
+  for (size_t b = 0; b < B; b++) {
+    const Graph& a = *first[first.size() == 1 ? 0 : b];
+    const Graph& g = *second[second.size() == 1 ? 0 : b];
+    const bool s1 = intersectMode ? (a.ilabelSorted() || a.olabelSorted()) : a.olabelSorted();
+    const bool s2 = intersectMode ? (g.ilabelSorted() || g.olabelSorted()) : g.ilabelSorted();
+    kind[b] = (s1 && s2) ? 3 : (s1 ? 1 : (s2 ? 2 : 0));
+  }
+  gtnb_composed* res = nullptr;
+  int rc;
+  {
+    std::lock_guard<std::mutex> l(c->lock);
+    rc = gtnb_compose_graphs(c->ctx, (int)B, w1.data(), (int)w1.size(), w2.data(), (int)w2.size(), kind.data(), &res);
+  }
+  if (rc == GTNB_ERR_UNSUPPORTED) return false;
+  check(c, rc);
+  struct Guard {
+    std::shared_ptr<Context> c;
+    gtnb_composed* r;
+    ~Guard() {
+      std::lock_guard<std::mutex> l(c->lock);
+      gtnb_composed_destroy(c->ctx, r);
+    }
+  } guard{c, res};
+  out.clear();
+  out.reserve(B);
+  for (size_t b = 0; b < B; b++) {
+    int32_t N = 0, A = 0;
+    gtnb_composed_sizes(res, (int)b, &N, &A);
+    std::vector<uint8_t> fl(N);
+    std::vector<int32_t> src(A), dst(A), il(A), ol(A), gi1(A), gi2(A);
+    std::vector<float> w(A);
+    {
+      std::lock_guard<std::mutex> l(c->lock);
+      check(c, gtnb_composed_download(c->ctx, res, (int)b, fl.data(), src.data(), dst.data(), il.data(), ol.data(),
+                                      w.data(), gi1.data(), gi2.data()));
+    }
+    const Graph& a = *first[first.size() == 1 ? 0 : b];
+    const Graph& g = *second[second.size() == 1 ? 0 : b];
+    Graph ng(nullptr, {a, g});
+    for (int n = 0; n < N; n++) ng.addNode(fl[n] & 1, fl[n] & 2);
+    for (int k = 0; k < A; k++) ng.addArc(src[k], dst[k], il[k], ol[k], w[k]);
+    // compose's gradFunc (compose.cpp:496-518)
+    auto gradFunc = [gi1 = std::move(gi1), gi2 = std::move(gi2)](std::vector<Graph>& inputs, Graph& deltas) {
+      const bool c1 = inputs[0].calcGrad(), c2 = inputs[1].calcGrad();
+      std::vector<float> g1(c1 ? inputs[0].numArcs() : 0, 0.0f), g2(c2 ? inputs[1].numArcs() : 0, 0.0f);
+      for (size_t k = 0; k < gi1.size(); k++) {
+        const float d = deltas.weight(k);
+        if (c1 && gi1[k] >= 0) g1[gi1[k]] += d;
+        if (c2 && gi2[k] >= 0) g2[gi2[k]] += d;
+      }
+      inputs[0].addGrad(std::move(g1));
+      inputs[1].addGrad(std::move(g2));
+    };
+    ng.setGradFunc(std::move(gradFunc));
+    out.push_back(std::move(ng));
+  }
+  return true;
+}
+
+namespace {
+
+/* does the device take this general pair?  (see composeDevicePolicy) */
+bool generalOnDevice(const Graph& g1, const Graph& g2) {
+  const int policy = composeDevicePolicy();
+  if (policy == 2 || g1.isDeviceResident() || g2.isDeviceResident() || deviceCount() == 0) return false;
+  return policy == 1 || (double)g1.numNodes() * (double)g2.numNodes() >= 16384.0;
+}
+
 Graph composeDispatch(const Graph& g1, const Graph& g2, bool intersectMode) {
   Graph out;
   // the frame-synchronous device path needs one operand to be the emissions chain
   if (g2.isLinear() && !g1.isLinear() && composeLinearDevice(g1, g2, false, out)) return out;
   if (g1.isLinear() && composeLinearDevice(g1, g2, true, out)) return out;
   if (g2.isLinear() && composeLinearDevice(g1, g2, false, out)) return out;
+  if (generalOnDevice(g1, g2)) {
+    std::vector<Graph> res;
+    if (composeGraphsDevice({&g1}, {&g2}, intersectMode, res)) return res[0];
+  }
   return composeHost(g1, g2, intersectMode);
 }
 

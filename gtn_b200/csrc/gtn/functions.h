@@ -69,6 +69,19 @@ namespace detail {
 Graph composeHost(const Graph& first, const Graph& second, bool intersectMode);
 /** Does an arc of g carry epsilon on the side matched against a linear graph's labels? */
 bool matchedSideHasEpsilon(const Graph& g, bool useIlabel);
+/** detail::compose (compose.cpp:377-522) for B arbitrary operand pairs in one device call (k_gcompose.cu):
+ * same node / arc numbering and gradInfo as the reference.  Size-1 lists broadcast.  Returns false (and
+ * leaves `out` alone) when the device cannot take the batch (product state space too large). */
+bool composeGraphsDevice(
+    const std::vector<const Graph*>& first, const std::vector<const Graph*>& second, bool intersectMode,
+    std::vector<Graph>& out);
+/** GTNB_COMPOSE_DEVICE = auto (default) | always | never: whether compose / intersect of two arbitrary
+ * graphs runs on the device.  auto: when there is a GPU and the pair's product state space (or the list's
+ * total) has at least 2^14 states -- below that the two launches and the round trip cost more than the
+ * host construction. */
+int composeDevicePolicy(); // 0 auto, 1 always, 2 never
+void setComposeDevicePolicy(int policy);
+int deviceCount();
 } // namespace detail
 
 } // namespace gtn

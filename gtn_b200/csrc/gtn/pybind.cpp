@@ -281,6 +281,22 @@ PYBIND11_MODULE(_gtn, m) {
       "graphs"_a, "grads"_a, "retain_graphs"_a = std::vector<int>({0}));
 
   // B200 addition: kernels launched so far by the calling thread's context (tests / bench bookkeeping)
+  // test / tuning hooks (not part of the reference's surface)
+  m.def("compose_device_policy", []() { return detail::composeDevicePolicy(); });
+  m.def("set_compose_device_policy", [](int p) { detail::setComposeDevicePolicy(p); }, "policy"_a);
+  m.def("arc_lists", [](const Graph& g) {
+    detail::ViewStorage vs;
+    detail::makeView(g, vs);
+    auto arr = [](const std::vector<int32_t>& v) { return py::array_t<int32_t>((py::ssize_t)v.size(), v.data()); };
+    py::dict d;
+    d["in_ptr"] = arr(vs.inPtr);
+    d["in_arcs"] = arr(vs.inArcs);
+    d["out_ptr"] = arr(vs.outPtr);
+    d["out_arcs"] = arr(vs.outArcs);
+    d["start"] = arr(vs.start);
+    d["accept"] = arr(vs.accept);
+    return d;
+  }, "g"_a);
   m.def("device_launch_count", []() {
     auto c = detail::threadContext();
     return (long long)gtnb_ctx_launch_count(c->ctx);

@@ -1,0 +1,635 @@
+/*
+ * k_gcompose.cu -- composition of two arbitrary graphs on the device: epsilon arcs on the matched side,
+ * cyclic operands, neither operand a chain (the frame-synchronous case is
+ * k_compose.cu).  Target workload: intersect(ctc, transitions) of timeNgramCtc (benchmarks/ctc.cpp:107-134),
+ * lexicon / n-gram operands, batched over the B pairs of a list call.
+ *
+ * What detail::compose does (compose.cpp:377-522), restated for one CTA per pair of graphs:
+ *
+ *   1. findReachable (compose.cpp:64-104): the product states (n1, n2) from which an accepting pair can be
+ *      reached, by a backward search over label-matched in-arc pairs (epsilon:epsilon pairs included, as the
+ *      matcher yields them) plus the epsilon in-arcs of either side alone (:146-208 mirrored backward).
+ *      Here: a frontier search over a bitmap in global memory, atomicOr + an append-only queue.  The order
+ *      of discovery is irrelevant for a set.
+ *   2. the forward construction (compose.cpp:389-489): a FIFO search from the start pairs; a popped pair
+ *      enumerates its label-matched out-arc pairs in the MATCHER's order (:211-374), then the first operand's
+ *      epsilon-output arcs, then the second operand's epsilon-input arcs (the epsMatched / accept filter of
+ *      :461-488), keeps the arcs whose destination pair is co-reachable, and numbers a destination pair the
+ *      first time it is seen.  A FIFO search is level-synchronous, so the reference's numbering can be
+ *      reproduced EXACTLY in parallel: per level, every candidate arc gets its global index k by a prefix sum
+ *      over the frontier in queue order (that index IS the reference's arc id), every undiscovered destination
+ *      keeps the smallest k that reaches it (atomicMax on -2 - k), and the winners are numbered by a second
+ *      prefix sum in k order.  Node ids, arc ids, arc order inside a node and gradInfo (compose.cpp:445,
+ *      201-205) therefore equal the reference's, not merely up to isomorphism -- which keeps downstream
+ *      float sums (in-arc order, shortest.cpp:121-128) and Viterbi ties (:212-218) identical too.
+ *   3. gcompose_fill_kernel: one thread per output node re-enumerates its arcs and writes them at the offsets
+ *      of step 2 (the arc storage is allocated between the two kernels, once the totals are known).
+ *
+ * One thread enumerates one product state; the nested / binary-search matching below is the three matchers
+ * of the reference collapsed into "for each arc of the query list, in list order, the arcs of the searched
+ * list with the same label, in list order" -- which is what all three produce (the sorted ones find the run
+ * by binary search, :282-374).
+ */
+#ifdef GTNB_HOST_EMU // this file compiled by g++ against tests/emu/simt_emu.h (CPU test suite)
+#include <algorithm>
+
+#include "gtnb_gcompose.h"
+#include "simt_emu.h"
+#else
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "gtnb_gcompose.h"
+#include "gtnb_internal.h"
+#endif
+
+namespace gtnb {
+
+namespace gc {
+
+constexpr int kThreads = 256;
+constexpr int kEps = -1; // gtn::epsilon (graph.h:21)
+
+__device__ __forceinline__ bool reach_get(const uint32_t* reach, long long p) {
+  return (reach[p >> 5] >> (p & 31)) & 1u;
+}
+
+/* arcs of the list `s` (ns arc ids, sorted by label) whose label is >= v: first position */
+__device__ __forceinline__ int lower_bound_label(const int32_t* s, int ns, const int32_t* label, int v) {
+  int lo = 0, hi = ns;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (label[s[mid]] < v)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+/*
+ * The matcher: calls f(i, j) for the arc pairs (i of g1, j of g2) of the lists of (n1, n2) -- in-arc lists if
+ * `in`, else out-arc lists -- with olabel1(i) == ilabel2(j), in the reference's order (compose.cpp:211-374):
+ *   kind 0  nothing sorted: for i in list1: for j in list2
+ *   kind 1  g1's list sorted on the matched label: for j in list2: the run of list1 with that label
+ *   kind 2  g2's list sorted: for i in list1: the run of list2
+ *   kind 3  both sorted: the LONGER list is searched (g1's if it is strictly longer, :341-345)
+ */
+template <class F>
+__device__ __forceinline__ void for_matches(const GView& g1, const GView& g2, int n1, int n2, bool in, int kind, F f) {
+  const int32_t* l = in ? g1.in_arcs + g1.in_ptr[n1] : g1.out_arcs + g1.out_ptr[n1];
+  const int nl = in ? g1.in_ptr[n1 + 1] - g1.in_ptr[n1] : g1.out_ptr[n1 + 1] - g1.out_ptr[n1];
+  const int32_t* r = in ? g2.in_arcs + g2.in_ptr[n2] : g2.out_arcs + g2.out_ptr[n2];
+  const int nr = in ? g2.in_ptr[n2 + 1] - g2.in_ptr[n2] : g2.out_ptr[n2 + 1] - g2.out_ptr[n2];
+  if (kind == 0) {
+    for (int a = 0; a < nl; a++) {
+      const int i = l[a], lab = g1.ol[i];
+      for (int b = 0; b < nr; b++)
+        if (g2.il[r[b]] == lab) f(i, r[b]);
+    }
+    return;
+  }
+  const bool search1 = kind == 3 ? nl > nr : kind == 1;
+  if (search1) {
+    for (int b = 0; b < nr; b++) {
+      const int j = r[b], lab = g2.il[j];
+      for (int a = lower_bound_label(l, nl, g1.ol, lab); a < nl && g1.ol[l[a]] == lab; a++) f(l[a], j);
+    }
+  } else {
+    for (int a = 0; a < nl; a++) {
+      const int i = l[a], lab = g1.ol[i];
+      for (int b = lower_bound_label(r, nr, g2.il, lab); b < nr && g2.il[r[b]] == lab; b++) f(i, r[b]);
+    }
+  }
+}
+
+/*
+ * The out-arcs of the product state (n1, n2), in the reference's order (compose.cpp:437-488): f(i, j, d1, d2)
+ * with j == -1 for an epsilon-output arc of g1 taken alone, i == -1 for an epsilon-input arc of g2 taken alone.
+ * Only arcs whose destination is co-reachable.
+ */
+template <class F>
+__device__ __forceinline__ void for_out_arcs(const PairDev& P, int n1, int n2, F f) {
+  const GView& g1 = P.g1;
+  const GView& g2 = P.g2;
+  const long long N1 = g1.N;
+  bool eps_matched = false;
+  for_matches(g1, g2, n1, n2, false, P.kind, [&](int i, int j) {
+    if (g1.ol[i] == kEps) { // epsilon:epsilon is not an arc of the product (:441-444)
+      eps_matched = true;
+      return;
+    }
+    const int d1 = g1.dst[i], d2 = g2.dst[j];
+    if (reach_get(P.reach, d1 + N1 * d2)) f(i, j, d1, d2);
+  });
+  const bool acc1 = g1.flags[n1] & 2, acc2 = g2.flags[n2] & 2;
+  if (!eps_matched || acc2 || !acc1) {
+    const int32_t* l = g1.out_arcs + g1.out_ptr[n1];
+    const int nl = g1.out_ptr[n1 + 1] - g1.out_ptr[n1];
+    for (int a = 0; a < nl; a++) {
+      const int i = l[a];
+      if (g1.ol[i] != kEps) continue;
+      const int d1 = g1.dst[i];
+      if (reach_get(P.reach, d1 + N1 * n2)) f(i, -1, d1, n2);
+    }
+  }
+  if (!eps_matched || acc1) {
+    const int32_t* r = g2.out_arcs + g2.out_ptr[n2];
+    const int nr = g2.out_ptr[n2 + 1] - g2.out_ptr[n2];
+    for (int b = 0; b < nr; b++) {
+      const int j = r[b];
+      if (g2.il[j] != kEps) continue;
+      const int d2 = g2.dst[j];
+      if (reach_get(P.reach, n1 + N1 * d2)) f(-1, j, n1, d2);
+    }
+  }
+}
+
+/* exclusive prefix sum over the CTA (kThreads threads); returns this thread's prefix, *total the sum */
+__device__ __forceinline__ int block_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int w = 0; w < kThreads / 32; w++) {
+    const int s = warp_sums[w];
+    if (w < warp) base += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + x - v;
+}
+
+/* steps 1 and 2: one CTA per pair.  Needs P.reach zeroed and P.ids filled with kUndiscovered. */
+__global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev* __restrict__ pairs) {
+  GTNB_STATIC_SMEM(int, warp_sums, kThreads / 32);
+  GTNB_STATIC_SMEM(int, q_tail, 1);
+  const PairDev P = pairs[blockIdx.x];
+  const GView& g1 = P.g1;
+  const GView& g2 = P.g2;
+  const long long N1 = g1.N;
+  const int tid = threadIdx.x;
+  int32_t* queue = P.queue;
+
+  // ---- 1. co-reachability (compose.cpp:64-104)
+  if (tid == 0) *q_tail = 0;
+  __syncthreads();
+  for (long long k = tid; k < (long long)g1.n_accept * g2.n_accept; k += kThreads) {
+    const int f = g1.accept[k / g2.n_accept], s = g2.accept[k % g2.n_accept];
+    const long long p = f + N1 * s;
+    const uint32_t bit = 1u << (p & 31);
+    if (!(atomicOr(&P.reach[p >> 5], bit) & bit)) queue[atomicAdd(q_tail, 1)] = (int32_t)p;
+  }
+  __syncthreads();
+  auto mark = [&](int u1, int u2) {
+    const long long p = u1 + N1 * u2;
+    const uint32_t bit = 1u << (p & 31);
+    if (P.reach[p >> 5] & bit) return; // (plain read first: most hits are repeats)
+    if (!(atomicOr(&P.reach[p >> 5], bit) & bit)) queue[atomicAdd(q_tail, 1)] = (int32_t)p;
+  };
+  for (int head = 0;;) {
+    const int tail = *q_tail;
+    __syncthreads(); // everybody has read the tail before anybody moves it
+    if (head == tail) break;
+    for (int at = head + tid; at < tail; at += kThreads) {
+      const int p = queue[at];
+      const int n1 = (int)(p % N1), n2 = (int)(p / N1);
+      for_matches(g1, g2, n1, n2, true, P.kind, [&](int i, int j) { mark(g1.src[i], g2.src[j]); });
+      for (int a = g1.in_ptr[n1]; a < g1.in_ptr[n1 + 1]; a++) {
+        const int i = g1.in_arcs[a];
+        if (g1.ol[i] == kEps) mark(g1.src[i], n2);
+      }
+      for (int b = g2.in_ptr[n2]; b < g2.in_ptr[n2 + 1]; b++) {
+        const int j = g2.in_arcs[b];
+        if (g2.il[j] == kEps) mark(n1, g2.src[j]);
+      }
+    }
+    head = tail;
+    __syncthreads();
+  }
+
+  // ---- 2. forward construction in the reference's order (compose.cpp:389-489)
+  // start pairs, in (g1.start() x g2.start()) order: serial, the lists are short
+  if (tid == 0) {
+    int n = 0;
+    for (int a = 0; a < g1.n_start; a++)
+      for (int b = 0; b < g2.n_start; b++) {
+        const long long p = g1.start[a] + N1 * g2.start[b];
+        if (reach_get(P.reach, p) && P.ids[p] < 0) {
+          P.ids[p] = n;
+          queue[n++] = (int32_t)p;
+        }
+      }
+    *q_tail = n;
+  }
+  __syncthreads();
+  int lo = 0, hi = *q_tail; // the current level: node ids [lo, hi)
+  int next_id = hi, arc_base = 0;
+  while (lo < hi) {
+    for (int c0 = lo; c0 < hi; c0 += kThreads) {
+      const int id = c0 + tid;
+      const bool on = id < hi;
+      int n1 = 0, n2 = 0;
+      if (on) {
+        const int p = queue[id];
+        n1 = (int)(p % N1);
+        n2 = (int)(p / N1);
+      }
+      // (a) the arcs of every state of the chunk: counts -> the reference's arc ids
+      int cnt = 0;
+      if (on) for_out_arcs(P, n1, n2, [&](int, int, int, int) { cnt++; });
+      int total;
+      const int off = arc_base + block_scan(cnt, warp_sums, &total);
+      if (on) P.arc_off[id] = off;
+      arc_base += total;
+      // (b) every undiscovered destination keeps the smallest arc id that reaches it
+      if (on) {
+        int k = off;
+        for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
+          const long long p = d1 + N1 * d2;
+          if (P.ids[p] < 0) atomicMax(&P.ids[p], -2 - k);
+          k++;
+        });
+      }
+      __syncthreads();
+      // (c) the winners, numbered in arc-id order
+      int wins = 0;
+      if (on) {
+        int k = off;
+        for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
+          wins += P.ids[d1 + N1 * d2] == -2 - k;
+          k++;
+        });
+      }
+      const int wbase = next_id + block_scan(wins, warp_sums, &total);
+      if (on && wins) {
+        int k = off, w = wbase;
+        for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
+          const long long p = d1 + N1 * d2;
+          if (P.ids[p] == -2 - k) {
+            P.ids[p] = w;
+            queue[w] = (int32_t)p;
+            w++;
+          }
+          k++;
+        });
+      }
+      next_id += total;
+      __syncthreads();
+    }
+    lo = hi;
+    hi = next_id;
+  }
+  if (tid == 0) {
+    P.arc_off[next_id] = arc_base;
+    P.counts[0] = next_id;
+    P.counts[1] = arc_base;
+  }
+}
+
+/* step 3: one thread per output node; grid = pairs x blocks_per_pair (ceil(max nodes / kThreads)) */
+__global__ void __launch_bounds__(kThreads) gcompose_fill_kernel(const PairDev* __restrict__ pairs, int blocks_per_pair) {
+  const PairDev P = pairs[blockIdx.x / blocks_per_pair];
+  const int id = (blockIdx.x % blocks_per_pair) * kThreads + threadIdx.x;
+  if (id >= P.counts[0]) return;
+  const GView& g1 = P.g1;
+  const GView& g2 = P.g2;
+  const long long N1 = g1.N;
+  const int p = P.queue[id];
+  const int n1 = (int)(p % N1), n2 = (int)(p / N1);
+  P.out_flags[id] = (uint8_t)(((g1.flags[n1] & g2.flags[n2]) & 1) | ((g1.flags[n1] & g2.flags[n2]) & 2));
+  int k = P.arc_off[id];
+  for_out_arcs(P, n1, n2, [&](int i, int j, int d1, int d2) {
+    P.out_src[k] = id;
+    P.out_dst[k] = P.ids[d1 + N1 * d2];
+    P.out_il[k] = i >= 0 ? g1.il[i] : kEps;
+    P.out_ol[k] = j >= 0 ? g2.ol[j] : kEps;
+    // compose.cpp:435 adds the two weights; an epsilon arc carries its own (:201-205)
+    P.out_w[k] = i >= 0 && j >= 0 ? g1.w[i] + g2.w[j] : (i >= 0 ? g1.w[i] : g2.w[j]);
+    P.out_gi1[k] = i;
+    P.out_gi2[k] = j;
+    k++;
+  });
+}
+
+} // namespace gc
+
+#ifndef GTNB_HOST_EMU
+
+namespace {
+
+int launch_gcompose_search(gtnb_ctx* ctx, const gc::PairDev* pairs_dev, int n_pairs) {
+  GTNB_LAUNCH(ctx, "gcompose_search", gc::gcompose_search_kernel<<<n_pairs, gc::kThreads, 0, ctx->stream>>>(pairs_dev));
+  return GTNB_OK;
+}
+
+int launch_gcompose_fill(gtnb_ctx* ctx, const gc::PairDev* pairs_dev, int n_pairs, int max_nodes) {
+  const int bpp = (max_nodes + gc::kThreads - 1) / gc::kThreads;
+  GTNB_LAUNCH(ctx, "gcompose_fill",
+              gc::gcompose_fill_kernel<<<(unsigned)((long long)bpp * n_pairs), gc::kThreads, 0, ctx->stream>>>(pairs_dev, bpp));
+  return GTNB_OK;
+}
+
+/* one operand graph in the three staging buffers (int32 / float / byte); offsets in elements */
+struct Staged {
+  long long flags, src, dst, il, ol, w, in_ptr, in_arcs, out_ptr, out_arcs, start, accept;
+  int N, A, n_start, n_accept;
+};
+
+int stage_graph(gtnb_ctx* ctx, const gtnb_graph_view& v, std::vector<int32_t>& si, std::vector<float>& sf,
+                std::vector<uint8_t>& sb, Staged& o) {
+  if (v.num_nodes < 0 || v.num_arcs < 0 || (v.num_nodes && !v.node_flags) ||
+      (v.num_arcs && (!v.arc_src || !v.arc_dst || !v.arc_ilabel || !v.arc_olabel)))
+    return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_compose_graphs: incomplete graph view");
+  const int N = v.num_nodes, A = v.num_arcs;
+  o.N = N;
+  o.A = A;
+  for (int a = 0; a < A; a++)
+    if (v.arc_src[a] < 0 || v.arc_src[a] >= N || v.arc_dst[a] < 0 || v.arc_dst[a] >= N)
+      return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_compose_graphs: arc endpoint out of range");
+  auto put = [&](const int32_t* p, long long n) {
+    const long long at = (long long)si.size();
+    si.insert(si.end(), p, p + n);
+    return at;
+  };
+  o.flags = (long long)sb.size();
+  sb.insert(sb.end(), v.node_flags, v.node_flags + N);
+  sb.resize((sb.size() + 3) & ~(size_t)3);
+  o.src = put(v.arc_src, A);
+  o.dst = put(v.arc_dst, A);
+  o.il = put(v.arc_ilabel, A);
+  o.ol = put(v.arc_olabel, A);
+  o.w = (long long)sf.size();
+  if (v.weights)
+    sf.insert(sf.end(), v.weights, v.weights + A);
+  else
+    sf.resize(sf.size() + A, 0.0f);
+  // g.in(n) / g.out(n): the caller's lists (the Graph's current order), else insertion order
+  auto lists = [&](const int32_t* ptr, const int32_t* arcs, const int32_t* key, long long& optr, long long& oarcs) {
+    if (ptr && (arcs || A == 0)) {
+      optr = put(ptr, N + 1);
+      oarcs = put(arcs, A);
+      return;
+    }
+    std::vector<int32_t> p(N + 1, 0), l(A);
+    for (int a = 0; a < A; a++) p[key[a] + 1]++;
+    for (int n = 0; n < N; n++) p[n + 1] += p[n];
+    std::vector<int32_t> at(p.begin(), p.end() - 1);
+    for (int a = 0; a < A; a++) l[at[key[a]]++] = a;
+    optr = put(p.data(), N + 1);
+    oarcs = put(l.data(), A);
+  };
+  lists(v.in_ptr, v.in_arcs, v.arc_dst, o.in_ptr, o.in_arcs);
+  lists(v.out_ptr, v.out_arcs, v.arc_src, o.out_ptr, o.out_arcs);
+  auto marked = [&](const int32_t* given, int n_given, uint8_t bit, long long& at, int& n) {
+    if (given) {
+      at = put(given, n_given);
+      n = n_given;
+      return;
+    }
+    std::vector<int32_t> l;
+    for (int u = 0; u < N; u++)
+      if (v.node_flags[u] & bit) l.push_back(u);
+    at = put(l.data(), (long long)l.size());
+    n = (int)l.size();
+  };
+  marked(v.start, v.num_start, 1, o.start, o.n_start);
+  marked(v.accept, v.num_accept, 2, o.accept, o.n_accept);
+  return GTNB_OK;
+}
+
+} // namespace
+
+#endif
+
+} // namespace gtnb
+
+#ifndef GTNB_HOST_EMU
+
+/* the result of gtnb_compose_graphs: the composed graphs, on the device until downloaded */
+struct gtnb_composed {
+  int n_pairs = 0;
+  std::vector<int32_t> nodes, arcs; // per pair
+  std::vector<long long> node_off, arc_off; // into the slabs below
+  uint8_t* flags = nullptr;
+  int32_t* ints = nullptr; // [6][total arcs]: src, dst, ilabel, olabel, gradInfo first, second
+  float* w = nullptr;
+  long long tot_nodes = 0, tot_arcs = 0;
+};
+
+extern "C" {
+
+int gtnb_compose_graphs(
+    gtnb_ctx* ctx, int n_pairs, const gtnb_graph_view* first, int n_first, const gtnb_graph_view* second, int n_second,
+    const int32_t* match_kind, gtnb_composed** out) {
+  using namespace gtnb;
+  if (!ctx || !out || n_pairs < 0 || (n_pairs && (!first || !second || !match_kind)) ||
+      (n_first != 1 && n_first != n_pairs) || (n_second != 1 && n_second != n_pairs))
+    return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_compose_graphs: bad arguments");
+  *out = nullptr;
+  GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
+  auto res = new gtnb_composed();
+  res->n_pairs = n_pairs;
+  res->nodes.assign(n_pairs, 0);
+  res->arcs.assign(n_pairs, 0);
+  res->node_off.assign(n_pairs + 1, 0);
+  res->arc_off.assign(n_pairs + 1, 0);
+  if (n_pairs == 0) {
+    *out = res;
+    return GTNB_OK;
+  }
+  int rc = GTNB_OK;
+  std::vector<int32_t> si;
+  std::vector<float> sf;
+  std::vector<uint8_t> sb;
+  std::vector<Staged> g1(n_first), g2(n_second);
+  for (int g = 0; g < n_first && !rc; g++) rc = stage_graph(ctx, first[g], si, sf, sb, g1[g]);
+  for (int g = 0; g < n_second && !rc; g++) rc = stage_graph(ctx, second[g], si, sf, sb, g2[g]);
+  // scratch per pair: reach bitmap, ids, queue, arc offsets, counts
+  std::vector<long long> S(n_pairs), reach_at(n_pairs), ids_at(n_pairs), queue_at(n_pairs), aoff_at(n_pairs);
+  long long words = 0, ints = 0;
+  for (int b = 0; b < n_pairs && !rc; b++) {
+    const Staged &a = g1[n_first == 1 ? 0 : b], &c = g2[n_second == 1 ? 0 : b];
+    if (match_kind[b] < 0 || match_kind[b] > 3) rc = fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_compose_graphs: match_kind");
+    S[b] = (long long)a.N * c.N;
+    if (S[b] >= (1ll << 27))
+      rc = fail(ctx, GTNB_ERR_UNSUPPORTED, "gtnb_compose_graphs: more than 2^27 product states");
+    reach_at[b] = words;
+    words += (S[b] + 31) / 32 + 4;
+    ids_at[b] = ints;
+    ints += S[b] + 4;
+    queue_at[b] = ints;
+    ints += S[b] + 4;
+    aoff_at[b] = ints;
+    ints += S[b] + 4;
+  }
+  const size_t need = (size_t)(words + ints + (long long)si.size() + (long long)sf.size()) * 4 + sb.size();
+  if (!rc && ctx->total_mem && need > ctx->total_mem / 2)
+    rc = fail(ctx, GTNB_ERR_UNSUPPORTED, "gtnb_compose_graphs: scratch larger than half of the device memory");
+  int32_t *si_dev = nullptr, *ints_dev = nullptr, *counts_dev = nullptr;
+  float* sf_dev = nullptr;
+  uint8_t* sb_dev = nullptr;
+  uint32_t* words_dev = nullptr;
+  gc::PairDev* pairs_dev = nullptr;
+  std::vector<gc::PairDev> pairs(n_pairs);
+  std::vector<int32_t> counts(2 * (size_t)n_pairs);
+#define TRY(x)               \
+  do {                       \
+    if (!rc) rc = (x);       \
+  } while (0)
+  TRY(dev_alloc(ctx, &si_dev, (long long)si.size()));
+  TRY(dev_alloc(ctx, &sf_dev, (long long)sf.size()));
+  TRY(dev_alloc(ctx, &sb_dev, (long long)sb.size()));
+  TRY(dev_alloc(ctx, &words_dev, words));
+  TRY(dev_alloc(ctx, &ints_dev, ints));
+  TRY(dev_alloc(ctx, &counts_dev, 2ll * n_pairs));
+  TRY(dev_alloc(ctx, &pairs_dev, n_pairs));
+  TRY(upload(ctx, si_dev, si.data(), (long long)si.size()));
+  TRY(upload(ctx, sf_dev, sf.data(), (long long)sf.size()));
+  TRY(upload(ctx, sb_dev, sb.data(), (long long)sb.size()));
+  if (!rc) {
+    auto view = [&](const Staged& s) {
+      gc::GView v;
+      v.N = s.N;
+      v.A = s.A;
+      v.flags = sb_dev + s.flags;
+      v.src = si_dev + s.src;
+      v.dst = si_dev + s.dst;
+      v.il = si_dev + s.il;
+      v.ol = si_dev + s.ol;
+      v.w = sf_dev + s.w;
+      v.in_ptr = si_dev + s.in_ptr;
+      v.in_arcs = si_dev + s.in_arcs;
+      v.out_ptr = si_dev + s.out_ptr;
+      v.out_arcs = si_dev + s.out_arcs;
+      v.start = si_dev + s.start;
+      v.n_start = s.n_start;
+      v.accept = si_dev + s.accept;
+      v.n_accept = s.n_accept;
+      return v;
+    };
+    for (int b = 0; b < n_pairs; b++) {
+      gc::PairDev& P = pairs[b];
+      std::memset(&P, 0, sizeof(P));
+      P.g1 = view(g1[n_first == 1 ? 0 : b]);
+      P.g2 = view(g2[n_second == 1 ? 0 : b]);
+      P.kind = match_kind[b];
+      P.reach = words_dev + reach_at[b];
+      P.ids = ints_dev + ids_at[b];
+      P.queue = ints_dev + queue_at[b];
+      P.arc_off = ints_dev + aoff_at[b];
+      P.counts = counts_dev + 2 * b;
+    }
+    cudaError_t e = cudaMemsetAsync(words_dev, 0, sizeof(uint32_t) * (size_t)words, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ints_dev, 0x80, sizeof(int32_t) * (size_t)ints, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * 2 * (size_t)n_pairs, ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaMemsetAsync", __FILE__, __LINE__);
+  }
+  TRY(upload(ctx, pairs_dev, pairs.data(), n_pairs));
+  TRY(launch_gcompose_search(ctx, pairs_dev, n_pairs));
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(counts.data(), counts_dev, sizeof(int32_t) * counts.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "read-back of the composed sizes", __FILE__, __LINE__);
+  }
+  int max_nodes = 0;
+  if (!rc) {
+    for (int b = 0; b < n_pairs; b++) {
+      res->nodes[b] = counts[2 * b];
+      res->arcs[b] = counts[2 * b + 1];
+      res->node_off[b + 1] = res->node_off[b] + ((counts[2 * b] + 3) & ~3);
+      res->arc_off[b + 1] = res->arc_off[b] + ((counts[2 * b + 1] + 3) & ~3);
+      max_nodes = std::max(max_nodes, counts[2 * b]);
+    }
+    res->tot_nodes = res->node_off[n_pairs];
+    res->tot_arcs = res->arc_off[n_pairs];
+  }
+  TRY(dev_alloc(ctx, &res->flags, res->tot_nodes));
+  TRY(dev_alloc(ctx, &res->ints, 6 * res->tot_arcs));
+  TRY(dev_alloc(ctx, &res->w, res->tot_arcs));
+  if (!rc && max_nodes > 0) {
+    for (int b = 0; b < n_pairs; b++) {
+      gc::PairDev& P = pairs[b];
+      P.out_flags = res->flags + res->node_off[b];
+      int32_t* base = res->ints + res->arc_off[b];
+      P.out_src = base;
+      P.out_dst = base + res->tot_arcs;
+      P.out_il = base + 2 * res->tot_arcs;
+      P.out_ol = base + 3 * res->tot_arcs;
+      P.out_gi1 = base + 4 * res->tot_arcs;
+      P.out_gi2 = base + 5 * res->tot_arcs;
+      P.out_w = res->w + res->arc_off[b];
+    }
+    TRY(upload(ctx, pairs_dev, pairs.data(), n_pairs));
+    TRY(launch_gcompose_fill(ctx, pairs_dev, n_pairs, max_nodes));
+  }
+#undef TRY
+  // the scratch goes back (stream-ordered: after the kernels above)
+  dev_free(ctx, si_dev);
+  dev_free(ctx, sf_dev);
+  dev_free(ctx, sb_dev);
+  dev_free(ctx, words_dev);
+  dev_free(ctx, ints_dev);
+  dev_free(ctx, counts_dev);
+  dev_free(ctx, pairs_dev);
+  if (rc) {
+    gtnb_composed_destroy(ctx, res);
+    return rc;
+  }
+  *out = res;
+  return GTNB_OK;
+}
+
+int gtnb_composed_sizes(const gtnb_composed* c, int pair, int32_t* num_nodes, int32_t* num_arcs) {
+  if (!c || pair < 0 || pair >= c->n_pairs) return GTNB_ERR_INVALID_ARGUMENT;
+  if (num_nodes) *num_nodes = c->nodes[pair];
+  if (num_arcs) *num_arcs = c->arcs[pair];
+  return GTNB_OK;
+}
+
+int gtnb_composed_download(
+    gtnb_ctx* ctx, gtnb_composed* c, int pair, uint8_t* node_flags, int32_t* arc_src, int32_t* arc_dst,
+    int32_t* arc_ilabel, int32_t* arc_olabel, float* weights, int32_t* gi_first, int32_t* gi_second) {
+  using namespace gtnb;
+  if (!ctx || !c || pair < 0 || pair >= c->n_pairs)
+    return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_composed_download: bad arguments");
+  GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t N = (size_t)c->nodes[pair], A = (size_t)c->arcs[pair];
+  if (node_flags && N)
+    GTNB_CUDA(ctx, cudaMemcpyAsync(node_flags, c->flags + c->node_off[pair], N, cudaMemcpyDeviceToHost, ctx->stream));
+  int32_t* outs[6] = {arc_src, arc_dst, arc_ilabel, arc_olabel, gi_first, gi_second};
+  for (int k = 0; k < 6; k++)
+    if (outs[k] && A)
+      GTNB_CUDA(ctx, cudaMemcpyAsync(outs[k], c->ints + c->arc_off[pair] + k * c->tot_arcs, sizeof(int32_t) * A,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+  if (weights && A)
+    GTNB_CUDA(ctx, cudaMemcpyAsync(weights, c->w + c->arc_off[pair], sizeof(float) * A, cudaMemcpyDeviceToHost, ctx->stream));
+  GTNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GTNB_OK;
+}
+
+void gtnb_composed_destroy(gtnb_ctx* ctx, gtnb_composed* c) {
+  using namespace gtnb;
+  if (!c) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    dev_free(ctx, c->flags);
+    dev_free(ctx, c->ints);
+    dev_free(ctx, c->w);
+  }
+  delete c;
+}
+
+} // extern "C"
+
+#endif // GTNB_HOST_EMU

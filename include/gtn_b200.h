@@ -173,6 +173,43 @@ int gtnb_compose_linear(
     int64_t emissions_stride,
     gtnb_lattice** out);
 
+/*
+ * General composition on the device (k_gcompose.cu): replaces detail::compose (compose.cpp:377-522) for
+ * operand pairs that are NOT frame-synchronous -- epsilon arcs on the matched side (compose.cpp:146-208,
+ * 461-488), cyclic graphs, neither operand a chain (intersect(ctc, transitions) of timeNgramCtc,
+ * benchmarks/ctc.cpp:118-123).  n_pairs pairs in one call, one CTA each; n_first / n_second are n_pairs, or 1
+ * for an operand shared by every pair (parallel_map.h:77-89).  match_kind[b] is the matcher functions.cpp:225-251
+ * would pick: 0 unsorted, 1 only the first operand sorted on the matched label, 2 only the second, 3 both.
+ * The composed graphs keep the reference's node ids, arc ids and per-node arc order exactly.
+ * GTNB_ERR_UNSUPPORTED when the product state space does not fit (>= 2^27 states per pair, or scratch larger
+ * than half of the device memory).
+ */
+typedef struct gtnb_composed gtnb_composed;
+int gtnb_compose_graphs(
+    gtnb_ctx* ctx,
+    int n_pairs,
+    const gtnb_graph_view* first,
+    int n_first,
+    const gtnb_graph_view* second,
+    int n_second,
+    const int32_t* match_kind,
+    gtnb_composed** out);
+int gtnb_composed_sizes(const gtnb_composed* c, int pair, int32_t* num_nodes, int32_t* num_arcs);
+/* any pointer may be NULL; gi_first / gi_second: compose.cpp:445's gradInfo (-1 on the epsilon side, :201-205) */
+int gtnb_composed_download(
+    gtnb_ctx* ctx,
+    gtnb_composed* c,
+    int pair,
+    uint8_t* node_flags,
+    int32_t* arc_src,
+    int32_t* arc_dst,
+    int32_t* arc_ilabel,
+    int32_t* arc_olabel,
+    float* weights,
+    int32_t* gi_first,
+    int32_t* gi_second);
+void gtnb_composed_destroy(gtnb_ctx* ctx, gtnb_composed* c);
+
 void gtnb_lattice_destroy(gtnb_ctx* ctx, gtnb_lattice* lat);
 int gtnb_lattice_batch(const gtnb_lattice* lat);
 /* per-graph node / arc counts (synchronises) */

@@ -387,6 +387,13 @@ inline int __syncthreads_and(int pred) {
 inline int atomicAdd(int* p, int v) {
   return std::atomic_ref<int>(*p).fetch_add(v);
 }
+inline int atomicMax(int* p, int v) {
+  std::atomic_ref<int> a(*p);
+  int cur = a.load();
+  while (cur < v && !a.compare_exchange_weak(cur, v)) {
+  }
+  return cur;
+}
 struct int2 {
   int x, y;
 };
