@@ -64,6 +64,12 @@ SYMBOLS = [
     ("gtnb_compose_linear", C.c_int,
      [_vp, C.c_int, C.POINTER(GraphView), C.c_int, C.c_int, _i32p, C.c_int, _vp, C.c_int64,
       C.POINTER(_vp)]),
+    ("gtnb_compose_graphs", C.c_int,
+     [_vp, C.c_int, C.POINTER(GraphView), C.c_int, C.POINTER(GraphView), C.c_int, _i32p, C.POINTER(_vp)]),
+    ("gtnb_composed_sizes", C.c_int, [_vp, C.c_int, _i32p, _i32p]),
+    ("gtnb_composed_download", C.c_int,
+     [_vp, _vp, C.c_int, _u8p, _i32p, _i32p, _i32p, _i32p, _f32p, _i32p, _i32p]),
+    ("gtnb_composed_destroy", None, [_vp, _vp]),
     ("gtnb_lattice_destroy", None, [_vp, _vp]),
     ("gtnb_lattice_batch", C.c_int, [_vp]),
     ("gtnb_lattice_sizes", C.c_int, [_vp, _vp, _i32p, _i32p]),
