@@ -198,13 +198,16 @@ std::vector<Graph> composeBatch(const std::vector<Graph>& a, const std::vector<G
     bool general = n >= 2 && policy != 2 && detail::deviceCount() > 0 && (a.size() == n || a.size() == 1) &&
                    (b.size() == n || b.size() == 1);
     double states = 0.0;
+    bool chain = false;
     for (size_t i = 0; general && i < n; i++) {
       const Graph& x = a[a.size() == 1 ? 0 : i];
       const Graph& y = b[b.size() == 1 ? 0 : i];
-      general = !x.isLinear() && !y.isLinear() && !x.isDeviceResident() && !y.isDeviceResident();
+      general = !x.isDeviceResident() && !y.isDeviceResident();
+      chain = chain || x.isLinear() || y.isLinear();
       states += (double)x.numNodes() * (double)y.numNodes();
     }
-    if (general && (policy == 1 || states >= 16384.0)) {
+    // (same rule as the single-pair dispatch, functions.cpp generalOnDevice)
+    if (general && (policy == 1 || (chain && states >= 16384.0))) {
       std::vector<const Graph*> pa(a.size()), pb(b.size());
       for (size_t i = 0; i < a.size(); i++) pa[i] = &a[i];
       for (size_t i = 0; i < b.size(); i++) pb[i] = &b[i];

@@ -545,7 +545,11 @@ namespace {
 bool generalOnDevice(const Graph& g1, const Graph& g2) {
   const int policy = composeDevicePolicy();
   if (policy == 2 || g1.isDeviceResident() || g2.isDeviceResident() || deviceCount() == 0) return false;
-  return policy == 1 || (double)g1.numNodes() * (double)g2.numNodes() >= 16384.0;
+  // measured (profiles/r2_gcompose.md): one CTA per pair wins where the search frontier is wide and the node
+  // degrees small -- an operand with epsilons against the emissions chain; small or high-degree operands
+  // (n-gram x ctc, lexicon x LM) are faster through the host construction and stay there unless forced
+  return policy == 1 ||
+         ((g1.isLinear() || g2.isLinear()) && (double)g1.numNodes() * (double)g2.numNodes() >= 16384.0);
 }
 
 Graph composeDispatch(const Graph& g1, const Graph& g2, bool intersectMode) {

@@ -50,11 +50,16 @@ namespace gtnb {
 
 namespace gc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024; // one CTA per pair: every warp it can get to hide the latency of the dependent global loads
 constexpr int kEps = -1; // gtn::epsilon (graph.h:21)
 
+/* reach[] and ids[] are updated with atomics (performed in L2): every read goes to L2 as well (ld.global.cg),
+ * a line cached in L1 before the update would be stale */
 __device__ __forceinline__ bool reach_get(const uint32_t* reach, long long p) {
-  return (reach[p >> 5] >> (p & 31)) & 1u;
+  return (__ldcg(&reach[p >> 5]) >> (p & 31)) & 1u;
+}
+__device__ __forceinline__ int32_t id_get(const int32_t* ids, long long p) {
+  return __ldcg(&ids[p]);
 }
 
 /* arcs of the list `s` (ns arc ids, sorted by label) whose label is >= v: first position */
@@ -102,6 +107,75 @@ __device__ __forceinline__ void for_matches(const GView& g1, const GView& g2, in
     for (int a = 0; a < nl; a++) {
       const int i = l[a], lab = g1.ol[i];
       for (int b = lower_bound_label(r, nr, g2.il, lab); b < nr && g2.il[r[b]] == lab; b++) f(i, r[b]);
+    }
+  }
+}
+
+/*
+ * The same pairs for the co-reachability search, where the order does not matter: ONE WARP per product state,
+ * the pairs spread over its lanes (a thread walking them alone issues one dependent atomic after the other:
+ * 90 in-arc pairs per state for ctc x bigram, 0.7 us each).  Sorted kinds: every lane takes one arc of the query
+ * list and finds its run in the searched list, a warp prefix sum lays the runs end to end, and the lanes stride
+ * over that flat index space.  Unsorted: the nl x nr rectangle, flat.
+ */
+template <class F>
+__device__ __forceinline__ void warp_matches(const GView& g1, const GView& g2, int n1, int n2, bool in, int kind, F f) {
+  const int lane = threadIdx.x & 31;
+  const int32_t* l = in ? g1.in_arcs + g1.in_ptr[n1] : g1.out_arcs + g1.out_ptr[n1];
+  const int nl = in ? g1.in_ptr[n1 + 1] - g1.in_ptr[n1] : g1.out_ptr[n1 + 1] - g1.out_ptr[n1];
+  const int32_t* r = in ? g2.in_arcs + g2.in_ptr[n2] : g2.out_arcs + g2.out_ptr[n2];
+  const int nr = in ? g2.in_ptr[n2 + 1] - g2.in_ptr[n2] : g2.out_ptr[n2 + 1] - g2.out_ptr[n2];
+  if (kind == 0) {
+    const long long tot = (long long)nl * nr;
+    for (long long t = lane; t < tot; t += 32) {
+      const int i = l[t / nr], j = r[t % nr];
+      if (g1.ol[i] == g2.il[j]) f(i, j);
+    }
+    return;
+  }
+  const bool search1 = kind == 3 ? nl > nr : kind == 1;
+  const int32_t* q = search1 ? r : l; // query list
+  const int nq = search1 ? nr : nl;
+  const int32_t* sl = search1 ? l : r; // searched list, sorted on its label
+  const int ns = search1 ? nl : nr;
+  const int32_t* qlab = search1 ? g2.il : g1.ol;
+  const int32_t* slab = search1 ? g1.ol : g2.il;
+  for (int base = 0; base < nq; base += 32) {
+    int qa = -1, lo = 0, len = 0;
+    if (base + lane < nq) {
+      qa = q[base + lane];
+      const int lab = qlab[qa];
+      lo = lower_bound_label(sl, ns, slab, lab);
+      len = lower_bound_label(sl, ns, slab, lab + 1) - lo;
+    }
+    int incl = len; // inclusive prefix sum of the run lengths over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    for (int t0 = 0; t0 < tot; t0 += 32) {
+      const int t = t0 + lane;
+      // owner of flat index t: the first lane whose inclusive sum exceeds it (every lane takes part in the shuffles)
+      int own = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int probe = __shfl_sync(0xffffffffu, incl, min(own + step - 1, 31));
+        if (own + step <= 32 && probe <= t) own += step;
+      }
+      own = min(own, 31);
+      const int o_incl = __shfl_sync(0xffffffffu, incl, own);
+      const int o_len = __shfl_sync(0xffffffffu, len, own);
+      const int o_lo = __shfl_sync(0xffffffffu, lo, own);
+      const int o_qa = __shfl_sync(0xffffffffu, qa, own);
+      if (t < tot) {
+        const int sa = sl[o_lo + (t - (o_incl - o_len))];
+        if (search1)
+          f(sa, o_qa);
+        else
+          f(o_qa, sa);
+      }
     }
   }
 }
@@ -194,22 +268,23 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
   auto mark = [&](int u1, int u2) {
     const long long p = u1 + N1 * u2;
     const uint32_t bit = 1u << (p & 31);
-    if (P.reach[p >> 5] & bit) return; // (plain read first: most hits are repeats)
+    if (__ldcg(&P.reach[p >> 5]) & bit) return; // most hits are repeats: an L2 read instead of an atomic
     if (!(atomicOr(&P.reach[p >> 5], bit) & bit)) queue[atomicAdd(q_tail, 1)] = (int32_t)p;
   };
+  const int lane = tid & 31, warp = tid >> 5;
   for (int head = 0;;) {
     const int tail = *q_tail;
     __syncthreads(); // everybody has read the tail before anybody moves it
     if (head == tail) break;
-    for (int at = head + tid; at < tail; at += kThreads) {
+    for (int at = head + warp; at < tail; at += kThreads / 32) { // one warp per product state
       const int p = queue[at];
       const int n1 = (int)(p % N1), n2 = (int)(p / N1);
-      for_matches(g1, g2, n1, n2, true, P.kind, [&](int i, int j) { mark(g1.src[i], g2.src[j]); });
-      for (int a = g1.in_ptr[n1]; a < g1.in_ptr[n1 + 1]; a++) {
+      warp_matches(g1, g2, n1, n2, true, P.kind, [&](int i, int j) { mark(g1.src[i], g2.src[j]); });
+      for (int a = g1.in_ptr[n1] + lane; a < g1.in_ptr[n1 + 1]; a += 32) {
         const int i = g1.in_arcs[a];
         if (g1.ol[i] == kEps) mark(g1.src[i], n2);
       }
-      for (int b = g2.in_ptr[n2]; b < g2.in_ptr[n2 + 1]; b++) {
+      for (int b = g2.in_ptr[n2] + lane; b < g2.in_ptr[n2 + 1]; b += 32) {
         const int j = g2.in_arcs[b];
         if (g2.il[j] == kEps) mark(n1, g2.src[j]);
       }
@@ -225,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
     for (int a = 0; a < g1.n_start; a++)
       for (int b = 0; b < g2.n_start; b++) {
         const long long p = g1.start[a] + N1 * g2.start[b];
-        if (reach_get(P.reach, p) && P.ids[p] < 0) {
+        if (reach_get(P.reach, p) && id_get(P.ids, p) < 0) {
           P.ids[p] = n;
           queue[n++] = (int32_t)p;
         }
@@ -257,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
         int k = off;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
           const long long p = d1 + N1 * d2;
-          if (P.ids[p] < 0) atomicMax(&P.ids[p], -2 - k);
+          if (id_get(P.ids, p) < 0) atomicMax(&P.ids[p], -2 - k);
           k++;
         });
       }
@@ -267,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
       if (on) {
         int k = off;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
-          wins += P.ids[d1 + N1 * d2] == -2 - k;
+          wins += id_get(P.ids, d1 + N1 * d2) == -2 - k;
           k++;
         });
       }
@@ -276,7 +351,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
         int k = off, w = wbase;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
           const long long p = d1 + N1 * d2;
-          if (P.ids[p] == -2 - k) {
+          if (id_get(P.ids, p) == -2 - k) {
             P.ids[p] = w;
             queue[w] = (int32_t)p;
             w++;
@@ -311,7 +386,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_fill_kernel(const PairDev* 
   int k = P.arc_off[id];
   for_out_arcs(P, n1, n2, [&](int i, int j, int d1, int d2) {
     P.out_src[k] = id;
-    P.out_dst[k] = P.ids[d1 + N1 * d2];
+    P.out_dst[k] = id_get(P.ids, d1 + N1 * d2);
     P.out_il[k] = i >= 0 ? g1.il[i] : kEps;
     P.out_ol[k] = j >= 0 ? g2.ol[j] : kEps;
     // compose.cpp:435 adds the two weights; an epsilon arc carries its own (:201-205)

@@ -50,7 +50,7 @@ def word_lm(rng, words, fanout):
     return g
 
 
-rng = np.random.default_rng(0)
+rng = np.random.default_rng(0)  # (module level: scripts/prof_gcompose.py imports `cases`)
 cases = {}
 ctc10 = ctc_graph(gtn, rng.integers(1, 30, 10))
 cases["ngram_ctc U=10 x bigram M=30 (benchmarks/ctc.cpp:107-123)"] = (ctc10, transitions_graph(gtn, 30, 2, rng), True)
@@ -59,21 +59,44 @@ cases["ctc U=100 x trigram M=30 (900 states, 27000 arcs)"] = (ctc100, transition
 lex = lexicon(rng, 2000, 28, 8)
 cases["lexicon 2000 words x word LM (64 states, fan-out 200)"] = (lex, word_lm(rng, 2000, 200), False)
 
-out = {}
-for name, (a, b, inter) in cases.items():
-    op = gtn.intersect if inter else gtn.compose
-    row = {"states": a.num_nodes() * b.num_nodes()}
-    for pol, key in ((2, "host_ms"), (1, "device_ms")):
-        gtn.set_compose_device_policy(pol)
-        reps = 20 if key == "device_ms" else 3
-        row[key] = timed(lambda: op(a, b), reps)
-        r = op(a, b)
-        row["nodes"], row["arcs"] = r.num_nodes(), r.num_arcs()
-    # a list of 32 such pairs: one batched device call against parallelMap of the host construction
-    for pol, key in ((2, "host_list32_ms"), (1, "device_list32_ms")):
-        gtn.set_compose_device_policy(pol)
-        row[key] = timed(lambda: op([a] * 32, [b] * 32), 3)
-    out[name] = row
-    print(name, row, file=sys.stderr)
-gtn.set_compose_device_policy(0)
-print(json.dumps(out, indent=1))
+def eps_graph(rng, n, C):
+    """a left-to-right graph with self-loops and a few epsilon-output arcs (not frame-synchronous)"""
+    g = gtn.Graph(False)
+    for i in range(n):
+        g.add_node(i == 0, i == n - 1)
+    for i in range(n - 1):
+        g.add_arc(i, i + 1, int(rng.integers(0, C)), int(rng.integers(0, C)), 0.0)
+        g.add_arc(i, i, int(rng.integers(0, C)), int(rng.integers(0, C)), 0.0)
+        if i % 5 == 0:
+            g.add_arc(i, i + 1, int(rng.integers(0, C)), gtn.epsilon, 0.0)
+    return g
+
+
+em = gtn.linear_graph(1000, 64, False)
+em.set_weights(rng.uniform(-5, 5, 64000).astype(np.float32).tolist())
+cases["201-node graph with epsilon outputs x emissions T=1000 C=64"] = (eps_graph(rng, 201, 64), em, False)
+
+
+def main():
+  out = {}
+  for name, (a, b, inter) in cases.items():
+      op = gtn.intersect if inter else gtn.compose
+      row = {"states": a.num_nodes() * b.num_nodes()}
+      for pol, key in ((2, "host_ms"), (1, "device_ms")):
+          gtn.set_compose_device_policy(pol)
+          reps = 20 if key == "device_ms" else 3
+          row[key] = timed(lambda: op(a, b), reps)
+          r = op(a, b)
+          row["nodes"], row["arcs"] = r.num_nodes(), r.num_arcs()
+      # a list of 32 such pairs: one batched device call against parallelMap of the host construction
+      for pol, key in ((2, "host_list32_ms"), (1, "device_list32_ms")):
+          gtn.set_compose_device_policy(pol)
+          row[key] = timed(lambda: op([a] * 32, [b] * 32), 3)
+      out[name] = row
+      print(name, row, file=sys.stderr)
+  gtn.set_compose_device_policy(0)
+  print(json.dumps(out, indent=1))
+
+
+if __name__ == '__main__':
+  main()
