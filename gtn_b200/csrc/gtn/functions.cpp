@@ -21,6 +21,7 @@
 #include <cuda_runtime_api.h>
 
 #include "gtn/device.h"
+#include "gtn/parallel.h"
 
 namespace gtn {
 
@@ -470,13 +471,23 @@ bool composeGraphsDevice(
   auto c = threadContext();
   std::vector<ViewStorage> v1(first.size()), v2(second.size());
   std::vector<gtnb_graph_view> w1(first.size()), w2(second.size());
-  for (size_t i = 0; i < first.size(); i++) {
-    makeView(*first[i], v1[i]);
-    w1[i] = v1[i].view;
-  }
-  for (size_t i = 0; i < second.size(); i++) {
-    makeView(*second[i], v2[i]);
-    w2[i] = v2[i].view;
+  {
+    // the host views of all operands, on the reference's own worker threads (parallel_map.h)
+    std::vector<int> idx(first.size() + second.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+    auto one = [&](int i) {
+      if ((size_t)i < first.size())
+        makeView(*first[i], v1[i]);
+      else
+        makeView(*second[i - first.size()], v2[i - first.size()]);
+      return 0;
+    };
+    if (idx.size() > 2)
+      parallelMap(one, idx);
+    else
+      for (int i : idx) one(i);
+    for (size_t i = 0; i < first.size(); i++) w1[i] = v1[i].view;
+    for (size_t i = 0; i < second.size(); i++) w2[i] = v2[i].view;
   }
   // which matcher the reference would pick (functions.cpp:225-251)
   std::vector<int32_t> kind(B);
@@ -503,9 +514,8 @@ bool composeGraphsDevice(
       gtnb_composed_destroy(c->ctx, r);
     }
   } guard{c, res};
-  out.clear();
-  out.reserve(B);
-  for (size_t b = 0; b < B; b++) {
+  auto buildOne = [&](int bi) {
+    const size_t b = (size_t)bi;
     int32_t N = 0, A = 0;
     gtnb_composed_sizes(res, (int)b, &N, &A);
     std::vector<uint8_t> fl(N);
@@ -534,7 +544,16 @@ bool composeGraphsDevice(
       inputs[1].addGrad(std::move(g2));
     };
     ng.setGradFunc(std::move(gradFunc));
-    out.push_back(std::move(ng));
+    return ng;
+  };
+  // the B host Graphs: downloads one after the other (one stream), construction on the worker threads
+  std::vector<int> idx(B);
+  for (size_t b = 0; b < B; b++) idx[b] = (int)b;
+  if (B > 1) {
+    out = parallelMap(buildOne, idx);
+  } else {
+    out.clear();
+    out.push_back(buildOne(0));
   }
   return true;
 }
@@ -545,11 +564,16 @@ namespace {
 bool generalOnDevice(const Graph& g1, const Graph& g2) {
   const int policy = composeDevicePolicy();
   if (policy == 2 || g1.isDeviceResident() || g2.isDeviceResident() || deviceCount() == 0) return false;
-  // measured (profiles/r2_gcompose.md): one CTA per pair wins where the search frontier is wide and the node
-  // degrees small -- an operand with epsilons against the emissions chain; small or high-degree operands
-  // (n-gram x ctc, lexicon x LM) are faster through the host construction and stay there unless forced
-  return policy == 1 ||
-         ((g1.isLinear() || g2.isLinear()) && (double)g1.numNodes() * (double)g2.numNodes() >= 16384.0);
+  if (policy == 1) return true;
+  // measured (profiles/r2_gcompose.md): one CTA per pair beats the host construction when there are enough
+  // product states to search (>= 2^14) and no node has a long arc list (one thread walks a state's lists in the
+  // ordered forward pass: the 2000-arc root of a lexicon serialises it) -- ctc x trigram 17 vs 29 ms, an
+  // epsilon operand x the emissions chain 85 vs 112 ms; tiny pairs and high-degree operands stay on the host
+  if ((double)g1.numNodes() * (double)g2.numNodes() < 16384.0) return false;
+  for (const Graph* g : {&g1, &g2})
+    for (size_t n = 0; n < g->numNodes(); n++)
+      if (g->numOut(n) > 64 || g->numIn(n) > 64) return false;
+  return true;
 }
 
 Graph composeDispatch(const Graph& g1, const Graph& g2, bool intersectMode) {
