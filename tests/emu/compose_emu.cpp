@@ -324,7 +324,8 @@ int emu_viterbi_exact(
     ab += A;
   }
   std::vector<int32_t> relax((size_t)L.ta + 16, 0);
-  emu::launch(B, kOrderThreads, sizeof(int) * 4 * std::max(maxN, 1), [&] {
+  // launch_relax_order's shared-memory size: positions / keys + the key bitmaps and their prefix popcounts
+  emu::launch(B, kOrderThreads, sizeof(int) * (4 * std::max(maxN, 1) + 4 * ((std::max(maxN, 1) * (max_out + 1) + 31) / 32)), [&] {
     lattice_relax_order_kernel(L.meta.data(), L.sg_flags.data(), L.sg_ptr.data(), L.sg_src.data(), L.sg_lab.data(),
                                sg_out_pos.data(), sg_start_rank.data(), L.alive.data(), L.W, L.maxT, max_out + 1,
                                L.lnp.data(), L.rp.data(), relax.data(), L.acc_stage.data());
