@@ -32,7 +32,7 @@ struct PairDev {
   int32_t* ids; // [N1 * N2] kUndiscovered: node id of a product state
   int32_t* queue; // [N1 * N2]: search queue, then product state of every output node
   int32_t* arc_off; // [nodes + 1] first arc id of every output node
-  int32_t* counts; // [2]: nodes, arcs
+  int32_t* counts; // [4]: nodes, arcs, microseconds of the co-reachability search and of the forward construction
   // written by gcompose_fill_kernel (allocated once the counts are known)
   uint8_t* out_flags;
   int32_t *out_src, *out_dst, *out_il, *out_ol, *out_gi1, *out_gi2;

@@ -39,6 +39,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -50,8 +52,22 @@ namespace gtnb {
 
 namespace gc {
 
+#ifdef GTNB_HOST_EMU
+constexpr int kThreads = 128; // (the emulation runs one std::thread per CUDA thread: keep the CTA small; same code paths)
+#else
 constexpr int kThreads = 1024; // one CTA per pair: every warp it can get to hide the latency of the dependent global loads
+#endif
 constexpr int kEps = -1; // gtn::epsilon (graph.h:21)
+
+__device__ __forceinline__ long long now_ns() {
+#ifdef GTNB_HOST_EMU
+  return 0;
+#else
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+#endif
+}
 
 /* reach[] and ids[] are updated with atomics (performed in L2): every read goes to L2 as well (ld.global.cg),
  * a line cached in L1 before the update would be stale */
@@ -120,6 +136,8 @@ __device__ __forceinline__ void for_matches(const GView& g1, const GView& g2, in
  */
 template <class F>
 __device__ __forceinline__ void warp_matches(const GView& g1, const GView& g2, int n1, int n2, bool in, int kind, F f) {
+  // f(has, i, j) is called by ALL 32 lanes for every chunk of 32 flat positions (has: this lane holds a pair), in
+  // flat order -- which is the reference's enumeration order -- so that f may use warp collectives
   const int lane = threadIdx.x & 31;
   const int32_t* l = in ? g1.in_arcs + g1.in_ptr[n1] : g1.out_arcs + g1.out_ptr[n1];
   const int nl = in ? g1.in_ptr[n1 + 1] - g1.in_ptr[n1] : g1.out_ptr[n1 + 1] - g1.out_ptr[n1];
@@ -127,9 +145,16 @@ __device__ __forceinline__ void warp_matches(const GView& g1, const GView& g2, i
   const int nr = in ? g2.in_ptr[n2 + 1] - g2.in_ptr[n2] : g2.out_ptr[n2 + 1] - g2.out_ptr[n2];
   if (kind == 0) {
     const long long tot = (long long)nl * nr;
-    for (long long t = lane; t < tot; t += 32) {
-      const int i = l[t / nr], j = r[t % nr];
-      if (g1.ol[i] == g2.il[j]) f(i, j);
+    for (long long t0 = 0; t0 < tot; t0 += 32) {
+      const long long t = t0 + lane;
+      int i = -1, j = -1;
+      bool has = false;
+      if (t < tot) {
+        i = l[t / nr];
+        j = r[t % nr];
+        has = g1.ol[i] == g2.il[j];
+      }
+      f(has, i, j);
     }
     return;
   }
@@ -169,13 +194,9 @@ __device__ __forceinline__ void warp_matches(const GView& g1, const GView& g2, i
       const int o_len = __shfl_sync(0xffffffffu, len, own);
       const int o_lo = __shfl_sync(0xffffffffu, lo, own);
       const int o_qa = __shfl_sync(0xffffffffu, qa, own);
-      if (t < tot) {
-        const int sa = sl[o_lo + (t - (o_incl - o_len))];
-        if (search1)
-          f(sa, o_qa);
-        else
-          f(o_qa, sa);
-      }
+      int sa = -1;
+      if (t < tot) sa = sl[o_lo + (t - (o_incl - o_len))];
+      f(t < tot, search1 ? sa : o_qa, search1 ? o_qa : sa);
     }
   }
 }
@@ -222,6 +243,86 @@ __device__ __forceinline__ void for_out_arcs(const PairDev& P, int n1, int n2, F
   }
 }
 
+/*
+ * The same by ONE WARP, for product states with long arc lists (a lexicon's root against a language-model state:
+ * 2000 x 200 arcs to match -- milliseconds for a single thread): f(valid, i, j, d1, d2, ord) is called by all 32
+ * lanes per chunk of the flat enumeration, ord = the arc's position among the state's arcs in the reference's order
+ * (ballot prefix counts).  Returns the number of arcs (in every lane).
+ */
+template <class F>
+__device__ __forceinline__ int warp_out_arcs(const PairDev& P, int n1, int n2, F f) {
+  const GView& g1 = P.g1;
+  const GView& g2 = P.g2;
+  const long long N1 = g1.N;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int base = 0;
+  bool eps_matched = false;
+  warp_matches(g1, g2, n1, n2, false, P.kind, [&](bool has, int i, int j) {
+    const bool eps = has && g1.ol[i] == kEps;
+    int d1 = 0, d2 = 0;
+    bool valid = false;
+    if (has && !eps) {
+      d1 = g1.dst[i];
+      d2 = g2.dst[j];
+      valid = reach_get(P.reach, d1 + N1 * d2);
+    }
+    eps_matched = eps_matched || __ballot_sync(0xffffffffu, eps) != 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    f(valid, i, j, d1, d2, base + __popc(m & lt));
+    base += __popc(m);
+  });
+  const bool acc1 = g1.flags[n1] & 2, acc2 = g2.flags[n2] & 2;
+  if (!eps_matched || acc2 || !acc1) {
+    const int32_t* l = g1.out_arcs + g1.out_ptr[n1];
+    const int nl = g1.out_ptr[n1 + 1] - g1.out_ptr[n1];
+    for (int a0 = 0; a0 < nl; a0 += 32) {
+      int i = -1, d1 = 0;
+      bool valid = false;
+      if (a0 + lane < nl) {
+        i = l[a0 + lane];
+        if (g1.ol[i] == kEps) {
+          d1 = g1.dst[i];
+          valid = reach_get(P.reach, d1 + N1 * n2);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      f(valid, i, -1, d1, n2, base + __popc(m & lt));
+      base += __popc(m);
+    }
+  }
+  if (!eps_matched || acc1) {
+    const int32_t* r = g2.out_arcs + g2.out_ptr[n2];
+    const int nr = g2.out_ptr[n2 + 1] - g2.out_ptr[n2];
+    for (int b0 = 0; b0 < nr; b0 += 32) {
+      int j = -1, d2 = 0;
+      bool valid = false;
+      if (b0 + lane < nr) {
+        j = r[b0 + lane];
+        if (g2.il[j] == kEps) {
+          d2 = g2.dst[j];
+          valid = reach_get(P.reach, n1 + N1 * d2);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      f(valid, -1, j, n1, d2, base + __popc(m & lt));
+      base += __popc(m);
+    }
+  }
+  return base;
+}
+
+/* a state goes to a warp when one thread would have to walk more than this many candidate pairs */
+#ifdef GTNB_HOST_EMU
+constexpr int kHeavyPairs = 12; // (small test graphs must reach the warp path too)
+#else
+constexpr int kHeavyPairs = 96;
+#endif
+__device__ __forceinline__ bool heavy_state(const GView& g1, const GView& g2, int n1, int n2) {
+  const long long d1 = g1.out_ptr[n1 + 1] - g1.out_ptr[n1], d2 = g2.out_ptr[n2 + 1] - g2.out_ptr[n2];
+  return d1 * d2 > kHeavyPairs || d1 > kHeavyPairs || d2 > kHeavyPairs;
+}
+
 /* exclusive prefix sum over the CTA (kThreads threads); returns this thread's prefix, *total the sum */
 __device__ __forceinline__ int block_scan(int v, int* warp_sums, int* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -248,6 +349,10 @@ __device__ __forceinline__ int block_scan(int v, int* warp_sums, int* total) {
 __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev* __restrict__ pairs) {
   GTNB_STATIC_SMEM(int, warp_sums, kThreads / 32);
   GTNB_STATIC_SMEM(int, q_tail, 1);
+  GTNB_STATIC_SMEM(int, n_heavy, 1);
+  GTNB_STATIC_SMEM(int, h_list, kThreads); // slots (thread ids) of the chunk's heavy states
+  GTNB_STATIC_SMEM(int, h_val, kThreads); // per slot: arc count, then first arc id
+  GTNB_STATIC_SMEM(int, h_wins, kThreads); // per slot: winners, then first new node id
   const PairDev P = pairs[blockIdx.x];
   const GView& g1 = P.g1;
   const GView& g2 = P.g2;
@@ -255,6 +360,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
   const int tid = threadIdx.x;
   int32_t* queue = P.queue;
 
+  const long long t_start = now_ns();
   // ---- 1. co-reachability (compose.cpp:64-104)
   if (tid == 0) *q_tail = 0;
   __syncthreads();
@@ -279,7 +385,9 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
     for (int at = head + warp; at < tail; at += kThreads / 32) { // one warp per product state
       const int p = queue[at];
       const int n1 = (int)(p % N1), n2 = (int)(p / N1);
-      warp_matches(g1, g2, n1, n2, true, P.kind, [&](int i, int j) { mark(g1.src[i], g2.src[j]); });
+      warp_matches(g1, g2, n1, n2, true, P.kind, [&](bool has, int i, int j) {
+        if (has) mark(g1.src[i], g2.src[j]);
+      });
       for (int a = g1.in_ptr[n1] + lane; a < g1.in_ptr[n1 + 1]; a += 32) {
         const int i = g1.in_arcs[a];
         if (g1.ol[i] == kEps) mark(g1.src[i], n2);
@@ -293,6 +401,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
     __syncthreads();
   }
 
+  const long long t_reach = now_ns();
   // ---- 2. forward construction in the reference's order (compose.cpp:389-489)
   // start pairs, in (g1.start() x g2.start()) order: serial, the lists are short
   if (tid == 0) {
@@ -315,20 +424,43 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
       const int id = c0 + tid;
       const bool on = id < hi;
       int n1 = 0, n2 = 0;
+      bool heavy = false;
       if (on) {
         const int p = queue[id];
         n1 = (int)(p % N1);
         n2 = (int)(p / N1);
+        heavy = heavy_state(g1, g2, n1, n2);
       }
+      // states with long arc lists are enumerated by whole warps (h_list: their slots in this chunk)
+      if (tid == 0) *n_heavy = 0;
+      __syncthreads();
+      if (heavy) h_list[atomicAdd(n_heavy, 1)] = tid;
+      __syncthreads();
+      const int nh = *n_heavy;
+      auto state_of = [&](int slot, int& m1, int& m2) {
+        const int p = queue[c0 + slot];
+        m1 = (int)(p % N1);
+        m2 = (int)(p / N1);
+      };
       // (a) the arcs of every state of the chunk: counts -> the reference's arc ids
       int cnt = 0;
-      if (on) for_out_arcs(P, n1, n2, [&](int, int, int, int) { cnt++; });
+      if (on && !heavy) for_out_arcs(P, n1, n2, [&](int, int, int, int) { cnt++; });
+      for (int h = warp; h < nh; h += kThreads / 32) {
+        int m1, m2;
+        state_of(h_list[h], m1, m2);
+        const int c = warp_out_arcs(P, m1, m2, [&](bool, int, int, int, int, int) {});
+        if (lane == 0) h_val[h_list[h]] = c;
+      }
+      if (nh) __syncthreads();
+      if (heavy) cnt = h_val[tid];
       int total;
       const int off = arc_base + block_scan(cnt, warp_sums, &total);
       if (on) P.arc_off[id] = off;
+      if (heavy) h_val[tid] = off;
       arc_base += total;
+      if (nh) __syncthreads();
       // (b) every undiscovered destination keeps the smallest arc id that reaches it
-      if (on) {
+      if (on && !heavy) {
         int k = off;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
           const long long p = d1 + N1 * d2;
@@ -336,18 +468,42 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
           k++;
         });
       }
+      for (int h = warp; h < nh; h += kThreads / 32) {
+        int m1, m2;
+        state_of(h_list[h], m1, m2);
+        const int o = h_val[h_list[h]];
+        warp_out_arcs(P, m1, m2, [&](bool valid, int, int, int d1, int d2, int ord) {
+          if (!valid) return;
+          const long long p = d1 + N1 * d2;
+          if (id_get(P.ids, p) < 0) atomicMax(&P.ids[p], -2 - (o + ord));
+        });
+      }
       __syncthreads();
       // (c) the winners, numbered in arc-id order
       int wins = 0;
-      if (on) {
+      if (on && !heavy) {
         int k = off;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
           wins += id_get(P.ids, d1 + N1 * d2) == -2 - k;
           k++;
         });
       }
+      for (int h = warp; h < nh; h += kThreads / 32) {
+        int m1, m2;
+        state_of(h_list[h], m1, m2);
+        const int o = h_val[h_list[h]];
+        int w = 0;
+        warp_out_arcs(P, m1, m2, [&](bool valid, int, int, int d1, int d2, int ord) {
+          const bool win = valid && id_get(P.ids, d1 + N1 * d2) == -2 - (o + ord);
+          w += __popc(__ballot_sync(0xffffffffu, win));
+        });
+        if (lane == 0) h_wins[h_list[h]] = w;
+      }
+      if (nh) __syncthreads();
+      if (heavy) wins = h_wins[tid];
       const int wbase = next_id + block_scan(wins, warp_sums, &total);
-      if (on && wins) {
+      if (heavy) h_wins[tid] = wbase;
+      if (on && !heavy && wins) {
         int k = off, w = wbase;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
           const long long p = d1 + N1 * d2;
@@ -357,6 +513,25 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
             w++;
           }
           k++;
+        });
+      }
+      if (nh) __syncthreads();
+      for (int h = warp; h < nh; h += kThreads / 32) {
+        int m1, m2;
+        state_of(h_list[h], m1, m2);
+        const int o = h_val[h_list[h]];
+        int w = h_wins[h_list[h]];
+        const unsigned lt = (1u << lane) - 1u;
+        warp_out_arcs(P, m1, m2, [&](bool valid, int, int, int d1, int d2, int ord) {
+          const long long p = d1 + N1 * d2;
+          const bool win = valid && id_get(P.ids, p) == -2 - (o + ord);
+          const unsigned wm = __ballot_sync(0xffffffffu, win);
+          if (win) {
+            const int nid = w + __popc(wm & lt);
+            P.ids[p] = nid;
+            queue[nid] = (int32_t)p;
+          }
+          w += __popc(wm);
         });
       }
       next_id += total;
@@ -369,6 +544,8 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
     P.arc_off[next_id] = arc_base;
     P.counts[0] = next_id;
     P.counts[1] = arc_base;
+    P.counts[2] = (int32_t)((t_reach - t_start) / 1000); // microseconds of the two phases (GTNB_GC_TIMES=1 prints them)
+    P.counts[3] = (int32_t)((now_ns() - t_reach) / 1000);
   }
 }
 
@@ -557,7 +734,7 @@ int gtnb_compose_graphs(
   uint32_t* words_dev = nullptr;
   gc::PairDev* pairs_dev = nullptr;
   std::vector<gc::PairDev> pairs(n_pairs);
-  std::vector<int32_t> counts(2 * (size_t)n_pairs);
+  std::vector<int32_t> counts(4 * (size_t)n_pairs);
 #define TRY(x)               \
   do {                       \
     if (!rc) rc = (x);       \
@@ -567,7 +744,7 @@ int gtnb_compose_graphs(
   TRY(dev_alloc(ctx, &sb_dev, (long long)sb.size()));
   TRY(dev_alloc(ctx, &words_dev, words));
   TRY(dev_alloc(ctx, &ints_dev, ints));
-  TRY(dev_alloc(ctx, &counts_dev, 2ll * n_pairs));
+  TRY(dev_alloc(ctx, &counts_dev, 4ll * n_pairs));
   TRY(dev_alloc(ctx, &pairs_dev, n_pairs));
   TRY(upload(ctx, si_dev, si.data(), (long long)si.size()));
   TRY(upload(ctx, sf_dev, sf.data(), (long long)sf.size()));
@@ -603,11 +780,11 @@ int gtnb_compose_graphs(
       P.ids = ints_dev + ids_at[b];
       P.queue = ints_dev + queue_at[b];
       P.arc_off = ints_dev + aoff_at[b];
-      P.counts = counts_dev + 2 * b;
+      P.counts = counts_dev + 4 * b;
     }
     cudaError_t e = cudaMemsetAsync(words_dev, 0, sizeof(uint32_t) * (size_t)words, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ints_dev, 0x80, sizeof(int32_t) * (size_t)ints, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * 2 * (size_t)n_pairs, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * 4 * (size_t)n_pairs, ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaMemsetAsync", __FILE__, __LINE__);
   }
   TRY(upload(ctx, pairs_dev, pairs.data(), n_pairs));
@@ -620,11 +797,14 @@ int gtnb_compose_graphs(
   int max_nodes = 0;
   if (!rc) {
     for (int b = 0; b < n_pairs; b++) {
-      res->nodes[b] = counts[2 * b];
-      res->arcs[b] = counts[2 * b + 1];
-      res->node_off[b + 1] = res->node_off[b] + ((counts[2 * b] + 3) & ~3);
-      res->arc_off[b + 1] = res->arc_off[b] + ((counts[2 * b + 1] + 3) & ~3);
-      max_nodes = std::max(max_nodes, counts[2 * b]);
+      res->nodes[b] = counts[4 * b];
+      res->arcs[b] = counts[4 * b + 1];
+      res->node_off[b + 1] = res->node_off[b] + ((counts[4 * b] + 3) & ~3);
+      res->arc_off[b + 1] = res->arc_off[b] + ((counts[4 * b + 1] + 3) & ~3);
+      max_nodes = std::max(max_nodes, counts[4 * b]);
+      if (b == 0 && std::getenv("GTNB_GC_TIMES"))
+        std::fprintf(stderr, "[gtnb_compose_graphs] pair 0: %d nodes, %d arcs, co-reachability %d us, forward %d us\n",
+                     counts[0], counts[1], counts[2], counts[3]);
     }
     res->tot_nodes = res->node_off[n_pairs];
     res->tot_arcs = res->arc_off[n_pairs];

@@ -50,7 +50,7 @@ int emu_gcompose(
   const long long S = (long long)a->N * b->N;
   std::vector<uint32_t> reach((size_t)(S + 31) / 32 + 4, 0u);
   std::vector<int32_t> ids((size_t)S + 4, gc::kUndiscovered), queue((size_t)S + 4, 0), arc_off((size_t)S + 4, 0);
-  int32_t counts[2] = {0, 0};
+  int32_t counts[4] = {0, 0, 0, 0};
   gc::PairDev P;
   std::memset(&P, 0, sizeof(P));
   P.g1 = view(a);

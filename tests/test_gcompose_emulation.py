@@ -123,11 +123,12 @@ def test_kernel_source_reproduces_the_reference_numbering(emu, gtn, seed):
                 assert np.array_equal(g, t.grad().weights())
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(4))
 def test_kernel_source_on_wide_frontiers(emu, gtn, seed):
-    """Dense operands: levels of more than one 256-thread chunk, parallel arcs racing for the same destination."""
+    """Dense operands: levels of more than one chunk of the (emulated: 128-thread) CTA, parallel arcs racing for the
+    same destination, and states with long arc lists, which whole warps enumerate (warp_out_arcs)."""
     rng = np.random.default_rng(40 + seed)
-    a, b, intersect = case(rng, seed, 40, 400, 0.1)
+    a, b, intersect = case(rng, seed, 20, 110, 0.1)
     ma, mb = ours_from(gtn, a), ours_from(gtn, b)
     if seed & 1:
         ma.arc_sort(True)
