@@ -32,6 +32,8 @@ struct PairDev {
   int32_t* ids; // [N1 * N2] kUndiscovered: node id of a product state
   int32_t* queue; // [N1 * N2]: search queue, then product state of every output node
   int32_t* arc_off; // [nodes + 1] first arc id of every output node
+  int32_t* sync; // [8] zeroed: gcompose_reach_kernel's queue counters and grid barrier (several CTAs per pair)
+  int32_t reach_done; // the co-reachable set and nothing else is in place: gcompose_search_kernel skips its step 1
   int32_t* counts; // [4]: nodes, arcs, microseconds of the co-reachability search and of the forward construction
   // written by gcompose_fill_kernel (allocated once the counts are known)
   uint8_t* out_flags;

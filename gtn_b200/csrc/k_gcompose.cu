@@ -312,15 +312,18 @@ __device__ __forceinline__ int warp_out_arcs(const PairDev& P, int n1, int n2, F
   return base;
 }
 
-/* a state goes to a warp when one thread would have to walk more than this many candidate pairs */
+/* a state goes to a warp when one thread would have to walk a long list: the whole d1 x d2 rectangle when nothing
+ * is sorted, the query list (one binary search per arc) otherwise */
 #ifdef GTNB_HOST_EMU
-constexpr int kHeavyPairs = 12; // (small test graphs must reach the warp path too)
+constexpr int kHeavyPairs = 12, kHeavyQuery = 4; // (small test graphs must reach the warp path too)
 #else
-constexpr int kHeavyPairs = 96;
+constexpr int kHeavyPairs = 96, kHeavyQuery = 32;
 #endif
-__device__ __forceinline__ bool heavy_state(const GView& g1, const GView& g2, int n1, int n2) {
+__device__ __forceinline__ bool heavy_state(const GView& g1, const GView& g2, int n1, int n2, int kind) {
   const long long d1 = g1.out_ptr[n1 + 1] - g1.out_ptr[n1], d2 = g2.out_ptr[n2 + 1] - g2.out_ptr[n2];
-  return d1 * d2 > kHeavyPairs || d1 > kHeavyPairs || d2 > kHeavyPairs;
+  if (kind == 0) return d1 * d2 > kHeavyPairs;
+  const bool search1 = kind == 3 ? d1 > d2 : kind == 1;
+  return (search1 ? d2 : d1) > kHeavyQuery || d1 + d2 > 8 * kHeavyQuery; // (the epsilon scans walk both lists)
 }
 
 /* exclusive prefix sum over the CTA (kThreads threads); returns this thread's prefix, *total the sum */
@@ -345,6 +348,84 @@ __device__ __forceinline__ int block_scan(int v, int* warp_sums, int* total) {
   return base + x - v;
 }
 
+/*
+ * Step 1 with SEVERAL CTAs per pair (a cooperative launch: they must all be resident), for product state spaces
+ * large enough that one SM's 32 warps are the bottleneck (lexicon x LM: 77 of 112 ms).  The search is a set
+ * computation, so the CTAs simply share the frontier of every wave: warp w of CTA c takes the states
+ * head + c * W + w, + G * W, ...; new states are appended behind the wave's end through one of three rotating
+ * counters (the one of wave k is read after the barrier that ends wave k and reset during wave k + 1, when nobody
+ * uses it), and a software barrier over the pair's G CTAs separates the waves.
+ * sync[0..2]: the counters, sync[3]: arrivals, sync[4]: generation, sync[5]: end of the initial frontier.
+ */
+__device__ __forceinline__ void pair_barrier(int32_t* sync, int G) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int gen = atomicAdd(&sync[4], 0);
+    if (atomicAdd(&sync[3], 1) == G - 1) {
+      atomicExch(&sync[3], 0);
+      __threadfence();
+      atomicAdd(&sync[4], 1);
+    } else {
+      while (atomicAdd(&sync[4], 0) == gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads) gcompose_reach_kernel(const PairDev* __restrict__ pairs, int G) {
+  const PairDev P = pairs[blockIdx.x / G];
+  const int c = blockIdx.x % G;
+  const GView& g1 = P.g1;
+  const GView& g2 = P.g2;
+  const long long N1 = g1.N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int W = kThreads / 32;
+  int32_t* queue = P.queue;
+  int32_t* sync = P.sync;
+  // the accepting pairs: CTA 0 (the lists are short)
+  if (c == 0) {
+    for (long long k = tid; k < (long long)g1.n_accept * g2.n_accept; k += kThreads) {
+      const int f = g1.accept[k / g2.n_accept], s = g2.accept[k % g2.n_accept];
+      const long long p = f + N1 * s;
+      const uint32_t bit = 1u << (p & 31);
+      if (!(atomicOr(&P.reach[p >> 5], bit) & bit)) queue[atomicAdd(&sync[5], 1)] = (int32_t)p;
+    }
+  }
+  pair_barrier(sync, G);
+  int head = 0, tail = atomicAdd(&sync[5], 0);
+  for (int wave = 0; head < tail; wave++) {
+    int32_t* cnt = &sync[wave % 3];
+    if (c == 0 && tid == 0) atomicExch(&sync[(wave + 1) % 3], 0);
+    auto mark = [&](int u1, int u2) {
+      const long long p = u1 + N1 * u2;
+      const uint32_t bit = 1u << (p & 31);
+      if (__ldcg(&P.reach[p >> 5]) & bit) return;
+      if (!(atomicOr(&P.reach[p >> 5], bit) & bit)) queue[tail + atomicAdd(cnt, 1)] = (int32_t)p;
+    };
+    for (int at = head + c * W + warp; at < tail; at += G * W) {
+      const int p = __ldcg(&queue[at]);
+      const int n1 = (int)(p % N1), n2 = (int)(p / N1);
+      warp_matches(g1, g2, n1, n2, true, P.kind, [&](bool has, int i, int j) {
+        if (has) mark(g1.src[i], g2.src[j]);
+      });
+      for (int a = g1.in_ptr[n1] + lane; a < g1.in_ptr[n1 + 1]; a += 32) {
+        const int i = g1.in_arcs[a];
+        if (g1.ol[i] == kEps) mark(g1.src[i], n2);
+      }
+      for (int b = g2.in_ptr[n2] + lane; b < g2.in_ptr[n2 + 1]; b += 32) {
+        const int j = g2.in_arcs[b];
+        if (g2.il[j] == kEps) mark(n1, g2.src[j]);
+      }
+    }
+    pair_barrier(sync, G);
+    head = tail;
+    tail += atomicAdd(cnt, 0);
+  }
+}
+
 /* steps 1 and 2: one CTA per pair.  Needs P.reach zeroed and P.ids filled with kUndiscovered. */
 __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev* __restrict__ pairs) {
   GTNB_STATIC_SMEM(int, warp_sums, kThreads / 32);
@@ -361,9 +442,11 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
   int32_t* queue = P.queue;
 
   const long long t_start = now_ns();
-  // ---- 1. co-reachability (compose.cpp:64-104)
+  const int lane = tid & 31, warp = tid >> 5;
+  // ---- 1. co-reachability (compose.cpp:64-104), unless gcompose_reach_kernel has been there
   if (tid == 0) *q_tail = 0;
   __syncthreads();
+  if (!P.reach_done) {
   for (long long k = tid; k < (long long)g1.n_accept * g2.n_accept; k += kThreads) {
     const int f = g1.accept[k / g2.n_accept], s = g2.accept[k % g2.n_accept];
     const long long p = f + N1 * s;
@@ -377,7 +460,6 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
     if (__ldcg(&P.reach[p >> 5]) & bit) return; // most hits are repeats: an L2 read instead of an atomic
     if (!(atomicOr(&P.reach[p >> 5], bit) & bit)) queue[atomicAdd(q_tail, 1)] = (int32_t)p;
   };
-  const int lane = tid & 31, warp = tid >> 5;
   for (int head = 0;;) {
     const int tail = *q_tail;
     __syncthreads(); // everybody has read the tail before anybody moves it
@@ -400,6 +482,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
     head = tail;
     __syncthreads();
   }
+  } // !reach_done
 
   const long long t_reach = now_ns();
   // ---- 2. forward construction in the reference's order (compose.cpp:389-489)
@@ -429,7 +512,7 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
         const int p = queue[id];
         n1 = (int)(p % N1);
         n2 = (int)(p / N1);
-        heavy = heavy_state(g1, g2, n1, n2);
+        heavy = heavy_state(g1, g2, n1, n2, P.kind);
       }
       // states with long arc lists are enumerated by whole warps (h_list: their slots in this chunk)
       if (tid == 0) *n_heavy = 0;
@@ -728,7 +811,7 @@ int gtnb_compose_graphs(
   const size_t need = (size_t)(words + ints + (long long)si.size() + (long long)sf.size()) * 4 + sb.size();
   if (!rc && ctx->total_mem && need > ctx->total_mem / 2)
     rc = fail(ctx, GTNB_ERR_UNSUPPORTED, "gtnb_compose_graphs: scratch larger than half of the device memory");
-  int32_t *si_dev = nullptr, *ints_dev = nullptr, *counts_dev = nullptr;
+  int32_t *si_dev = nullptr, *ints_dev = nullptr, *counts_dev = nullptr, *sync_dev = nullptr;
   float* sf_dev = nullptr;
   uint8_t* sb_dev = nullptr;
   uint32_t* words_dev = nullptr;
@@ -745,6 +828,7 @@ int gtnb_compose_graphs(
   TRY(dev_alloc(ctx, &words_dev, words));
   TRY(dev_alloc(ctx, &ints_dev, ints));
   TRY(dev_alloc(ctx, &counts_dev, 4ll * n_pairs));
+  TRY(dev_alloc(ctx, &sync_dev, 8ll * n_pairs));
   TRY(dev_alloc(ctx, &pairs_dev, n_pairs));
   TRY(upload(ctx, si_dev, si.data(), (long long)si.size()));
   TRY(upload(ctx, sf_dev, sf.data(), (long long)sf.size()));
@@ -781,13 +865,44 @@ int gtnb_compose_graphs(
       P.queue = ints_dev + queue_at[b];
       P.arc_off = ints_dev + aoff_at[b];
       P.counts = counts_dev + 4 * b;
+      P.sync = sync_dev + 8 * b;
     }
     cudaError_t e = cudaMemsetAsync(words_dev, 0, sizeof(uint32_t) * (size_t)words, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ints_dev, 0x80, sizeof(int32_t) * (size_t)ints, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * 4 * (size_t)n_pairs, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sync_dev, 0, sizeof(int32_t) * 8 * (size_t)n_pairs, ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaMemsetAsync", __FILE__, __LINE__);
   }
+  // large product state spaces: the co-reachability search on several SMs per pair (cooperative launch)
+  int G = 1;
+  if (!rc) {
+    long long maxS = 0;
+    for (int b = 0; b < n_pairs; b++) maxS = std::max(maxS, S[b]);
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc::gcompose_reach_kernel, gc::kThreads, 0);
+    const long long room = (long long)sms * per_sm / n_pairs;
+    if (maxS >= 65536 && room >= 2) G = (int)std::min<long long>(std::min<long long>(room, 64), maxS / 16384);
+    if (G < 2) G = 1;
+    for (int b = 0; b < n_pairs; b++) pairs[b].reach_done = G > 1 ? 1 : 0;
+  }
   TRY(upload(ctx, pairs_dev, pairs.data(), n_pairs));
+  if (!rc && G > 1) {
+    const gc::PairDev* pd = pairs_dev;
+    void* args[] = {(void*)&pd, (void*)&G};
+    prof_begin(ctx, "gcompose_reach");
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)gc::gcompose_reach_kernel, dim3((unsigned)(n_pairs * G)),
+                                                dim3(gc::kThreads), args, 0, ctx->stream);
+    prof_end(ctx);
+    if (e != cudaSuccess) { // not co-resident right now: the single-CTA search does step 1 itself
+      cudaGetLastError();
+      G = 1;
+      for (int b = 0; b < n_pairs; b++) pairs[b].reach_done = 0;
+      TRY(upload(ctx, pairs_dev, pairs.data(), n_pairs));
+    } else {
+      ctx->launches++;
+    }
+  }
   TRY(launch_gcompose_search(ctx, pairs_dev, n_pairs));
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(counts.data(), counts_dev, sizeof(int32_t) * counts.size(), cudaMemcpyDeviceToHost, ctx->stream);
@@ -836,6 +951,7 @@ int gtnb_compose_graphs(
   dev_free(ctx, words_dev);
   dev_free(ctx, ints_dev);
   dev_free(ctx, counts_dev);
+  dev_free(ctx, sync_dev);
   dev_free(ctx, pairs_dev);
   if (rc) {
     gtnb_composed_destroy(ctx, res);

@@ -24,7 +24,8 @@ struct EmuGraph {
 
 /* composes one pair; outputs up to cap_nodes / cap_arcs entries, the true sizes in n_nodes / n_arcs */
 int emu_gcompose(
-    const EmuGraph* a, const EmuGraph* b, int kind, int cap_nodes, int cap_arcs, int32_t* n_nodes, int32_t* n_arcs,
+    const EmuGraph* a, const EmuGraph* b, int kind, int reach_ctas, int cap_nodes, int cap_arcs, int32_t* n_nodes,
+    int32_t* n_arcs,
     uint8_t* flags, int32_t* src, int32_t* dst, int32_t* il, int32_t* ol, float* w, int32_t* gi1, int32_t* gi2) {
   using namespace gtnb;
   auto view = [](const EmuGraph* g) {
@@ -61,6 +62,14 @@ int emu_gcompose(
   P.queue = queue.data();
   P.arc_off = arc_off.data();
   P.counts = counts;
+  int32_t sync[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  P.sync = sync;
+  if (reach_ctas > 1) {
+    // gtnb_compose_graphs' cooperative launch: the G CTAs of the pair run concurrently
+    P.reach_done = 1;
+    emu::launch_clusters(reach_ctas, reach_ctas, gc::kThreads, 0, [&] { gc::gcompose_reach_kernel(&P, reach_ctas); });
+    if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads;
+  }
   emu::launch(1, gc::kThreads, 0, [&] { gc::gcompose_search_kernel(&P); });
   if (emu::g_launch_failed.exchange(false)) return emu::kEmuNoThreads;
   *n_nodes = counts[0];

@@ -387,6 +387,12 @@ inline int __syncthreads_and(int pred) {
 inline int atomicAdd(int* p, int v) {
   return std::atomic_ref<int>(*p).fetch_add(v);
 }
+inline int atomicExch(int* p, int v) {
+  return std::atomic_ref<int>(*p).exchange(v);
+}
+inline void __threadfence() {
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+}
 inline int atomicMax(int* p, int v) {
   std::atomic_ref<int> a(*p);
   int cur = a.load();

@@ -28,7 +28,7 @@ def gtn():
 @pytest.fixture(scope="module")
 def emu():
     lib = C.CDLL(emu_build.build('gcompose', ['k_gcompose.cu', 'gtnb_gcompose.h']))
-    lib.emu_gcompose.argtypes = [C.POINTER(EmuGraph), C.POINTER(EmuGraph), C.c_int, C.c_int, C.c_int, i32p, i32p, u8p,
+    lib.emu_gcompose.argtypes = [C.POINTER(EmuGraph), C.POINTER(EmuGraph), C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, u8p,
                                  i32p, i32p, i32p, i32p, f32p, i32p, i32p]
     return lib
 
@@ -53,14 +53,14 @@ def kind_of(ga, gb, intersect):
     return 3 if (s1 and s2) else (1 if s1 else (2 if s2 else 0))
 
 
-def run(emu, gtn, ga, gb, intersect, cap=1 << 16):
+def run(emu, gtn, ga, gb, intersect, cap=1 << 16, reach_ctas=1):
     ea, ka = pack(gtn, ga)
     eb, kb = pack(gtn, gb)
     nn, na = C.c_int32(0), C.c_int32(0)
     fl = np.zeros(cap, np.uint8)
     ints = [np.zeros(cap, np.int32) for _ in range(6)]
     w = np.zeros(cap, np.float32)
-    rc = emu.emu_gcompose(C.byref(ea), C.byref(eb), kind_of(ga, gb, intersect), cap, cap, C.byref(nn), C.byref(na),
+    rc = emu.emu_gcompose(C.byref(ea), C.byref(eb), kind_of(ga, gb, intersect), reach_ctas, cap, cap, C.byref(nn), C.byref(na),
                           fl.ctypes.data_as(u8p), ints[0].ctypes.data_as(i32p), ints[1].ctypes.data_as(i32p),
                           ints[2].ctypes.data_as(i32p), ints[3].ctypes.data_as(i32p), w.ctypes.data_as(f32p),
                           ints[4].ctypes.data_as(i32p), ints[5].ctypes.data_as(i32p))
@@ -96,7 +96,8 @@ def test_kernel_source_reproduces_the_reference_numbering(emu, gtn, seed):
         ma.arc_sort(True)
     if seed & 2:
         mb.arc_sort(False)
-    out = run(emu, gtn, ma, mb, intersect)
+    # every third case: the co-reachability search on 2 or 3 concurrent CTAs (gcompose_reach_kernel)
+    out = run(emu, gtn, ma, mb, intersect, reach_ctas=(1, 1, 2, 1, 1, 3)[seed % 6])
     # the host construction of the gtn:: layer (pinned against the live reference by tests/test_host_api.py)
     gtn.set_compose_device_policy(2)
     try:
@@ -134,7 +135,7 @@ def test_kernel_source_on_wide_frontiers(emu, gtn, seed):
         ma.arc_sort(True)
     if seed & 2:
         mb.arc_sort(False)
-    out = run(emu, gtn, ma, mb, intersect, cap=1 << 20)
+    out = run(emu, gtn, ma, mb, intersect, cap=1 << 20, reach_ctas=1 + seed % 3)
     gtn.set_compose_device_policy(2)
     try:
         host = gtn.intersect(ma, mb) if intersect else gtn.compose(ma, mb)
