@@ -198,20 +198,14 @@ std::vector<Graph> composeBatch(const std::vector<Graph>& a, const std::vector<G
     bool general = n >= 2 && policy != 2 && detail::deviceCount() > 0 && (a.size() == n || a.size() == 1) &&
                    (b.size() == n || b.size() == 1);
     double states = 0.0;
-    bool lowDegree = true;
     for (size_t i = 0; general && i < n; i++) {
       const Graph& x = a[a.size() == 1 ? 0 : i];
       const Graph& y = b[b.size() == 1 ? 0 : i];
       general = !x.isDeviceResident() && !y.isDeviceResident();
       states += (double)x.numNodes() * (double)y.numNodes();
-      if (policy == 0 && general && (a.size() == n || i == 0))
-        for (size_t u = 0; lowDegree && u < x.numNodes(); u++) lowDegree = x.numOut(u) <= 64 && x.numIn(u) <= 64;
-      if (policy == 0 && general && (b.size() == n || i == 0))
-        for (size_t u = 0; lowDegree && u < y.numNodes(); u++) lowDegree = y.numOut(u) <= 64 && y.numIn(u) <= 64;
     }
-    // (same rule as the single-pair dispatch, functions.cpp generalOnDevice: enough product states per pair on
-    // average, no long arc lists)
-    if (general && (policy == 1 || (lowDegree && states >= 16384.0 * (double)n))) {
+    // (same rule as the single-pair dispatch, functions.cpp generalOnDevice: enough product states per pair)
+    if (general && (policy == 1 || states >= 16384.0 * (double)n)) {
       std::vector<const Graph*> pa(a.size()), pb(b.size());
       for (size_t i = 0; i < a.size(); i++) pa[i] = &a[i];
       for (size_t i = 0; i < b.size(); i++) pb[i] = &b[i];

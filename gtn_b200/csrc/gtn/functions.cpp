@@ -565,15 +565,11 @@ bool generalOnDevice(const Graph& g1, const Graph& g2) {
   const int policy = composeDevicePolicy();
   if (policy == 2 || g1.isDeviceResident() || g2.isDeviceResident() || deviceCount() == 0) return false;
   if (policy == 1) return true;
-  // measured (profiles/r2_gcompose.md): one CTA per pair beats the host construction when there are enough
-  // product states to search (>= 2^14) and no node has a long arc list (one thread walks a state's lists in the
-  // ordered forward pass: the 2000-arc root of a lexicon serialises it) -- ctc x trigram 17 vs 29 ms, an
-  // epsilon operand x the emissions chain 85 vs 112 ms; tiny pairs and high-degree operands stay on the host
-  if ((double)g1.numNodes() * (double)g2.numNodes() < 16384.0) return false;
-  for (const Graph* g : {&g1, &g2})
-    for (size_t n = 0; n < g->numNodes(); n++)
-      if (g->numOut(n) > 64 || g->numIn(n) > 64) return false;
-  return true;
+  // measured (profiles/r2_gcompose.md): the device beats the host construction once there are enough product
+  // states to search -- ctc x trigram 7.5 vs 30 ms, lexicon x LM 38 vs 92 ms, an epsilon operand x the emissions
+  // chain 80 vs 115 ms; a tiny pair (n-gram x ctc of timeNgramCtc: 630 states) costs 0.6 ms of launches and
+  // round trips against 0.13 ms on the host and stays there unless forced
+  return (double)g1.numNodes() * (double)g2.numNodes() >= 16384.0;
 }
 
 Graph composeDispatch(const Graph& g1, const Graph& g2, bool intersectMode) {

@@ -76,9 +76,8 @@ bool composeGraphsDevice(
     const std::vector<const Graph*>& first, const std::vector<const Graph*>& second, bool intersectMode,
     std::vector<Graph>& out);
 /** GTNB_COMPOSE_DEVICE = auto (default) | always | never: whether compose / intersect of two arbitrary
- * graphs runs on the device.  auto: when there is a GPU, the product state space has at least 2^14 states and
- * no node of either operand has more than 64 arcs in or out -- the shapes where the one-CTA-per-pair search
- * was measured faster than the host construction (profiles/r2_gcompose.md). */
+ * graphs runs on the device.  auto: when there is a GPU and the product state space has at least 2^14 states
+ * -- from there on the device search was measured faster than the host construction (profiles/r2_gcompose.md). */
 int composeDevicePolicy(); // 0 auto, 1 always, 2 never
 void setComposeDevicePolicy(int policy);
 int deviceCount();

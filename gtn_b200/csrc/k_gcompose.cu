@@ -58,6 +58,7 @@ constexpr int kThreads = 128; // (the emulation runs one std::thread per CUDA th
 constexpr int kThreads = 1024; // one CTA per pair: every warp it can get to hide the latency of the dependent global loads
 #endif
 constexpr int kEps = -1; // gtn::epsilon (graph.h:21)
+constexpr int kCache = 4; // destinations of a light state kept in registers between the passes of the ordered search
 
 __device__ __forceinline__ long long now_ns() {
 #ifdef GTNB_HOST_EMU
@@ -526,8 +527,21 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
         m2 = (int)(p / N1);
       };
       // (a) the arcs of every state of the chunk: counts -> the reference's arc ids
+      // (a light state's first kCache destinations are kept in registers: the three passes below then need no
+      // second walk through its arc lists -- every state of a CTC-like lattice qualifies)
       int cnt = 0;
-      if (on && !heavy) for_out_arcs(P, n1, n2, [&](int, int, int, int) { cnt++; });
+      int cand[kCache];
+#pragma unroll
+      for (int q = 0; q < kCache; q++) cand[q] = 0;
+      if (on && !heavy)
+        for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
+          const int v = (int)(d1 + N1 * d2);
+#pragma unroll
+          for (int q = 0; q < kCache; q++)
+            if (cnt == q) cand[q] = v;
+          cnt++;
+        });
+      const bool cached = !heavy && cnt <= kCache;
       for (int h = warp; h < nh; h += kThreads / 32) {
         int m1, m2;
         state_of(h_list[h], m1, m2);
@@ -543,7 +557,11 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
       arc_base += total;
       if (nh) __syncthreads();
       // (b) every undiscovered destination keeps the smallest arc id that reaches it
-      if (on && !heavy) {
+      if (on && cached) {
+#pragma unroll
+        for (int q = 0; q < kCache; q++)
+          if (q < cnt && id_get(P.ids, cand[q]) < 0) atomicMax(&P.ids[cand[q]], -2 - (off + q));
+      } else if (on && !heavy) {
         int k = off;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
           const long long p = d1 + N1 * d2;
@@ -564,7 +582,10 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
       __syncthreads();
       // (c) the winners, numbered in arc-id order
       int wins = 0;
-      if (on && !heavy) {
+      if (on && cached) {
+#pragma unroll
+        for (int q = 0; q < kCache; q++) wins += q < cnt && id_get(P.ids, cand[q]) == -2 - (off + q);
+      } else if (on && !heavy) {
         int k = off;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
           wins += id_get(P.ids, d1 + N1 * d2) == -2 - k;
@@ -586,7 +607,16 @@ __global__ void __launch_bounds__(kThreads) gcompose_search_kernel(const PairDev
       if (heavy) wins = h_wins[tid];
       const int wbase = next_id + block_scan(wins, warp_sums, &total);
       if (heavy) h_wins[tid] = wbase;
-      if (on && !heavy && wins) {
+      if (on && cached && wins) {
+        int w = wbase;
+#pragma unroll
+        for (int q = 0; q < kCache; q++)
+          if (q < cnt && id_get(P.ids, cand[q]) == -2 - (off + q)) {
+            P.ids[cand[q]] = w;
+            queue[w] = cand[q];
+            w++;
+          }
+      } else if (on && !heavy && wins) {
         int k = off, w = wbase;
         for_out_arcs(P, n1, n2, [&](int, int, int d1, int d2) {
           const long long p = d1 + N1 * d2;
