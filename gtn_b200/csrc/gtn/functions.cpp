@@ -566,9 +566,9 @@ bool generalOnDevice(const Graph& g1, const Graph& g2) {
   if (policy == 2 || g1.isDeviceResident() || g2.isDeviceResident() || deviceCount() == 0) return false;
   if (policy == 1) return true;
   // measured (profiles/r2_gcompose.md): the device beats the host construction once there are enough product
-  // states to search -- ctc x trigram 7.5 vs 30 ms, lexicon x LM 38 vs 92 ms, an epsilon operand x the emissions
-  // chain 80 vs 115 ms; a tiny pair (n-gram x ctc of timeNgramCtc: 630 states) costs 0.6 ms of launches and
-  // round trips against 0.13 ms on the host and stays there unless forced
+  // states to search -- ctc x trigram 5.8 vs 29 ms, lexicon x LM 26 vs 92 ms, an epsilon operand x the emissions
+  // chain 58 vs 113 ms; a tiny pair (n-gram x ctc of timeNgramCtc: 630 states) costs 0.4 ms of launches and
+  // round trips against 0.12 ms on the host and stays there unless forced
   return (double)g1.numNodes() * (double)g2.numNodes() >= 16384.0;
 }
 
