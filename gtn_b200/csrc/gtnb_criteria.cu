@@ -327,7 +327,7 @@ extern "C" int gtnb_ctc_loss(
  * dense transitions graph of test/criterion_test.cpp:244-254 / :316-326, through the
  * factored kernel (k_dense.cu): the T*C*C lattice is never materialised.
  */
-extern "C" int gtnb_viterbi_dense(
+static int viterbi_dense_run(
     gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
     const int32_t* input_lens, const float* trans_w_host, int32_t* paths_host, float* scores_host) {
   if (!ctx || B < 0 || T < 0 || C <= 0 || !emissions || !trans_w_host)
@@ -388,6 +388,18 @@ done:
 #undef TRYCUDA
 }
 
+/* (the device scratch of a call comes from the context's call-scoped arena, as in gtnb_ctc_loss: no stream-ordered
+ * allocations on the path after the first call of a shape) */
+extern "C" int gtnb_viterbi_dense(
+    gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
+    const int32_t* input_lens, const float* trans_w_host, int32_t* paths_host, float* scores_host) {
+  if (ctx) arena_begin(ctx);
+  const int rc = viterbi_dense_run(ctx, B, T, C, emissions, emissions_on_device, input_lens, trans_w_host, paths_host,
+                                   scores_host);
+  if (ctx) arena_end(ctx);
+  return rc;
+}
+
 /*
  * ASG criterion for a whole minibatch (test/criterion_test.cpp:244-305, examples/asg.cpp:59-81):
  *   loss_b = forwardScore(compose(e_b, transitions))
@@ -397,7 +409,7 @@ done:
  * is materialised on the device (C + (T-1) C^2 arcs per utterance); compose(fal_b,
  * transitions) is a 2U-arc chain built on the host from the target (pure construction).
  */
-extern "C" int gtnb_asg_loss(
+static int asg_loss_run(
     gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
     const float* trans_w_host, const int32_t* targets, const int32_t* target_lens,
     float* losses_host, float* grads, int grads_on_device, float* trans_grad_host) {
@@ -608,4 +620,15 @@ done:
   return rc;
 #undef TRY
 #undef TRYCUDA
+}
+
+extern "C" int gtnb_asg_loss(
+    gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
+    const float* trans_w_host, const int32_t* targets, const int32_t* target_lens,
+    float* losses_host, float* grads, int grads_on_device, float* trans_grad_host) {
+  if (ctx) arena_begin(ctx);
+  const int rc = asg_loss_run(ctx, B, T, C, emissions, emissions_on_device, trans_w_host, targets, target_lens,
+                              losses_host, grads, grads_on_device, trans_grad_host);
+  if (ctx) arena_end(ctx);
+  return rc;
 }
