@@ -517,7 +517,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=B_DEF, help="utterances per GPU")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="utterances per GPU (default %d); with --strong: of the whole job (default 2048 = configs[4])" % B_DEF)
     ap.add_argument("--T", type=int, default=T_DEF)
     ap.add_argument("--C", type=int, default=C_DEF)
     ap.add_argument("--U", type=int, default=U_DEF)
@@ -530,6 +531,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-path", action="store_true")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 2048 if args.strong else B_DEF
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -426,6 +426,7 @@ static int asg_loss_run(
   int32_t* status_dev = nullptr;
   bool implicit = false, needs_exact = false;
   gtnb_lattice *den = nullptr, *num = nullptr;
+  cudaStream_t asg_main = ctx->stream;
 
   // transitions graph view (criterion_test.cpp:244-254)
   std::vector<uint8_t> tflags(C + 1, 2);
@@ -548,10 +549,19 @@ static int asg_loss_run(
     }
   }
   if (implicit) {
+    TRY(ensure_side_streams(ctx, 0, 0));
     TRY(dev_alloc(ctx, &status_dev, 2ll * B));
     TRYCUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t) * 2 * B, ctx->stream));
+    // the numerator's sweeps (forced-alignment chains: small) run on the second stream beside the
+    // denominator's (dense transitions: wide); they share nothing but the emission gradient, which both
+    // accumulate with red.global.add
+    TRYCUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    TRYCUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
     TRY(launch_implicit_forward(ctx, den, status_dev));
-    TRY(launch_implicit_forward(ctx, num, status_dev + B));
+    ctx->stream = ctx->copy_stream;
+    rc = launch_implicit_forward(ctx, num, status_dev + B);
+    ctx->stream = asg_main;
+    if (rc) goto done;
   } else {
     TRY(gtnb_compose_linear(ctx, B, &tview, 1, 1, Tb.data(), C, e_dev, per, &den));
     TRY(gtnb_compose_linear(ctx, B, fviews.data(), B, 0, Tb.data(), C, e_dev, per, &num));
@@ -566,13 +576,22 @@ static int asg_loss_run(
       TRY(stage_end(ctx));
       // +1 / -1: subtract's gradFunc (functions.cpp:53-58); graph-side gradients straight into
       // the transitions' (shared by the batch) and the forced-alignment chains' slabs
+      TRYCUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); // the staged -1 seeds
+      TRYCUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
       TRY(launch_implicit_backward(ctx, den, nullptr, g_dev, per, 0, -1, tg_dev));
-      TRY(launch_implicit_backward(ctx, num, minus1, g_dev, per, 0, -1, ft_grad));
+      ctx->stream = ctx->copy_stream;
+      rc = launch_implicit_backward(ctx, num, minus1, g_dev, per, 0, -1, ft_grad);
+      ctx->stream = asg_main;
+      if (rc) goto done;
     } else {
       TRY(gtnb_backward(ctx, den, 0, nullptr)); // +1 (subtract's gradFunc, functions.cpp:53-58)
       TRY(gtnb_backward(ctx, num, 0, m1.data())); // -1
       TRY(gtnb_compose_grad(ctx, den, tg_dev, g_dev, per));
       TRY(gtnb_compose_grad(ctx, num, ft_grad, g_dev, per));
+    }
+    if (implicit) { // join the numerator's stream
+      TRYCUDA(cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+      TRYCUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
     if (nFt) {
       TRY(stage_begin(ctx));
@@ -584,6 +603,10 @@ static int asg_loss_run(
       TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
     if (trans_grad_host)
       TRYCUDA(cudaMemcpyAsync(trans_grad_host, tg_dev, sizeof(float) * nTrans, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (implicit && !want) { // loss only: the numerator's forward sweep is still on the second stream
+    TRYCUDA(cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+    TRYCUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   }
   TRY(readback_reserve(ctx, 4 * sizeof(float) * B));
   {
