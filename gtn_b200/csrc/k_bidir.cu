@@ -13,7 +13,7 @@
  *   CTA B (cluster rank 1)  beta_s[u]  = logsumexp over out-arcs (u -> v, w) of w + e[s][label(v)] + beta_{s+1}[v]
  *                           for levels s = T .. 1   (beta_T = 0 on accept nodes)
  *
- * With M = T/2 rounded down to a multiple of 8, A saves alpha_1..alpha_M and B saves beta_T..beta_{M+1}
+ * With M = T/2 rounded up to a multiple of 8 (B starts later: it gets the shorter first phase), A saves alpha_1..alpha_M and B saves beta_T..beta_{M+1}
  * (phase 1, T/2 dependent steps each, concurrently); one barrier.cluster later A continues through
  * levels M+1..T reading B's saved beta, B through levels M..1 reading A's saved alpha (phase 2), and the
  * node posterior gamma_s[u] = exp(alpha_s[u] + beta_s[u] - Z) is formed ON THE FLY, off the serial
@@ -1017,7 +1017,10 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
   const int nw_act = (N1 + 31) >> 5; // node warps of THIS utterance
   const int nact = 32 * nw_act;
   const int nblk = (T + kBlk - 1) / kBlk;
-  const int M = ((T / 2) / kBlk) * kBlk; // levels 1..M: alpha saved, posterior by B; M+1..T: beta saved, posterior by A
+  // levels 1..M: alpha saved, posterior by B; M+1..T: beta saved, posterior by A.  T/2 rounded UP to a block: CTA B
+  // starts later (it gathers the out-arc tables first), so it gets the shorter first phase and A does not sit at
+  // the cluster barrier waiting for it
+  const int M = min(((T / 2 + kBlk - 1) / kBlk) * kBlk, (max(T - 1, 0) / kBlk) * kBlk); // (B keeps >= 1 level)
   const int jb = M / kBlk; // blocks [0, jb) belong to B's phase 2, [jb, nblk) to A's
   // blocks this CTA walks, in its own order: A 0, 1, ..; B nblk-1, nblk-2, ..
   const int n_ph1 = dir == 0 ? jb : nblk - jb;

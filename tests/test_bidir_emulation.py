@@ -52,6 +52,8 @@ def run(lib, e, targets, lens=None, blank=0, want_grad=True, zero_w=1):
     (1, 23, 128, 4),   # C = 128: 16 labels per helper lane
     (2, 1, 8, 0),      # T = 1, empty targets
     (2, 33, 8, 16),    # T = 2U + 1: a single feasible alignment per utterance
+    (2, 8, 8, 2),      # T = 8: one block, everything in CTA B's first phase
+    (1, 24, 8, 3),     # T = 24: M = 16, the halves differ by a block
 ])
 def test_bidir_kernel_source_matches_oracle(emu, oracle, shape):
     from oracle import f64
