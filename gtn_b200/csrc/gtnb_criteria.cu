@@ -185,7 +185,7 @@ static int ctc_loss_run(
     const int32_t* T_dev = small_dev + tot_t + 2ll * B;
     TRYCUDA(cudaEventRecord(ev_setup, main_stream));
     if (bidir && K == 1 && !h2d_event && !(grads && !grads_on_device)) {
-      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1, bidir_scores_dev));
+      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1, bidir_scores_dev, blank));
     } else if (bidir) {
       for (int k = 0; k < K && !rc; k++) {
         const int b0 = chunk_lo[k], nb = chunk_lo[k + 1] - chunk_lo[k];
@@ -193,7 +193,7 @@ static int ctc_loss_run(
         TRYCUDA(cudaStreamWaitEvent(cs, ev_setup, 0));
         if (h2d_event) TRYCUDA(cudaStreamWaitEvent(cs, ctx->side_events[k], 0));
         ctx->stream = cs;
-        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1, bidir_scores_dev);
+        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1, bidir_scores_dev, blank);
         ctx->stream = main_stream;
         if (rc) goto done;
         if (grads && !grads_on_device)

@@ -308,7 +308,8 @@ int bidir_blocks(int max_T);
 int bidir_zparts(); // partial sums of forwardScore(emissions) per CTA
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
-    int64_t grad_stride, int b0 = 0, int nb = -1, int zero_w = 0, float* out_scores_dev = nullptr);
+    int64_t grad_stride, int b0 = 0, int nb = -1, int zero_w = 0, float* out_scores_dev = nullptr,
+    int ctc_blank = -1); // ctc_blank >= 0: the graphs are ctc_build_kernel's (PAIR kernels)
 /* k_order.cu (experimental): a composed lattice's rows and accept list in the order the reference's shortestPath relaxes / creates them */
 int launch_relax_order(gtnb_ctx* ctx, gtnb_lattice* lat);
 /* k_banded.cu (experimental): same contract as the implicit sweeps, for band-shaped graph operands */

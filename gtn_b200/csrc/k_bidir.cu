@@ -79,6 +79,7 @@ namespace bidir {
 
 constexpr int kMaxNodes = 256; // table capacity
 constexpr int kMaxNodeWarps = 7; // graph nodes per utterance: at most 224, one per thread (4 CTAs of 12 warps per SM at 40 registers)
+constexpr int kMaxPairWarps = 4; // PAIR kernels: two nodes per thread, (U + 1) <= 112 pairs
 constexpr int kRowF = 264; // floats per chain row in shared memory
 constexpr int kDummy = 256; // slot of every chain row that holds kNeg (absent arcs point here)
 constexpr int kBlk = 8; // frames per block (one TMA copy, one helper pass, one renormalisation)
@@ -157,6 +158,7 @@ struct Params {
   int nwn; // node warps in the launch (ceil(max nodes / 32))
   int nblk_cap;
   int zero_w; // every arc weight of every graph is 0 (host knowledge: CTC / forced alignment targets)
+  int ctc_blank; // PAIR kernels: the graphs are ctc_build_kernel's, this is their blank label
   Layout lay;
 };
 
@@ -206,6 +208,23 @@ __device__ __forceinline__ void sts_u(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return *emu::shared_ptr<float4>(addr);
+}
+struct f2 {
+  float x, y;
+};
+__device__ __forceinline__ f2 lds_v2(uint32_t addr) {
+  f2 v;
+  v.x = *emu::shared_ptr<float>(addr);
+  v.y = *emu::shared_ptr<float>(addr + 4);
+  return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, float a, float b) {
+  *emu::shared_ptr<float>(addr) = a;
+  *emu::shared_ptr<float>(addr + 4) = b;
+}
+__device__ __forceinline__ void stg_v2(float* p, float a, float b) {
+  p[0] = a;
+  p[1] = b;
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   return *emu::shared_ptr<uint16_t>(addr);
@@ -330,6 +349,20 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+struct f2 {
+  float x, y;
+};
+__device__ __forceinline__ f2 lds_v2(uint32_t addr) {
+  f2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void stg_v2(float* p, float a, float b) {
+  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -402,6 +435,11 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + lg2(s);
 }
 
+/* logsumexp of two scores */
+__device__ __forceinline__ float lse2(float a, float b) { // max + lg2(1 + 2^-|a - b|): 2 MUFU
+  return fmaxf(a, b) + lg2(1.0f + ex2(-fabsf(a - b)));
+}
+
 struct NodeState {
   uint32_t so0, so1, so2; // byte offsets of the three neighbours in a chain row
   float w0, w1, w2; // arc weights, log2 units
@@ -437,7 +475,8 @@ struct NodeUni {
  * subtracts it from every score.  Integers subtract exactly and their sum D stays exact in fp32, so the
  * kept scores stay within a few hundred of zero (ulp ~ 3e-5) and nothing is lost: true = kept + D.
  */
-__device__ __forceinline__ void publish_block_max(NodeState& st, float stored) {
+template <class S>
+__device__ __forceinline__ void publish_block_max(S& st, float stored) {
   const int iv = __float2int_rn(fmaxf(stored, -2.0e9f));
   const int wm = __reduce_max_sync(0xffffffffu, iv);
   // two words, used alternately: the one the NEXT block will publish into is reset here (every thread
@@ -446,7 +485,8 @@ __device__ __forceinline__ void publish_block_max(NodeState& st, float stored) {
   if (threadIdx.x == 0) sts_u(st.redi ^ 4u, (uint32_t)kIntMin);
 }
 /* at the start of the next block: the adjustment every node thread applies (same value in all of them) */
-__device__ __forceinline__ void fetch_block_adjust(NodeState& st) {
+template <class S>
+__device__ __forceinline__ void fetch_block_adjust(S& st) {
   const int mx = (int)lds_u(st.redi);
   st.redi ^= 4u;
   // nothing alive (or nothing published yet): no adjustment
@@ -587,7 +627,7 @@ struct NodeCtx {
   float* saved;
   float* boff_own;
   float* out_score;
-  uint32_t bars, e_base, o_base, g_base, od_base, perm_a, red_a, spare, lab4, feas_a;
+  uint32_t bars, e_base, o_base, g_base, od_base, perm_a, red_a, spare, lab4, feas_a, blank4;
   int e_stage_bytes, o_stage_bytes, g_block_bytes, pg, C, T, pitch, nblk, n_ph1, n_ph2, nw_act;
   bool want_g;
 };
@@ -718,6 +758,256 @@ __device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool
       // offsets moved since the meeting level: all integers, the differences are exact
       st.zsub = st.Zl - ((st.D + doth) - st.Dc);
       node_rows<DIR, 2, ZW, NQ, FX>(st, un, nfr);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive_n(bar_e_empty(cx.bars, s), arr2);
+      mbar_arrive(bar_o_empty(cx.bars, so));
+      mbar_arrive(bar_g_full(cx.bars, sg));
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* node warps, CTC pair mode                                           */
+/* ------------------------------------------------------------------ */
+
+/*
+ * gtnb_ctc_loss only ever hands this kernel the graphs ctc_build_kernel made (benchmarks/ctc.cpp:40-58): node 2t is
+ * the t-th blank (self loop, arc from label 2t-1), node 2t-1 the t-th label (self loop, arc from blank 2t-2, skip
+ * arc from label 2t-3 unless the label repeats).  The PAIR kernels give thread t BOTH nodes (2t-1, 2t):
+ *   - half the node warps (4 instead of 7 at U = 100) and half the barrier arrivals per level;
+ *   - the thread's own scores stay in registers; what it needs from its neighbour is ONE LDS.64 (A: the pair
+ *     t-1) or one LDS (B: the label of pair t+1) instead of six loads, and its two results leave as one
+ *     STS.64 / STG.64;
+ *   - the blank's logsumexp has two terms: max + lg2(1 + 2^-|a-b|), 2 MUFU instead of 4;
+ *   - the blank's posterior is never formed: blank is the complement label of the helper warps.
+ * 28 / 34 SASS instructions per PAIR and level instead of 2 x 19 / 2 x 24, 6 / 7 MUFU instead of 8 / 10.
+ * Row layouts: slot(node n) = n + 1 in the saved-score rows (pair t = floats 2t, 2t+1: 8-byte aligned), n + 3 in
+ * the chain rows (pair t-1 of thread 0 and the label beyond the last pair read the row's kNeg).
+ */
+struct PairState {
+  float al, ab; // what the neighbours read of this thread's label / blank node (A: alpha, B: beta + emission)
+  uint32_t t8; // 8 * pair index
+  uint32_t pc, qc; // chain rows: read / write
+  uint32_t ea_l, ea_b; // emissions of the label / of blank in the current stage, first row of the block
+  uint32_t oa; // the partner's score of this thread's label node, first row of the block
+  uint32_t ga; // where the label's posterior goes
+  float* gs; // where the pair's scores are saved (phase 1)
+  float adj, D, Zh, zsub, Zl, Dc;
+  uint32_t redi;
+  bool skip; // A: label 2t-1 has the skip in-arc; B: label 2t+1 has it (= this thread's label has the skip out-arc)
+};
+
+template <int DIR, int PH, int NQ>
+__device__ __forceinline__ void pair_step(PairState& ps, const NodeUni& un, int r, bool last) {
+  using SD = Strd<NQ, true>;
+  const int rr = DIR ? -r : r;
+  const float xl = lds(ps.ea_l + (uint32_t)(rr * SD::c4(un)));
+  const float xb = lds(ps.ea_b + (uint32_t)(rr * SD::c4(un)));
+  float vl, vb;
+  if (DIR == 0) {
+    const f2 pv = lds_v2(ps.pc + ps.t8); // pair t-1: (label 2t-3, blank 2t-2)
+    vb = lse2(ps.ab, ps.al);
+    vl = lse3(ps.al, pv.y, ps.skip ? pv.x : kNeg);
+  } else {
+    const float nl = lds(ps.pc + ps.t8 + 16u); // label 2t+1
+    vb = lse2(ps.ab, nl);
+    vl = lse3(ps.al, ps.ab, ps.skip ? nl : kNeg);
+  }
+  const float val_l = DIR == 0 ? vl + fmaf(xl, kLog2e, -ps.adj) : vl - ps.adj;
+  const float val_b = DIR == 0 ? vb + fmaf(xb, kLog2e, -ps.adj) : vb - ps.adj;
+  ps.al = DIR == 0 ? val_l : fmaf(xl, kLog2e, val_l);
+  ps.ab = DIR == 0 ? val_b : fmaf(xb, kLog2e, val_b);
+  ps.adj = 0.0f;
+  if (DIR == 0)
+    sts_v2(ps.qc + ps.t8 + 8u, ps.al, ps.ab);
+  else
+    sts(ps.qc + ps.t8 + 8u, ps.al); // only the label is read by a neighbour
+  if (PH == 2)
+    sts(ps.ga + (uint32_t)(rr * SD::g4(un)),
+        ex2(((val_l - ps.Zh) + lds(ps.oa + (uint32_t)(rr * SD::p4(un)))) - ps.zsub));
+  if (last) publish_block_max(ps, fmaxf(ps.al, ps.ab));
+  bar_named(1, un.nact);
+  if (PH == 1) stg_v2(ps.gs + rr * SD::pitch(un), val_l, val_b);
+  const uint32_t t = ps.pc;
+  ps.pc = ps.qc;
+  ps.qc = t;
+}
+
+template <int DIR, int PH, int NQ>
+__device__ __forceinline__ void pair_rows(PairState& ps, const NodeUni& un, int n) {
+  if (n == kBlk) {
+#pragma unroll
+    for (int r = 0; r < kBlk; r++) pair_step<DIR, PH, NQ>(ps, un, r, r == kBlk - 1);
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < n; r++) pair_step<DIR, PH, NQ>(ps, un, r, r == n - 1);
+  }
+  if (PH == 1) ps.gs += (DIR ? -n : n) * Strd<NQ, true>::pitch(un);
+}
+
+/* the first level of phase 2 (see node_first_phase2): Z over BOTH nodes of every pair */
+template <int DIR, int NQ>
+__device__ __forceinline__ void pair_first_phase2(
+    PairState& ps, const NodeUni& un, bool act_l, bool act_b, uint32_t red, int warp, int nwarps, float doth, bool last,
+    float* z_out, uint32_t feas_a, bool want_g) {
+  using SD = Strd<NQ, true>;
+  const float xl = lds(ps.ea_l), xb = lds(ps.ea_b);
+  ps.ea_l += DIR ? -SD::c4(un) : SD::c4(un);
+  ps.ea_b += DIR ? -SD::c4(un) : SD::c4(un);
+  float vl, vb;
+  if (DIR == 0) {
+    const f2 pv = lds_v2(ps.pc + ps.t8);
+    vb = lse2(ps.ab, ps.al);
+    vl = lse3(ps.al, pv.y, ps.skip ? pv.x : kNeg);
+  } else {
+    const float nl = lds(ps.pc + ps.t8 + 16u);
+    vb = lse2(ps.ab, nl);
+    vl = lse3(ps.al, ps.ab, ps.skip ? nl : kNeg);
+  }
+  const float val_l = DIR == 0 ? vl + fmaf(xl, kLog2e, -ps.adj) : vl - ps.adj;
+  const float val_b = DIR == 0 ? vb + fmaf(xb, kLog2e, -ps.adj) : vb - ps.adj;
+  ps.al = DIR == 0 ? val_l : fmaf(xl, kLog2e, val_l);
+  ps.ab = DIR == 0 ? val_b : fmaf(xb, kLog2e, val_b);
+  ps.adj = 0.0f;
+  if (DIR == 0)
+    sts_v2(ps.qc + ps.t8 + 8u, ps.al, ps.ab);
+  else
+    sts(ps.qc + ps.t8 + 8u, ps.al);
+  const f2 o = lds_v2(ps.oa); // the partner's scores of (label, blank)
+  // TwoSum (Knuth) of both: hi + lo == val + o exactly
+  const float hl = val_l + o.x, bl = hl - val_l, ll = (val_l - (hl - bl)) + (o.x - bl);
+  const float hb = val_b + o.y, bb = hb - val_b, lb = (val_b - (hb - bb)) + (o.y - bb);
+  const float m = node_reduce_max(fmaxf(act_l ? hl : 2.0f * kNeg, act_b ? hb : 2.0f * kNeg), red, warp, nwarps, un.nact);
+  const bool live = m > 1.5f * kNeg;
+  const float term = (act_l && live ? ex2((hl - m) + ll) : 0.0f) + (act_b && live ? ex2((hb - m) + lb) : 0.0f);
+  const float S = node_reduce_sum(term, red, warp, nwarps, un.nact);
+  const bool feasible = m > kNeg * 0.5f && S > 0.0f;
+  ps.Zh = feasible ? m : 1.0e30f;
+  ps.Zl = feasible ? lg2(S) : 0.0f;
+  ps.Dc = ps.D + doth;
+  ps.zsub = ps.Zl;
+  if (threadIdx.x == 0) sts(feas_a, feasible ? 1.0f : 0.0f);
+  if (z_out && threadIdx.x == 0)
+    *z_out = feasible ? (float)(((double)ps.Dc + ((double)m + (double)ps.Zl)) * 0.6931471805599453) : -CUDART_INF_F;
+  if (want_g) {
+    sts(ps.ga, ex2(((val_l - ps.Zh) + o.x) - ps.zsub));
+    ps.ga += DIR ? -SD::g4(un) : SD::g4(un);
+  }
+  ps.oa += DIR ? -SD::p4(un) : SD::p4(un);
+  if (last) publish_block_max(ps, fmaxf(ps.al, ps.ab));
+  bar_named(1, un.nact);
+  const uint32_t t = ps.pc;
+  ps.pc = ps.qc;
+  ps.qc = t;
+}
+
+/* the pair warps of one CTA, both phases: node_role's protocol (stages, barriers, offsets) on pairs */
+template <int DIR, int NQ>
+__device__ __forceinline__ void pair_role(PairState& ps, const NodeCtx& cx, int tp, bool act, bool has_label) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  NodeUni un;
+  un.c4 = 4 * cx.C;
+  un.p4 = 4 * cx.pitch;
+  un.g4 = 4 * cx.pg;
+  un.pitch = cx.pitch;
+  un.nact = 32 * cx.nw_act;
+  const int nact = un.nact;
+  const int arr1 = (warp == 0 && cx.want_g) ? 1 + kHelpers : 1;
+  const int arr2 = (warp == 0 && !cx.want_g) ? 1 + kHelpers : 1;
+  const uint32_t dir_off = DIR ? (uint32_t)((kBlk - 1) * cx.C * 4) : 0u;
+  const uint32_t e_row0_l = cx.e_base + cx.lab4 + dir_off; // cx.lab4: this thread's label
+  const uint32_t e_row0_b = cx.e_base + cx.blank4 + dir_off;
+  const bool act_l = act && has_label;
+  int v = 0;
+  if (DIR == 0) {
+    // level 0: start nodes carry the implicit 0 (shortest.cpp:129-135)
+    ps.al = (has_label && (cx.fl[2 * tp - 1] & 1)) ? 0.0f : kNeg;
+    ps.ab = (cx.fl[2 * tp] & 1) ? 0.0f : kNeg;
+    sts_v2(ps.pc + ps.t8 + 8u, ps.al, ps.ab);
+    bar_named(1, nact);
+    ps.gs = cx.saved + 2 * tp;
+    for (; v < cx.n_ph1; v++) {
+      const int s = v & (kSE - 1);
+      mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+      ps.ea_l = e_row0_l + (uint32_t)(s * cx.e_stage_bytes);
+      ps.ea_b = e_row0_b + (uint32_t)(s * cx.e_stage_bytes);
+      if (v > 0) fetch_block_adjust(ps);
+      if (tid == 0) stg(cx.boff_own + 4 * v, ps.D);
+      pair_rows<0, 1, NQ>(ps, un, kBlk);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, s), arr1);
+    }
+  } else if (cx.T > 0) {
+    // level T: accept nodes carry 0; what the predecessors read is beta_T + e[T-1][label]
+    const int j0 = cx.nblk - 1, n0 = min(kBlk, cx.T - kBlk * j0);
+    mbar_wait(bar_e_full(cx.bars, 0), 0);
+    ps.ea_l = cx.e_base + (uint32_t)((n0 - 1) * cx.C * 4) + cx.lab4;
+    ps.ea_b = cx.e_base + (uint32_t)((n0 - 1) * cx.C * 4) + cx.blank4;
+    if (tid == 0) stg(cx.boff_own + 4 * j0, 0.0f);
+    {
+      const float el = lds(ps.ea_l) * kLog2e, eb = lds(ps.ea_b) * kLog2e;
+      ps.ea_l -= un.c4;
+      ps.ea_b -= un.c4;
+      const float val_l = (has_label && (cx.fl[2 * tp - 1] & 2)) ? 0.0f : kNeg;
+      const float val_b = (cx.fl[2 * tp] & 2) ? 0.0f : kNeg;
+      ps.al = val_l + el;
+      ps.ab = val_b + eb;
+      sts(ps.pc + ps.t8 + 8u, ps.al); // written to the row the first step READS
+      ps.gs = cx.saved + (long long)(cx.T - 1) * cx.pitch + 2 * tp;
+      if (n0 == 1) publish_block_max(ps, fmaxf(ps.al, ps.ab));
+      bar_named(1, nact);
+      stg_v2(ps.gs, val_l, val_b);
+      ps.gs -= un.pitch;
+    }
+    pair_rows<1, 1, NQ>(ps, un, n0 - 1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, 0), arr1);
+    for (v = 1; v < cx.n_ph1; v++) {
+      const int s = v & (kSE - 1);
+      mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+      ps.ea_l = e_row0_l + (uint32_t)(s * cx.e_stage_bytes);
+      ps.ea_b = e_row0_b + (uint32_t)(s * cx.e_stage_bytes);
+      fetch_block_adjust(ps);
+      if (tid == 0) stg(cx.boff_own + 4 * (cx.nblk - 1 - v), ps.D);
+      pair_rows<1, 1, NQ>(ps, un, kBlk);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, s), arr1);
+    }
+  }
+  cluster_sync_all();
+  // ---- phase 2
+  if (cx.n_ph2 <= 0) return;
+  const uint32_t o_row0 = cx.o_base + ps.t8 + (DIR ? (uint32_t)((kBlk - 1) * cx.pitch * 4) : 0u);
+  uint32_t g_row0 = 0;
+  int g_stride = 0;
+  if (cx.want_g) {
+    mbar_wait(bar_tbl_ready(cx.bars), 0); // the helper warps' tables
+    // the label's slot; a thread without a label node (pair 0) stores into the row's last word, which nobody reads
+    const uint32_t slot = has_label ? lds_u16(cx.perm_a + 2u * (uint32_t)(2 * tp - 1)) : 4u * (uint32_t)(cx.pg - 1);
+    g_row0 = cx.g_base + slot + (DIR ? (uint32_t)((kBlk - 1) * cx.pg * 4) : 0u);
+    g_stride = cx.g_block_bytes;
+  }
+  for (int v2 = 0; v2 < cx.n_ph2; v2++, v++) {
+    const int s = v & (kSE - 1), so = v2 & (kSO - 1), sg = v2 & (kSG - 1);
+    const int nfr = DIR ? kBlk : min(kBlk, cx.T - kBlk * v);
+    mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+    mbar_wait(bar_o_full(cx.bars, so), (v2 / kSO) & 1);
+    if (v2 >= kSG) mbar_wait(bar_g_empty(cx.bars, sg), ((v2 / kSG) - 1) & 1);
+    ps.ea_l = e_row0_l + (uint32_t)(s * cx.e_stage_bytes);
+    ps.ea_b = e_row0_b + (uint32_t)(s * cx.e_stage_bytes);
+    ps.oa = o_row0 + (uint32_t)(so * cx.o_stage_bytes);
+    ps.ga = g_row0 + (uint32_t)(sg * g_stride);
+    if (v > 0) fetch_block_adjust(ps);
+    const float doth = lds(cx.od_base + 16u * so);
+    if (v2 == 0) {
+      pair_first_phase2<DIR, NQ>(ps, un, act_l, act, cx.red_a, warp, cx.nw_act, doth, nfr == 1,
+                                 DIR == 0 ? cx.out_score : nullptr, cx.feas_a, cx.want_g);
+      if (cx.want_g) pair_rows<DIR, 2, NQ>(ps, un, nfr - 1);
+    } else {
+      ps.zsub = ps.Zl - ((ps.D + doth) - ps.Dc);
+      pair_rows<DIR, 2, NQ>(ps, un, nfr);
     }
     __syncwarp();
     if (lane == 0) {
@@ -987,8 +1277,9 @@ __device__ __forceinline__ void helper_block_fast(
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
 
-template <int NQ, bool ZW, bool FX>
-__global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_ctc_kernel(const Params P) {
+template <int NQ, bool ZW, bool FX, bool PAIR>
+__global__ void __launch_bounds__(32 * ((PAIR ? kMaxPairWarps : kMaxNodeWarps) + 1 + kHelpers), 4)
+    bidir_ctc_kernel(const Params P) {
   GTNB_DYNAMIC_SMEM_128(unsigned char, smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x >> 1;
@@ -1014,7 +1305,8 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
   const uint32_t tbl_ready = bars + 8u * (uint32_t)(2 * kSE + 2 * kSO + 2 * kSG);
   const uint32_t g_base = smem_u32(smem + L.off_g);
 
-  const int nw_act = (N1 + 31) >> 5; // node warps of THIS utterance
+  const int n_pairs = (N1 + 1) >> 1; // PAIR: U + 1
+  const int nw_act = PAIR ? (n_pairs + 31) >> 5 : (N1 + 31) >> 5; // node warps of THIS utterance
   const int nact = 32 * nw_act;
   const int nblk = (T + kBlk - 1) / kBlk;
   // levels 1..M: alpha saved, posterior by B; M+1..T: beta saved, posterior by A.  T/2 rounded UP to a block: CTA B
@@ -1091,7 +1383,71 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
   }
   __syncthreads();
 
-  if (warp < P.nwn) {
+  if (PAIR && warp < P.nwn) {
+    /* ============================ node warps, two nodes per thread ============================ */
+    const bool act = tid < n_pairs;
+    const int tp = min(tid, n_pairs - 1); // threads beyond the last pair clone it
+    const bool has_label = tp >= 1;
+    PairState ps;
+    ps.t8 = 8u * (uint32_t)tp;
+    const int lnode = 2 * tp - 1;
+    // A: does this thread's label have the skip in-arc; B: does the NEXT label (= this label's skip out-arc)
+    const int sk_node = dir == 0 ? lnode : lnode + 2;
+    ps.skip = sk_node >= 1 && sk_node < N1 && ip[sk_node + 1] - ip[sk_node] == 3;
+    const int labn = has_label ? il[ip[lnode]] : P.ctc_blank;
+    __syncthreads(); // (S1) all roles
+    if (warp >= nw_act) {
+      cluster_sync_all();
+      return;
+    }
+    ps.pc = smem_u32(ring);
+    ps.qc = smem_u32(ring + kRowF);
+    ps.gs = nullptr;
+    ps.al = ps.ab = kNeg;
+    ps.Zh = ps.zsub = ps.Zl = ps.Dc = 0.0f;
+    ps.adj = ps.D = 0.0f;
+    ps.ea_l = ps.ea_b = ps.oa = ps.ga = 0;
+    ps.redi = redi_a;
+    NodeCtx cx;
+    cx.fl = fl;
+    cx.saved = saved;
+    cx.boff_own = boff_own;
+    cx.out_score = P.out_scores + b;
+    cx.bars = bars;
+    cx.e_base = e_base;
+    cx.o_base = o_base;
+    cx.g_base = g_base;
+    cx.od_base = od_base;
+    cx.perm_a = perm_a;
+    cx.red_a = red_a;
+    cx.spare = 0;
+    cx.lab4 = 4u * (uint32_t)labn;
+    cx.blank4 = 4u * (uint32_t)P.ctc_blank;
+    cx.feas_a = hlist_a + 96u;
+    cx.e_stage_bytes = L.e_stage_bytes;
+    cx.o_stage_bytes = L.o_stage_bytes;
+    cx.g_block_bytes = L.g_block_bytes;
+    cx.pg = L.pg;
+    cx.C = C;
+    cx.T = T;
+    cx.pitch = pitch;
+    cx.nblk = nblk;
+    cx.n_ph1 = n_ph1;
+    cx.n_ph2 = n_ph2;
+    cx.nw_act = nw_act;
+    cx.want_g = want_g;
+    if (dir == 0)
+      pair_role<0, NQ>(ps, cx, tp, act, has_label);
+    else
+      pair_role<1, NQ>(ps, cx, tp, act, has_label);
+    if (T == 0 && dir == 0 && tid == 0) {
+      int n = 0;
+      for (int i = 0; i < N1; i++) n += (fl[i] & 3) == 3;
+      P.out_scores[b] = n ? logf((float)n) : -CUDART_INF_F;
+    }
+    return;
+  }
+  if (!PAIR && warp < P.nwn) {
     /* ============================ node warps ============================ */
     NodeState st;
     const bool act = tid < N1;
@@ -1164,6 +1520,7 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
     cx.red_a = red_a;
     cx.spare = spare;
     cx.lab4 = lab4;
+    cx.blank4 = 0;
     cx.feas_a = hlist_a + 96u;
     cx.e_stage_bytes = L.e_stage_bytes;
     cx.o_stage_bytes = L.o_stage_bytes;
@@ -1265,6 +1622,7 @@ __global__ void __launch_bounds__(32 * (kMaxNodeWarps + 1 + kHelpers), 4) bidir_
           comp = c;
         }
       }
+      if (PAIR) comp = P.ctc_blank; // the pair threads never form a blank posterior, whatever U is
       sts_u(hlist_a + 100u, (uint32_t)comp);
       int nh = 0, at = 0;
       for (int c = 0; c < C; c++) {
@@ -1405,7 +1763,7 @@ int bidir_zparts() {
 }
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
-    int64_t grad_stride, int b0, int nb, int zero_w, float* out_scores_dev) {
+    int64_t grad_stride, int b0, int nb, int zero_w, float* out_scores_dev, int ctc_blank) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
   bidir::Params P;
@@ -1432,15 +1790,21 @@ int launch_bidir_ctc(
   const int max_pitch = fx ? bidir::kFixedPitch : ((lat->max_lvl_nodes + 3) & ~3);
   P.lay = bidir::make_layout(lat->C, max_pitch);
   // NQ: float4 chunks of an emission row per helper lane
+  // PAIR: the graphs are ctc_build_kernel's (gtnb_ctc_loss): two nodes per thread
+  const bool pair = fx && zero_w && ctc_blank >= 0 && ctc_blank < lat->C && lat->max_lvl_nodes <= 2 * 32 * bidir::kMaxPairWarps - 1;
   void (*kern)(const bidir::Params);
-  if (fx && lat->C == 64)
-    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, true> : bidir::bidir_ctc_kernel<1, false, true>;
+  if (pair)
+    kern = lat->C == 64 ? bidir::bidir_ctc_kernel<1, true, true, true> : bidir::bidir_ctc_kernel<2, true, true, true>;
+  else if (fx && lat->C == 64)
+    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, true, false> : bidir::bidir_ctc_kernel<1, false, true, false>;
   else if (fx)
-    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, true> : bidir::bidir_ctc_kernel<2, false, true>;
+    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, true, false> : bidir::bidir_ctc_kernel<2, false, true, false>;
   else if (lat->C <= 64)
-    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, false> : bidir::bidir_ctc_kernel<1, false, false>;
+    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, false, false> : bidir::bidir_ctc_kernel<1, false, false, false>;
   else
-    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, false> : bidir::bidir_ctc_kernel<2, false, false>;
+    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, false, false> : bidir::bidir_ctc_kernel<2, false, false, false>;
+  if (pair) P.nwn = std::max(1, ((lat->max_lvl_nodes + 1) / 2 + 31) / 32);
+  P.ctc_blank = ctc_blank;
   P.zero_w = zero_w;
   if (P.lay.total > 48 * 1024) {
     int rc = ensure_max_smem(ctx, (const void*)kern);

@@ -59,7 +59,14 @@ def test_bidir_kernel_source_matches_oracle(emu, oracle, shape):
     from oracle import f64
     B, T, Cn, U = shape
     e, targets = util.bench_inputs(B, T, Cn, U, seed=77 + T)
-    loss, grad, status = run(emu, e, targets, zero_w=T % 2)  # both weight variants over the shapes
+    # zero_w: 0 the general weighted kernel, 1 gtnb_ctc_loss's choice (C = 64 / 128: the PAIR kernels, two nodes per
+    # thread), 2 the general zero-weight kernel on the same graphs
+    for zero_w in ((T % 2,) if Cn not in (64, 128) else (0, 1, 2)):
+        check_one(emu, oracle, f64, e, targets, B, T, zero_w)
+
+
+def check_one(emu, oracle, f64, e, targets, B, T, zero_w):
+    loss, grad, status = run(emu, e, targets, zero_w=zero_w)
     assert not status.any()
     for b in range(B):
         lo, go = oracle.ctc_loss(e[b], targets[b], 0, True)
@@ -72,10 +79,11 @@ def test_bidir_kernel_source_matches_oracle(emu, oracle, shape):
         assert util.grad_close(grad[b], go, 5.0 * T), b
 
 
-def test_bidir_ragged_lengths_repeats_and_infeasible(emu, oracle):
+@pytest.mark.parametrize("Cn", [8, 64])  # 64: the PAIR kernels (two nodes per thread)
+def test_bidir_ragged_lengths_repeats_and_infeasible(emu, oracle, Cn):
     """input_lens < T (rows beyond stay untouched), long runs of one label (a second heavy label next to
     blank), blank != 0, and a target too long for its T (no accepting path: +inf loss, gradient = softmax)."""
-    B, T, Cn = 5, 48, 8
+    B, T = 5, 48
     rng = np.random.default_rng(5)
     e = rng.uniform(-5, 5, (B, T, Cn)).astype(np.float32)
     targets = [rng.integers(0, Cn - 1, 6), np.full(14, 3), rng.integers(0, Cn - 1, 9), np.full(30, 2),
