@@ -275,6 +275,11 @@ int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value) {
     ctx->use_bidir = value < 0 ? kBidirDefault : value != 0; // -1: back to the default
     return GTNB_OK;
   }
+  if (ctx && name && std::string(name) == "bidir_mode") {
+    if (value < 0 || value > 2) return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctx_set_flag: bidir_mode is 0, 1 or 2");
+    ctx->bidir_mode = value;
+    return GTNB_OK;
+  }
   if (ctx && name && std::string(name) == "banded") {
     ctx->use_banded = value;
     return GTNB_OK;

@@ -80,6 +80,8 @@ namespace bidir {
 constexpr int kMaxNodes = 256; // table capacity
 constexpr int kMaxNodeWarps = 7; // graph nodes per utterance: at most 224, one per thread (4 CTAs of 12 warps per SM at 40 registers)
 constexpr int kMaxPairWarps = 4; // PAIR kernels: two nodes per thread, (U + 1) <= 112 pairs
+constexpr int kQuadSpare = 1; // QUAD kernels: idle warps that make the CTA 7 warps, so that the node warps of the four
+                              // CTAs of an SM land on four different schedulers (warp slot mod 4: 0, 3, 2, 1)
 constexpr int kRowF = 264; // floats per chain row in shared memory
 constexpr int kDummy = 256; // slot of every chain row that holds kNeg (absent arcs point here)
 constexpr int kBlk = 8; // frames per block (one TMA copy, one helper pass, one renormalisation)
@@ -1019,6 +1021,325 @@ __device__ __forceinline__ void pair_role(PairState& ps, const NodeCtx& cx, int 
 }
 
 /* ------------------------------------------------------------------ */
+/* node warp, CTC quad mode: ONE warp per CTA, four pairs per thread    */
+/* ------------------------------------------------------------------ */
+
+/*
+ * The pair kernels still pay one named barrier and one shared-memory round trip per level, and four warps whose
+ * chains the scheduler has to interleave.  Here thread t owns the pairs 4t .. 4t+3 (nodes 8t-1 .. 8t+6): three of
+ * its four neighbour pairs are its own registers, the fourth comes by ONE shuffle pair (A: pair 4t-1 from lane t-1)
+ * or one shuffle (B: the label of pair 4t+4 from lane t+1).  No chain rows, no barrier on the chain, eight
+ * independent logsumexps per thread and level to hide each other's latency; the renormalisation maximum is one
+ * REDUX.  Saved scores leave as two STG.128, the partner's arrive as two LDS.128 (slots 8t .. 8t+7 of a row).
+ * Pairs beyond the graph (k > U) are phantoms: in B nothing ever feeds them (they stay at kNeg), in A they only
+ * read lower pairs and nothing real reads them; they are kept out of Z, their posteriors go to the trash word, and
+ * lanes >= 28 (slots beyond the 224-float row) neither load nor store rows.
+ */
+constexpr int kQuad = 4; // pairs per thread
+
+struct QuadState {
+  float al[kQuad], ab[kQuad]; // what the neighbours read of the label / blank nodes (A: alpha, B: beta + emission)
+  uint32_t el[kQuad]; // byte offset of each label's emission inside a row
+  uint32_t gl[kQuad]; // byte offset of each label's posterior slot inside a row of the helpers' block
+  uint32_t skip; // bit i: A: label of pair 4t+i has the skip in-arc; B: label of pair 4t+i+1 has it
+  uint32_t eb; // byte offset of blank's emission
+  uint32_t ea, oa, ga; // first row of the block: emission stage, partner's scores (this thread's 8 slots), posteriors
+  float* gs; // where the thread's 8 scores are saved (phase 1)
+  float adj, D, Zh, zsub, Zl, Dc;
+  bool rows; // lane < 28: the thread's slots exist in a row
+};
+
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+/* the recursion of one level for the thread's four pairs; val_*: the scores proper (alpha / beta) */
+template <int DIR>
+__device__ __forceinline__ void quad_values(QuadState& q, const float* xl, float xb, float* val_l, float* val_b) {
+  const int lane = threadIdx.x & 31;
+  if (DIR == 0) {
+    // pair 4t-1 from the lane below (lane 0: nothing there)
+    float pl = __shfl_up_sync(0xffffffffu, q.al[kQuad - 1], 1);
+    float pb = __shfl_up_sync(0xffffffffu, q.ab[kQuad - 1], 1);
+    if (lane == 0) {
+      pl = kNeg;
+      pb = kNeg;
+    }
+    float nl[kQuad], nb[kQuad];
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) {
+      const float ql = i ? q.al[i - 1] : pl, qb = i ? q.ab[i - 1] : pb;
+      nb[i] = lse2(q.ab[i], q.al[i]) + fmaf(xb, kLog2e, -q.adj);
+      nl[i] = lse3(q.al[i], qb, (q.skip >> i) & 1u ? ql : kNeg) + fmaf(xl[i], kLog2e, -q.adj);
+    }
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) {
+      val_l[i] = q.al[i] = nl[i];
+      val_b[i] = q.ab[i] = nb[i];
+    }
+  } else {
+    float nx = __shfl_down_sync(0xffffffffu, q.al[0], 1); // the label of pair 4t+4
+    if (lane == 31) nx = kNeg;
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) {
+      const float ql = i + 1 < kQuad ? q.al[i + 1] : nx;
+      val_b[i] = lse2(q.ab[i], ql) - q.adj;
+      val_l[i] = lse3(q.al[i], q.ab[i], (q.skip >> i) & 1u ? ql : kNeg) - q.adj;
+    }
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) {
+      q.al[i] = fmaf(xl[i], kLog2e, val_l[i]);
+      q.ab[i] = fmaf(xb, kLog2e, val_b[i]);
+    }
+  }
+  q.adj = 0.0f;
+}
+
+/* the largest kept score of the warp as an integer (what the next block subtracts) */
+__device__ __forceinline__ float quad_block_max(const QuadState& q) {
+  float m = fmaxf(q.al[0], q.ab[0]);
+#pragma unroll
+  for (int i = 1; i < kQuad; i++) m = fmaxf(m, fmaxf(q.al[i], q.ab[i]));
+  const int iv = __reduce_max_sync(0xffffffffu, __float2int_rn(fmaxf(m, -2.0e9f)));
+  return iv <= -2000000000 ? 0.0f : (float)iv;
+}
+
+template <int DIR, int PH, int NQ>
+__device__ __forceinline__ void quad_step(QuadState& q, const NodeUni& un, int r, bool last, float& next_adj) {
+  using SD = Strd<NQ, true>;
+  const int rr = DIR ? -r : r;
+  const uint32_t er = q.ea + (uint32_t)(rr * SD::c4(un));
+  float xl[kQuad];
+#pragma unroll
+  for (int i = 0; i < kQuad; i++) xl[i] = lds(er + q.el[i]);
+  const float xb = lds(er + q.eb);
+  float val_l[kQuad], val_b[kQuad];
+  quad_values<DIR>(q, xl, xb, val_l, val_b);
+  if (PH == 2) {
+    const uint32_t orow = q.oa + (uint32_t)(rr * SD::p4(un));
+    const float4 o0 = lds_v4(orow), o1 = lds_v4(orow + 16u); // (label, blank) x 4
+    const float ol[kQuad] = {o0.x, o0.z, o1.x, o1.z};
+    const uint32_t grow = q.ga + (uint32_t)(rr * SD::g4(un));
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) sts(grow + q.gl[i], ex2(((val_l[i] - q.Zh) + ol[i]) - q.zsub));
+  }
+  if (PH == 1 && q.rows) {
+    float* g = q.gs + rr * SD::pitch(un);
+    stg_v4(g, make_float4(val_l[0], val_b[0], val_l[1], val_b[1]));
+    stg_v4(g + 4, make_float4(val_l[2], val_b[2], val_l[3], val_b[3]));
+  }
+  if (last) next_adj = quad_block_max(q);
+}
+
+template <int DIR, int PH, int NQ>
+__device__ __forceinline__ void quad_rows(QuadState& q, const NodeUni& un, int n, float& next_adj) {
+  if (n == kBlk) {
+#pragma unroll
+    for (int r = 0; r < kBlk; r++) quad_step<DIR, PH, NQ>(q, un, r, r == kBlk - 1, next_adj);
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < n; r++) quad_step<DIR, PH, NQ>(q, un, r, r == n - 1, next_adj);
+  }
+  if (PH == 1) q.gs += (DIR ? -n : n) * Strd<NQ, true>::pitch(un);
+}
+
+/* the first level of phase 2: Z over every real node (see node_first_phase2) */
+template <int DIR, int NQ>
+__device__ __forceinline__ void quad_first_phase2(
+    QuadState& q, const NodeUni& un, uint32_t act_l, uint32_t act_b, float doth, bool last, float* z_out, uint32_t feas_a,
+    bool want_g, float& next_adj) {
+  using SD = Strd<NQ, true>;
+  float xl[kQuad];
+#pragma unroll
+  for (int i = 0; i < kQuad; i++) xl[i] = lds(q.ea + q.el[i]);
+  const float xb = lds(q.ea + q.eb);
+  q.ea += DIR ? -SD::c4(un) : SD::c4(un);
+  float val_l[kQuad], val_b[kQuad];
+  quad_values<DIR>(q, xl, xb, val_l, val_b);
+  const float4 o0 = lds_v4(q.oa), o1 = lds_v4(q.oa + 16u);
+  const float ol[kQuad] = {o0.x, o0.z, o1.x, o1.z}, ob[kQuad] = {o0.y, o0.w, o1.y, o1.w};
+  float hl[kQuad], ll[kQuad], hb[kQuad], lb[kQuad];
+  float m = 2.0f * kNeg;
+#pragma unroll
+  for (int i = 0; i < kQuad; i++) {
+    // TwoSum (Knuth): hi + lo == val + o exactly
+    hl[i] = val_l[i] + ol[i];
+    const float bl = hl[i] - val_l[i];
+    ll[i] = (val_l[i] - (hl[i] - bl)) + (ol[i] - bl);
+    hb[i] = val_b[i] + ob[i];
+    const float bb = hb[i] - val_b[i];
+    lb[i] = (val_b[i] - (hb[i] - bb)) + (ob[i] - bb);
+    if ((act_l >> i) & 1u) m = fmaxf(m, hl[i]);
+    if ((act_b >> i) & 1u) m = fmaxf(m, hb[i]);
+  }
+  m = warp_max_f(m);
+  const bool live = m > 1.5f * kNeg;
+  float term = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kQuad; i++) {
+    if (live && ((act_l >> i) & 1u)) term += ex2((hl[i] - m) + ll[i]);
+    if (live && ((act_b >> i) & 1u)) term += ex2((hb[i] - m) + lb[i]);
+  }
+  const float S = warp_sum_f(term);
+  const bool feasible = m > kNeg * 0.5f && S > 0.0f;
+  q.Zh = feasible ? m : 1.0e30f;
+  q.Zl = feasible ? lg2(S) : 0.0f;
+  q.Dc = q.D + doth;
+  q.zsub = q.Zl;
+  if ((threadIdx.x & 31) == 0) sts(feas_a, feasible ? 1.0f : 0.0f);
+  if (z_out && (threadIdx.x & 31) == 0)
+    *z_out = feasible ? (float)(((double)q.Dc + ((double)m + (double)q.Zl)) * 0.6931471805599453) : -CUDART_INF_F;
+  if (want_g) {
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) sts(q.ga + q.gl[i], ex2(((val_l[i] - q.Zh) + ol[i]) - q.zsub));
+    q.ga += DIR ? -SD::g4(un) : SD::g4(un);
+  }
+  q.oa += DIR ? -SD::p4(un) : SD::p4(un);
+  if (last) next_adj = quad_block_max(q);
+}
+
+/* the node warp of one CTA, both phases (node_role's protocol; nw_act == 1) */
+template <int DIR, int NQ>
+__device__ __forceinline__ void quad_role(QuadState& q, const NodeCtx& cx, int n_pairs) {
+  const int lane = threadIdx.x & 31;
+  NodeUni un;
+  un.c4 = 4 * cx.C;
+  un.p4 = 4 * cx.pitch;
+  un.g4 = 4 * cx.pg;
+  un.pitch = cx.pitch;
+  un.nact = 32;
+  const int arr1 = cx.want_g ? 1 + kHelpers : 1;
+  const int arr2 = !cx.want_g ? 1 + kHelpers : 1;
+  const uint32_t dir_off = DIR ? (uint32_t)((kBlk - 1) * cx.C * 4) : 0u;
+  uint32_t act_l = 0, act_b = 0; // which of the thread's nodes exist
+#pragma unroll
+  for (int i = 0; i < kQuad; i++) {
+    const int k = kQuad * lane + i;
+    if (k < n_pairs) act_b |= 1u << i;
+    if (k >= 1 && k < n_pairs) act_l |= 1u << i;
+  }
+  float next_adj = 0.0f;
+  int v = 0;
+  if (DIR == 0) {
+    // level 0: start nodes carry the implicit 0 (shortest.cpp:129-135)
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) {
+      const int k = kQuad * lane + i;
+      q.al[i] = (((act_l >> i) & 1u) && (cx.fl[2 * k - 1] & 1)) ? 0.0f : kNeg;
+      q.ab[i] = (((act_b >> i) & 1u) && (cx.fl[2 * k] & 1)) ? 0.0f : kNeg;
+    }
+    q.gs = cx.saved + 8 * lane;
+    for (; v < cx.n_ph1; v++) {
+      const int s = v & (kSE - 1);
+      mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+      q.ea = cx.e_base + dir_off + (uint32_t)(s * cx.e_stage_bytes);
+      if (v > 0) {
+        q.adj = next_adj;
+        q.D += next_adj;
+      }
+      if (lane == 0) stg(cx.boff_own + 4 * v, q.D);
+      quad_rows<0, 1, NQ>(q, un, kBlk, next_adj);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, s), arr1);
+    }
+  } else if (cx.T > 0) {
+    // level T: accept nodes carry 0; what the predecessors read is beta_T + e[T-1][label]
+    const int j0 = cx.nblk - 1, n0 = min(kBlk, cx.T - kBlk * j0);
+    mbar_wait(bar_e_full(cx.bars, 0), 0);
+    q.ea = cx.e_base + (uint32_t)((n0 - 1) * cx.C * 4);
+    if (lane == 0) stg(cx.boff_own + 4 * j0, 0.0f);
+    {
+      float val_l[kQuad], val_b[kQuad];
+      const float eb = lds(q.ea + q.eb) * kLog2e;
+#pragma unroll
+      for (int i = 0; i < kQuad; i++) {
+        const int k = kQuad * lane + i;
+        val_l[i] = (((act_l >> i) & 1u) && (cx.fl[2 * k - 1] & 2)) ? 0.0f : kNeg;
+        val_b[i] = (((act_b >> i) & 1u) && (cx.fl[2 * k] & 2)) ? 0.0f : kNeg;
+        q.al[i] = val_l[i] + lds(q.ea + q.el[i]) * kLog2e;
+        q.ab[i] = val_b[i] + eb;
+      }
+      q.ea -= un.c4;
+      q.gs = cx.saved + (long long)(cx.T - 1) * cx.pitch + 8 * lane;
+      if (n0 == 1) next_adj = quad_block_max(q);
+      if (q.rows) {
+        stg_v4(q.gs, make_float4(val_l[0], val_b[0], val_l[1], val_b[1]));
+        stg_v4(q.gs + 4, make_float4(val_l[2], val_b[2], val_l[3], val_b[3]));
+      }
+      q.gs -= un.pitch;
+    }
+    quad_rows<1, 1, NQ>(q, un, n0 - 1, next_adj);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, 0), arr1);
+    for (v = 1; v < cx.n_ph1; v++) {
+      const int s = v & (kSE - 1);
+      mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+      q.ea = cx.e_base + dir_off + (uint32_t)(s * cx.e_stage_bytes);
+      q.adj = next_adj;
+      q.D += next_adj;
+      if (lane == 0) stg(cx.boff_own + 4 * (cx.nblk - 1 - v), q.D);
+      quad_rows<1, 1, NQ>(q, un, kBlk, next_adj);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(bar_e_empty(cx.bars, s), arr1);
+    }
+  }
+  cluster_sync_all();
+  // ---- phase 2
+  if (cx.n_ph2 <= 0) return;
+  // lanes >= 28 read (harmless) words of the stage / block that belong to other rows: keep them in bounds
+  const uint32_t o_row0 = cx.o_base + (q.rows ? 32u * (uint32_t)lane : 0u) + (DIR ? (uint32_t)((kBlk - 1) * cx.pitch * 4) : 0u);
+  uint32_t g_row0 = 0;
+  int g_stride = 0;
+  if (cx.want_g) {
+    mbar_wait(bar_tbl_ready(cx.bars), 0); // the helper warps' tables
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) {
+      const int k = kQuad * lane + i;
+      // a label that does not exist stores into the row's last word, which nobody reads
+      q.gl[i] = ((act_l >> i) & 1u) ? lds_u16(cx.perm_a + 2u * (uint32_t)(2 * k - 1)) : 4u * (uint32_t)(cx.pg - 1);
+    }
+    g_row0 = cx.g_base + (DIR ? (uint32_t)((kBlk - 1) * cx.pg * 4) : 0u);
+    g_stride = cx.g_block_bytes;
+  }
+  for (int v2 = 0; v2 < cx.n_ph2; v2++, v++) {
+    const int s = v & (kSE - 1), so = v2 & (kSO - 1), sg = v2 & (kSG - 1);
+    const int nfr = DIR ? kBlk : min(kBlk, cx.T - kBlk * v);
+    mbar_wait(bar_e_full(cx.bars, s), (v / kSE) & 1);
+    mbar_wait(bar_o_full(cx.bars, so), (v2 / kSO) & 1);
+    if (v2 >= kSG) mbar_wait(bar_g_empty(cx.bars, sg), ((v2 / kSG) - 1) & 1);
+    q.ea = cx.e_base + dir_off + (uint32_t)(s * cx.e_stage_bytes);
+    q.oa = o_row0 + (uint32_t)(so * cx.o_stage_bytes);
+    q.ga = g_row0 + (uint32_t)(sg * g_stride);
+    if (v > 0) {
+      q.adj = next_adj;
+      q.D += next_adj;
+    }
+    const float doth = lds(cx.od_base + 16u * so);
+    if (v2 == 0) {
+      quad_first_phase2<DIR, NQ>(q, un, act_l, act_b, doth, nfr == 1, DIR == 0 ? cx.out_score : nullptr, cx.feas_a,
+                                 cx.want_g, next_adj);
+      if (cx.want_g) quad_rows<DIR, 2, NQ>(q, un, nfr - 1, next_adj);
+    } else {
+      q.zsub = q.Zl - ((q.D + doth) - q.Dc);
+      quad_rows<DIR, 2, NQ>(q, un, nfr, next_adj);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive_n(bar_e_empty(cx.bars, s), arr2);
+      mbar_arrive(bar_o_empty(cx.bars, so));
+      mbar_arrive(bar_g_full(cx.bars, sg));
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
 /* helper warps                                                        */
 /* ------------------------------------------------------------------ */
 
@@ -1277,9 +1598,14 @@ __device__ __forceinline__ void helper_block_fast(
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
 
-template <int NQ, bool ZW, bool FX, bool PAIR>
-__global__ void __launch_bounds__(32 * ((PAIR ? kMaxPairWarps : kMaxNodeWarps) + 1 + kHelpers), 4)
+/* MODE 0: one node per thread (any graph in the envelope); 1: PAIR (CTC graphs, two nodes per thread); 2: QUAD (CTC
+ * graphs, one node warp with four pairs per thread, plus kQuadSpare idle warps: see launch_bidir_ctc) */
+template <int NQ, bool ZW, bool FX, int MODE>
+__global__ void __launch_bounds__(
+    32 * ((MODE == 2 ? 1 + kQuadSpare : MODE == 1 ? kMaxPairWarps : kMaxNodeWarps) + 1 + kHelpers), 4)
     bidir_ctc_kernel(const Params P) {
+  constexpr bool PAIR = MODE == 1;
+  constexpr bool QUAD = MODE == 2;
   GTNB_DYNAMIC_SMEM_128(unsigned char, smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x >> 1;
@@ -1306,7 +1632,7 @@ __global__ void __launch_bounds__(32 * ((PAIR ? kMaxPairWarps : kMaxNodeWarps) +
   const uint32_t g_base = smem_u32(smem + L.off_g);
 
   const int n_pairs = (N1 + 1) >> 1; // PAIR: U + 1
-  const int nw_act = PAIR ? (n_pairs + 31) >> 5 : (N1 + 31) >> 5; // node warps of THIS utterance
+  const int nw_act = QUAD ? 1 : PAIR ? (n_pairs + 31) >> 5 : (N1 + 31) >> 5; // node warps of THIS utterance
   const int nact = 32 * nw_act;
   const int nblk = (T + kBlk - 1) / kBlk;
   // levels 1..M: alpha saved, posterior by B; M+1..T: beta saved, posterior by A.  T/2 rounded UP to a block: CTA B
@@ -1383,6 +1709,67 @@ __global__ void __launch_bounds__(32 * ((PAIR ? kMaxPairWarps : kMaxNodeWarps) +
   }
   __syncthreads();
 
+  if (QUAD && warp < P.nwn) {
+    /* ============================ the node warp, four pairs per thread ============================ */
+    QuadState q;
+    q.skip = 0;
+    q.eb = 4u * (uint32_t)P.ctc_blank;
+#pragma unroll
+    for (int i = 0; i < kQuad; i++) {
+      const int k = kQuad * lane + i; // pair
+      const int lnode = 2 * k - 1;
+      const bool has = k >= 1 && k < n_pairs;
+      q.el[i] = 4u * (uint32_t)(has ? il[ip[lnode]] : P.ctc_blank);
+      q.gl[i] = 4u * (uint32_t)(L.pg - 1);
+      const int sk_node = dir == 0 ? lnode : lnode + 2;
+      if (sk_node >= 1 && sk_node < N1 && ip[sk_node + 1] - ip[sk_node] == 3) q.skip |= 1u << i;
+      q.al[i] = q.ab[i] = kNeg;
+    }
+    q.rows = 8 * lane + 7 < pitch;
+    q.gs = nullptr;
+    q.Zh = q.zsub = q.Zl = q.Dc = 0.0f;
+    q.adj = q.D = 0.0f;
+    q.ea = q.oa = q.ga = 0;
+    __syncthreads(); // (S1) all roles
+    NodeCtx cx;
+    cx.fl = fl;
+    cx.saved = saved;
+    cx.boff_own = boff_own;
+    cx.out_score = P.out_scores + b;
+    cx.bars = bars;
+    cx.e_base = e_base;
+    cx.o_base = o_base;
+    cx.g_base = g_base;
+    cx.od_base = od_base;
+    cx.perm_a = perm_a;
+    cx.red_a = red_a;
+    cx.spare = 0;
+    cx.lab4 = 0;
+    cx.blank4 = q.eb;
+    cx.feas_a = hlist_a + 96u;
+    cx.e_stage_bytes = L.e_stage_bytes;
+    cx.o_stage_bytes = L.o_stage_bytes;
+    cx.g_block_bytes = L.g_block_bytes;
+    cx.pg = L.pg;
+    cx.C = C;
+    cx.T = T;
+    cx.pitch = pitch;
+    cx.nblk = nblk;
+    cx.n_ph1 = n_ph1;
+    cx.n_ph2 = n_ph2;
+    cx.nw_act = 1;
+    cx.want_g = want_g;
+    if (dir == 0)
+      quad_role<0, NQ>(q, cx, n_pairs);
+    else
+      quad_role<1, NQ>(q, cx, n_pairs);
+    if (T == 0 && dir == 0 && tid == 0) {
+      int n = 0;
+      for (int i = 0; i < N1; i++) n += (fl[i] & 3) == 3;
+      P.out_scores[b] = n ? logf((float)n) : -CUDART_INF_F;
+    }
+    return;
+  }
   if (PAIR && warp < P.nwn) {
     /* ============================ node warps, two nodes per thread ============================ */
     const bool act = tid < n_pairs;
@@ -1447,7 +1834,7 @@ __global__ void __launch_bounds__(32 * ((PAIR ? kMaxPairWarps : kMaxNodeWarps) +
     }
     return;
   }
-  if (!PAIR && warp < P.nwn) {
+  if (MODE == 0 && warp < P.nwn) {
     /* ============================ node warps ============================ */
     NodeState st;
     const bool act = tid < N1;
@@ -1550,6 +1937,10 @@ __global__ void __launch_bounds__(32 * ((PAIR ? kMaxPairWarps : kMaxNodeWarps) +
 
   __syncthreads(); // (S1)
 
+  if (warp > P.nwn + kHelpers) { // QUAD: the idle warps
+    cluster_sync_all();
+    return;
+  }
   if (warp == P.nwn) {
     /* ============================ producer warp: TMA bulk copies ============================ */
     // Emission blocks all the way, and in phase 2 the partner's saved scores (with the block's offset).
@@ -1622,7 +2013,7 @@ __global__ void __launch_bounds__(32 * ((PAIR ? kMaxPairWarps : kMaxNodeWarps) +
           comp = c;
         }
       }
-      if (PAIR) comp = P.ctc_blank; // the pair threads never form a blank posterior, whatever U is
+      if (MODE != 0) comp = P.ctc_blank; // the pair / quad threads never form a blank posterior, whatever U is
       sts_u(hlist_a + 100u, (uint32_t)comp);
       int nh = 0, at = 0;
       for (int c = 0; c < C; c++) {
@@ -1790,20 +2181,27 @@ int launch_bidir_ctc(
   const int max_pitch = fx ? bidir::kFixedPitch : ((lat->max_lvl_nodes + 3) & ~3);
   P.lay = bidir::make_layout(lat->C, max_pitch);
   // NQ: float4 chunks of an emission row per helper lane
-  // PAIR: the graphs are ctc_build_kernel's (gtnb_ctc_loss): two nodes per thread
-  const bool pair = fx && zero_w && ctc_blank >= 0 && ctc_blank < lat->C && lat->max_lvl_nodes <= 2 * 32 * bidir::kMaxPairWarps - 1;
+  // the graphs are ctc_build_kernel's (gtnb_ctc_loss): PAIR (two nodes per thread; the default) or QUAD (one node
+  // warp, four pairs per thread) kernels; gtnb_ctx_set_flag("bidir_mode", 0 | 1 | 2) picks one for comparison
+  const bool ctc_ok = fx && zero_w && ctc_blank >= 0 && ctc_blank < lat->C &&
+                      lat->max_lvl_nodes <= 2 * 32 * bidir::kMaxPairWarps - 1;
+  const int mode = ctc_ok ? ctx->bidir_mode : 0;
   void (*kern)(const bidir::Params);
-  if (pair)
-    kern = lat->C == 64 ? bidir::bidir_ctc_kernel<1, true, true, true> : bidir::bidir_ctc_kernel<2, true, true, true>;
+  if (mode == 2)
+    kern = lat->C == 64 ? bidir::bidir_ctc_kernel<1, true, true, 2> : bidir::bidir_ctc_kernel<2, true, true, 2>;
+  else if (mode == 1)
+    kern = lat->C == 64 ? bidir::bidir_ctc_kernel<1, true, true, 1> : bidir::bidir_ctc_kernel<2, true, true, 1>;
   else if (fx && lat->C == 64)
-    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, true, false> : bidir::bidir_ctc_kernel<1, false, true, false>;
+    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, true, 0> : bidir::bidir_ctc_kernel<1, false, true, 0>;
   else if (fx)
-    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, true, false> : bidir::bidir_ctc_kernel<2, false, true, false>;
+    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, true, 0> : bidir::bidir_ctc_kernel<2, false, true, 0>;
   else if (lat->C <= 64)
-    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, false, false> : bidir::bidir_ctc_kernel<1, false, false, false>;
+    kern = zero_w ? bidir::bidir_ctc_kernel<1, true, false, 0> : bidir::bidir_ctc_kernel<1, false, false, 0>;
   else
-    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, false, false> : bidir::bidir_ctc_kernel<2, false, false, false>;
-  if (pair) P.nwn = std::max(1, ((lat->max_lvl_nodes + 1) / 2 + 31) / 32);
+    kern = zero_w ? bidir::bidir_ctc_kernel<2, true, false, 0> : bidir::bidir_ctc_kernel<2, false, false, 0>;
+  if (mode == 1) P.nwn = std::max(1, ((lat->max_lvl_nodes + 1) / 2 + 31) / 32);
+  if (mode == 2) P.nwn = 1;
+  const int spare_warps = mode == 2 ? bidir::kQuadSpare : 0;
   P.ctc_blank = ctc_blank;
   P.zero_w = zero_w;
   if (P.lay.total > 48 * 1024) {
@@ -1812,7 +2210,7 @@ int launch_bidir_ctc(
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * nb, 1, 1);
-  cfg.blockDim = dim3(32 * (P.nwn + 1 + bidir::kHelpers), 1, 1);
+  cfg.blockDim = dim3(32 * (P.nwn + 1 + bidir::kHelpers + spare_warps), 1, 1);
   cfg.dynamicSmemBytes = P.lay.total;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];

@@ -60,8 +60,9 @@ def test_bidir_kernel_source_matches_oracle(emu, oracle, shape):
     B, T, Cn, U = shape
     e, targets = util.bench_inputs(B, T, Cn, U, seed=77 + T)
     # zero_w: 0 the general weighted kernel, 1 gtnb_ctc_loss's choice (C = 64 / 128: the PAIR kernels, two nodes per
-    # thread), 2 the general zero-weight kernel on the same graphs
-    for zero_w in ((T % 2,) if Cn not in (64, 128) else (0, 1, 2)):
+    # thread), 2 the general zero-weight kernel on the same graphs, 3 the QUAD kernels (one node warp, four pairs per
+    # thread; "bidir_mode" 2)
+    for zero_w in ((T % 2,) if Cn not in (64, 128) else (0, 1, 2, 3)):
         check_one(emu, oracle, f64, e, targets, B, T, zero_w)
 
 
@@ -79,7 +80,7 @@ def check_one(emu, oracle, f64, e, targets, B, T, zero_w):
         assert util.grad_close(grad[b], go, 5.0 * T), b
 
 
-@pytest.mark.parametrize("Cn", [8, 64])  # 64: the PAIR kernels (two nodes per thread)
+@pytest.mark.parametrize("Cn", [8, 64])  # 64: the PAIR kernels (gtnb_ctc_loss's default)
 def test_bidir_ragged_lengths_repeats_and_infeasible(emu, oracle, Cn):
     """input_lens < T (rows beyond stay untouched), long runs of one label (a second heavy label next to
     blank), blank != 0, and a target too long for its T (no accepting path: +inf loss, gradient = softmax)."""
