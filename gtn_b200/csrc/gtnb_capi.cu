@@ -276,7 +276,7 @@ int gtnb_ctx_set_flag(gtnb_ctx* ctx, const char* name, int value) {
     return GTNB_OK;
   }
   if (ctx && name && std::string(name) == "bidir_mode") {
-    if (value < 0 || value > 2) return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctx_set_flag: bidir_mode is 0, 1 or 2");
+    if (value < -1 || value > 2) return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctx_set_flag: bidir_mode is -1 (auto), 0, 1 or 2");
     ctx->bidir_mode = value;
     return GTNB_OK;
   }

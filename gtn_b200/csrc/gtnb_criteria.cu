@@ -167,7 +167,9 @@ static int ctc_loss_run(
   }
 
   // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
-  TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
+  // (k_bidir.cu's PAIR / QUAD kernels take the CTC target graphs from the targets themselves: no tables to build)
+  if (!(bidir && ctx->bidir_mode != 0 && bidir_takes_targets(lat, 1, blank)))
+    TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
   if (implicit) {
     // the sweeps: k_implicit.cu, or (experimental flag) the temporally blocked ones of k_banded.cu
     const bool banded = ctx->use_banded != 0 && banded_supported(ctx, lat);
@@ -185,7 +187,7 @@ static int ctc_loss_run(
     const int32_t* T_dev = small_dev + tot_t + 2ll * B;
     TRYCUDA(cudaEventRecord(ev_setup, main_stream));
     if (bidir && K == 1 && !h2d_event && !(grads && !grads_on_device)) {
-      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1, bidir_scores_dev, blank));
+      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1, bidir_scores_dev, blank, small_dev, small_dev + tot_t));
     } else if (bidir) {
       for (int k = 0; k < K && !rc; k++) {
         const int b0 = chunk_lo[k], nb = chunk_lo[k + 1] - chunk_lo[k];
@@ -193,7 +195,7 @@ static int ctc_loss_run(
         TRYCUDA(cudaStreamWaitEvent(cs, ev_setup, 0));
         if (h2d_event) TRYCUDA(cudaStreamWaitEvent(cs, ctx->side_events[k], 0));
         ctx->stream = cs;
-        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1, bidir_scores_dev, blank);
+        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1, bidir_scores_dev, blank, small_dev, small_dev + tot_t);
         ctx->stream = main_stream;
         if (rc) goto done;
         if (grads && !grads_on_device)

@@ -160,7 +160,9 @@ struct Params {
   int nwn; // node warps in the launch (ceil(max nodes / 32))
   int nblk_cap;
   int zero_w; // every arc weight of every graph is 0 (host knowledge: CTC / forced alignment targets)
-  int ctc_blank; // PAIR kernels: the graphs are ctc_build_kernel's, this is their blank label
+  int ctc_blank; // PAIR / QUAD kernels: the graphs are CTC target graphs with this blank label ...
+  const int32_t* targets; // ... taken from the targets themselves: concatenated labels,
+  const int32_t* tgt_off; // [B] first label of utterance b (the kernel never reads ctc_build_kernel's tables)
   Layout lay;
 };
 
@@ -630,7 +632,7 @@ struct NodeCtx {
   float* boff_own;
   float* out_score;
   uint32_t bars, e_base, o_base, g_base, od_base, perm_a, red_a, spare, lab4, feas_a, blank4;
-  int e_stage_bytes, o_stage_bytes, g_block_bytes, pg, C, T, pitch, nblk, n_ph1, n_ph2, nw_act;
+  int e_stage_bytes, o_stage_bytes, g_block_bytes, pg, C, T, pitch, nblk, n_ph1, n_ph2, nw_act, N1;
   bool want_g;
 };
 
@@ -788,6 +790,16 @@ __device__ __forceinline__ void node_role(NodeState& st, const NodeCtx& cx, bool
  * Row layouts: slot(node n) = n + 1 in the saved-score rows (pair t = floats 2t, 2t+1: 8-byte aligned), n + 3 in
  * the chain rows (pair t-1 of thread 0 and the label beyond the last pair read the row's kNeg).
  */
+/* start / accept flags of node n of a CTC target graph with N1 = 2U + 1 nodes (benchmarks/ctc.cpp:43-44): the PAIR /
+ * QUAD kernels take the graph from the target itself and never read ctc_build_kernel's tables */
+/* does label node n (odd) have the skip in-arc from label n - 2: not for the first label, not for a repeat (:51-54) */
+__device__ __forceinline__ bool ctc_skip(const int32_t* tg, int n, int N1) {
+  return n >= 3 && n < N1 && tg[(n - 1) / 2] != tg[(n - 3) / 2];
+}
+__device__ __forceinline__ int ctc_flags(int n, int N1) {
+  return (n == 0 ? 1 : 0) | ((n == N1 - 1 || n == N1 - 2) ? 2 : 0);
+}
+
 struct PairState {
   float al, ab; // what the neighbours read of this thread's label / blank node (A: alpha, B: beta + emission)
   uint32_t t8; // 8 * pair index
@@ -925,8 +937,8 @@ __device__ __forceinline__ void pair_role(PairState& ps, const NodeCtx& cx, int 
   int v = 0;
   if (DIR == 0) {
     // level 0: start nodes carry the implicit 0 (shortest.cpp:129-135)
-    ps.al = (has_label && (cx.fl[2 * tp - 1] & 1)) ? 0.0f : kNeg;
-    ps.ab = (cx.fl[2 * tp] & 1) ? 0.0f : kNeg;
+    ps.al = (has_label && (ctc_flags(2 * tp - 1, cx.N1) & 1)) ? 0.0f : kNeg;
+    ps.ab = (ctc_flags(2 * tp, cx.N1) & 1) ? 0.0f : kNeg;
     sts_v2(ps.pc + ps.t8 + 8u, ps.al, ps.ab);
     bar_named(1, nact);
     ps.gs = cx.saved + 2 * tp;
@@ -952,8 +964,8 @@ __device__ __forceinline__ void pair_role(PairState& ps, const NodeCtx& cx, int 
       const float el = lds(ps.ea_l) * kLog2e, eb = lds(ps.ea_b) * kLog2e;
       ps.ea_l -= un.c4;
       ps.ea_b -= un.c4;
-      const float val_l = (has_label && (cx.fl[2 * tp - 1] & 2)) ? 0.0f : kNeg;
-      const float val_b = (cx.fl[2 * tp] & 2) ? 0.0f : kNeg;
+      const float val_l = (has_label && (ctc_flags(2 * tp - 1, cx.N1) & 2)) ? 0.0f : kNeg;
+      const float val_b = (ctc_flags(2 * tp, cx.N1) & 2) ? 0.0f : kNeg;
       ps.al = val_l + el;
       ps.ab = val_b + eb;
       sts(ps.pc + ps.t8 + 8u, ps.al); // written to the row the first step READS
@@ -1232,8 +1244,8 @@ __device__ __forceinline__ void quad_role(QuadState& q, const NodeCtx& cx, int n
 #pragma unroll
     for (int i = 0; i < kQuad; i++) {
       const int k = kQuad * lane + i;
-      q.al[i] = (((act_l >> i) & 1u) && (cx.fl[2 * k - 1] & 1)) ? 0.0f : kNeg;
-      q.ab[i] = (((act_b >> i) & 1u) && (cx.fl[2 * k] & 1)) ? 0.0f : kNeg;
+      q.al[i] = (((act_l >> i) & 1u) && (ctc_flags(2 * k - 1, cx.N1) & 1)) ? 0.0f : kNeg;
+      q.ab[i] = (((act_b >> i) & 1u) && (ctc_flags(2 * k, cx.N1) & 1)) ? 0.0f : kNeg;
     }
     q.gs = cx.saved + 8 * lane;
     for (; v < cx.n_ph1; v++) {
@@ -1261,8 +1273,8 @@ __device__ __forceinline__ void quad_role(QuadState& q, const NodeCtx& cx, int n
 #pragma unroll
       for (int i = 0; i < kQuad; i++) {
         const int k = kQuad * lane + i;
-        val_l[i] = (((act_l >> i) & 1u) && (cx.fl[2 * k - 1] & 2)) ? 0.0f : kNeg;
-        val_b[i] = (((act_b >> i) & 1u) && (cx.fl[2 * k] & 2)) ? 0.0f : kNeg;
+        val_l[i] = (((act_l >> i) & 1u) && (ctc_flags(2 * k - 1, cx.N1) & 2)) ? 0.0f : kNeg;
+        val_b[i] = (((act_b >> i) & 1u) && (ctc_flags(2 * k, cx.N1) & 2)) ? 0.0f : kNeg;
         q.al[i] = val_l[i] + lds(q.ea + q.el[i]) * kLog2e;
         q.ab[i] = val_b[i] + eb;
       }
@@ -1691,7 +1703,11 @@ __global__ void __launch_bounds__(
   __syncthreads();
   bool bad = false;
   int my_lab = 0, my_deg = 0;
-  if (tid < N1) {
+  const int32_t* tg = MODE != 0 ? P.targets + P.tgt_off[b] : nullptr; // this utterance's labels
+  if (MODE != 0) {
+    // CTC target graph: node n carries blank (even n) or label (n - 1) / 2 (odd n)
+    if (tid < N1) sts_s8(nlab_a + (uint32_t)tid, (tid & 1) ? tg[(tid - 1) >> 1] : P.ctc_blank);
+  } else if (tid < N1) {
     const int e0 = ip[tid];
     my_deg = ip[tid + 1] - e0;
     if (my_deg > 0) my_lab = il[e0];
@@ -1719,10 +1735,10 @@ __global__ void __launch_bounds__(
       const int k = kQuad * lane + i; // pair
       const int lnode = 2 * k - 1;
       const bool has = k >= 1 && k < n_pairs;
-      q.el[i] = 4u * (uint32_t)(has ? il[ip[lnode]] : P.ctc_blank);
+      q.el[i] = 4u * (uint32_t)(has ? tg[k - 1] : P.ctc_blank);
       q.gl[i] = 4u * (uint32_t)(L.pg - 1);
       const int sk_node = dir == 0 ? lnode : lnode + 2;
-      if (sk_node >= 1 && sk_node < N1 && ip[sk_node + 1] - ip[sk_node] == 3) q.skip |= 1u << i;
+      if (ctc_skip(tg, sk_node, N1)) q.skip |= 1u << i;
       q.al[i] = q.ab[i] = kNeg;
     }
     q.rows = 8 * lane + 7 < pitch;
@@ -1753,6 +1769,7 @@ __global__ void __launch_bounds__(
     cx.pg = L.pg;
     cx.C = C;
     cx.T = T;
+    cx.N1 = N1;
     cx.pitch = pitch;
     cx.nblk = nblk;
     cx.n_ph1 = n_ph1;
@@ -1765,7 +1782,7 @@ __global__ void __launch_bounds__(
       quad_role<1, NQ>(q, cx, n_pairs);
     if (T == 0 && dir == 0 && tid == 0) {
       int n = 0;
-      for (int i = 0; i < N1; i++) n += (fl[i] & 3) == 3;
+      for (int i = 0; i < N1; i++) n += (ctc_flags(i, N1) & 3) == 3;
       P.out_scores[b] = n ? logf((float)n) : -CUDART_INF_F;
     }
     return;
@@ -1780,8 +1797,8 @@ __global__ void __launch_bounds__(
     const int lnode = 2 * tp - 1;
     // A: does this thread's label have the skip in-arc; B: does the NEXT label (= this label's skip out-arc)
     const int sk_node = dir == 0 ? lnode : lnode + 2;
-    ps.skip = sk_node >= 1 && sk_node < N1 && ip[sk_node + 1] - ip[sk_node] == 3;
-    const int labn = has_label ? il[ip[lnode]] : P.ctc_blank;
+    ps.skip = ctc_skip(tg, sk_node, N1);
+    const int labn = has_label ? tg[tp - 1] : P.ctc_blank;
     __syncthreads(); // (S1) all roles
     if (warp >= nw_act) {
       cluster_sync_all();
@@ -1817,6 +1834,7 @@ __global__ void __launch_bounds__(
     cx.pg = L.pg;
     cx.C = C;
     cx.T = T;
+    cx.N1 = N1;
     cx.pitch = pitch;
     cx.nblk = nblk;
     cx.n_ph1 = n_ph1;
@@ -1829,7 +1847,7 @@ __global__ void __launch_bounds__(
       pair_role<1, NQ>(ps, cx, tp, act, has_label);
     if (T == 0 && dir == 0 && tid == 0) {
       int n = 0;
-      for (int i = 0; i < N1; i++) n += (fl[i] & 3) == 3;
+      for (int i = 0; i < N1; i++) n += (ctc_flags(i, N1) & 3) == 3;
       P.out_scores[b] = n ? logf((float)n) : -CUDART_INF_F;
     }
     return;
@@ -1915,6 +1933,7 @@ __global__ void __launch_bounds__(
     cx.pg = L.pg;
     cx.C = C;
     cx.T = T;
+    cx.N1 = N1;
     cx.pitch = pitch;
     cx.nblk = nblk;
     cx.n_ph1 = n_ph1;
@@ -2143,6 +2162,13 @@ bool bidir_supported(const gtnb_lattice* lat, const float* emissions, int64_t st
   return true;
 }
 
+/* true when launch_bidir_ctc would run its PAIR / QUAD kernels, which read the CTC target graphs from the targets
+ * themselves: the caller (gtnb_ctc_loss) then skips ctc_build_kernel altogether */
+bool bidir_takes_targets(const gtnb_lattice* lat, int zero_w, int ctc_blank) {
+  const bool fx = (lat->C == 64 || lat->C == 128) && lat->score_pitch == bidir::kFixedPitch;
+  return fx && zero_w && ctc_blank >= 0 && ctc_blank < lat->C && lat->max_lvl_nodes <= 2 * 32 * bidir::kMaxPairWarps - 1;
+}
+
 /* blocks of 8 frames per utterance: boff_dev holds B * 2 * bidir_blocks(max T) * 4 floats */
 int bidir_blocks(int max_T) {
   return std::max(1, (max_T + bidir::kBlk - 1) / bidir::kBlk);
@@ -2154,7 +2180,8 @@ int bidir_zparts() {
 }
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
-    int64_t grad_stride, int b0, int nb, int zero_w, float* out_scores_dev, int ctc_blank) {
+    int64_t grad_stride, int b0, int nb, int zero_w, float* out_scores_dev, int ctc_blank, const int32_t* targets_dev,
+    const int32_t* tgt_off_dev) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
   bidir::Params P;
@@ -2183,9 +2210,10 @@ int launch_bidir_ctc(
   // NQ: float4 chunks of an emission row per helper lane
   // the graphs are ctc_build_kernel's (gtnb_ctc_loss): PAIR (two nodes per thread; the default) or QUAD (one node
   // warp, four pairs per thread) kernels; gtnb_ctx_set_flag("bidir_mode", 0 | 1 | 2) picks one for comparison
-  const bool ctc_ok = fx && zero_w && ctc_blank >= 0 && ctc_blank < lat->C &&
-                      lat->max_lvl_nodes <= 2 * 32 * bidir::kMaxPairWarps - 1;
-  const int mode = ctc_ok ? ctx->bidir_mode : 0;
+  const bool ctc_ok = bidir_takes_targets(lat, zero_w, ctc_blank) && targets_dev && tgt_off_dev;
+  P.targets = targets_dev;
+  P.tgt_off = tgt_off_dev ? tgt_off_dev + b0 : nullptr;
+  const int mode = !ctc_ok ? 0 : ctx->bidir_mode >= 0 ? ctx->bidir_mode : (grad_emis ? 1 : 2);
   void (*kern)(const bidir::Params);
   if (mode == 2)
     kern = lat->C == 64 ? bidir::bidir_ctc_kernel<1, true, true, 2> : bidir::bidir_ctc_kernel<2, true, true, 2>;
