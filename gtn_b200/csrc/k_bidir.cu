@@ -23,29 +23,38 @@
  * at the meeting level equals forwardScore of the lattice.  The dependent chain is T steps instead of
  * 2T, and HBM traffic does not grow: each half of the saved scores is written once and read once.
  *
- * Inside a CTA (warp-specialised, 12 warps at 40 registers so that the four CTAs of two utterances share an SM):
- *   node warps    (<= 7) one graph node per thread; per level 3 LDS of the neighbours' scores (absent arcs read
- *                 a slot that holds a large negative finite number, so there is no -inf / NaN special casing on
- *                 the chain), FMNMX3, 3 ex2, lg2, one STS, one named barrier: 22 SASS instructions per level in
- *                 phase 1, 27 in phase 2.  Scores are kept in log2 units (emissions are multiplied by log2(e)
- *                 on the way in), which removes the multiply from every exp and log, and are RENORMALISED every
- *                 8 levels by an integer (see publish_block_max): the posteriors come out 4-5x closer to a
- *                 float64 evaluation than the reference's own fp32 gradient.
+ * Inside a CTA (warp-specialised):
+ *   node warps    the recursion.  Three variants (launch_bidir_ctc picks):
+ *                 - PAIR (gtnb_ctc_loss with a gradient, C = 64 / 128): the graphs are CTC target graphs, taken from
+ *                   the targets themselves (no ctc_build launch); thread t owns label 2t-1 AND blank 2t, keeps
+ *                   their scores in registers, reads its neighbour pair with one LDS.64 (A) / one LDS (B), writes
+ *                   one STS.64 / STG.64; the blank's two-term logsumexp costs 2 MUFU, the label's 3 (max + lg2(1 +
+ *                   two terms)), the blank's posterior is never formed (complement label).  <= 4 warps, 26 / 31
+ *                   SASS instructions per PAIR and level (the one-node-per-thread kernels: 2 x 19 / 2 x 24).
+ *                 - QUAD (loss-only calls): one node warp, four pairs per thread, neighbours by shuffle, no barrier
+ *                   on the chain at all.
+ *                 - one node per thread (any graph in the envelope; <= 7 warps): per level 3 LDS of the neighbours'
+ *                   scores (absent arcs read a slot that holds a large negative finite number, so there is no
+ *                   -inf / NaN special casing on the chain), one STS, one named barrier.
+ *                 Scores are kept in log2 units (emissions are multiplied by log2(e) on the way in), which removes
+ *                 the multiply from every exp and log, and are RENORMALISED every 8 levels by an integer (see
+ *                 publish_block_max): the posteriors come out 4-5x closer to a float64 evaluation than the
+ *                 reference's own fp32 gradient.
  *   producer warp cp.async.bulk (TMA 1-D bulk copies, mbarrier complete_tx) of 8 emission frames at a time into
  *                 a 4-stage ring and, in phase 2, of the partner's 8 saved score rows (+ that block's offset)
  *                 into a 2-stage ring.
  *   helper warps  (4) own two rows of a block each: row logsumexp of the emissions (forwardScore(emissions) and
  *                 its softmax gradient, k_linear.cu's job before) with LDS.128 and half-warp shuffles, the
  *                 posteriors summed by label -- the node threads write theirs into 4 slots per label of a
- *                 separate block, so a label's mass is one LDS.128; labels carried by more nodes (CTC: blank)
- *                 sit behind the slots and are summed by the row's 16 lanes together; no floating-point
- *                 atomics anywhere -- and the finished gradient row leaves as one 16-byte store per lane.
+ *                 separate block, so a label's mass is one LDS.128; labels on 5..16 nodes sit behind the slots and
+ *                 are summed by the row's 16 lanes together; the label with the MOST nodes (CTC: blank) stores
+ *                 nothing: its mass is the level's mass minus everybody else's; no floating-point atomics
+ *                 anywhere -- and the finished gradient row leaves as one 16-byte store per lane.
  *
- * What bounds it (profiles/r2_bidir_notes.md, scripts/ubench/chain*.cu): the SFU.  A level costs 4 MUFU per
- * node (+1 for the posterior) and the B200 retires 16 per clock and SM: 0.35 cycles per node-level measured at
- * saturation whatever the CTA shape, i.e. >= 0.14 ms for config 2.  The two sweeps of k_implicit.cu spend 7
- * MUFU per node and frame, this kernel 9 -- it halves the dependent chain but does MORE SFU work, which is
- * why it lands at 0.39 ms against 0.17 + 0.24 (+ 0.085 of k_linear.cu beside them) and not at half.
+ * What bounds it (profiles/r2_bidir_notes.md, scripts/ubench/chain*.cu): not HBM (1.7-2 TB/s of 6.5), not one pipe
+ * (XU 48 %, LSU 29 %, issue 54 % of active cycles): the dependent chain of a level (~150 cycles), four CTAs deep on
+ * 68 of the 148 SMs (512 CTAs: the SMs are idle a quarter of the kernel's duration waiting for those).  Round 2:
+ * 0.558 -> 0.389 (helper fast path) -> 0.351 (complement label, immediate addressing) -> 0.282 ms (PAIR kernels).
  *
  * Numerics: gamma's exponent is evaluated as ((x - Zh) + y) - zsub with x the larger of alpha/beta: both
  * subtractions are exact or nearly so (Sterbenz), so the posterior carries only the rounding error the
