@@ -53,6 +53,9 @@ def run(lib, e, targets, lens=None, blank=0, want_grad=True, zero_w=1):
     (2, 1, 8, 0),      # T = 1, empty targets
     (2, 33, 8, 16),    # T = 2U + 1: a single feasible alignment per utterance
     (2, 8, 8, 2),      # T = 8: one block, everything in CTA B's first phase
+    (2, 12, 64, 0),    # PAIR / QUAD kernels on an empty target (one pair: the blank alone)
+    (2, 20, 64, 1),    # ... and on a single label
+    (1, 232, 64, 111), # ... and on the longest target they take (223 nodes: 112 pairs, 28 lanes of the QUAD warp)
     (1, 24, 8, 3),     # T = 24: M = 16, the halves differ by a block
 ])
 def test_bidir_kernel_source_matches_oracle(emu, oracle, shape):

@@ -628,6 +628,42 @@ def test_ctc_bidir_agrees_with_two_sweeps_and_oracle(ctx, oracle, shape, want_gr
             assert not res[1][1][b, lens[b]:].any()
 
 
+@pytest.mark.parametrize("shape", [(6, 300, 64, 30), (3, 41, 64, 0), (2, 250, 128, 111), (4, 16, 64, 1)])
+def test_ctc_bidir_node_warp_variants_agree(ctx, oracle, shape):
+    """k_bidir.cu's three node-warp variants on the same CTC batch (C = 64 / 128): "bidir_mode" 0 one node per
+    thread (reads ctc_build's tables), 1 PAIR (label + blank per thread, graphs from the targets, one launch), 2 QUAD
+    (one node warp, four pairs per thread); -1 = the default choice.  Loss and gradient against the oracle and the
+    float64 referee for each; ragged lengths; blank = C - 1 for the second half of the modes."""
+    from oracle import f64
+    B, T, C, U = shape
+    e, targets = util.bench_inputs(B, T, C, U, seed=91)
+    lens = np.array([T - (3 * b) % max(T // 2, 1) for b in range(B)], np.int32)
+    for mode in (0, 1, 2, -1):
+        ctx.set_flag("bidir_mode", mode)
+        ctx.profile(True)
+        ctx.profile_read()
+        try:
+            for want_grad in (True, False):
+                before = ctx.launches
+                loss, grad = ctx.ctc_loss(e, targets, input_lens=lens, want_grad=want_grad)
+                if mode != 0:
+                    assert ctx.launches - before == 1, "PAIR / QUAD: the criterion is one launch"
+                for b in range(B):
+                    lo, go = oracle.ctc_loss(e[b, :lens[b]], targets[b], 0, want_grad)
+                    assert util.close(loss[b], lo), (mode, b, loss[b], lo)
+                    if want_grad and np.isfinite(lo):
+                        _, g64 = f64.ctc_f64(e[b, :lens[b]], targets[b])
+                        oracle_err = np.abs(go - g64).max()
+                        assert np.abs(grad[b, :lens[b]] - g64).max() <= 2.0 * oracle_err + 2e-6, (mode, b)
+                        assert not grad[b, lens[b]:].any()
+        finally:
+            ctx.set_flag("bidir_mode", -1)
+        names = set(ctx.profile_read())
+        ctx.profile(False)
+        assert "bidir_ctc" in names and "implicit_forward" not in names, names
+        assert ("ctc_build" in names) == (mode == 0), names
+
+
 def test_ctc_bidir_falls_back_on_non_finite_emissions(ctx):
     """a non-finite emission raises the status bit and the call is repeated materialised, like the
     two-sweep path (C = 8: bidir eligible)."""
