@@ -64,6 +64,31 @@ int stage_upload(gtnb_ctx* ctx, void* dst_dev, const void* src_host, size_t byte
   return GTNB_OK;
 }
 
+int stage_reserve(gtnb_ctx* ctx, size_t bytes) {
+  const size_t need = ctx->stage_used + bytes;
+  if (need <= ctx->stage_bytes) return GTNB_OK;
+  GTNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // copies already issued from the old buffer
+  size_t nb = std::max(need * 2, (size_t)1 << 20);
+  unsigned char* fresh = nullptr;
+  GTNB_CUDA(ctx, cudaMallocHost((void**)&fresh, nb));
+  if (ctx->stage_used) std::memcpy(fresh, ctx->stage, ctx->stage_used);
+  if (ctx->stage) cudaFreeHost(ctx->stage);
+  ctx->stage = fresh;
+  ctx->stage_bytes = nb;
+  return GTNB_OK;
+}
+
+int stage_place(gtnb_ctx* ctx, const void* src_host, size_t bytes, void** where) {
+  const size_t sz = (bytes + 255) & ~(size_t)255;
+  if (ctx->stage_used + sz > ctx->stage_bytes)
+    return fail(ctx, GTNB_ERR_LOGIC, "stage_place: stage_reserve the pass first (placed addresses must stay valid)");
+  unsigned char* p = ctx->stage + ctx->stage_used;
+  if (bytes) std::memcpy(p, src_host, bytes);
+  ctx->stage_used += sz;
+  *where = p;
+  return GTNB_OK;
+}
+
 int stage_end(gtnb_ctx* ctx) {
   GTNB_CUDA(ctx, cudaEventRecord(ctx->stage_ev, ctx->stream));
   ctx->stage_pending = true;

@@ -6,7 +6,11 @@
  */
 #include <algorithm>
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "gtnb_internal.h"
@@ -18,6 +22,25 @@ using namespace gtnb;
  * when the target graphs qualify; *needs_exact is set when that sweep met a non-finite weight,
  * in which case the outputs are not to be used and the caller repeats the call materialised.
  */
+namespace {
+/* GTNB_TIMES=1: wall-clock microseconds between the host-side phases of one gtnb_ctc_loss call (stderr) */
+struct PhaseClock {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  std::string line;
+  PhaseClock() : on(std::getenv("GTNB_TIMES") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    line += std::string(what) + " " + std::to_string(std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count() / 1000.0) + "  ";
+    t = n;
+  }
+  ~PhaseClock() {
+    if (on) std::fprintf(stderr, "[gtnb_ctc_loss us] %s\n", line.c_str());
+  }
+};
+} // namespace
+
 static int ctc_loss_run(
     gtnb_ctx* ctx, int B, int T, int C, const float* emissions, int emissions_on_device,
     const int32_t* input_lens, const int32_t* targets, const int32_t* target_lens, int blank,
@@ -27,6 +50,11 @@ static int ctc_loss_run(
     return fail(ctx, GTNB_ERR_INVALID_ARGUMENT, "gtnb_ctc_loss: bad arguments");
   if (B == 0) return GTNB_OK;
   GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PhaseClock pc;
+  bool direct = false;
+  const bool bidir_direct_ok = true;
+  const GraphMeta* meta_mapped = nullptr;
+  const int32_t* small_mapped = nullptr;
   const long long per = (long long)T * C;
   int rc = GTNB_OK;
   float* e_dev = nullptr;
@@ -73,6 +101,7 @@ static int ctc_loss_run(
   }
   int maxT = 0;
   for (int b = 0; b < B; b++) maxT = std::max(maxT, Tb[b]);
+  pc.mark("sizes");
 
 #define TRY(x)                 \
   do {                         \
@@ -118,9 +147,23 @@ static int ctc_loss_run(
   TRY(dev_alloc(ctx, &deltas_dev, B));
   TRY(dev_alloc(ctx, &small_dev, tot_t + 3ll * B));
   TRY(composed_alloc(ctx, B, dims.data(), B, 0, Tb.data(), C, e_dev, per, sgn, sga, &lat, implicit));
+  pc.mark("alloc+meta");
   // the whole criterion in one launch per sub-batch (k_bidir.cu) when the batch qualifies
   bidir = implicit && ctx->use_bidir && ctx->use_banded == 0 && bidir_supported(lat, e_dev, per, g_dev, per);
-  if (bidir) {
+  // PAIR / QUAD kernels (graphs from the targets, one launch): everything small goes through MAPPED pinned memory --
+  // the kernel reads the descriptors and targets in place and writes its results straight into the read-back
+  // block; no upload, no memset, no download on the path (23 of the step's 47 us of host work were those enqueues)
+  direct = bidir_direct_ok && implicit && ctx->use_bidir && ctx->use_banded == 0 && ctx->bidir_mode != 0 &&
+           bidir_supported(lat, e_dev, per, g_dev, per) && bidir_takes_targets(lat, 1, blank);
+  if (bidir && direct) {
+    const long long zpb = 2ll * B * bidir_zparts();
+    TRY(readback_reserve(ctx, (zpb + 2ll * B) * sizeof(float)));
+    zparts_dev = reinterpret_cast<float*>(ctx->readback);
+    bidir_scores_dev = zparts_dev + zpb;
+    status_dev = reinterpret_cast<int32_t*>(zparts_dev + zpb + B);
+    std::memset(status_dev, 0, sizeof(int32_t) * B);
+    TRY(dev_alloc(ctx, &boff_dev, 8ll * B * bidir_blocks(maxT)));
+  } else if (bidir) {
     // one block for everything that is read back: [partial sums of forwardScore(e) | lattice scores | status]
     const long long zpb = 2ll * B * bidir_zparts();
     TRY(dev_alloc(ctx, &zparts_dev, zpb + 2ll * B));
@@ -136,21 +179,36 @@ static int ctc_loss_run(
 
   // one pinned staging pass for everything the kernels need from the host
   TRY(stage_begin(ctx));
-  TRY(stage_upload(ctx, lat->meta, lat->meta_h.data(), sizeof(GraphMeta) * B));
   {
     // [targets | offsets | lens | T] in ONE copy (each small copy costs microseconds of stream latency)
-    std::vector<int32_t> small_h((size_t)(tot_t + 3ll * B));
-    if (tot_t) std::memcpy(small_h.data(), targets, sizeof(int32_t) * tot_t);
-    std::memcpy(small_h.data() + tot_t, off.data(), sizeof(int32_t) * B);
-    std::memcpy(small_h.data() + tot_t + B, target_lens, sizeof(int32_t) * B);
-    std::memcpy(small_h.data() + tot_t + 2ll * B, Tb.data(), sizeof(int32_t) * B);
-    TRY(stage_upload(ctx, small_dev, small_h.data(), sizeof(int32_t) * small_h.size()));
+    std::vector<int32_t> small_h;
+    if (!(bidir && direct)) {
+      small_h.resize((size_t)(tot_t + 3ll * B));
+      if (tot_t) std::memcpy(small_h.data(), targets, sizeof(int32_t) * tot_t);
+      std::memcpy(small_h.data() + tot_t, off.data(), sizeof(int32_t) * B);
+      std::memcpy(small_h.data() + tot_t + B, target_lens, sizeof(int32_t) * B);
+      std::memcpy(small_h.data() + tot_t + 2ll * B, Tb.data(), sizeof(int32_t) * B);
+    }
+    if (bidir && direct) {
+      // the kernel needs the descriptors (with the target offsets) and the labels, nothing else
+      void *m = nullptr, *t = nullptr;
+      for (int b = 0; b < B; b++) lat->meta_h[b].tgt_off = off[b];
+      TRY(stage_reserve(ctx, sizeof(GraphMeta) * B + sizeof(int32_t) * (size_t)tot_t + 1024));
+      TRY(stage_place(ctx, lat->meta_h.data(), sizeof(GraphMeta) * B, &m));
+      TRY(stage_place(ctx, targets, sizeof(int32_t) * (size_t)tot_t, &t));
+      meta_mapped = static_cast<const GraphMeta*>(m);
+      small_mapped = static_cast<const int32_t*>(t);
+    } else {
+      TRY(stage_upload(ctx, lat->meta, lat->meta_h.data(), sizeof(GraphMeta) * B));
+      TRY(stage_upload(ctx, small_dev, small_h.data(), sizeof(int32_t) * small_h.size()));
+    }
   }
   if (!bidir) {
     std::vector<float> minus1(B, -1.0f); // subtract's gradFunc, functions.cpp:53-58
     TRY(stage_upload(ctx, deltas_dev, minus1.data(), sizeof(float) * B));
   }
   TRY(stage_end(ctx));
+  pc.mark("staging");
   if (!emissions_on_device) {
     // enqueued AFTER the small staged upload: the copy engine serves one direction in
     // submission order, and the graphs must not queue behind 65 MB of emissions
@@ -168,7 +226,7 @@ static int ctc_loss_run(
 
   // ctcGraph -> intersect(ctc, emissions) -> forwardScore -> backward(-1) -> compose gradFunc
   // (k_bidir.cu's PAIR / QUAD kernels take the CTC target graphs from the targets themselves: no tables to build)
-  if (!(bidir && ctx->bidir_mode != 0 && bidir_takes_targets(lat, 1, blank)))
+  if (!(bidir && direct))
     TRY(launch_ctc_build(ctx, lat, small_dev, small_dev + tot_t, small_dev + tot_t + B, blank));
   if (implicit) {
     // the sweeps: k_implicit.cu, or (experimental flag) the temporally blocked ones of k_banded.cu
@@ -187,7 +245,8 @@ static int ctc_loss_run(
     const int32_t* T_dev = small_dev + tot_t + 2ll * B;
     TRYCUDA(cudaEventRecord(ev_setup, main_stream));
     if (bidir && K == 1 && !h2d_event && !(grads && !grads_on_device)) {
-      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1, bidir_scores_dev, blank, small_dev, small_dev + tot_t));
+      TRY(launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, 0, -1, /*zero_w=*/1, bidir_scores_dev, blank, direct ? small_mapped : small_dev,
+                               (direct ? small_mapped : small_dev) + tot_t, direct ? meta_mapped : nullptr));
     } else if (bidir) {
       for (int k = 0; k < K && !rc; k++) {
         const int b0 = chunk_lo[k], nb = chunk_lo[k + 1] - chunk_lo[k];
@@ -195,7 +254,8 @@ static int ctc_loss_run(
         TRYCUDA(cudaStreamWaitEvent(cs, ev_setup, 0));
         if (h2d_event) TRYCUDA(cudaStreamWaitEvent(cs, ctx->side_events[k], 0));
         ctx->stream = cs;
-        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1, bidir_scores_dev, blank, small_dev, small_dev + tot_t);
+        rc = launch_bidir_ctc(ctx, lat, status_dev, zparts_dev, boff_dev, g_dev, per, b0, nb, /*zero_w=*/1, bidir_scores_dev, blank, direct ? small_mapped : small_dev,
+                               (direct ? small_mapped : small_dev) + tot_t, direct ? meta_mapped : nullptr);
         ctx->stream = main_stream;
         if (rc) goto done;
         if (grads && !grads_on_device)
@@ -259,13 +319,16 @@ static int ctc_loss_run(
     if (!grads_on_device)
       TRYCUDA(cudaMemcpyAsync(grads, g_dev, sizeof(float) * per * B, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  pc.mark("launches");
   zp = bidir ? 2 * bidir_zparts() : 1; // partial sums of forwardScore(emissions) per utterance
   TRY(readback_reserve(ctx, (zp + 2) * sizeof(float) * B));
   {
     float* z = reinterpret_cast<float*>(ctx->readback);
     float* s = z + (long long)zp * B;
     int32_t* st = reinterpret_cast<int32_t*>(s + B);
-    if (bidir) { // one copy: the block is laid out like the host buffer
+    if (bidir && direct) {
+      // the kernel wrote straight into this block
+    } else if (bidir) { // one copy: the block is laid out like the host buffer
       TRYCUDA(cudaMemcpyAsync(z, zparts_dev, sizeof(float) * (zp + 2) * B, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
       TRYCUDA(cudaMemcpyAsync(z, z_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx->stream));
@@ -273,7 +336,9 @@ static int ctc_loss_run(
       if (implicit)
         TRYCUDA(cudaMemcpyAsync(st, status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    pc.mark("readback enqueue");
     TRYCUDA(cudaStreamSynchronize(ctx->stream));
+    pc.mark("sync");
     for (int b = 0; b < B; b++) { // subtract, functions.cpp:52
       float zb = 0.0f;
       for (int k = 0; k < zp; k++) zb += z[(long long)zp * b + k];
@@ -293,7 +358,7 @@ done:
   }
   if (!bidir) dev_free(ctx, status_dev); // (bidir: part of the zparts block)
   dev_free(ctx, row_scratch);
-  dev_free(ctx, zparts_dev);
+  if (!direct) dev_free(ctx, zparts_dev);
   dev_free(ctx, boff_dev);
   if (lat) gtnb_lattice_destroy(ctx, lat);
   if (!emissions_on_device) dev_free(ctx, e_dev);

@@ -163,6 +163,10 @@ int composed_alloc(
 int stage_begin(gtnb_ctx* ctx);
 int stage_upload(gtnb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int stage_end(gtnb_ctx* ctx);
+/* copies into the pinned staging buffer WITHOUT an upload and returns the address: pinned memory is mapped into the
+ * device's address space (unified addressing), a kernel may read it in place */
+int stage_reserve(gtnb_ctx* ctx, size_t bytes); // room for everything the pass will place (256-byte granules)
+int stage_place(gtnb_ctx* ctx, const void* src_host, size_t bytes, void** where);
 int readback_reserve(gtnb_ctx* ctx, size_t bytes);
 int launch_ctc_build(
     gtnb_ctx* ctx, gtnb_lattice* lat, const int32_t* targets_dev, const int32_t* tgt_off_dev,
@@ -310,7 +314,8 @@ int bidir_zparts(); // partial sums of forwardScore(emissions) per CTA
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
     int64_t grad_stride, int b0 = 0, int nb = -1, int zero_w = 0, float* out_scores_dev = nullptr,
-    int ctc_blank = -1, const int32_t* targets_dev = nullptr, const int32_t* tgt_off_dev = nullptr);
+    int ctc_blank = -1, const int32_t* targets_dev = nullptr, const int32_t* tgt_off_dev = nullptr,
+    const GraphMeta* meta_src = nullptr); // meta_src: the descriptors somewhere else than lat->meta (mapped host memory)
 // ctc_blank >= 0 + the targets: CTC target graphs, taken from the targets themselves (PAIR / QUAD kernels)
 bool bidir_takes_targets(const gtnb_lattice* lat, int zero_w, int ctc_blank);
 /* k_order.cu (experimental): a composed lattice's rows and accept list in the order the reference's shortestPath relaxes / creates them */

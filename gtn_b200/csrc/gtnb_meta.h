@@ -57,6 +57,8 @@ struct GraphMeta {
   int cap_N; // slab capacities
   int cap_A;
   int cap_L;
+  int tgt_off; // gtnb_ctc_loss: first label of this utterance in the concatenated targets (k_bidir.cu PAIR / QUAD)
+  int pad_;
 };
 
 } // namespace gtnb

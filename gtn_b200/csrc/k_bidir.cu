@@ -171,7 +171,7 @@ struct Params {
   int zero_w; // every arc weight of every graph is 0 (host knowledge: CTC / forced alignment targets)
   int ctc_blank; // PAIR / QUAD kernels: the graphs are CTC target graphs with this blank label ...
   const int32_t* targets; // ... taken from the targets themselves: concatenated labels,
-  const int32_t* tgt_off; // [B] first label of utterance b (the kernel never reads ctc_build_kernel's tables)
+  // at GraphMeta::tgt_off of utterance b (the kernel never reads ctc_build_kernel's tables)
   Layout lay;
 };
 
@@ -1714,7 +1714,7 @@ __global__ void __launch_bounds__(
   __syncthreads();
   bool bad = false;
   int my_lab = 0, my_deg = 0;
-  const int32_t* tg = MODE != 0 ? P.targets + P.tgt_off[b] : nullptr; // this utterance's labels
+  const int32_t* tg = MODE != 0 ? P.targets + m.tgt_off : nullptr; // this utterance's labels
   if (MODE != 0) {
     // CTC target graph: node n carries blank (even n) or label (n - 1) / 2 (odd n)
     if (tid < N1) sts_s8(nlab_a + (uint32_t)tid, (tid & 1) ? tg[(tid - 1) >> 1] : P.ctc_blank);
@@ -1955,7 +1955,7 @@ __global__ void __launch_bounds__(
       node_role<0, ZW, NQ, FX>(st, cx, act, nid);
     else
       node_role<1, ZW, NQ, FX>(st, cx, act, nid);
-    if (bad) atomicOr(&P.status[b], 1);
+    if (bad) *(volatile int32_t*)&P.status[b] = 1; // (every writer stores the same 1: no atomic needed)
     if (T == 0 && dir == 0 && tid == 0) {
       // no frames: the lattice is the graph's start-and-accept nodes, each with score 0
       int n = 0;
@@ -2151,7 +2151,7 @@ __global__ void __launch_bounds__(
   float z = hs.l16 == 0 ? hs.zacc : 0.0f;
   z += __shfl_xor_sync(0xffffffffu, z, 16);
   if (lane == 0) P.zparts[(2 * b + dir) * kHelpers + hs.hw] = z;
-  if (hs.bad) atomicOr(&P.status[b], 1);
+  if (hs.bad) *(volatile int32_t*)&P.status[b] = 1;
 }
 
 } // namespace bidir
@@ -2192,11 +2192,11 @@ int bidir_zparts() {
 int launch_bidir_ctc(
     gtnb_ctx* ctx, gtnb_lattice* lat, int32_t* status_dev, float* zparts_dev, float* boff_dev, float* grad_emis,
     int64_t grad_stride, int b0, int nb, int zero_w, float* out_scores_dev, int ctc_blank, const int32_t* targets_dev,
-    const int32_t* tgt_off_dev) {
+    const int32_t* tgt_off_dev, const GraphMeta* meta_src) {
   if (nb < 0) nb = lat->B - b0;
   if (nb <= 0) return GTNB_OK;
   bidir::Params P;
-  P.meta = lat->meta + b0;
+  P.meta = (meta_src ? meta_src : lat->meta) + b0;
   P.sg_flags = lat->sg_flags;
   P.sg_in_ptr = lat->sg_in_ptr;
   P.sg_in_src = lat->sg_in_src;
@@ -2221,9 +2221,9 @@ int launch_bidir_ctc(
   // NQ: float4 chunks of an emission row per helper lane
   // the graphs are ctc_build_kernel's (gtnb_ctc_loss): PAIR (two nodes per thread; the default) or QUAD (one node
   // warp, four pairs per thread) kernels; gtnb_ctx_set_flag("bidir_mode", 0 | 1 | 2) picks one for comparison
-  const bool ctc_ok = bidir_takes_targets(lat, zero_w, ctc_blank) && targets_dev && tgt_off_dev;
+  (void)tgt_off_dev; // (the offsets travel in the descriptors: GraphMeta::tgt_off)
+  const bool ctc_ok = bidir_takes_targets(lat, zero_w, ctc_blank) && targets_dev;
   P.targets = targets_dev;
-  P.tgt_off = tgt_off_dev ? tgt_off_dev + b0 : nullptr;
   const int mode = !ctc_ok ? 0 : ctx->bidir_mode >= 0 ? ctx->bidir_mode : (grad_emis ? 1 : 2);
   void (*kern)(const bidir::Params);
   if (mode == 2)

@@ -88,7 +88,7 @@ int emu_bidir_ctc(
   const bool pair = ctc_ok && zero_w == 1, quad = ctc_ok && zero_w == 3; // 1: gtnb_ctc_loss's default, 3: "bidir_mode" 2
   P.ctc_blank = blank;
   P.targets = targets;
-  P.tgt_off = tgt_off.data();
+  for (int b = 0; b < B; b++) meta[b].tgt_off = tgt_off[b];
   P.nwn = quad ? 1 : pair ? std::max(1, ((maxN + 1) / 2 + 31) / 32) : std::max(1, (maxN + 31) / 32);
   P.lay = bidir::make_layout(C, fx ? bidir::kFixedPitch : ((maxN + 3) & ~3));
   const unsigned block = 32 * (P.nwn + 1 + bidir::kHelpers + (quad ? bidir::kQuadSpare : 0));
