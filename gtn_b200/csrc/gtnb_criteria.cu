@@ -90,8 +90,11 @@ static int ctc_loss_run(
     const int32_t* tg = targets + tot_t;
     int skips = 0;
     int all_valid = blank >= 0 && blank < C;
-    for (int u = 1; u < U; u++) skips += tg[u] != tg[u - 1];
-    for (int u = 0; u < U; u++) all_valid &= tg[u] >= 0 && tg[u] < C;
+    if (U > 0) all_valid &= (unsigned)tg[0] < (unsigned)C;
+    for (int u = 1; u < U; u++) { // one pass: skip arcs exist where consecutive labels differ; labels in [0, C)
+      skips += tg[u] != tg[u - 1];
+      all_valid &= (unsigned)tg[u] < (unsigned)C;
+    }
     const int L = 2 * U + 1;
     dims[b] = SgDims{L, L + (L - 1) + skips, L >= 2 ? 2 : 1, all_valid, /*uniform=*/1, /*max_in=*/3, /*max_out=*/3};
     tot_t += U;
@@ -207,7 +210,7 @@ static int ctc_loss_run(
     std::vector<float> minus1(B, -1.0f); // subtract's gradFunc, functions.cpp:53-58
     TRY(stage_upload(ctx, deltas_dev, minus1.data(), sizeof(float) * B));
   }
-  TRY(stage_end(ctx));
+  if (!(bidir && direct)) TRY(stage_end(ctx)); // (direct: no copy was issued from the staging buffer; the call synchronises before it returns)
   pc.mark("staging");
   if (!emissions_on_device) {
     // enqueued AFTER the small staged upload: the copy engine serves one direction in
