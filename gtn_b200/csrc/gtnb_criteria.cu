@@ -51,8 +51,7 @@ static int ctc_loss_run(
   if (B == 0) return GTNB_OK;
   GTNB_CUDA(ctx, cudaSetDevice(ctx->device));
   PhaseClock pc;
-  bool direct = false;
-  const bool bidir_direct_ok = true;
+  bool direct = false; // the PAIR / QUAD kernels of k_bidir.cu on mapped pinned memory (see below)
   const GraphMeta* meta_mapped = nullptr;
   const int32_t* small_mapped = nullptr;
   const long long per = (long long)T * C;
@@ -156,7 +155,7 @@ static int ctc_loss_run(
   // PAIR / QUAD kernels (graphs from the targets, one launch): everything small goes through MAPPED pinned memory --
   // the kernel reads the descriptors and targets in place and writes its results straight into the read-back
   // block; no upload, no memset, no download on the path (23 of the step's 47 us of host work were those enqueues)
-  direct = bidir_direct_ok && implicit && ctx->use_bidir && ctx->use_banded == 0 && ctx->bidir_mode != 0 &&
+  direct = implicit && ctx->use_bidir && ctx->use_banded == 0 && ctx->bidir_mode != 0 &&
            bidir_supported(lat, e_dev, per, g_dev, per) && bidir_takes_targets(lat, 1, blank);
   if (bidir && direct) {
     const long long zpb = 2ll * B * bidir_zparts();
