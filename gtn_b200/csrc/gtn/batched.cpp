@@ -160,6 +160,7 @@ void flushLattice(const std::shared_ptr<LatticeHandle>& h) {
  * read-back, a device read otherwise */
 void fetchBatchSlice(const std::shared_ptr<Context>& c, int slot, const void* owner, const float* dev, size_t off,
                      size_t n, std::vector<float>& out);
+bool addBatchSlice(const std::shared_ptr<Context>& c, int slot, const void* owner, size_t off, size_t n, float* dst, size_t dn);
 
 void fetchSlice(const std::shared_ptr<Context>& c, const float* dev, size_t n, std::vector<float>& out) {
   out.resize(n);
@@ -293,11 +294,18 @@ std::vector<Graph> composeBatch(const std::vector<Graph>& a, const std::vector<G
         flushLattice(handle);
         fetchSlice(c, handle->batch->dGraph->ptr + handle->batch->graphOff[bi], graphArcs, v);
       });
-      gLinear.addLazyGrad(emisArcs, [handle, bi, emisArcs, c](std::vector<float>& v) {
-        flushLattice(handle);
-        BatchState& bs = *handle->batch;
-        fetchBatchSlice(c, 0, &bs, bs.dLinear->ptr, (size_t)bi * bs.stride, emisArcs, v);
-      });
+      gLinear.addLazyGrad(
+          emisArcs,
+          [handle, bi, emisArcs, c](std::vector<float>& v) {
+            flushLattice(handle);
+            BatchState& bs = *handle->batch;
+            fetchBatchSlice(c, 0, &bs, bs.dLinear->ptr, (size_t)bi * bs.stride, emisArcs, v);
+          },
+          [handle, bi, emisArcs, c](float* dst, size_t dn) {
+            flushLattice(handle);
+            BatchState& bs = *handle->batch;
+            return addBatchSlice(c, 0, &bs, (size_t)bi * bs.stride, emisArcs, dst, dn);
+          });
     };
     out.push_back(Graph::fromLattice(handle, bi, gradFunc, {a[i], b[i]}));
   }
@@ -314,6 +322,15 @@ void fetchBatchSlice(const std::shared_ptr<Context>& c, int slot, const void* ow
     }
   }
   fetchSlice(c, dev + off, n, out);
+}
+
+/* adds a batch's slice into dst when the context's pinned block still holds that batch's read-back */
+bool addBatchSlice(const std::shared_ptr<Context>& c, int slot, const void* owner, size_t off, size_t n, float* dst, size_t dn) {
+  std::lock_guard<std::mutex> l(c->lock);
+  if (c->pinnedOwner[slot] != owner || !c->pinned[slot]) return false;
+  const float* src = c->pinned[slot] + off;
+  for (size_t i = 0; i < n && i < dn; i++) dst[i] += src[i];
+  return true;
 }
 
 Graph scalarResult(Graph::GradFunc gradFunc, const Graph& input, float score) {
@@ -451,10 +468,16 @@ std::vector<Graph> scoreBatch(const std::vector<Graph>& gs, bool tropical) {
             if (lb->flushed) throw std::logic_error("[gtn::forwardScore] the batched backward of this list has already run");
             lb->delta[bi] += deltas.item();
           }
-          inputs[0].addLazyGrad(n, [lb, bi, n](std::vector<float>& v) {
-            flushLinear(lb);
-            fetchBatchSlice(lb->c, 1, lb.get(), lb->grad->ptr, (size_t)bi * lb->stride, n, v);
-          });
+          inputs[0].addLazyGrad(
+              n,
+              [lb, bi, n](std::vector<float>& v) {
+                flushLinear(lb);
+                fetchBatchSlice(lb->c, 1, lb.get(), lb->grad->ptr, (size_t)bi * lb->stride, n, v);
+              },
+              [lb, bi, n](float* dst, size_t dn) {
+                flushLinear(lb);
+                return addBatchSlice(lb->c, 1, lb.get(), (size_t)bi * lb->stride, n, dst, dn);
+              });
         };
         out.push_back(scalarResult(gradFunc, gs[i], scores[i]));
       }

@@ -369,10 +369,13 @@ std::vector<float>& Graph::hostWeights() const {
   }
   if (!sw.lazyAdds.empty()) {
     std::lock_guard<std::mutex> l(sw.lock);
-    std::vector<float> part;
-    for (auto& f : sw.lazyAdds) {
-      part.assign(sw.host.size(), 0.0f);
-      f(part);
+    // (256 entries x 256 KB per minibatch come through here: no zero fill, no temporary where the source can add
+    // in place, one scratch vector per thread otherwise)
+    thread_local std::vector<float> part;
+    for (auto& a : sw.lazyAdds) {
+      if (a.acc && a.acc(sw.host.data(), sw.host.size())) continue;
+      part.clear();
+      a.fetch(part);
       for (size_t i = 0; i < sw.host.size() && i < part.size(); i++) sw.host[i] += part[i];
     }
     sw.lazyAdds.clear();
@@ -536,7 +539,8 @@ void Graph::addGrad(std::vector<float>&& other) {
   }
 }
 
-void Graph::addLazyGrad(size_t n, std::function<void(std::vector<float>&)> fetch) {
+void Graph::addLazyGrad(
+    size_t n, std::function<void(std::vector<float>&)> fetch, std::function<bool(float*, size_t)> acc) {
   if (!calcGrad()) return;
   {
     std::lock_guard<std::mutex> lock(sharedGraph_->grad_lock);
@@ -554,7 +558,7 @@ void Graph::addLazyGrad(size_t n, std::function<void(std::vector<float>&)> fetch
     auto& gw = *sharedGrad_->grad->sharedWeights_;
     if (gw.lazyFetch || !gw.lazyAdds.empty()) {
       std::lock_guard<std::mutex> l(gw.lock);
-      gw.lazyAdds.push_back(std::move(fetch));
+      gw.lazyAdds.push_back({std::move(fetch), std::move(acc)});
       return;
     }
   }

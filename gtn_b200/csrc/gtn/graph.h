@@ -229,7 +229,11 @@ class Graph {
    * vector the first time anybody reads it.  Falls back to an eager fetch + addGrad
    * when a gradient is already present.  (Used by the shortest-distance gradFunc.)
    */
-  void addLazyGrad(size_t numArcs, std::function<void(std::vector<float>&)> fetch);
+  /** acc (optional): adds the contribution straight into dst (no temporary); returns false if it cannot, then
+   * fetch + add is used. */
+  void addLazyGrad(
+      size_t numArcs, std::function<void(std::vector<float>&)> fetch,
+      std::function<bool(float* dst, size_t n)> acc = nullptr);
   /** True while this graph's weights are still device-only (see addLazyGrad). */
   bool hasLazyWeights() const {
     return sharedWeights_ && sharedWeights_->lazyFetch != nullptr;
@@ -267,7 +271,11 @@ class Graph {
     std::function<void(std::vector<float>&)> lazyFetch; // see addLazyGrad, fromLattice
     // further device-side contributions that arrived while the first one was still pending: added to the
     // host vector when somebody reads it (the batched list ops install one per op and entry)
-    std::vector<std::function<void(std::vector<float>&)>> lazyAdds;
+    struct LazyAdd {
+      std::function<void(std::vector<float>&)> fetch;
+      std::function<bool(float*, size_t)> acc; // may be empty
+    };
+    std::vector<LazyAdd> lazyAdds;
     // a slice of a batch-wide device buffer that holds exactly these weights (gathered by a batched list
     // op, gtn/batched.cpp); dropped with `device` whenever the weights may change
     std::shared_ptr<detail::DeviceBuffer> batch;
